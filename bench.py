@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py — the hot path's headline benchmark (BASELINE.json): RHO radix hash join throughput in
+(|R|+|S|) Mtuples/s with the scan's GB/s beside it, against the HBM roofline.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = one complete join (histogram -> prefix sums -> pass-1 scatter -> pass-2 scatter ->
+build/probe) of device-resident relations |R|=2^27, |S|=2^29 (BASELINE config 3; 5 GiB of input, far
+larger than the 126 MB L2, so no cache flush is needed between steps). Prints ONE JSON line.
+
+  value     join throughput, inputs resident in HBM, device time (CUDA events), max over ranks
+  e2e       same join through the drop-in C ABI call run_join(result_t*, R, S, "RHO", cfg) with
+            pinned HOST relations: H2D of 8(|R|+|S|) bytes and the result read-back are inside the
+            timed region
+  roofline  the dominant kernel (radix_scatter_kernel, 4 launches per join): algorithmic bytes per
+            launch (16 B/tuple) / its mean launch time from the library's CUDA events
+  join_roofline  the whole join at SURVEY.md §8d's graded 56 B/tuple
+  scan      bitvector and row-id scans over 2^30 uint8 (BASELINE config 2), GB/s of input and
+            fraction of the HBM peak at 1.125 B/value resp. (1 + 8 sel) B/value
+  cpu_baseline   the reference's own RHO (oracle/_ref, compiled from /root/reference) on this box's
+            host cores on a bounded sample — a reported baseline, not the target
+
+--impl reference runs only that CPU reference arm and prints the same line shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "sgxv2-analytical-query-processing-benchmarks_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+LOG_R, LOG_S = 27, 29          # BASELINE config 3
+SCAN_LOG_N = 30                # BASELINE config 2
+JOIN_BYTES_PER_TUPLE = 56      # 8 * (3 P + 1) with P = 2 passes
+SCATTER_BYTES_PER_TUPLE = 16   # read 8 + write 8
+METRIC = "rho_join_throughput"
+UNIT = "Mtuples/s"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"   # B200_PROFILING.md fallback
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU reference arm (oracle/_ref = the unmodified reference compiled from /root/reference)
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_join(steps: int, warmup: int, log_r: int = 24, log_s: int = 26):
+    """The reference's RHO on the host cores on a bounded sample (2^24 x 2^26 = BASELINE config 1, 1/8
+    of the headline workload). Throughput from the reference's own 'Total Join Time (cycles)' divided
+    by the measured TSC rate. Falls back to the oracle port if oracle/_ref cannot run."""
+    import oracle as O
+    nR, nS = 1 << log_r, 1 << log_s
+    cores = os.cpu_count() or 1
+    t0 = time.time()
+    if O.have_ref():
+        R = O.ref_gen_pk(nR, 11111)
+        S = O.ref_gen_fk(nS, nR, 22222)
+        kind = "reference"
+    else:
+        R = O.gen_pk(nR, 11111)
+        S = O.gen_fk(nS, nR, 22222)
+        kind = "port"
+        cores = 1
+    O.set_rowid_payload(R)
+    O.set_rowid_payload(S)
+    gen_s = time.time() - t0
+    times = []
+    matches = None
+    best_flags = None
+    if kind == "reference":
+        # paper-best flags UNROLL+FORCE_2_PHASES and the automatic pass count; keep the better
+        probe = {}
+        for force2 in (True, False):
+            r = O.ref_rho(R, S, nthreads=cores, force_2_passes=force2)
+            probe[force2] = r["seconds"]
+        best_flags = min(probe, key=probe.get)
+        for i in range(warmup + steps):
+            r = O.ref_rho(R, S, nthreads=cores, force_2_passes=best_flags)
+            matches = r["matches"]
+            if i >= warmup:
+                times.append(r["seconds"])
+    else:
+        for i in range(max(1, min(steps, 3))):
+            t = time.time()
+            r = O.rho(R, S, nthreads=1)
+            times.append(time.time() - t)
+            matches = r["matches"]
+    assert matches == nS
+    mean = sum(times) / len(times)
+    return {"value": (nR + nS) / mean / 1e6, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"|R|=2^{log_r} |S|=2^{log_s} uniform FK (1/8 of the workload), {len(times)} runs, "
+                      f"flags UNROLL{'+FORCE_2_PHASES' if best_flags else ''}, generation {gen_s:.1f}s untimed",
+            "ms_per_step": mean * 1e3}
+
+
+def cpu_reference_scan(log_n: int = 28):
+    import numpy as np
+    import oracle as O
+    if not O.have_ref():
+        return None
+    n = 1 << log_n
+    cores = os.cpu_count() or 1
+    col = O.aligned_u8(n)
+    col[:] = O.tiled_column(n)
+    out = np.zeros(n // 64, dtype=np.uint64)
+    L = O.ref_scan()
+    res = {"cores": cores, "kind": "reference", "sample": f"2^{log_n} tiled uint8, 3 runs after 1 warm-up"}
+    s = L.ref_scan_mt(0, 0, 26, col.ctypes.data, n, cores, 1, 3, out.ctypes.data)
+    res["bitvector_gbs"] = n * 3 / s / 1e9
+    for name, hi in (("rowid_sel10_gbs", 26), ("rowid_sel100_gbs", 255)):
+        s = L.ref_scan_mt(1, 0, hi, col.ctypes.data, n, cores, 1, 3, None)
+        res[name] = n * 3 / s / 1e9
+    return res
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_reference_join(args.steps, args.warmup)
+    scan = cpu_reference_scan()
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": f"RHO join |R|=2^{LOG_R} |S|=2^{LOG_S} 8-byte tuples uniform FK "
+                                   "(reference timed on a bounded sample, see cpu_baseline.sample)"},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "scan": scan}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------------
+def bench_scan(A, torch, dev, peak, steps, warmup, n_gpus=1, rank=0):
+    """Row-range shard of the 2^30 column on this rank (trivially parallel, no exchange)."""
+    n_total = 1 << SCAN_LOG_N
+    n = n_total // n_gpus
+    begin = rank * n
+    data = torch.empty(n, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    assert A.lib().b200_fill_tiled_column_device(data.data_ptr(), n, begin, st) == 0
+    bv = torch.empty(n // 64, dtype=torch.int64, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    out = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timeit(fn):
+        for _ in range(max(warmup, 3)):
+            fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    ms = timeit(lambda: A.bitvector_scan_device(0, 26, data.data_ptr(), n, bv.data_ptr(), st))
+    out["bitvector"] = {"predicate": [0, 26], "ms": ms, "input_gbs": n / ms / 1e6,
+                        "roofline": {"bound": "hbm", "achieved": 1.125 * n / ms / 1e6, "peak": peak, "unit": "GB/s",
+                                     "frac": 1.125 * n / ms / 1e6 / peak}}
+    # 0.39 % / 10.5 % / 50.4 % / 100 % true selectivity on the tiled column (types.hpp:125 mapping)
+    for label, hi in (("sel0.4", 0), ("sel10", 26), ("sel50", 128), ("sel100", 255)):
+        k = n // 256 * (hi + 1)
+        ids = torch.empty(k, dtype=torch.int64, device=dev)
+        ms = timeit(lambda: A.index_scan_device(0, hi, data.data_ptr(), n, ids.data_ptr(), k, cnt.data_ptr(),
+                                                id_base=begin, stream=st))
+        assert int(cnt.item()) == k
+        alg = n + 8 * k
+        out["rowid_" + label] = {"predicate": [0, hi], "selectivity": k / n, "ms": ms, "input_gbs": n / ms / 1e6,
+                                 "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": peak, "unit": "GB/s",
+                                              "frac": alg / ms / 1e6 / peak}}
+        del ids
+    out["n_values_per_gpu"] = n
+    return out
+
+
+def run_b200_arm(args):
+    import torch
+    import b200aqp as A
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libb200aqp has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    A.init(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        import b200aqp.dist as D
+    peak, peak_src = measured_peaks()
+    nR, nS = 1 << LOG_R, 1 << LOG_S
+    st = torch.cuda.current_stream().cuda_stream
+    launches0 = A.kernel_launch_count()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- inputs generated straight into HBM (row-range shard per rank) ------------------------------
+    nR_loc, nS_loc = nR // world, nS // world
+    R = torch.empty(nR_loc * 2, dtype=torch.int32, device=dev)
+    S = torch.empty(nS_loc * 2, dtype=torch.int32, device=dev)
+    A.gen_pk_device(R.data_ptr(), nR, 11111, rank * nR_loc, nR_loc, st)
+    A.gen_fk_device(S.data_ptr(), nS, nR, 22222, rank * nS_loc, nS_loc, st)
+    torch.cuda.synchronize()
+
+    if world == 1:
+        def step():
+            return A.join_device(R.data_ptr(), nR, S.data_ptr(), nS, stream=st)
+    else:
+        plan = D.ShardedJoin(nR, nS, dev)
+
+        def step():
+            return plan.run(R, S)
+
+    for _ in range(max(args.warmup, 3)):
+        s = step()
+    assert s["matches"] == nS, s
+    rep = nS // nR
+    assert s["keysum"] == rep * nR * (nR + 1) // 2 and s["checksum"] == rep * (nR * (nR - 1) // 2) + nS * (nS - 1) // 2
+
+    sampler = ClockSampler(local_rank)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    phase = {"ms_hist": 0.0, "ms_pass1": 0.0, "ms_pass2": 0.0, "ms_join": 0.0, "ms_total": 0.0, "ms_exchange": 0.0}
+    l_before = A.kernel_launch_count()
+    barrier()
+    sampler.start()
+    e0.record()
+    for _ in range(args.steps):
+        s = step()
+        for k in phase:
+            phase[k] += s.get(k, 0.0)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches_timed = A.kernel_launch_count() - l_before
+    ms_step = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms_step], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = float(t.item())
+    for k in phase:
+        phase[k] /= args.steps
+    value = (nR + nS) / ms_step / 1e3   # Mtuples/s
+
+    # dominant kernel: radix_scatter_kernel, 4 launches per join (R and S, pass 1 and pass 2)
+    scatter_ms = (phase["ms_pass1"] + phase["ms_pass2"]) / 4
+    scatter_bytes = SCATTER_BYTES_PER_TUPLE * (nR_loc + nS_loc) * 2 / 4
+    roof = {"bound": "hbm", "kernel": "radix_scatter_kernel", "achieved": scatter_bytes / scatter_ms / 1e6 if scatter_ms else None,
+            "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": None,
+            "bytes_per_launch": scatter_bytes, "ms_per_launch": scatter_ms}
+    roof["frac"] = roof["achieved"] / peak if roof["achieved"] else None
+    join_bytes = JOIN_BYTES_PER_TUPLE * (nR + nS) / world
+    join_roof = {"bound": "hbm", "bytes_per_tuple": JOIN_BYTES_PER_TUPLE, "achieved": join_bytes / ms_step / 1e6,
+                 "peak": peak, "unit": "GB/s", "frac": join_bytes / ms_step / 1e6 / peak,
+                 "actual_bytes_per_tuple": 48, "note": "the pass-2 histogram read is avoided: one full-width histogram serves both passes"}
+
+    # ---- e2e through run_join() with pinned host relations (N=1 path of the drop-in API) ----------
+    e2e = None
+    if world == 1:
+        import numpy as np
+        hR = torch.empty(nR * 2, dtype=torch.int32).pin_memory()
+        hS = torch.empty(nS * 2, dtype=torch.int32).pin_memory()
+        hR.copy_(R)
+        hS.copy_(S)
+        torch.cuda.synchronize()
+        npR = hR.numpy().view(A.ROW).reshape(nR)
+        npS = hS.numpy().view(A.ROW).reshape(nS)
+        e2e_steps = max(1, min(args.steps, 5))
+        for _ in range(2):
+            g = A.run_join(npR, npS)
+        assert g["matches"] == nS
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            g = A.run_join(npR, npS)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / e2e_steps
+        e2e = {"value": (nR + nS) / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": 8 * (nR + nS),
+               "d2h_bytes_per_step": 32, "ms_per_step": dt * 1e3, "steps": e2e_steps,
+               "api": "run_join(result_t*, R, S, \"RHO\", joinconfig_t*) on pinned host relations"}
+        del hR, hS, npR, npS
+    del R, S
+    torch.cuda.empty_cache()
+
+    scan = bench_scan(A, torch, dev, peak, max(args.steps, 5), args.warmup, world, rank)
+    if world > 1:
+        for k, v in scan.items():
+            if isinstance(v, dict):
+                t = torch.tensor([v["ms"]], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                v["ms"] = float(t.item())
+                n_tot = 1 << SCAN_LOG_N
+                v["input_gbs"] = n_tot / v["ms"] / 1e6
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cpu = cpu_reference_join(3, 1)
+                cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                cs = cpu_reference_scan()
+                if cs:
+                    cpu["scan"] = cs
+            except Exception as ex:   # the baseline is reporting only; never fail the bench on it
+                cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                "config": {"workload": f"RHO join |R|=2^{LOG_R} |S|=2^{LOG_S} 8-byte tuples (u32 key, u32 payload), "
+                                       "uniform FK keys, count+checksum (BASELINE config 3)",
+                           "generator": "on-device bijection, seeds 11111/22222", "radix_bits": s["radix_bits"],
+                           "passes": s["num_passes"],
+                           "cache": "inputs (5 GiB) exceed the 126 MB L2; no flush between steps",
+                           "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: pass-1 routes by low key bits, NCCL all-to-all"},
+                "phases_ms": phase, "roofline": roof, "join_roofline": join_roof, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": launches_timed, "gpu_launches_total": A.kernel_launch_count() - launches0,
+                "clocks": clocks, "scan": scan}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

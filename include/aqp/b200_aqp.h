@@ -1,0 +1,210 @@
+/*
+ * aqp/b200_aqp.h — C ABI of libb200aqp.so, the B200 (sm_100a) implementation of the reference's
+ * RHO radix hash join and uint8 column scans.
+ *
+ * Every entry point is extern "C", takes plain pointers / sizes (no C++ or torch types) and cites
+ * the reference interface it replaces (paths relative to /root/reference/).  Three layers:
+ *
+ *   1. Drop-in operator API, HOST buffers      : run_join, RHO, destroy_table, the generators,
+ *                                                 b200_bitvector_scan_user / b200_index_scan_user.
+ *   2. ECALL-shaped preload/run split          : b200_preload_relations + b200_join_preload
+ *                                                 (H2D once, then time the kernels only).
+ *   3. Device-resident API, DEVICE pointers    : b200_*_device — what a multi-GPU host (one process
+ *                                                 per GPU) and bench.py drive; caller owns memory.
+ *
+ * There is no CPU fallback anywhere: if no CUDA device is usable every call fails loudly
+ * (non-zero return, or for the void reference-shaped calls a message on stderr and exit(1), the
+ * reference's own error convention — Joins/src/util.cpp:12-19, joins.cpp:70-73).
+ */
+#ifndef AQP_B200_AQP_H
+#define AQP_B200_AQP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "data_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------
+ * 0. library / device
+ * ---------------------------------------------------------------------------------------------- */
+/* 0 on success. device < 0 keeps the current CUDA device. Idempotent. */
+int b200_init(int device);
+/* release every cached device buffer, stream and event of the calling context */
+void b200_shutdown(void);
+const char *b200_last_error(void);
+/* 0 = silent (default), 1 = print the reference's logger lines scraped by
+ * Join-Benchmarks/SGXv2Scripts/scripts/helpers/runner.py:19-53 ("Throughput (M rec/sec) : ...") */
+void b200_set_verbose(int level);
+/* pinned host memory for callers that want full-speed H2D (plain malloc'd memory also works) */
+void *b200_host_alloc(size_t bytes);
+void b200_host_free(void *p);
+void *b200_device_alloc(size_t bytes);
+void b200_device_free(void *p);
+int b200_memcpy_h2d(void *dst, const void *src, size_t bytes);
+int b200_memcpy_d2h(void *dst, const void *src, size_t bytes);
+int b200_device_sync(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * 1. join — drop-in operator API (host buffers)
+ * ---------------------------------------------------------------------------------------------- */
+/* Join-Benchmarks/lib/Joins/include/joins.hpp:4-6 (impl joins.cpp:55-78). Only "RHO" is served by
+ * this library; any other name -> error message + exit(EXIT_FAILURE) like joins.cpp:70-73. */
+void run_join(struct result_t *res, const struct table_t *relR, const struct table_t *relS,
+              const char *algorithm_name, const struct joinconfig_t *config);
+
+/* Join-Benchmarks/lib/Joins/include/radix/radix_join.h:30 (impl radix_join.cpp:1640-1643).
+ * R = build side (PK), S = probe side. Returns a malloc'd result_t the caller frees; when
+ * result_type == 1, result->result is a chunked_table_t* owned by the caller
+ * (destroy_table() + free(), as Join-Benchmarks/lib/TPCH-Queries/src/tpch.cpp:82 does). */
+struct result_t *RHO(const struct table_t *relR, const struct table_t *relS, const struct joinconfig_t *config);
+
+/* Join-Benchmarks/lib/Joins/src/ChunkedTable.cpp:128-136 */
+void destroy_table(struct chunked_table_t *table);
+
+/* Extra facts about the most recent join on this thread's context. The reference's result_t has
+ * no checksum; checksum = sum over matches of (uint64)Rpayload + (uint64)Spayload
+ * (CHT's convention, Joins/include/cht/CHTJoin.hpp:174), keysum = sum over matches of key. */
+struct b200_join_stats_t {
+    int64_t matches;
+    uint64_t checksum;
+    uint64_t keysum;
+    uint32_t radix_bits;      /* total radix bits used */
+    uint32_t num_passes;      /* partitioning passes (1 or 2) */
+    uint32_t bits_pass1;
+    uint32_t bits_pass2;
+    uint32_t kernel_launches; /* kernels launched for this join */
+    uint32_t reserved;
+    float ms_total;           /* device time, CUDA events: histogram .. build/probe */
+    float ms_hist;
+    float ms_pass1;
+    float ms_pass2;
+    float ms_join;
+    float ms_h2d;             /* 0 for device-resident calls */
+    float ms_d2h;
+    float ms_materialize_host;
+};
+void b200_last_join_stats(struct b200_join_stats_t *out);
+
+/* ------------------------------------------------------------------------------------------------
+ * 2. join — ECALL-shaped split. Replaces ecall_preload_relations / ecall_join_preload
+ *    (Join-Benchmarks/Enclave/Enclave.edl:46-53, secure_joins.cpp:34-58): copy once, run many.
+ * ---------------------------------------------------------------------------------------------- */
+int b200_preload_relations(const struct table_t *relR, const struct table_t *relS);
+int b200_join_preload(const char *algorithm_name, const struct joinconfig_t *config, struct result_t *res);
+void b200_free_preload(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * 3. join — device-resident API (device pointers; stream = cudaStream_t or NULL for the
+ *    library's own stream)
+ * ---------------------------------------------------------------------------------------------- */
+/* Whole local join on device-resident relations. If d_out != NULL up to out_capacity matches are
+ * materialised as output_triple_t (order unspecified, like the reference's per-thread chunk
+ * lists); stats->matches is always the full count. d_R / d_S are not modified. */
+int b200_join_device(const struct row_t *d_R, uint64_t nR, const struct row_t *d_S, uint64_t nS,
+                     struct output_triple_t *d_out, uint64_t out_capacity,
+                     struct b200_join_stats_t *stats, void *stream);
+
+/* Radix bits the GPU path picks for a build side of nR tuples (its analogue of
+ * calc_num_radix_bits / calc_num_passes, radix_join.cpp:295-329, re-derived for shared memory). */
+void b200_join_plan(uint64_t nR, uint32_t *total_bits, uint32_t *bits_pass1, uint32_t *bits_pass2);
+
+/* Stage-level entry points (replace partition_hist :617-654, the prefix step :886-915 and
+ * partition_copy :659-697 of radix_join.cpp). Used by the multi-GPU exchange path and by the
+ * per-pass parity tests.
+ *   hist    : d_hist[2^bits] (uint32) += count of digit ((key >> shift) & (2^bits-1)); caller zeroes.
+ *   scatter : single-segment scatter of d_in[0..n) into d_out by digit. d_offsets[2^bits+1]
+ *             (uint32, exclusive prefix of the histogram, on device) gives partition starts;
+ *             d_cursors[2^bits] is scratch the call initialises from d_offsets. */
+int b200_radix_hist_device(const struct row_t *d_in, uint64_t n, uint32_t shift, uint32_t bits,
+                           uint32_t *d_hist, void *stream);
+int b200_exclusive_scan_u32_device(const uint32_t *d_in, uint32_t n, uint32_t *d_out /* n+1 */, void *stream);
+int b200_radix_scatter_device(const struct row_t *d_in, uint64_t n, uint32_t shift, uint32_t bits,
+                              const uint32_t *d_offsets, uint32_t *d_cursors, struct row_t *d_out,
+                              void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 4. relation generators
+ * ---------------------------------------------------------------------------------------------- */
+/* Host generators, bit-identical to the reference for the same seed (they run the same libc
+ * srand()/rand() sequence): Join-Benchmarks/lib/AppUtilities/include/generator.h:26-107,
+ * src/generator.cpp:75,:352,:474,:515,:638,:663. tuples are malloc'd; payload is set to 0
+ * (the reference leaves it uninitialised). Return 0 on success. */
+void seed_generator(unsigned int seed);
+int create_relation_pk(struct table_t *reln, uint64_t ntuples, int sorted);
+int create_relation_fk(struct table_t *reln, uint64_t ntuples, const int64_t maxid, int sorted);
+int create_relation_fk_sel(struct table_t *reln, uint64_t ntuples, const int64_t maxid, int sorted);
+/* The reference seeds Zipf from std::random_device (genzipf.cpp:44-45,:104-105); this one draws its
+ * std::mt19937_64 seed from the seed_generator() value so runs are repeatable. Same LUT + binary
+ * search algorithm (genzipf.cpp:58-137). */
+int create_relation_zipf(struct table_t *reln, uint64_t ntuples, const int64_t maxid, const double zipfparam,
+                         int sorted);
+void delete_relation(struct table_t *reln);
+
+/* Device generators ("gpu" mode): write tuples [row_begin, row_begin+n) of a
+ * relation of n_total tuples straight into HBM at d_rel[0..n). Same key *distribution* as the
+ * reference (PK: a permutation of 1..n_total; FK: floor(n_total/maxid) independent permutations of
+ * 1..maxid laid end to end, + remainder 1..rem), different permutation (counter-based bijection
+ * instead of the sequential glibc Knuth shuffle). payload = global row index. */
+int b200_gen_pk_device(struct row_t *d_rel, uint64_t n_total, uint64_t row_begin, uint64_t n,
+                       uint64_t seed, void *stream);
+int b200_gen_fk_device(struct row_t *d_rel, uint64_t n_total, uint64_t maxid, uint64_t row_begin, uint64_t n,
+                       uint64_t seed, void *stream);
+/* payload[i] = row_begin + i for an existing device relation (TPC-H loader convention,
+ * Join-Benchmarks/App/TpcH/TpcHCommons.cpp:332,:413) */
+int b200_set_rowid_payload_device(struct row_t *d_rel, uint64_t row_begin, uint64_t n, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 5. scans over a packed uint8 column: predicate lo <= v <= hi (unsigned, inclusive); only
+ *    num_records/64 whole 64-value blocks are processed, like every SIMD512 loop
+ *    (Scan-Micro-Benchmarks/shared_libraries/SimdScan/src/SIMD512.cpp:216,:234,:264).
+ * ---------------------------------------------------------------------------------------------- */
+/* Replaces ecall_bitvector_scan_user (SimdScanMulti/Enclave/Enclave.edl:71-79, Enclave.cpp:270-299)
+ * = SIMD512::bitvector_scan (SIMD512.cpp:210-222). Host buffers: data[num_records] and
+ * output_buffer[num_records/64]. Does warmup_runs untimed + num_runs timed passes over
+ * device-resident data (unique_data != 0 forces 1 run / 0 warm-ups) and ADDS the timed device
+ * nanoseconds to *time_cntr (the reference adds TSC cycles to *cpu_cntr). The H2D/D2H copies are
+ * outside that counter (the reference's data is already in memory); see b200_scan_last_copy_ns. */
+void b200_bitvector_scan_user(uint8_t predicate_low, uint8_t predicate_high, const uint8_t *data,
+                              size_t num_records, uint64_t *output_buffer, uint64_t *time_cntr,
+                              size_t num_runs, size_t warmup_runs, int unique_data);
+
+/* Replaces ecall_index_scan_user (Enclave.edl:33-41, Enclave.cpp:100-133) =
+ * SIMD512::implicit_index_scan_self_alloc (SIMD512.cpp:251-287) with a plain output array instead
+ * of a CacheAlignedVector*: writes the ascending uint64 positions (relative to `data`) of matching
+ * values to output_buffer[0..min(count, output_capacity)) and the match count to *output_count. */
+void b200_index_scan_user(uint8_t predicate_low, uint8_t predicate_high, const uint8_t *data,
+                          size_t num_records, uint64_t *output_buffer, size_t output_capacity,
+                          size_t *output_count, uint64_t *time_cntr, size_t num_runs, size_t warmup_runs,
+                          int unique_data);
+/* H2D + D2H nanoseconds (host clock) of the most recent *_user scan call */
+uint64_t b200_scan_last_copy_ns(void);
+
+/* Device-resident forms. d_data must be 16-byte aligned. */
+int b200_bitvector_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t num_records,
+                               uint64_t *d_out, void *stream);
+/* SIMD512::count (SIMD512.cpp:7-32); result written to *d_count (device uint64) */
+int b200_scan_count_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t num_records,
+                           uint64_t *d_count, void *stream);
+/* row ids = id_base + position; *d_count (device uint64) receives the match count; ids beyond
+ * out_capacity are dropped (count is still exact). */
+int b200_index_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t num_records,
+                           uint64_t id_base, uint64_t *d_out_ids, uint64_t out_capacity,
+                           uint64_t *d_count, void *stream);
+/* Allocator.hpp:95-109 tiled 0..255 column, generated in HBM; value at global position p is p mod 256 */
+int b200_fill_tiled_column_device(uint8_t *d_data, size_t n, uint64_t pos_begin, void *stream);
+/* seeded skewed column for selectivities the tiled column cannot express:
+ * v = 0 with probability p_zero_ppm / 1e6, else uniform in 1..255 */
+int b200_fill_skewed_column_device(uint8_t *d_data, size_t n, uint64_t pos_begin, uint32_t p_zero_ppm,
+                                   uint64_t seed, void *stream);
+
+/* number of CUDA kernels this library launched since load (bench.py reports the delta) */
+uint64_t b200_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AQP_B200_AQP_H */

@@ -127,8 +127,9 @@ def rho(R: np.ndarray, S: np.ndarray, nthreads: int = 1, force_2_passes: bool = 
     cs, ks = C.c_uint64(0), C.c_uint64(0)
     out = None
     cap = 0
-    if materialize:
-        cap = int(S.shape[0]) * 2 + 16
+    if materialize:   # size the output with a count-only run first (duplicate build keys can exceed |S|)
+        cap = int(lib().oracle_rho(_ptr(R), R.shape[0], _ptr(S), S.shape[0], nthreads, int(force_2_passes),
+                                   None, None, None, 0)) + 16
         out = np.zeros(cap, dtype=TRIPLE)
     m = lib().oracle_rho(_ptr(R), R.shape[0], _ptr(S), S.shape[0], nthreads, int(force_2_passes),
                          C.byref(cs), C.byref(ks), _ptr(out) if out is not None else None, cap)
@@ -181,7 +182,7 @@ def host_has_avx512() -> bool:
         flags = open("/proc/cpuinfo").read()
     except OSError:
         return False
-    return all(f in flags for f in ("avx512f", "avx512bw", "avx512vl", "avx512dq", "avx512cd", "avx512vbmi2"))
+    return all(f in flags for f in ("avx512f", "avx512bw", "avx512vl", "avx512dq", "avx512cd", "avx512vbmi", "avx512_vbmi2"))
 
 
 def have_ref() -> bool:

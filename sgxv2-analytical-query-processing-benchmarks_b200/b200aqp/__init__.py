@@ -1,0 +1,332 @@
+"""b200aqp — thin ctypes binding of libb200aqp.so (include/aqp/b200_aqp.h).
+
+This is plumbing for tests/ and bench.py, not the product: every function here forwards to one
+extern "C" entry point of the CUDA library. There is no CPU path; if the shared library is
+missing, or no B200 is visible when a compute entry point is called, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(PKG_DIR, "libb200aqp.so")
+
+ROW = np.dtype([("key", np.uint32), ("payload", np.uint32)])
+TRIPLE = np.dtype([("key", np.uint32), ("Rpayload", np.uint32), ("Spayload", np.uint32)])
+TUPLES_PER_CHUNK = (16 * 1024 - 8) // 12
+CHUNK_BYTES = 8 + 12 * TUPLES_PER_CHUNK
+
+
+class Row(C.Structure):
+    _fields_ = [("key", C.c_uint32), ("payload", C.c_uint32)]
+
+
+class Table(C.Structure):          # struct table_t
+    _fields_ = [("tuples", C.c_void_p), ("num_tuples", C.c_uint64), ("ratio_holes", C.c_int), ("sorted", C.c_int)]
+
+
+class ChunkedTable(C.Structure):   # struct chunked_table_t
+    _fields_ = [("chunks", C.POINTER(C.c_void_p)), ("current_chunk", C.c_uint64), ("num_chunks", C.c_uint64),
+                ("chunk_capacity", C.c_uint64), ("num_tuples", C.c_uint64)]
+
+
+class Result(C.Structure):         # struct result_t
+    _fields_ = [("totalresults", C.c_int64), ("nthreads", C.c_int), ("throughput", C.c_double),
+                ("materialized", C.c_int), ("result", C.c_void_p), ("result_type", C.c_int)]
+
+
+class JoinConfig(C.Structure):     # struct joinconfig_t
+    _fields_ = [("NTHREADS", C.c_int), ("PARTFANOUT", C.c_int), ("SCALARSORT", C.c_int), ("SCALARMERGE", C.c_int),
+                ("MWAYMERGEBUFFERSIZE", C.c_int), ("NUMASTRATEGY", C.c_int), ("RADIXBITS", C.c_int),
+                ("WRITETOFILE", C.c_int), ("MATERIALIZE", C.c_int), ("PRINT", C.c_int), ("CRACKING_THRESHOLD", C.c_int),
+                ("ALLOC_CORE", C.c_int)]
+
+
+class JoinStats(C.Structure):      # struct b200_join_stats_t
+    _fields_ = [("matches", C.c_int64), ("checksum", C.c_uint64), ("keysum", C.c_uint64), ("radix_bits", C.c_uint32),
+                ("num_passes", C.c_uint32), ("bits_pass1", C.c_uint32), ("bits_pass2", C.c_uint32),
+                ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32), ("ms_total", C.c_float),
+                ("ms_hist", C.c_float), ("ms_pass1", C.c_float), ("ms_pass2", C.c_float), ("ms_join", C.c_float),
+                ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("ms_materialize_host", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+# every symbol include/aqp/b200_aqp.h declares: (restype, argtypes)
+_vp, _u64, _u32, _u8, _sz, _int = C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint8, C.c_size_t, C.c_int
+SYMBOLS = {
+    "b200_init": (_int, [_int]),
+    "b200_shutdown": (None, []),
+    "b200_last_error": (C.c_char_p, []),
+    "b200_set_verbose": (None, [_int]),
+    "b200_host_alloc": (_vp, [_sz]),
+    "b200_host_free": (None, [_vp]),
+    "b200_device_alloc": (_vp, [_sz]),
+    "b200_device_free": (None, [_vp]),
+    "b200_memcpy_h2d": (_int, [_vp, _vp, _sz]),
+    "b200_memcpy_d2h": (_int, [_vp, _vp, _sz]),
+    "b200_device_sync": (_int, []),
+    "run_join": (None, [C.POINTER(Result), C.POINTER(Table), C.POINTER(Table), C.c_char_p, C.POINTER(JoinConfig)]),
+    "RHO": (C.POINTER(Result), [C.POINTER(Table), C.POINTER(Table), C.POINTER(JoinConfig)]),
+    "destroy_table": (None, [C.POINTER(ChunkedTable)]),
+    "b200_last_join_stats": (None, [C.POINTER(JoinStats)]),
+    "b200_preload_relations": (_int, [C.POINTER(Table), C.POINTER(Table)]),
+    "b200_join_preload": (_int, [C.c_char_p, C.POINTER(JoinConfig), C.POINTER(Result)]),
+    "b200_free_preload": (None, []),
+    "b200_join_device": (_int, [_vp, _u64, _vp, _u64, _vp, _u64, C.POINTER(JoinStats), _vp]),
+    "b200_join_plan": (None, [_u64, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
+    "b200_radix_hist_device": (_int, [_vp, _u64, _u32, _u32, _vp, _vp]),
+    "b200_exclusive_scan_u32_device": (_int, [_vp, _u32, _vp, _vp]),
+    "b200_radix_scatter_device": (_int, [_vp, _u64, _u32, _u32, _vp, _vp, _vp, _vp]),
+    "seed_generator": (None, [C.c_uint]),
+    "create_relation_pk": (_int, [C.POINTER(Table), _u64, _int]),
+    "create_relation_fk": (_int, [C.POINTER(Table), _u64, C.c_int64, _int]),
+    "create_relation_fk_sel": (_int, [C.POINTER(Table), _u64, C.c_int64, _int]),
+    "create_relation_zipf": (_int, [C.POINTER(Table), _u64, C.c_int64, C.c_double, _int]),
+    "delete_relation": (None, [C.POINTER(Table)]),
+    "b200_gen_pk_device": (_int, [_vp, _u64, _u64, _u64, _u64, _vp]),
+    "b200_gen_fk_device": (_int, [_vp, _u64, _u64, _u64, _u64, _u64, _vp]),
+    "b200_set_rowid_payload_device": (_int, [_vp, _u64, _u64, _vp]),
+    "b200_bitvector_scan_user": (None, [_u8, _u8, _vp, _sz, _vp, C.POINTER(_u64), _sz, _sz, _int]),
+    "b200_index_scan_user": (None, [_u8, _u8, _vp, _sz, _vp, _sz, C.POINTER(_sz), C.POINTER(_u64), _sz, _sz, _int]),
+    "b200_scan_last_copy_ns": (_u64, []),
+    "b200_bitvector_scan_device": (_int, [_u8, _u8, _vp, _sz, _vp, _vp]),
+    "b200_scan_count_device": (_int, [_u8, _u8, _vp, _sz, _vp, _vp]),
+    "b200_index_scan_device": (_int, [_u8, _u8, _vp, _sz, _u64, _vp, _u64, _vp, _vp]),
+    "b200_fill_tiled_column_device": (_int, [_vp, _sz, _u64, _vp]),
+    "b200_fill_skewed_column_device": (_int, [_vp, _sz, _u64, _u32, _u64, _vp]),
+    "b200_kernel_launch_count": (_u64, []),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libb200aqp.so (fails loudly when it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `make -C {PKG_DIR}` "
+                               "(or __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            f = getattr(L, name)   # AttributeError if the library does not export a declared symbol
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+class AqpError(RuntimeError):
+    pass
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise AqpError(f"{what}: {lib().b200_last_error().decode()}")
+
+
+def init(device: int = -1):
+    _check(lib().b200_init(device), "b200_init")
+
+
+def _table(rel: np.ndarray) -> Table:
+    assert rel.dtype == ROW and rel.flags["C_CONTIGUOUS"]
+    return Table(rel.ctypes.data, rel.shape[0], 0, 0)
+
+
+def last_join_stats() -> dict:
+    s = JoinStats()
+    lib().b200_last_join_stats(C.byref(s))
+    return s.as_dict()
+
+
+def _collect_result(res: Result, materialize: bool) -> dict:
+    out = {"matches": int(res.totalresults), "nthreads": res.nthreads, "materialized": res.materialized,
+           "result_type": res.result_type, "throughput": res.throughput}
+    ct = C.cast(res.result, C.POINTER(ChunkedTable))
+    if materialize:
+        t = ct.contents
+        parts = []
+        for c in range(t.num_chunks):
+            base = t.chunks[c]
+            n = C.cast(base, C.POINTER(C.c_uint64))[0]
+            assert n <= TUPLES_PER_CHUNK
+            buf = (C.c_uint8 * (12 * n)).from_address(base + 8)
+            parts.append(np.frombuffer(buf, dtype=TRIPLE).copy())
+        out["triples"] = np.concatenate(parts) if parts else np.zeros(0, dtype=TRIPLE)
+        out["num_chunks"] = int(t.num_chunks)
+        out["table_num_tuples"] = int(t.num_tuples)
+    # release exactly as a reference caller does: destroy_table() + free() (tpch.cpp:82)
+    lib().destroy_table(ct)
+    C.CDLL(None).free(C.c_void_p(res.result))
+    out.update({k: v for k, v in last_join_stats().items() if k != "matches"})
+    return out
+
+
+def run_join(R: np.ndarray, S: np.ndarray, materialize: bool = False, nthreads: int = 1, algorithm: bytes = b"RHO"):
+    """run_join(result_t*, R, S, "RHO", joinconfig_t*) on HOST relations (joins.hpp:4-6)."""
+    cfg = JoinConfig()
+    cfg.NTHREADS = nthreads
+    cfg.MATERIALIZE = int(materialize)
+    res = Result()
+    tR, tS = _table(R), _table(S)
+    lib().run_join(C.byref(res), C.byref(tR), C.byref(tS), algorithm, C.byref(cfg))
+    return _collect_result(res, materialize)
+
+
+def preload_relations(R: np.ndarray, S: np.ndarray):
+    tR, tS = _table(R), _table(S)
+    _check(lib().b200_preload_relations(C.byref(tR), C.byref(tS)), "b200_preload_relations")
+
+
+def join_preload(materialize: bool = False, nthreads: int = 1):
+    cfg = JoinConfig()
+    cfg.NTHREADS = nthreads
+    cfg.MATERIALIZE = int(materialize)
+    res = Result()
+    _check(lib().b200_join_preload(b"RHO", C.byref(cfg), C.byref(res)), "b200_join_preload")
+    return _collect_result(res, materialize)
+
+
+def join_device(d_R: int, nR: int, d_S: int, nS: int, d_out: int = 0, out_capacity: int = 0, stream: int = 0) -> dict:
+    s = JoinStats()
+    _check(lib().b200_join_device(d_R, nR, d_S, nS, d_out or None, out_capacity, C.byref(s), stream or None),
+           "b200_join_device")
+    return s.as_dict()
+
+
+def join_plan(nR: int):
+    t, a, b = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    lib().b200_join_plan(nR, C.byref(t), C.byref(a), C.byref(b))
+    return t.value, a.value, b.value
+
+
+# ---- device memory helpers (used when torch is not the allocator) -----------------------------------
+class DeviceBuffer:
+    def __init__(self, nbytes: int):
+        init()
+        self.nbytes = nbytes
+        self.ptr = lib().b200_device_alloc(nbytes)
+        if not self.ptr:
+            raise AqpError(f"device alloc of {nbytes} bytes failed: {lib().b200_last_error().decode()}")
+
+    def upload(self, a: np.ndarray):
+        assert a.nbytes <= self.nbytes
+        _check(lib().b200_memcpy_h2d(self.ptr, a.ctypes.data, a.nbytes), "h2d")
+        return self
+
+    def download(self, dtype, count) -> np.ndarray:
+        a = np.empty(count, dtype=dtype)
+        assert a.nbytes <= self.nbytes
+        _check(lib().b200_memcpy_d2h(a.ctypes.data, self.ptr, a.nbytes), "d2h")
+        return a
+
+    def free(self):
+        if self.ptr:
+            lib().b200_device_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def to_device(a: np.ndarray) -> DeviceBuffer:
+    return DeviceBuffer(max(a.nbytes, 16)).upload(np.ascontiguousarray(a))
+
+
+# ---- generators ------------------------------------------------------------------------------------------
+def _take_relation(t: Table) -> np.ndarray:
+    n = t.num_tuples
+    buf = (C.c_uint8 * (8 * n)).from_address(t.tuples) if n else b""
+    a = np.frombuffer(buf, dtype=ROW).copy()
+    lib().delete_relation(C.byref(t))
+    return a
+
+
+def host_gen_pk(n: int, seed: int) -> np.ndarray:
+    t = Table()
+    lib().seed_generator(seed)
+    assert lib().create_relation_pk(C.byref(t), n, 0) == 0
+    return _take_relation(t)
+
+
+def host_gen_fk(n: int, maxid: int, seed: int) -> np.ndarray:
+    t = Table()
+    lib().seed_generator(seed)
+    assert lib().create_relation_fk(C.byref(t), n, maxid, 0) == 0
+    return _take_relation(t)
+
+
+def host_gen_fk_sel(n: int, maxid: int, seed: int) -> np.ndarray:
+    t = Table()
+    lib().seed_generator(seed)
+    assert lib().create_relation_fk_sel(C.byref(t), n, maxid, 0) == 0
+    return _take_relation(t)
+
+
+def host_gen_zipf(n: int, maxid: int, z: float, seed: int) -> np.ndarray:
+    t = Table()
+    lib().seed_generator(seed)
+    assert lib().create_relation_zipf(C.byref(t), n, maxid, z, 0) == 0
+    return _take_relation(t)
+
+
+def gen_pk_device(d_rel: int, n_total: int, seed: int, row_begin: int = 0, n: int | None = None, stream: int = 0):
+    _check(lib().b200_gen_pk_device(d_rel, n_total, row_begin, n_total if n is None else n, seed, stream or None),
+           "b200_gen_pk_device")
+
+
+def gen_fk_device(d_rel: int, n_total: int, maxid: int, seed: int, row_begin: int = 0, n: int | None = None,
+                  stream: int = 0):
+    _check(lib().b200_gen_fk_device(d_rel, n_total, maxid, row_begin, n_total if n is None else n, seed,
+                                    stream or None), "b200_gen_fk_device")
+
+
+# ---- scans -------------------------------------------------------------------------------------------------
+def bitvector_scan_user(lo: int, hi: int, data: np.ndarray, num_runs: int = 1, warmup_runs: int = 0,
+                        unique_data: bool = True):
+    assert data.dtype == np.uint8 and data.flags["C_CONTIGUOUS"]
+    n = data.shape[0]
+    out = np.zeros(n // 64, dtype=np.uint64)
+    t = C.c_uint64(0)
+    lib().b200_bitvector_scan_user(lo, hi, data.ctypes.data, n, out.ctypes.data, C.byref(t), num_runs, warmup_runs,
+                                   int(unique_data))
+    return out, int(t.value)
+
+
+def index_scan_user(lo: int, hi: int, data: np.ndarray, capacity: int | None = None, num_runs: int = 1,
+                    warmup_runs: int = 0, unique_data: bool = True):
+    assert data.dtype == np.uint8 and data.flags["C_CONTIGUOUS"]
+    n = data.shape[0]
+    cap = n if capacity is None else capacity
+    out = np.zeros(max(cap, 1), dtype=np.uint64)
+    cnt = C.c_size_t(0)
+    t = C.c_uint64(0)
+    lib().b200_index_scan_user(lo, hi, data.ctypes.data, n, out.ctypes.data, cap, C.byref(cnt), C.byref(t), num_runs,
+                               warmup_runs, int(unique_data))
+    return out[:min(cnt.value, cap)], int(cnt.value), int(t.value)
+
+
+def bitvector_scan_device(lo, hi, d_data, n, d_out, stream=0):
+    _check(lib().b200_bitvector_scan_device(lo, hi, d_data, n, d_out, stream or None), "b200_bitvector_scan_device")
+
+
+def scan_count_device(lo, hi, d_data, n, d_count, stream=0):
+    _check(lib().b200_scan_count_device(lo, hi, d_data, n, d_count, stream or None), "b200_scan_count_device")
+
+
+def index_scan_device(lo, hi, d_data, n, d_out, capacity, d_count, id_base=0, stream=0):
+    _check(lib().b200_index_scan_device(lo, hi, d_data, n, id_base, d_out, capacity, d_count, stream or None),
+           "b200_index_scan_device")
+
+
+def kernel_launch_count() -> int:
+    return int(lib().b200_kernel_launch_count())

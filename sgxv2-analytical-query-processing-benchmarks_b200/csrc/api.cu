@@ -1,0 +1,797 @@
+// api.cu — the extern "C" boundary of libb200aqp.so (see include/aqp/b200_aqp.h) and the host-side
+// orchestration of the join: context, workspace, pass planning, phase timing, result hand-back in
+// the reference's layouts.
+//
+// Host-side counterpart of join_init_run / prj_thread / RHO
+// (Join-Benchmarks/lib/Joins/src/radix/radix_join.cpp:1369-1643, :1067-1356) and of the scan ECALLs
+// (Scan-Micro-Benchmarks/microbenchmarks/SimdScanMulti/Enclave/Enclave.cpp:100-133,:270-299).
+// The reference's threads, barriers and task queues have no equivalent here: a phase is one kernel
+// launch on one stream and stream order is the barrier.
+#include <chrono>
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+#include "join_internal.cuh"
+
+namespace aqp {
+
+thread_local std::string g_last_error;
+unsigned long long g_kernel_launches = 0;
+
+void set_error(const std::string &msg) {
+    g_last_error = msg;
+    if (getenv("B200_AQP_DEBUG")) fprintf(stderr, "b200aqp: %s\n", msg.c_str());
+}
+
+static double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// grow-only device buffer
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + (bytes >> 4) + 256;   // a little slack so near-equal sizes do not re-allocate
+        AQP_CUDA_OK(cudaMalloc(&p, want));
+        cap = want;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Ctx {
+    bool inited = false;
+    int device = -1;
+    int verbose = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    DevBuf tmp[4];        // pass-1 R, pass-1 S, pass-2 R, pass-2 S
+    DevBuf meta;          // histograms, offsets, cursors, work list, result accumulators
+    DevBuf relR, relS;    // H2D copies of host relations (run_join / preload)
+    DevBuf out;           // materialised triples
+    DevBuf scan_in, scan_out, scan_scratch;
+    uint64_t preR = 0, preS = 0;
+    bool preloaded = false;
+    b200_join_stats_t last = {};
+    uint64_t scan_copy_ns = 0;
+    double t0 = 0;
+};
+static Ctx g;
+static std::recursive_mutex g_mu;
+
+static int ensure_init() {
+    if (g.inited) return 0;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error(std::string("no usable CUDA device (") + cudaGetErrorString(e) +
+                  "); libb200aqp has no CPU fallback");
+        return -1;
+    }
+    int dev = 0;
+    AQP_CUDA_OK(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    AQP_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) {
+        set_error(std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                  std::to_string(prop.minor) + "; libb200aqp is built for sm_100a (B200) only");
+        return -1;
+    }
+    g.device = dev;
+    AQP_CUDA_OK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    for (auto &e2 : g.ev) AQP_CUDA_OK(cudaEventCreate(&e2));
+    g.t0 = now_s();
+    g.inited = true;
+    return 0;
+}
+
+// the reference's logger line format (Join-Benchmarks/lib/Logger/src/Logger.cpp:71-75) without colours
+static void log_info(const char *fmt, ...) {
+    if (!g.verbose) return;
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    printf("[%8.4f][ INFO] %s\n", now_s() - g.t0, buf);
+}
+
+[[noreturn]] static void die(const char *what) {
+    fprintf(stderr, "[b200aqp][ERROR] %s: %s\n", what, g_last_error.c_str());
+    exit(EXIT_FAILURE);
+}
+
+// ---------------------------------------------------------------------------------------------
+// join planning — the GPU analogue of calc_num_radix_bits / calc_num_passes
+// (radix_join.cpp:295-329): partitions are sized so the build side of a co-partition fits the
+// shared-memory hash table (kBuildCap tuples) instead of a quarter of the CPU's L2.
+// ---------------------------------------------------------------------------------------------
+static void plan_bits(uint64_t nR, uint32_t *total, uint32_t *b1, uint32_t *b2) {
+    uint64_t parts = (nR + kBuildCap - 1) / kBuildCap;
+    uint32_t bits = 0;
+    while ((1ull << bits) < parts) ++bits;
+    if (bits > 2 * kMaxFanoutBits) bits = 2 * kMaxFanoutBits;   // larger build sides use several build rounds
+    if (const char *e = getenv("B200_AQP_RADIX_BITS")) {
+        int v = atoi(e);
+        if (v >= 0 && v <= 2 * kMaxFanoutBits) bits = (uint32_t) v;
+    }
+    *total = bits;
+    if (bits <= (uint32_t) kMaxFanoutBits) {
+        *b1 = bits;
+        *b2 = 0;
+    } else {
+        *b1 = bits / 2;   // pass-1 bits = floor(bits / passes), pass 2 takes the rest (:331-337)
+        *b2 = bits - *b1;
+    }
+}
+
+static __global__ void trivial_offsets_kernel(uint32_t *offR, uint32_t nR, uint32_t *offS, uint32_t nS) {
+    offR[0] = 0;
+    offR[1] = nR;
+    offS[0] = 0;
+    offS[1] = nS;
+}
+
+// chunked_table_t layout on the device (data-types.h:68-92): slot g of the flat result lives at
+// chunk g / TUPLES_PER_CHUNK, entry g % TUPLES_PER_CHUNK.
+static __global__ void chunkify_kernel(const output_triple_t *flat, unsigned char *chunks, uint64_t n) {
+    uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t c = i / TUPLES_PER_CHUNK, k = i % TUPLES_PER_CHUNK;
+        output_triple_t t = flat[i];
+        uint32_t *dst = reinterpret_cast<uint32_t *>(chunks + c * sizeof(table_chunk_t) + 8 + k * sizeof(output_triple_t));
+        dst[0] = t.key;
+        dst[1] = t.Rpayload;
+        dst[2] = t.Spayload;
+        if (k == 0) {
+            uint64_t left = n - i;
+            *reinterpret_cast<uint64_t *>(chunks + c * sizeof(table_chunk_t)) =
+                left < TUPLES_PER_CHUNK ? left : (uint64_t) TUPLES_PER_CHUNK;
+        }
+    }
+}
+
+struct MetaLayout {
+    size_t histR, histS, offR, offS, cur1R, cur1S, cur2R, cur2S, segR, segS, tileR, tileS, seg1R, seg1S, item_start,
+        items, result, total, zero_bytes;
+};
+static MetaLayout meta_layout(uint32_t bits, uint32_t b1, uint64_t nS) {
+    const size_t P = (size_t) 1 << bits, F1 = (size_t) 1 << b1;
+    MetaLayout m{};
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        size_t r = o;
+        o += (bytes + 255) & ~(size_t) 255;
+        return r;
+    };
+    // zeroed region first: histograms + result accumulators
+    m.histR = take(P * 4);
+    m.histS = take(P * 4);
+    m.result = take(sizeof(JoinResult));
+    m.zero_bytes = o;
+    m.offR = take((P + 1) * 4);
+    m.offS = take((P + 1) * 4);
+    m.cur1R = take(F1 * 4);
+    m.cur1S = take(F1 * 4);
+    m.cur2R = take(P * 4);
+    m.cur2S = take(P * 4);
+    m.segR = take((F1 + 1) * 4);
+    m.segS = take((F1 + 1) * 4);
+    m.tileR = take((F1 + 1) * 4);
+    m.tileS = take((F1 + 1) * 4);
+    m.seg1R = take(16);
+    m.seg1S = take(16);
+    m.item_start = take((P + 1) * 4);
+    m.items = take((nS / kProbeChunk + P + 1) * sizeof(uint2));
+    m.total = o;
+    return m;
+}
+
+// The whole local join on device-resident relations. Phases and their reference counterparts:
+//   histogram  -> partition_hist              (radix_join.cpp:617-654)
+//   plan       -> prefix sums                 (:886-915)
+//   pass 1/2   -> partition_copy / radix_cluster (:659-697, :715-761)
+//   join       -> bucket_chaining_join        (:359-458)
+static int join_device_locked(const row_t *dR, uint64_t nR, const row_t *dS, uint64_t nS, output_triple_t *d_out,
+                              uint64_t out_cap, b200_join_stats_t *stats, cudaStream_t st, bool keep_partitions) {
+    (void) keep_partitions;
+    if (ensure_init()) return -1;
+    if (nR >= 0xFFFF0000ull || nS >= 0xFFFF0000ull) {
+        set_error("join: relations of 2^32 tuples or more are not supported on one GPU");
+        return -1;
+    }
+    const unsigned long long launches0 = g_kernel_launches;
+    uint32_t bits, b1, b2;
+    plan_bits(nR, &bits, &b1, &b2);
+    const uint32_t P = 1u << bits, F1 = 1u << b1;
+    const int passes = bits == 0 ? 0 : (b2 ? 2 : 1);
+
+    MetaLayout m = meta_layout(bits, b1, nS);
+    if (g.meta.ensure(m.total)) return -1;
+    if (passes >= 1 && (g.tmp[0].ensure(nR * sizeof(row_t)) || g.tmp[1].ensure(nS * sizeof(row_t)))) return -1;
+    if (passes == 2 && (g.tmp[2].ensure(nR * sizeof(row_t)) || g.tmp[3].ensure(nS * sizeof(row_t)))) return -1;
+    unsigned char *mb = static_cast<unsigned char *>(g.meta.p);
+    auto u32 = [&](size_t off) { return reinterpret_cast<uint32_t *>(mb + off); };
+    JoinResult *d_res = reinterpret_cast<JoinResult *>(mb + m.result);
+
+    AQP_CUDA_OK(cudaEventRecord(g.ev[0], st));
+    AQP_CUDA_OK(cudaMemsetAsync(mb, 0, m.zero_bytes, st));
+
+    const row_t *finR = dR, *finS = dS;
+    if (passes == 0) {
+        trivial_offsets_kernel<<<1, 1, 0, st>>>(u32(m.offR), (uint32_t) nR, u32(m.offS), (uint32_t) nS);
+        AQP_LAUNCHED();
+        AQP_CUDA_OK(cudaEventRecord(g.ev[1], st));
+        AQP_CUDA_OK(cudaEventRecord(g.ev[2], st));
+        AQP_CUDA_OK(cudaEventRecord(g.ev[3], st));
+    } else {
+        if (radix_hist_device(dR, nR, 0, bits, u32(m.histR), st)) return -1;
+        if (radix_hist_device(dS, nS, 0, bits, u32(m.histS), st)) return -1;
+        PlanArgs pa{};
+        pa.bits1 = b1;
+        pa.bits2 = b2;
+        pa.rel[0] = RelPlan{u32(m.histR), u32(m.offR), u32(m.cur1R), u32(m.cur2R), u32(m.segR), u32(m.tileR), u32(m.seg1R)};
+        pa.rel[1] = RelPlan{u32(m.histS), u32(m.offS), u32(m.cur1S), u32(m.cur2S), u32(m.segS), u32(m.tileS), u32(m.seg1S)};
+        if (plan_offsets_device(pa, st)) return -1;
+        AQP_CUDA_OK(cudaEventRecord(g.ev[1], st));
+
+        row_t *t1R = static_cast<row_t *>(g.tmp[0].p), *t1S = static_cast<row_t *>(g.tmp[1].p);
+        if (radix_scatter_launch(dR, t1R, u32(m.seg1R), u32(m.seg1R) + 2, 1, nR, 0, b1, u32(m.cur1R), st)) return -1;
+        if (radix_scatter_launch(dS, t1S, u32(m.seg1S), u32(m.seg1S) + 2, 1, nS, 0, b1, u32(m.cur1S), st)) return -1;
+        AQP_CUDA_OK(cudaEventRecord(g.ev[2], st));
+        finR = t1R;
+        finS = t1S;
+        if (passes == 2) {
+            row_t *t2R = static_cast<row_t *>(g.tmp[2].p), *t2S = static_cast<row_t *>(g.tmp[3].p);
+            if (radix_scatter_launch(t1R, t2R, u32(m.segR), u32(m.tileR), F1, nR, b1, b2, u32(m.cur2R), st)) return -1;
+            if (radix_scatter_launch(t1S, t2S, u32(m.segS), u32(m.tileS), F1, nS, b1, b2, u32(m.cur2S), st)) return -1;
+            finR = t2R;
+            finS = t2S;
+        }
+        AQP_CUDA_OK(cudaEventRecord(g.ev[3], st));
+    }
+
+    uint2 *d_items = reinterpret_cast<uint2 *>(mb + m.items);
+    if (join_items_device(u32(m.offR), u32(m.offS), P, u32(m.item_start), d_items, st)) return -1;
+    if (build_probe_device(finR, u32(m.offR), finS, u32(m.offS), u32(m.item_start), d_items, P,
+                           nS / kProbeChunk + P + 1, bits, d_res, d_out, out_cap, st))
+        return -1;
+    AQP_CUDA_OK(cudaEventRecord(g.ev[4], st));
+
+    JoinResult h{};
+    AQP_CUDA_OK(cudaMemcpyAsync(&h, d_res, sizeof h, cudaMemcpyDeviceToHost, st));
+    AQP_CUDA_OK(cudaStreamSynchronize(st));
+
+    b200_join_stats_t s{};
+    s.matches = (int64_t) h.matches;
+    s.checksum = h.checksum;
+    s.keysum = h.keysum;
+    s.radix_bits = bits;
+    s.num_passes = (uint32_t) passes;
+    s.bits_pass1 = b1;
+    s.bits_pass2 = b2;
+    cudaEventElapsedTime(&s.ms_hist, g.ev[0], g.ev[1]);
+    cudaEventElapsedTime(&s.ms_pass1, g.ev[1], g.ev[2]);
+    cudaEventElapsedTime(&s.ms_pass2, g.ev[2], g.ev[3]);
+    cudaEventElapsedTime(&s.ms_join, g.ev[3], g.ev[4]);
+    cudaEventElapsedTime(&s.ms_total, g.ev[0], g.ev[4]);
+    s.kernel_launches = (uint32_t) (g_kernel_launches - launches0);
+    g.last = s;
+    if (stats) *stats = s;
+    return 0;
+}
+
+// re-run only build/probe on the partitions left in the workspace by the last join (used when the
+// materialisation buffer turned out too small)
+static int rerun_probe_locked(uint64_t nS, output_triple_t *d_out, uint64_t out_cap, cudaStream_t st,
+                              const row_t *dR, const row_t *dS) {
+    const uint32_t bits = g.last.radix_bits, b1 = g.last.bits_pass1;
+    const uint32_t P = 1u << bits;
+    MetaLayout m = meta_layout(bits, b1, nS);
+    unsigned char *mb = static_cast<unsigned char *>(g.meta.p);
+    auto u32 = [&](size_t off) { return reinterpret_cast<uint32_t *>(mb + off); };
+    JoinResult *d_res = reinterpret_cast<JoinResult *>(mb + m.result);
+    AQP_CUDA_OK(cudaMemsetAsync(d_res, 0, sizeof(JoinResult), st));
+    const row_t *finR = g.last.num_passes == 0 ? dR : static_cast<row_t *>(g.tmp[g.last.num_passes == 2 ? 2 : 0].p);
+    const row_t *finS = g.last.num_passes == 0 ? dS : static_cast<row_t *>(g.tmp[g.last.num_passes == 2 ? 3 : 1].p);
+    if (build_probe_device(finR, u32(m.offR), finS, u32(m.offS), u32(m.item_start), reinterpret_cast<uint2 *>(mb + m.items),
+                           P, nS / kProbeChunk + P + 1, bits, d_res, d_out, out_cap, st))
+        return -1;
+    AQP_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// chunk-array pointer -> slab that backs all its chunks (see destroy_table)
+static std::unordered_map<void *, void *> g_slabs;
+
+static void print_reference_timing_lines(uint64_t nR, uint64_t nS) {
+    // radix_join.cpp:252-293 — the lines SGXv2Scripts/scripts/helpers/runner.py:19-53 scrapes. "cycles"
+    // are device microseconds x 1000 (a nominal 1 GHz counter), so CPMS=1000 recovers microseconds.
+    const b200_join_stats_t &s = g.last;
+    auto cyc = [](float ms) { return (unsigned long) (ms * 1e6f); };
+    uint64_t n = nR + nS;
+    uint64_t us = (uint64_t) (s.ms_total * 1000.0f);
+    log_info("Total input tuples : %lu", (unsigned long) n);
+    log_info("Result tuples : %lu", (unsigned long) s.matches);
+    log_info("Total Join Time (cycles)    : %lu", cyc(s.ms_total));
+    log_info("Partition Overall (cycles)  : %lu", cyc(s.ms_hist + s.ms_pass1 + s.ms_pass2));
+    log_info("Partition Pass One (cycles) : %lu", cyc(s.ms_hist + s.ms_pass1));
+    log_info("Partition One Hist (cycles) : %lu", cyc(s.ms_hist));
+    log_info("Partition One Copy (cycles) : %lu", cyc(s.ms_pass1));
+    log_info("Partition Pass Two (cycles) : %lu", cyc(s.ms_pass2));
+    log_info("Partition Two Hist (cycles) : %lu", 0ul);
+    log_info("Partition Two Copy (cycles) : %lu", cyc(s.ms_pass2));
+    log_info("Build+Join Overall (cycles) : %lu", cyc(s.ms_join));
+    log_info("Pure Join Runtime (us) : %lu ", (unsigned long) us);
+    log_info("Throughput (M rec/sec) : %.2lf", us ? (double) n / (double) us : 0.0);
+    log_info("H2D copy (us) : %lu ", (unsigned long) (s.ms_h2d * 1000.0f));
+    log_info("Checksum : %lu", (unsigned long) s.checksum);
+}
+
+// host-buffer join: H2D, device join, results back in the reference's layout
+static int join_host_locked(const table_t *R, const table_t *S, const joinconfig_t *cfg, result_t *res,
+                            bool use_preloaded) {
+    if (ensure_init()) return -1;
+    cudaStream_t st = g.stream;
+    uint64_t nR, nS;
+    float ms_h2d = 0;
+    if (use_preloaded) {
+        if (!g.preloaded) {
+            set_error("b200_join_preload called without b200_preload_relations");
+            return -1;
+        }
+        nR = g.preR;
+        nS = g.preS;
+    } else {
+        nR = R->num_tuples;
+        nS = S->num_tuples;
+        if (g.relR.ensure(nR * sizeof(row_t) + 16) || g.relS.ensure(nS * sizeof(row_t) + 16)) return -1;
+        double t = now_s();
+        AQP_CUDA_OK(cudaMemcpyAsync(g.relR.p, R->tuples, nR * sizeof(row_t), cudaMemcpyHostToDevice, st));
+        AQP_CUDA_OK(cudaMemcpyAsync(g.relS.p, S->tuples, nS * sizeof(row_t), cudaMemcpyHostToDevice, st));
+        AQP_CUDA_OK(cudaStreamSynchronize(st));
+        ms_h2d = (float) ((now_s() - t) * 1e3);
+        g.preloaded = false;
+    }
+    const row_t *dR = static_cast<row_t *>(g.relR.p), *dS = static_cast<row_t *>(g.relS.p);
+    const bool mat = cfg && cfg->MATERIALIZE;
+
+    output_triple_t *d_out = nullptr;
+    uint64_t cap = 0;
+    if (mat) {
+        cap = nS ? nS : 1;   // exact for PK-FK joins; grown below if R has duplicate keys
+        if (g.out.ensure(cap * sizeof(output_triple_t))) return -1;
+        d_out = static_cast<output_triple_t *>(g.out.p);
+    }
+    b200_join_stats_t s{};
+    if (join_device_locked(dR, nR, dS, nS, d_out, cap, &s, st, true)) return -1;
+    if (mat && (uint64_t) s.matches > cap) {
+        cap = (uint64_t) s.matches;
+        if (g.out.ensure(cap * sizeof(output_triple_t))) return -1;
+        d_out = static_cast<output_triple_t *>(g.out.p);
+        if (rerun_probe_locked(nS, d_out, cap, st, dR, dS)) return -1;
+    }
+    g.last.ms_h2d = ms_h2d;
+
+    res->totalresults = s.matches;
+    res->nthreads = cfg ? cfg->NTHREADS : 0;
+    res->materialized = mat ? 1 : 0;
+    res->result_type = 1;
+    res->throughput = s.ms_total > 0 ? (double) (nR + nS) / (s.ms_total * 1e3) : 0.0;   // M tuples/s
+
+    // result table (radix_join.cpp:1556 concatenate(): always a chunked_table_t, empty if !MATERIALIZE)
+    chunked_table_t *ct = static_cast<chunked_table_t *>(calloc(1, sizeof(chunked_table_t)));
+    if (!ct) {
+        set_error("out of host memory");
+        return -1;
+    }
+    if (mat && s.matches > 0) {
+        double t = now_s();
+        const uint64_t n = (uint64_t) s.matches;
+        const uint64_t nchunks = (n + TUPLES_PER_CHUNK - 1) / TUPLES_PER_CHUNK;
+        const size_t bytes = nchunks * sizeof(table_chunk_t);
+        // lay the chunks out on the device, then one D2H into one host slab
+        if (g.tmp[0].ensure(bytes)) return -1;   // partitions are dead by now; reuse their space
+        chunkify_kernel<<<kNumSMs * 8, 256, 0, st>>>(d_out, static_cast<unsigned char *>(g.tmp[0].p), n);
+        AQP_LAUNCHED();
+        unsigned char *slab = static_cast<unsigned char *>(malloc(bytes));
+        table_chunk_t **arr = static_cast<table_chunk_t **>(malloc(sizeof(table_chunk_t *) * nchunks));
+        if (!slab || !arr) {
+            set_error("out of host memory for the materialised result");
+            return -1;
+        }
+        AQP_CUDA_OK(cudaMemcpyAsync(slab, g.tmp[0].p, bytes, cudaMemcpyDeviceToHost, st));
+        AQP_CUDA_OK(cudaStreamSynchronize(st));
+        for (uint64_t c = 0; c < nchunks; ++c) arr[c] = reinterpret_cast<table_chunk_t *>(slab + c * sizeof(table_chunk_t));
+        ct->chunks = arr;
+        ct->num_chunks = nchunks;
+        ct->chunk_capacity = nchunks;
+        ct->current_chunk = nchunks - 1;
+        ct->num_tuples = n;
+        g_slabs[arr] = slab;
+        g.last.ms_materialize_host = (float) ((now_s() - t) * 1e3);
+    } else {
+        ct->chunks = static_cast<table_chunk_t **>(malloc(sizeof(table_chunk_t *)));
+        ct->current_chunk = (uint64_t) -1;   // num_chunks - 1 with num_chunks == 0, as concatenate() leaves it
+    }
+    res->result = ct;
+
+    log_info("Running RHO (B200) with %u passes and %u radix bits", s.num_passes, s.radix_bits);
+    if (mat) log_info("Materializing the output");
+    print_reference_timing_lines(nR, nS);
+    return 0;
+}
+
+}  // namespace aqp
+
+using namespace aqp;
+
+// =================================================================================================
+// extern "C" surface
+// =================================================================================================
+extern "C" {
+
+int b200_init(int device) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (device >= 0) {
+        cudaError_t e = cudaSetDevice(device);
+        if (e != cudaSuccess) {
+            set_error(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+            return -1;
+        }
+        if (g.inited && g.device != device) {
+            set_error("b200_init: context already bound to another device; call b200_shutdown first");
+            return -1;
+        }
+    }
+    return ensure_init();
+}
+
+void b200_shutdown(void) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (!g.inited) return;
+    cudaStreamSynchronize(g.stream);
+    for (auto &b : g.tmp) b.release();
+    g.meta.release();
+    g.relR.release();
+    g.relS.release();
+    g.out.release();
+    g.scan_in.release();
+    g.scan_out.release();
+    g.scan_scratch.release();
+    for (auto &e : g.ev) cudaEventDestroy(e);
+    cudaStreamDestroy(g.stream);
+    g.stream = nullptr;
+    g.inited = false;
+    g.preloaded = false;
+}
+
+const char *b200_last_error(void) { return g_last_error.c_str(); }
+void b200_set_verbose(int level) { g.verbose = level; }
+uint64_t b200_kernel_launch_count(void) { return g_kernel_launches; }
+
+void *b200_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (ensure_init()) return nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void b200_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+void *b200_device_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (ensure_init()) return nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        return nullptr;
+    }
+    return p;
+}
+void b200_device_free(void *p) {
+    if (p) cudaFree(p);
+}
+int b200_memcpy_h2d(void *dst, const void *src, size_t bytes) {
+    if (ensure_init()) return -1;
+    AQP_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g.stream));
+    AQP_CUDA_OK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+int b200_memcpy_d2h(void *dst, const void *src, size_t bytes) {
+    if (ensure_init()) return -1;
+    AQP_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g.stream));
+    AQP_CUDA_OK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+int b200_device_sync(void) {
+    if (ensure_init()) return -1;
+    AQP_CUDA_OK(cudaDeviceSynchronize());
+    return 0;
+}
+
+// ---- join ---------------------------------------------------------------------------------------
+struct result_t *RHO(const struct table_t *relR, const struct table_t *relS, const struct joinconfig_t *config) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    result_t *res = static_cast<result_t *>(calloc(1, sizeof(result_t)));
+    if (!res || join_host_locked(relR, relS, config, res, false)) die("RHO");
+    return res;
+}
+
+void run_join(struct result_t *res, const struct table_t *relR, const struct table_t *relS,
+              const char *algorithm_name, const struct joinconfig_t *config) {
+    if (!algorithm_name || strcmp(algorithm_name, "RHO") != 0) {
+        // joins.cpp:70-73: unknown algorithm -> log + exit
+        fprintf(stderr, "[b200aqp][ERROR] Algorithm not found: %s (this library serves RHO only)\n",
+                algorithm_name ? algorithm_name : "(null)");
+        exit(EXIT_FAILURE);
+    }
+    result_t *tmp = RHO(relR, relS, config);
+    memcpy(res, tmp, sizeof(result_t));   // joins.cpp:74-77
+    free(tmp);
+}
+
+void destroy_table(struct chunked_table_t *table) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (!table) return;
+    auto it = table->chunks ? g_slabs.find(table->chunks) : g_slabs.end();
+    if (it != g_slabs.end()) {
+        free(it->second);   // all chunks live in one slab
+        g_slabs.erase(it);
+    } else {
+        for (uint64_t i = 0; i < table->num_chunks; ++i) free(table->chunks[i]);   // ChunkedTable.cpp:128-136
+    }
+    free(table->chunks);
+    table->chunks = nullptr;
+    table->chunk_capacity = 0;
+    table->num_chunks = 0;
+    table->current_chunk = 0;
+}
+
+void b200_last_join_stats(struct b200_join_stats_t *out) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (out) *out = g.last;
+}
+
+int b200_preload_relations(const struct table_t *relR, const struct table_t *relS) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    const uint64_t nR = relR->num_tuples, nS = relS->num_tuples;
+    if (g.relR.ensure(nR * sizeof(row_t) + 16) || g.relS.ensure(nS * sizeof(row_t) + 16)) return -1;
+    AQP_CUDA_OK(cudaMemcpyAsync(g.relR.p, relR->tuples, nR * sizeof(row_t), cudaMemcpyHostToDevice, g.stream));
+    AQP_CUDA_OK(cudaMemcpyAsync(g.relS.p, relS->tuples, nS * sizeof(row_t), cudaMemcpyHostToDevice, g.stream));
+    AQP_CUDA_OK(cudaStreamSynchronize(g.stream));
+    g.preR = nR;
+    g.preS = nS;
+    g.preloaded = true;
+    return 0;
+}
+
+int b200_join_preload(const char *algorithm_name, const struct joinconfig_t *config, struct result_t *res) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (!algorithm_name || strcmp(algorithm_name, "RHO") != 0) {
+        set_error("b200_join_preload: only RHO is served");
+        return -1;
+    }
+    return join_host_locked(nullptr, nullptr, config, res, true);
+}
+
+void b200_free_preload(void) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    g.relR.release();
+    g.relS.release();
+    g.preloaded = false;
+}
+
+int b200_join_device(const struct row_t *d_R, uint64_t nR, const struct row_t *d_S, uint64_t nS,
+                     struct output_triple_t *d_out, uint64_t out_capacity, struct b200_join_stats_t *stats,
+                     void *stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : g.stream;
+    return join_device_locked(d_R, nR, d_S, nS, d_out, out_capacity, stats, st, false);
+}
+
+void b200_join_plan(uint64_t nR, uint32_t *total_bits, uint32_t *bits_pass1, uint32_t *bits_pass2) {
+    uint32_t t, a, b;
+    plan_bits(nR, &t, &a, &b);
+    if (total_bits) *total_bits = t;
+    if (bits_pass1) *bits_pass1 = a;
+    if (bits_pass2) *bits_pass2 = b;
+}
+
+int b200_radix_hist_device(const struct row_t *d_in, uint64_t n, uint32_t shift, uint32_t bits, uint32_t *d_hist,
+                           void *stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    return radix_hist_device(d_in, n, shift, bits, d_hist, stream ? static_cast<cudaStream_t>(stream) : g.stream);
+}
+
+int b200_exclusive_scan_u32_device(const uint32_t *d_in, uint32_t n, uint32_t *d_out, void *stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    return exclusive_scan_u32_device(d_in, n, d_out, stream ? static_cast<cudaStream_t>(stream) : g.stream);
+}
+
+int b200_radix_scatter_device(const struct row_t *d_in, uint64_t n, uint32_t shift, uint32_t bits,
+                              const uint32_t *d_offsets, uint32_t *d_cursors, struct row_t *d_out, void *stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    if (n >= 0xFFFF0000ull || bits > (uint32_t) kMaxFanoutBits) {
+        set_error("radix_scatter: n must be < 2^32 and bits <= 8");
+        return -1;
+    }
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : g.stream;
+    // the 4-entry single-segment table lives behind the cursors in the caller's scratch? No: keep it in
+    // our own meta-independent buffer so the caller's d_cursors stays exactly 2^bits entries.
+    static DevBuf seg;
+    if (seg.ensure(64)) return -1;
+    uint32_t *d_seg = static_cast<uint32_t *>(seg.p);
+    if (single_segment_setup((uint32_t) n, d_offsets, 1u << bits, d_cursors, d_seg, st)) return -1;
+    return radix_scatter_launch(d_in, d_out, d_seg, d_seg + 2, 1, n, shift, bits, d_cursors, st);
+}
+
+// ---- generators (device) --------------------------------------------------------------------------
+int b200_gen_pk_device(struct row_t *d_rel, uint64_t n_total, uint64_t row_begin, uint64_t n, uint64_t seed,
+                       void *stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    return gen_pk_device(d_rel, n_total, row_begin, n, seed, stream ? static_cast<cudaStream_t>(stream) : g.stream);
+}
+int b200_gen_fk_device(struct row_t *d_rel, uint64_t n_total, uint64_t maxid, uint64_t row_begin, uint64_t n,
+                       uint64_t seed, void *stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    return gen_fk_device(d_rel, n_total, maxid, row_begin, n, seed, stream ? static_cast<cudaStream_t>(stream) : g.stream);
+}
+int b200_set_rowid_payload_device(struct row_t *d_rel, uint64_t row_begin, uint64_t n, void *stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    return set_rowid_payload_device(d_rel, row_begin, n, stream ? static_cast<cudaStream_t>(stream) : g.stream);
+}
+
+// ---- scans ----------------------------------------------------------------------------------------
+int b200_bitvector_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, uint64_t *d_out, void *stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    return bitvector_scan_device(lo, hi, d_data, n, d_out, stream ? static_cast<cudaStream_t>(stream) : g.stream);
+}
+
+int b200_scan_count_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, uint64_t *d_count, void *stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    return scan_count_device(lo, hi, d_data, n, d_count, stream ? static_cast<cudaStream_t>(stream) : g.stream);
+}
+
+int b200_index_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, uint64_t id_base,
+                           uint64_t *d_out_ids, uint64_t out_capacity, uint64_t *d_count, void *stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    if (g.scan_scratch.ensure(index_scan_scratch_bytes(n))) return -1;
+    return index_scan_device(lo, hi, d_data, n, id_base, d_out_ids, out_capacity, d_count, g.scan_scratch.p,
+                             stream ? static_cast<cudaStream_t>(stream) : g.stream);
+}
+
+int b200_fill_tiled_column_device(uint8_t *d_data, size_t n, uint64_t pos_begin, void *stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    return fill_tiled_column_device(d_data, n, pos_begin, stream ? static_cast<cudaStream_t>(stream) : g.stream);
+}
+
+int b200_fill_skewed_column_device(uint8_t *d_data, size_t n, uint64_t pos_begin, uint32_t p_zero_ppm, uint64_t seed,
+                                   void *stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    return fill_skewed_column_device(d_data, n, pos_begin, p_zero_ppm, seed,
+                                     stream ? static_cast<cudaStream_t>(stream) : g.stream);
+}
+
+uint64_t b200_scan_last_copy_ns(void) { return g.scan_copy_ns; }
+
+// Enclave.cpp:270-299 shape: warm-ups, then num_runs timed passes accumulated into *time_cntr
+void b200_bitvector_scan_user(uint8_t lo, uint8_t hi, const uint8_t *data, size_t n, uint64_t *output_buffer,
+                              uint64_t *time_cntr, size_t num_runs, size_t warmup_runs, int unique_data) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init()) die("b200_bitvector_scan_user");
+    if (unique_data) {
+        num_runs = 1;
+        warmup_runs = 0;
+    }
+    const size_t nblk = n / 64;
+    cudaStream_t st = g.stream;
+    if (g.scan_in.ensure(n + 64) || g.scan_out.ensure(nblk * 8 + 64)) die("b200_bitvector_scan_user");
+    double t = now_s();
+    cudaMemcpyAsync(g.scan_in.p, data, nblk * 64, cudaMemcpyHostToDevice, st);
+    cudaStreamSynchronize(st);
+    uint64_t copy_ns = (uint64_t) ((now_s() - t) * 1e9);
+    const uint8_t *d_in = static_cast<const uint8_t *>(g.scan_in.p);
+    uint64_t *d_out = static_cast<uint64_t *>(g.scan_out.p);
+    for (size_t i = 0; i < warmup_runs; ++i)
+        if (bitvector_scan_device(lo, hi, d_in, n, d_out, st)) die("b200_bitvector_scan_user");
+    cudaEventRecord(g.ev[5], st);
+    for (size_t i = 0; i < num_runs; ++i)
+        if (bitvector_scan_device(lo, hi, d_in, n, d_out, st)) die("b200_bitvector_scan_user");
+    cudaEventRecord(g.ev[6], st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) {
+        set_error("bitvector scan kernel failed");
+        die("b200_bitvector_scan_user");
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, g.ev[5], g.ev[6]);
+    if (time_cntr) *time_cntr += (uint64_t) ((double) ms * 1e6);
+    t = now_s();
+    cudaMemcpyAsync(output_buffer, d_out, nblk * 8, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) {
+        set_error("bitvector scan D2H failed");
+        die("b200_bitvector_scan_user");
+    }
+    g.scan_copy_ns = copy_ns + (uint64_t) ((now_s() - t) * 1e9);
+}
+
+// Enclave.cpp:100-133 shape
+void b200_index_scan_user(uint8_t lo, uint8_t hi, const uint8_t *data, size_t n, uint64_t *output_buffer,
+                          size_t output_capacity, size_t *output_count, uint64_t *time_cntr, size_t num_runs,
+                          size_t warmup_runs, int unique_data) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init()) die("b200_index_scan_user");
+    if (unique_data) {
+        num_runs = 1;
+        warmup_runs = 0;
+    }
+    const size_t nblk = n / 64;
+    cudaStream_t st = g.stream;
+    if (g.scan_in.ensure(n + 64) || g.scan_scratch.ensure(index_scan_scratch_bytes(n))) die("b200_index_scan_user");
+    double t = now_s();
+    cudaMemcpyAsync(g.scan_in.p, data, nblk * 64, cudaMemcpyHostToDevice, st);
+    cudaStreamSynchronize(st);
+    uint64_t copy_ns = (uint64_t) ((now_s() - t) * 1e9);
+    const uint8_t *d_in = static_cast<const uint8_t *>(g.scan_in.p);
+    // size the device output like pre_alloc_per_thread does with SIMD512::count (ResultAllocators.hpp:8-19), untimed
+    static DevBuf cnt;
+    if (cnt.ensure(16)) die("b200_index_scan_user");
+    uint64_t *d_count = static_cast<uint64_t *>(cnt.p);
+    uint64_t h_count = 0;
+    if (scan_count_device(lo, hi, d_in, n, d_count, st)) die("b200_index_scan_user");
+    cudaMemcpyAsync(&h_count, d_count, 8, cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    uint64_t cap = h_count < output_capacity ? h_count : output_capacity;
+    if (g.scan_out.ensure(cap * 8 + 64)) die("b200_index_scan_user");
+    uint64_t *d_out = static_cast<uint64_t *>(g.scan_out.p);
+    for (size_t i = 0; i < warmup_runs; ++i)
+        if (index_scan_device(lo, hi, d_in, n, 0, d_out, cap, d_count, g.scan_scratch.p, st)) die("b200_index_scan_user");
+    cudaEventRecord(g.ev[5], st);
+    for (size_t i = 0; i < num_runs; ++i)
+        if (index_scan_device(lo, hi, d_in, n, 0, d_out, cap, d_count, g.scan_scratch.p, st)) die("b200_index_scan_user");
+    cudaEventRecord(g.ev[6], st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) {
+        set_error("index scan kernel failed");
+        die("b200_index_scan_user");
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, g.ev[5], g.ev[6]);
+    if (time_cntr) *time_cntr += (uint64_t) ((double) ms * 1e6);
+    t = now_s();
+    cudaMemcpyAsync(&h_count, d_count, 8, cudaMemcpyDeviceToHost, st);
+    if (cap) cudaMemcpyAsync(output_buffer, d_out, cap * 8, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) {
+        set_error("index scan D2H failed");
+        die("b200_index_scan_user");
+    }
+    if (output_count) *output_count = (size_t) h_count;
+    g.scan_copy_ns = copy_ns + (uint64_t) ((now_s() - t) * 1e9);
+}
+
+}  // extern "C"

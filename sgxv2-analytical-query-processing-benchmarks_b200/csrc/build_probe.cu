@@ -1,0 +1,195 @@
+// build_probe.cu — bucket-chained hash join of co-partitions in shared memory (sm_100a).
+//
+// Replaces bucket_chaining_join (Join-Benchmarks/lib/Joins/src/radix/radix_join.cpp:359-458) and the
+// join-task queue that feeds it (:1174-1222, :818-836, :1320-1334):
+//   * N = next_pow2(|R_p|) buckets, hash = the key bits ABOVE all radix bits,
+//     (key >> num_radix_bits) & (N-1)                                   (:373-378)
+//   * build: next[i] = bucket[h]; bucket[h] = i+1 (1-based chain heads)    (:386-412) — done here by
+//     all threads at once with an atomic exchange, which yields the same chains in another order
+//   * probe: walk the chain, compare keys, count / emit {key, Rpayload, Spayload}  (:428-447)
+//   * co-partitions where R or S is empty are skipped                      (:1196,:820)
+// A work item is (co-partition, chunk of its S side): a CTA loads the R side into shared memory,
+// builds bucket/next there and streams its S chunk past it. Splitting S by chunks keeps every SM
+// busy when partitions are few (small R) or one partition is huge (Zipf-skewed S); R sides larger
+// than the table capacity are processed in several build rounds.
+#include "common.cuh"
+#include "join_internal.cuh"
+#include "block_scan.cuh"
+
+namespace aqp {
+
+// ---------------------------------------------------------------------------------------------
+// work list: items[i] = {partition, S-chunk}
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kScanBlock)
+join_items_kernel(const uint32_t *__restrict__ offR, const uint32_t *__restrict__ offS, uint32_t nparts,
+                  uint32_t *__restrict__ item_start, uint2 *__restrict__ items) {
+    auto chunks_of = [&](uint32_t p) {
+        uint32_t nr = offR[p + 1] - offR[p], ns = offS[p + 1] - offS[p];
+        return (nr > 0 && ns > 0) ? (ns + kProbeChunk - 1) / kProbeChunk : 0u;
+    };
+    uint32_t total = block_exclusive_scan(nparts, chunks_of, [&](uint32_t p, uint32_t v) { item_start[p] = v; });
+    if (threadIdx.x == 0) item_start[nparts] = total;
+    __syncthreads();
+    for (uint32_t p = threadIdx.x; p < nparts; p += kScanBlock) {
+        uint32_t b = item_start[p], c = chunks_of(p);
+        for (uint32_t k = 0; k < c; ++k) items[b + k] = make_uint2(p, k);
+    }
+}
+
+int join_items_device(const uint32_t *d_offR, const uint32_t *d_offS, uint32_t nparts, uint32_t *d_item_start,
+                      uint2 *d_items, cudaStream_t st) {
+    join_items_kernel<<<1, kScanBlock, 0, st>>>(d_offR, d_offS, nparts, d_item_start, d_items);
+    AQP_LAUNCHED();
+    AQP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// build + probe
+// ---------------------------------------------------------------------------------------------
+constexpr int kProbeUnroll = 4;
+constexpr size_t kJoinSmemBytes = (size_t) kBuildCap * (sizeof(uint2) + sizeof(uint32_t) + sizeof(uint16_t));
+
+template <bool kMaterialize>
+__global__ void __launch_bounds__(kJoinThreads, 2)
+build_probe_kernel(const uint2 *__restrict__ R, const uint32_t *__restrict__ offR, const uint2 *__restrict__ S,
+                   const uint32_t *__restrict__ offS, const uint32_t *__restrict__ item_start,
+                   const uint2 *__restrict__ items, uint32_t nparts, uint32_t hash_shift,
+                   JoinResult *__restrict__ res, output_triple_t *__restrict__ out, unsigned long long out_cap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint2 *rt = reinterpret_cast<uint2 *>(smem_raw);                                     // R tuples
+    uint32_t *bucket = reinterpret_cast<uint32_t *>(rt + kBuildCap);                     // chain heads (1-based)
+    uint16_t *next = reinterpret_cast<uint16_t *>(bucket + kBuildCap);                   // chain links (1-based)
+
+    const uint32_t nitems = item_start[nparts];
+    unsigned long long matches = 0, checksum = 0, keysum = 0;
+
+    for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x) {
+        const uint2 item = items[it];
+        const uint32_t p = item.x;
+        const uint32_t rbeg = offR[p], rend = offR[p + 1];
+        const uint32_t sbeg = offS[p] + item.y * kProbeChunk;
+        const uint32_t send = min(sbeg + (uint32_t) kProbeChunk, offS[p + 1]);
+
+        for (uint32_t rb = rbeg; rb < rend; rb += kBuildCap) {
+            const uint32_t nr = min((uint32_t) kBuildCap, rend - rb);
+            uint32_t N = 1;
+            while (N < nr) N <<= 1;
+            const uint32_t hmask = N - 1;
+            __syncthreads();   // previous round's probe done before the table is cleared
+            for (uint32_t i = threadIdx.x; i < N; i += kJoinThreads) bucket[i] = 0;
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < nr; i += kJoinThreads) {
+                uint2 t = R[rb + i];
+                rt[i] = t;
+                next[i] = (uint16_t) atomicExch(&bucket[(t.x >> hash_shift) & hmask], i + 1);
+            }
+            __syncthreads();
+
+            // uniform trip count so the materialising variant can use warp-wide primitives
+            for (uint32_t base = sbeg; base < send; base += kJoinThreads * kProbeUnroll) {
+                uint2 s[kProbeUnroll];
+                bool valid[kProbeUnroll];
+#pragma unroll
+                for (int j = 0; j < kProbeUnroll; ++j) {
+                    uint32_t i = base + j * kJoinThreads + threadIdx.x;
+                    valid[j] = i < send;
+                    if (valid[j]) s[j] = ld_stream_v2(S + i);
+                }
+#pragma unroll
+                for (int j = 0; j < kProbeUnroll; ++j) {
+                    uint32_t hit = valid[j] ? bucket[(s[j].x >> hash_shift) & hmask] : 0u;
+                    if (!kMaterialize) {
+                        while (hit) {
+                            uint2 r = rt[hit - 1];
+                            if (r.x == s[j].x) {
+                                ++matches;
+                                checksum += (unsigned long long) r.y + s[j].y;
+                                keysum += s[j].x;
+                            }
+                            hit = next[hit - 1];
+                        }
+                    } else {
+                        while (__any_sync(0xffffffffu, hit != 0)) {
+                            bool m = false;
+                            uint2 r = make_uint2(0, 0);
+                            if (hit) {
+                                r = rt[hit - 1];
+                                m = r.x == s[j].x;
+                                hit = next[hit - 1];
+                            }
+                            unsigned mm = __ballot_sync(0xffffffffu, m);
+                            if (mm) {
+                                unsigned long long slot = 0;
+                                int leader = __ffs(mm) - 1;
+                                if ((int) lane_id() == leader) slot = atomicAdd(&res->out_count, (unsigned long long) __popc(mm));
+                                slot = __shfl_sync(0xffffffffu, slot, leader);
+                                if (m) {
+                                    ++matches;
+                                    checksum += (unsigned long long) r.y + s[j].y;
+                                    keysum += s[j].x;
+                                    slot += __popc(mm & lanemask_lt());
+                                    if (slot < out_cap) {
+                                        output_triple_t t;
+                                        t.key = s[j].x;
+                                        t.Rpayload = r.y;
+                                        t.Spayload = s[j].y;
+                                        out[slot] = t;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    // block reduction of the three accumulators -> 3 global atomics per CTA
+    __shared__ unsigned long long red[3][kJoinThreads / 32];
+    matches = warp_sum(matches);
+    checksum = warp_sum(checksum);
+    keysum = warp_sum(keysum);
+    __syncthreads();
+    if (lane_id() == 0) {
+        red[0][threadIdx.x >> 5] = matches;
+        red[1][threadIdx.x >> 5] = checksum;
+        red[2][threadIdx.x >> 5] = keysum;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        unsigned long long t = 0;
+        for (int w = 0; w < kJoinThreads / 32; ++w) t += red[threadIdx.x][w];
+        unsigned long long *dst = threadIdx.x == 0 ? &res->matches : (threadIdx.x == 1 ? &res->checksum : &res->keysum);
+        if (t) atomicAdd(dst, t);
+    }
+}
+
+int build_probe_device(const row_t *d_R, const uint32_t *d_offR, const row_t *d_S, const uint32_t *d_offS,
+                       const uint32_t *d_item_start, const uint2 *d_items, uint32_t nparts, uint64_t max_items,
+                       uint32_t hash_shift, JoinResult *d_res, output_triple_t *d_out, uint64_t out_cap,
+                       cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        AQP_CUDA_OK(cudaFuncSetAttribute(build_probe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int) kJoinSmemBytes));
+        AQP_CUDA_OK(cudaFuncSetAttribute(build_probe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int) kJoinSmemBytes));
+        attr_set = true;
+    }
+    if (max_items == 0) return 0;
+    int grid = (int) (max_items < (uint64_t) kNumSMs * 2 ? max_items : (uint64_t) kNumSMs * 2);
+    const uint2 *R = reinterpret_cast<const uint2 *>(d_R), *S = reinterpret_cast<const uint2 *>(d_S);
+    if (d_out)
+        build_probe_kernel<true><<<grid, kJoinThreads, kJoinSmemBytes, st>>>(R, d_offR, S, d_offS, d_item_start, d_items,
+                                                                             nparts, hash_shift, d_res, d_out, out_cap);
+    else
+        build_probe_kernel<false><<<grid, kJoinThreads, kJoinSmemBytes, st>>>(R, d_offR, S, d_offS, d_item_start, d_items,
+                                                                              nparts, hash_shift, d_res, nullptr, 0);
+    AQP_LAUNCHED();
+    AQP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace aqp

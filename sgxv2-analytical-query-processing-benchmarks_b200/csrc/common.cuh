@@ -1,0 +1,81 @@
+// common.cuh — shared device helpers and host-side context for libb200aqp (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+#include "aqp/b200_aqp.h"
+
+namespace aqp {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+// ---------------------------------------------------------------------------------------------
+// error handling
+// ---------------------------------------------------------------------------------------------
+void set_error(const std::string &msg);
+extern thread_local std::string g_last_error;
+
+#define AQP_CUDA_OK(expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            ::aqp::set_error(std::string(#expr) + " -> " + cudaGetErrorString(_e) + " (" +        \
+                             __FILE__ + ":" + std::to_string(__LINE__) + ")");                    \
+            return -1;                                                                            \
+        }                                                                                         \
+    } while (0)
+
+// count every kernel this library launches (bench.py reports it as gpu_launches)
+extern unsigned long long g_kernel_launches;
+#define AQP_LAUNCHED() (++::aqp::g_kernel_launches)
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// streaming (read-once) 128-bit load: bypass L1 allocation
+__device__ __forceinline__ uint4 ld_stream_v4(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ld_stream_v2(const uint2 *p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// inclusive warp scan
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane_id() >= (unsigned) o) v += t;
+    }
+    return v;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace aqp

@@ -1,0 +1,74 @@
+// join_internal.cuh — constants, plan structs and launcher declarations shared by the join's
+// translation units (partition.cu, build_probe.cu, gen.cu, api.cu).
+#pragma once
+
+#include "common.cuh"
+
+namespace aqp {
+
+// ---- partitioning geometry ---------------------------------------------------------------------
+constexpr int kMaxFanoutBits = 8;                 // bits per pass
+constexpr int kMaxFanout = 1 << kMaxFanoutBits;
+constexpr int kMaxSmemHistBits = 15;              // widest shared-memory histogram (128 KiB)
+constexpr int kScatterTile = 4096;                // tuples per scatter tile (32 KiB staging)
+
+// ---- build/probe geometry ------------------------------------------------------------------------
+constexpr int kBuildCap = 8192;                   // R tuples per shared-memory hash table (64 KiB)
+constexpr int kProbeChunk = 32768;                // S tuples per work item
+constexpr int kJoinThreads = 512;
+
+struct RelPlan {
+    const uint32_t *hist;       // [2^B]   raw-digit histogram
+    uint32_t *part_off;         // [2^B+1] final partition starts, order f = p1*F2 + p2
+    uint32_t *cursor1;          // [F1]    pass-1 write cursors
+    uint32_t *cursor2;          // [2^B]   pass-2 write cursors
+    uint32_t *seg_off;          // [F1+1]  pass-1 partition starts (= pass-2 input segments)
+    uint32_t *seg_tile_start;   // [F1+1]  first pass-2 tile of each segment
+    uint32_t *seg1;             // [4]     pass-1 single-segment tables {0, n, 0, ceil(n/tile)}
+};
+struct PlanArgs {
+    RelPlan rel[2];
+    uint32_t bits1, bits2;
+};
+
+struct JoinResult {              // device-side accumulators
+    unsigned long long matches;
+    unsigned long long checksum;
+    unsigned long long keysum;
+    unsigned long long out_count;   // triples reserved in the output buffer
+};
+
+// partition.cu
+int radix_hist_device(const row_t *d_in, uint64_t n, uint32_t shift, uint32_t bits, uint32_t *d_hist, cudaStream_t st);
+int exclusive_scan_u32_device(const uint32_t *d_in, uint32_t n, uint32_t *d_out, cudaStream_t st);
+int plan_offsets_device(const PlanArgs &a, cudaStream_t st);
+int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_off, const uint32_t *d_seg_tile_start,
+                         uint32_t nseg, uint64_t n_total, uint32_t shift, uint32_t bits, uint32_t *d_cursors,
+                         cudaStream_t st);
+int single_segment_setup(uint32_t n, const uint32_t *d_offsets, uint32_t fan, uint32_t *d_cursors,
+                         uint32_t *d_seg_tables, cudaStream_t st);
+
+// build_probe.cu
+int join_items_device(const uint32_t *d_offR, const uint32_t *d_offS, uint32_t nparts, uint32_t *d_item_start,
+                      uint2 *d_items, cudaStream_t st);
+int build_probe_device(const row_t *d_R, const uint32_t *d_offR, const row_t *d_S, const uint32_t *d_offS,
+                       const uint32_t *d_item_start, const uint2 *d_items, uint32_t nparts, uint64_t max_items,
+                       uint32_t hash_shift, JoinResult *d_res, output_triple_t *d_out, uint64_t out_cap,
+                       cudaStream_t st);
+
+// gen.cu
+int gen_pk_device(row_t *d_rel, uint64_t n_total, uint64_t row_begin, uint64_t n, uint64_t seed, cudaStream_t st);
+int gen_fk_device(row_t *d_rel, uint64_t n_total, uint64_t maxid, uint64_t row_begin, uint64_t n, uint64_t seed,
+                  cudaStream_t st);
+int set_rowid_payload_device(row_t *d_rel, uint64_t row_begin, uint64_t n, cudaStream_t st);
+
+// scan.cu
+int bitvector_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, uint64_t *d_out, cudaStream_t st);
+int scan_count_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, uint64_t *d_count, cudaStream_t st);
+size_t index_scan_scratch_bytes(size_t n);
+int index_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, uint64_t id_base, uint64_t *d_out,
+                      uint64_t cap, uint64_t *d_count, void *d_scratch, cudaStream_t st);
+int fill_tiled_column_device(uint8_t *d, size_t n, uint64_t pos_begin, cudaStream_t st);
+int fill_skewed_column_device(uint8_t *d, size_t n, uint64_t pos_begin, uint32_t ppm, uint64_t seed, cudaStream_t st);
+
+}  // namespace aqp

@@ -1,0 +1,177 @@
+"""GPU parity: the RHO join through the C ABI vs the CPU oracle — match count, checksum and keysum
+bit-exact, materialised triples identical as a set — on the reference-seeded inputs, the committed
+reference fixtures, edge cases, and closed forms at the full benchmark sizes."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import expected_pkfk, sha, sorted_triples
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(gpu, oracle, R, S, materialize=True, expect=None):
+    o = oracle.rho(R, S, nthreads=4, materialize=materialize) if expect is None else expect
+    g = gpu.run_join(R, S, materialize=materialize, nthreads=4)
+    assert (g["matches"], g["checksum"], g["keysum"]) == (o["matches"], o["checksum"], o["keysum"])
+    assert g["result_type"] == 1 and g["nthreads"] == 4
+    if materialize:
+        assert g["table_num_tuples"] == o["matches"]
+        assert np.array_equal(sorted_triples(g["triples"]), sorted_triples(o["triples"]))
+    return g
+
+
+def _inputs(oracle, c, zipf_inputs):
+    R = oracle.set_rowid_payload(oracle.gen_pk(c["nR"], 11111))
+    if c["kind"] == "fk":
+        S = oracle.gen_fk(c["nS"], c["nR"], 22222)
+    elif c["kind"] == "fk_sel":
+        S = oracle.gen_fk_sel(c["nS"], 100 * c["nR"] // c["sel"], 22222)
+    else:
+        S = np.zeros(c["nS"], dtype=oracle.ROW)
+        S["key"] = zipf_inputs[f"S_z{c['z']}"]
+    return R, oracle.set_rowid_payload(S)
+
+
+def test_join_matches_golden(gpu, oracle, golden, zipf_inputs):
+    for c in golden["join"]:
+        if not c["force_2_passes"]:
+            continue   # same inputs, same expected values
+        R, S = _inputs(oracle, c, zipf_inputs)
+        g = gpu.run_join(R, S, materialize=True)
+        assert (g["matches"], g["checksum"], g["keysum"]) == (c["matches"], c["checksum"], c["keysum"]), c
+        assert sha(sorted_triples(g["triples"])) == c["sha256_sorted_triples"], c
+
+
+@pytest.mark.parametrize("nR,nS", [(1, 1), (1, 1000), (7, 3), (8192, 8192), (8193, 50000), (100003, 250007),
+                                   (1 << 16, 1 << 18), (1 << 20, 1 << 22), (3_000_017, 5_000_011)])
+def test_pkfk_vs_oracle(gpu, oracle, nR, nS):
+    R = oracle.set_rowid_payload(oracle.gen_pk(nR, 11111))
+    S = oracle.set_rowid_payload(oracle.gen_fk(nS, nR, 22222))
+    g = _check(gpu, oracle, R, S, materialize=nS <= (1 << 22))
+    assert g["matches"] == nS
+
+
+def test_config1_reference_seeds(gpu, oracle):
+    """BASELINE config 1: |R|=2^24, |S|=2^26, seeds 11111/22222 (native.cpp:35-36); expected values are
+    the survey's known answers and the oracle."""
+    nR, nS = 1 << 24, 1 << 26
+    R = oracle.set_rowid_payload(oracle.gen_pk(nR, 11111))
+    S = oracle.set_rowid_payload(oracle.gen_fk(nS, nR, 22222))
+    assert list(R["key"][:4]) == [14386915, 8878978, 11266848, 11599710]
+    assert list(S["key"][:4]) == [4221318, 11571670, 11656028, 6314437]
+    g = gpu.run_join(R, S, materialize=False)
+    assert g["matches"] == 67108864 and g["keysum"] == 562949986975744
+    o = oracle.rho(R, S, nthreads=8)
+    assert (g["matches"], g["checksum"], g["keysum"]) == (o["matches"], o["checksum"], o["keysum"])
+    assert (g["radix_bits"], g["num_passes"]) == (11, 2)
+
+
+def test_duplicates_misses_and_key_zero(gpu, oracle):
+    rng = np.random.default_rng(5)
+    R = np.zeros(30000, dtype=oracle.ROW)
+    R["key"] = rng.integers(0, 5000, 30000)           # duplicates (chains > 1) and key 0
+    S = np.zeros(100000, dtype=oracle.ROW)
+    S["key"] = rng.integers(0, 10000, 100000)         # half miss
+    oracle.set_rowid_payload(R)
+    oracle.set_rowid_payload(S)
+    g = _check(gpu, oracle, R, S)
+    assert g["matches"] > len(S)                      # output larger than |S|: exercises the capacity re-run
+
+
+def test_empty_relations(gpu, oracle):
+    E = np.zeros(0, dtype=oracle.ROW)
+    R = oracle.set_rowid_payload(oracle.gen_pk(1000, 1))
+    for a, b in ((E, R), (R, E), (E, E)):
+        g = gpu.run_join(a, b, materialize=True)
+        assert g["matches"] == 0 and g["checksum"] == 0 and len(g["triples"]) == 0 and g["num_chunks"] == 0
+
+
+def test_sparse_keys_unbalanced_partitions(gpu, oracle):
+    """TPC-H-style sparse keys (dbgen orderkeys use 8 of every 32 values) and keys that agree on all
+    radix bits: partitions are unbalanced and exceed the shared-memory table, forcing several build rounds."""
+    n = 200000
+    i = np.arange(n, dtype=np.uint64)
+    R = np.zeros(n, dtype=oracle.ROW)
+    R["key"] = ((i // 8) * 32 + (i % 8) + 1).astype(np.uint32)
+    S = np.zeros(4 * n, dtype=oracle.ROW)
+    S["key"] = np.random.default_rng(2).choice(R["key"], 4 * n)
+    oracle.set_rowid_payload(R)
+    oracle.set_rowid_payload(S)
+    _check(gpu, oracle, R, S)
+    R2 = R.copy()
+    R2["key"] = (np.arange(n, dtype=np.uint32) << 12) | 5      # every key lands in ONE partition
+    S2 = S.copy()
+    S2["key"] = np.random.default_rng(3).choice(R2["key"], 4 * n)
+    _check(gpu, oracle, R2, S2)
+
+
+def test_zipf_skew(gpu, oracle):
+    nR, nS = 1 << 18, 1 << 21
+    R = oracle.set_rowid_payload(oracle.gen_pk(nR, 11111))
+    for z in (0.5, 1.0, 1.5):
+        S = oracle.set_rowid_payload(oracle.gen_zipf(nS, nR, z, seed=9))
+        g = _check(gpu, oracle, R, S, materialize=False)
+        assert g["matches"] == nS
+
+
+@pytest.mark.parametrize("bits", [0, 3, 8, 9, 16])
+def test_forced_radix_bits(gpu, oracle, bits):
+    """Every pass configuration (none / one pass / two passes) gives the same result."""
+    R = oracle.set_rowid_payload(oracle.gen_pk(300007, 11111))
+    S = oracle.set_rowid_payload(oracle.gen_fk(1000003, 300007, 22222))
+    os.environ["B200_AQP_RADIX_BITS"] = str(bits)
+    try:
+        g = _check(gpu, oracle, R, S, materialize=False)
+        assert g["radix_bits"] == bits
+    finally:
+        del os.environ["B200_AQP_RADIX_BITS"]
+
+
+def test_preload_split(gpu, oracle):
+    R = oracle.set_rowid_payload(oracle.gen_pk(1 << 16, 11111))
+    S = oracle.set_rowid_payload(oracle.gen_fk(1 << 18, 1 << 16, 22222))
+    o = oracle.rho(R, S)
+    gpu.preload_relations(R, S)
+    for _ in range(3):
+        g = gpu.join_preload()
+        assert (g["matches"], g["checksum"], g["keysum"]) == (o["matches"], o["checksum"], o["keysum"])
+        assert g["ms_h2d"] == 0.0
+    gpu.lib().b200_free_preload()
+    with pytest.raises(gpu.AqpError):
+        gpu.join_preload()
+
+
+def test_chunked_table_layout(gpu, oracle):
+    R = oracle.set_rowid_payload(oracle.gen_pk(5000, 1))
+    S = oracle.set_rowid_payload(oracle.gen_fk(20000, 5000, 2))
+    g = gpu.run_join(R, S, materialize=True)
+    assert g["num_chunks"] == -(-20000 // gpu.TUPLES_PER_CHUNK)
+    assert len(g["triples"]) == 20000
+    m, cs, ks = expected_pkfk(R, S)
+    t = g["triples"]
+    assert int(t["Rpayload"].astype(np.uint64).sum() + t["Spayload"].astype(np.uint64).sum()) == cs
+    assert int(t["key"].astype(np.uint64).sum()) == ks
+
+
+@pytest.mark.parametrize("logR,logS", [(24, 26), (27, 29)])
+def test_full_size_device_generated(gpu, logR, logS):
+    """BASELINE configs 1 and 3 with the on-device generators: matches = |S|, keysum and checksum
+    have closed forms because every block of |R| S-tuples is a permutation of the R keys and
+    payload = row id."""
+    import torch
+    nR, nS = 1 << logR, 1 << logS
+    dev = torch.device("cuda:0")
+    R = torch.empty(nR * 2, dtype=torch.int32, device=dev)
+    S = torch.empty(nS * 2, dtype=torch.int32, device=dev)
+    gpu.gen_pk_device(R.data_ptr(), nR, seed=11111)
+    gpu.gen_fk_device(S.data_ptr(), nS, nR, seed=22222)
+    torch.cuda.synchronize()
+    s = gpu.join_device(R.data_ptr(), nR, S.data_ptr(), nS)
+    rep = nS // nR
+    assert s["matches"] == nS
+    assert s["keysum"] == rep * nR * (nR + 1) // 2
+    assert s["checksum"] == rep * (nR * (nR - 1) // 2) + nS * (nS - 1) // 2
+    s2 = gpu.join_device(R.data_ptr(), nR, S.data_ptr(), nS)   # idempotent, inputs untouched
+    assert (s2["matches"], s2["checksum"], s2["keysum"]) == (s["matches"], s["checksum"], s["keysum"])
