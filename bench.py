@@ -201,7 +201,7 @@ def bench_scan(A, torch, dev, peak, steps, warmup, n_gpus=1, rank=0):
     begin = rank * n
     data = torch.empty(n, dtype=torch.uint8, device=dev)
     st = torch.cuda.current_stream().cuda_stream
-    assert A.lib().b200_fill_tiled_column_device(data.data_ptr(), n, begin, st) == 0
+    assert A.lib().b200_fill_tiled_column_device(data.data_ptr(), n, begin, A._st(st)) == 0
     bv = torch.empty(n // 64, dtype=torch.int64, device=dev)
     cnt = torch.zeros(1, dtype=torch.int64, device=dev)
     out = {}

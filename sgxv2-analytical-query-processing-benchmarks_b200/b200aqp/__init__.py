@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(PKG_DIR, "libb200aqp.so")
+# B200_AQP_LIB selects an alternative build of the same library (tuning sweeps only)
+LIB_PATH = os.environ.get("B200_AQP_LIB") or os.path.join(PKG_DIR, "libb200aqp.so")
 
 ROW = np.dtype([("key", np.uint32), ("payload", np.uint32)])
 TRIPLE = np.dtype([("key", np.uint32), ("Rpayload", np.uint32), ("Spayload", np.uint32)])
@@ -125,6 +126,15 @@ class AqpError(RuntimeError):
     pass
 
 
+def _st(stream):
+    """None -> the library's own stream (NULL in the C ABI); an integer cudaStream_t handle otherwise.
+    Handle 0 (what torch reports for its default stream) is passed as cudaStreamLegacy (0x1) because
+    NULL already means "library stream" in this ABI."""
+    if stream is None:
+        return None
+    return int(stream) if int(stream) != 0 else 1
+
+
 def _check(rc, what):
     if rc != 0:
         raise AqpError(f"{what}: {lib().b200_last_error().decode()}")
@@ -193,9 +203,9 @@ def join_preload(materialize: bool = False, nthreads: int = 1):
     return _collect_result(res, materialize)
 
 
-def join_device(d_R: int, nR: int, d_S: int, nS: int, d_out: int = 0, out_capacity: int = 0, stream: int = 0) -> dict:
+def join_device(d_R: int, nR: int, d_S: int, nS: int, d_out: int = 0, out_capacity: int = 0, stream=None) -> dict:
     s = JoinStats()
-    _check(lib().b200_join_device(d_R, nR, d_S, nS, d_out or None, out_capacity, C.byref(s), stream or None),
+    _check(lib().b200_join_device(d_R, nR, d_S, nS, d_out or None, out_capacity, C.byref(s), _st(stream)),
            "b200_join_device")
     return s.as_dict()
 
@@ -279,15 +289,15 @@ def host_gen_zipf(n: int, maxid: int, z: float, seed: int) -> np.ndarray:
     return _take_relation(t)
 
 
-def gen_pk_device(d_rel: int, n_total: int, seed: int, row_begin: int = 0, n: int | None = None, stream: int = 0):
-    _check(lib().b200_gen_pk_device(d_rel, n_total, row_begin, n_total if n is None else n, seed, stream or None),
+def gen_pk_device(d_rel: int, n_total: int, seed: int, row_begin: int = 0, n: int | None = None, stream=None):
+    _check(lib().b200_gen_pk_device(d_rel, n_total, row_begin, n_total if n is None else n, seed, _st(stream)),
            "b200_gen_pk_device")
 
 
 def gen_fk_device(d_rel: int, n_total: int, maxid: int, seed: int, row_begin: int = 0, n: int | None = None,
-                  stream: int = 0):
+                  stream=None):
     _check(lib().b200_gen_fk_device(d_rel, n_total, maxid, row_begin, n_total if n is None else n, seed,
-                                    stream or None), "b200_gen_fk_device")
+                                    _st(stream)), "b200_gen_fk_device")
 
 
 # ---- scans -------------------------------------------------------------------------------------------------
@@ -315,16 +325,16 @@ def index_scan_user(lo: int, hi: int, data: np.ndarray, capacity: int | None = N
     return out[:min(cnt.value, cap)], int(cnt.value), int(t.value)
 
 
-def bitvector_scan_device(lo, hi, d_data, n, d_out, stream=0):
-    _check(lib().b200_bitvector_scan_device(lo, hi, d_data, n, d_out, stream or None), "b200_bitvector_scan_device")
+def bitvector_scan_device(lo, hi, d_data, n, d_out, stream=None):
+    _check(lib().b200_bitvector_scan_device(lo, hi, d_data, n, d_out, _st(stream)), "b200_bitvector_scan_device")
 
 
-def scan_count_device(lo, hi, d_data, n, d_count, stream=0):
-    _check(lib().b200_scan_count_device(lo, hi, d_data, n, d_count, stream or None), "b200_scan_count_device")
+def scan_count_device(lo, hi, d_data, n, d_count, stream=None):
+    _check(lib().b200_scan_count_device(lo, hi, d_data, n, d_count, _st(stream)), "b200_scan_count_device")
 
 
-def index_scan_device(lo, hi, d_data, n, d_out, capacity, d_count, id_base=0, stream=0):
-    _check(lib().b200_index_scan_device(lo, hi, d_data, n, id_base, d_out, capacity, d_count, stream or None),
+def index_scan_device(lo, hi, d_data, n, d_out, capacity, d_count, id_base=0, stream=None):
+    _check(lib().b200_index_scan_device(lo, hi, d_data, n, id_base, d_out, capacity, d_count, _st(stream)),
            "b200_index_scan_device")
 
 

@@ -166,7 +166,7 @@ static __global__ void chunkify_kernel(const output_triple_t *flat, unsigned cha
 
 struct MetaLayout {
     size_t histR, histS, offR, offS, cur1R, cur1S, cur2R, cur2S, segR, segS, tileR, tileS, seg1R, seg1S, item_start,
-        items, result, total, zero_bytes;
+        items, result, bhR, bhS, bbR, bbS, total, zero_bytes;
 };
 static MetaLayout meta_layout(uint32_t bits, uint32_t b1, uint64_t nS) {
     const size_t P = (size_t) 1 << bits, F1 = (size_t) 1 << b1;
@@ -194,6 +194,11 @@ static MetaLayout meta_layout(uint32_t bits, uint32_t b1, uint64_t nS) {
     m.tileS = take((F1 + 1) * 4);
     m.seg1R = take(16);
     m.seg1S = take(16);
+    const size_t NB = pass1_blocks();
+    m.bhR = take(NB * F1 * 4);
+    m.bhS = take(NB * F1 * 4);
+    m.bbR = take(NB * F1 * 4);
+    m.bbS = take(NB * F1 * 4);
     m.item_start = take((P + 1) * 4);
     m.items = take((nS / kProbeChunk + P + 1) * sizeof(uint2));
     m.total = o;
@@ -238,26 +243,45 @@ static int join_device_locked(const row_t *dR, uint64_t nR, const row_t *dS, uin
         AQP_CUDA_OK(cudaEventRecord(g.ev[2], st));
         AQP_CUDA_OK(cudaEventRecord(g.ev[3], st));
     } else {
-        if (radix_hist_device(dR, nR, 0, bits, u32(m.histR), st)) return -1;
-        if (radix_hist_device(dS, nS, 0, bits, u32(m.histS), st)) return -1;
+        // pass-1 scatter geometry: NB CTAs, CTA b owns tiles [b*tpb, (b+1)*tpb) of its relation; the
+        // histogram kernel runs with the same geometry so it can emit per-CTA pass-1 histogram rows
+        const uint32_t NB = pass1_blocks();
+        const bool priv = bits <= (uint32_t) kMaxSmemHistBits && !getenv("B200_AQP_ATOMIC_PASS1");
+        const uint32_t tpbR = (uint32_t) (((nR + kScatterTile - 1) / kScatterTile + NB - 1) / NB);
+        const uint32_t tpbS = (uint32_t) (((nS + kScatterTile - 1) / kScatterTile + NB - 1) / NB);
+        if (radix_hist_device(dR, nR, 0, bits, u32(m.histR), priv ? NB : 0, (uint64_t) tpbR * kScatterTile, b1,
+                              u32(m.bhR), st))
+            return -1;
+        if (radix_hist_device(dS, nS, 0, bits, u32(m.histS), priv ? NB : 0, (uint64_t) tpbS * kScatterTile, b1,
+                              u32(m.bhS), st))
+            return -1;
         PlanArgs pa{};
         pa.bits1 = b1;
         pa.bits2 = b2;
-        pa.rel[0] = RelPlan{u32(m.histR), u32(m.offR), u32(m.cur1R), u32(m.cur2R), u32(m.segR), u32(m.tileR), u32(m.seg1R)};
-        pa.rel[1] = RelPlan{u32(m.histS), u32(m.offS), u32(m.cur1S), u32(m.cur2S), u32(m.segS), u32(m.tileS), u32(m.seg1S)};
+        pa.nblocks1 = NB;
+        pa.rel[0] = RelPlan{u32(m.histR), u32(m.offR), u32(m.cur1R), u32(m.cur2R), u32(m.segR), u32(m.tileR), u32(m.seg1R),
+                            priv ? u32(m.bhR) : nullptr, u32(m.bbR)};
+        pa.rel[1] = RelPlan{u32(m.histS), u32(m.offS), u32(m.cur1S), u32(m.cur2S), u32(m.segS), u32(m.tileS), u32(m.seg1S),
+                            priv ? u32(m.bhS) : nullptr, u32(m.bbS)};
         if (plan_offsets_device(pa, st)) return -1;
         AQP_CUDA_OK(cudaEventRecord(g.ev[1], st));
 
         row_t *t1R = static_cast<row_t *>(g.tmp[0].p), *t1S = static_cast<row_t *>(g.tmp[1].p);
-        if (radix_scatter_launch(dR, t1R, u32(m.seg1R), u32(m.seg1R) + 2, 1, nR, 0, b1, u32(m.cur1R), st)) return -1;
-        if (radix_scatter_launch(dS, t1S, u32(m.seg1S), u32(m.seg1S) + 2, 1, nS, 0, b1, u32(m.cur1S), st)) return -1;
+        if (radix_scatter_launch(dR, t1R, u32(m.seg1R), u32(m.seg1R) + 2, 1, nR, 0, b1, u32(m.cur1R),
+                                 priv ? u32(m.bbR) : nullptr, NB, tpbR, st))
+            return -1;
+        if (radix_scatter_launch(dS, t1S, u32(m.seg1S), u32(m.seg1S) + 2, 1, nS, 0, b1, u32(m.cur1S),
+                                 priv ? u32(m.bbS) : nullptr, NB, tpbS, st))
+            return -1;
         AQP_CUDA_OK(cudaEventRecord(g.ev[2], st));
         finR = t1R;
         finS = t1S;
         if (passes == 2) {
             row_t *t2R = static_cast<row_t *>(g.tmp[2].p), *t2S = static_cast<row_t *>(g.tmp[3].p);
-            if (radix_scatter_launch(t1R, t2R, u32(m.segR), u32(m.tileR), F1, nR, b1, b2, u32(m.cur2R), st)) return -1;
-            if (radix_scatter_launch(t1S, t2S, u32(m.segS), u32(m.tileS), F1, nS, b1, b2, u32(m.cur2S), st)) return -1;
+            if (radix_scatter_launch(t1R, t2R, u32(m.segR), u32(m.tileR), F1, nR, b1, b2, u32(m.cur2R), nullptr, 0, 0, st))
+                return -1;
+            if (radix_scatter_launch(t1S, t2S, u32(m.segS), u32(m.tileS), F1, nS, b1, b2, u32(m.cur2S), nullptr, 0, 0, st))
+                return -1;
             finR = t2R;
             finS = t2S;
         }
@@ -617,7 +641,8 @@ int b200_radix_hist_device(const struct row_t *d_in, uint64_t n, uint32_t shift,
                            void *stream) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (ensure_init()) return -1;
-    return radix_hist_device(d_in, n, shift, bits, d_hist, stream ? static_cast<cudaStream_t>(stream) : g.stream);
+    return radix_hist_device(d_in, n, shift, bits, d_hist, 0, 0, 0, nullptr,
+                             stream ? static_cast<cudaStream_t>(stream) : g.stream);
 }
 
 int b200_exclusive_scan_u32_device(const uint32_t *d_in, uint32_t n, uint32_t *d_out, void *stream) {
@@ -641,7 +666,7 @@ int b200_radix_scatter_device(const struct row_t *d_in, uint64_t n, uint32_t shi
     if (seg.ensure(64)) return -1;
     uint32_t *d_seg = static_cast<uint32_t *>(seg.p);
     if (single_segment_setup((uint32_t) n, d_offsets, 1u << bits, d_cursors, d_seg, st)) return -1;
-    return radix_scatter_launch(d_in, d_out, d_seg, d_seg + 2, 1, n, shift, bits, d_cursors, st);
+    return radix_scatter_launch(d_in, d_out, d_seg, d_seg + 2, 1, n, shift, bits, d_cursors, nullptr, 0, 0, st);
 }
 
 // ---- generators (device) --------------------------------------------------------------------------

@@ -48,7 +48,8 @@ int join_items_device(const uint32_t *d_offR, const uint32_t *d_offS, uint32_t n
 // ---------------------------------------------------------------------------------------------
 // build + probe
 // ---------------------------------------------------------------------------------------------
-constexpr int kProbeUnroll = 4;
+constexpr int kProbeUnroll = 8;
+constexpr uint32_t kChainFlag = 0x80000000u;   // set in a bucket head when its chain holds more than one tuple
 constexpr size_t kJoinSmemBytes = (size_t) kBuildCap * (sizeof(uint2) + sizeof(uint32_t) + sizeof(uint16_t));
 
 template <bool kMaterialize>
@@ -83,7 +84,10 @@ build_probe_kernel(const uint2 *__restrict__ R, const uint32_t *__restrict__ off
             for (uint32_t i = threadIdx.x; i < nr; i += kJoinThreads) {
                 uint2 t = R[rb + i];
                 rt[i] = t;
-                next[i] = (uint16_t) atomicExch(&bucket[(t.x >> hash_shift) & hmask], i + 1);
+                uint32_t *b = &bucket[(t.x >> hash_shift) & hmask];
+                uint32_t old = atomicExch(b, i + 1);
+                next[i] = (uint16_t) old;             // low 16 bits: previous head (0 = end of chain)
+                if (old) atomicOr(b, kChainFlag);     // whoever is head in the end carries the flag
             }
             __syncthreads();
 
@@ -99,16 +103,29 @@ build_probe_kernel(const uint2 *__restrict__ R, const uint32_t *__restrict__ off
                 }
 #pragma unroll
                 for (int j = 0; j < kProbeUnroll; ++j) {
-                    uint32_t hit = valid[j] ? bucket[(s[j].x >> hash_shift) & hmask] : 0u;
+                    const uint32_t head = valid[j] ? bucket[(s[j].x >> hash_shift) & hmask] : 0u;
+                    uint32_t hit = head & 0xFFFFu;
                     if (!kMaterialize) {
-                        while (hit) {
-                            uint2 r = rt[hit - 1];
-                            if (r.x == s[j].x) {
-                                ++matches;
-                                checksum += (unsigned long long) r.y + s[j].y;
-                                keysum += s[j].x;
+                        if (!(head & kChainFlag)) {
+                            // single-tuple chain (always the case for a dense primary key): no link to follow
+                            if (hit) {
+                                uint2 r = rt[hit - 1];
+                                if (r.x == s[j].x) {
+                                    ++matches;
+                                    checksum += (unsigned long long) r.y + s[j].y;
+                                    keysum += s[j].x;
+                                }
                             }
-                            hit = next[hit - 1];
+                        } else {
+                            while (hit) {
+                                uint2 r = rt[hit - 1];
+                                if (r.x == s[j].x) {
+                                    ++matches;
+                                    checksum += (unsigned long long) r.y + s[j].y;
+                                    keysum += s[j].x;
+                                }
+                                hit = next[hit - 1];
+                            }
                         }
                     } else {
                         while (__any_sync(0xffffffffu, hit != 0)) {

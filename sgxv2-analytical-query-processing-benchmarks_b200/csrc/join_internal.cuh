@@ -10,7 +10,13 @@ namespace aqp {
 constexpr int kMaxFanoutBits = 8;                 // bits per pass
 constexpr int kMaxFanout = 1 << kMaxFanoutBits;
 constexpr int kMaxSmemHistBits = 15;              // widest shared-memory histogram (128 KiB)
-constexpr int kScatterTile = 4096;                // tuples per scatter tile (32 KiB staging)
+#ifndef AQP_SCATTER_TILE
+#define AQP_SCATTER_TILE 4096
+#endif
+#ifndef AQP_SCATTER_THREADS
+#define AQP_SCATTER_THREADS 512
+#endif
+constexpr int kScatterTile = AQP_SCATTER_TILE;    // tuples per scatter tile (32 KiB staging + 2 x 32 KiB TMA ring)
 
 // ---- build/probe geometry ------------------------------------------------------------------------
 constexpr int kBuildCap = 8192;                   // R tuples per shared-memory hash table (64 KiB)
@@ -25,10 +31,13 @@ struct RelPlan {
     uint32_t *seg_off;          // [F1+1]  pass-1 partition starts (= pass-2 input segments)
     uint32_t *seg_tile_start;   // [F1+1]  first pass-2 tile of each segment
     uint32_t *seg1;             // [4]     pass-1 single-segment tables {0, n, 0, ceil(n/tile)}
+    const uint32_t *block_hist; // [nblocks1][F1] pass-1 histogram of each pass-1 scatter block (or null)
+    uint32_t *block_base;       // [nblocks1][F1] private pass-1 write cursors of each block
 };
 struct PlanArgs {
     RelPlan rel[2];
     uint32_t bits1, bits2;
+    uint32_t nblocks1;          // CTAs of the pass-1 scatter (= rows of block_hist)
 };
 
 struct JoinResult {              // device-side accumulators
@@ -39,12 +48,17 @@ struct JoinResult {              // device-side accumulators
 };
 
 // partition.cu
-int radix_hist_device(const row_t *d_in, uint64_t n, uint32_t shift, uint32_t bits, uint32_t *d_hist, cudaStream_t st);
+int radix_hist_device(const row_t *d_in, uint64_t n, uint32_t shift, uint32_t bits, uint32_t *d_hist, uint32_t nblocks,
+                      uint64_t chunk, uint32_t bits1, uint32_t *d_block_hist, cudaStream_t st);
 int exclusive_scan_u32_device(const uint32_t *d_in, uint32_t n, uint32_t *d_out, cudaStream_t st);
 int plan_offsets_device(const PlanArgs &a, cudaStream_t st);
+// d_block_base == nullptr: runs are reserved with global atomics on d_cursors (any grid).
+// d_block_base != nullptr: exactly nblocks CTAs, CTA b owns tiles [b*tiles_per_block, ...) and writes at
+// its private cursors d_block_base[b][2^bits] (single segment only).
 int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_off, const uint32_t *d_seg_tile_start,
                          uint32_t nseg, uint64_t n_total, uint32_t shift, uint32_t bits, uint32_t *d_cursors,
-                         cudaStream_t st);
+                         const uint32_t *d_block_base, uint32_t nblocks, uint32_t tiles_per_block, cudaStream_t st);
+uint32_t pass1_blocks();
 int single_segment_setup(uint32_t n, const uint32_t *d_offsets, uint32_t fan, uint32_t *d_cursors,
                          uint32_t *d_seg_tables, cudaStream_t st);
 

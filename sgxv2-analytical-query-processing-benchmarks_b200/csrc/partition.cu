@@ -30,32 +30,48 @@ namespace aqp {
 constexpr int kHistThreads = 512;
 constexpr int kHistUnroll = 8;   // 8-byte loads in flight per thread
 
-// shared-memory privatised histogram (bits <= kMaxSmemHistBits), flushed with global REDs
+// shared-memory privatised histogram (bits <= kMaxSmemHistBits), flushed with global REDs.
+// Block b reads the contiguous chunk [b*chunk, (b+1)*chunk) — the same chunk the pass-1 scatter
+// assigns to block b — and, besides adding into the global full-width histogram, emits its own
+// pass-1 histogram row block_hist[b][p1] (p1 = low bits1 of the digit). Those rows give every
+// scatter block private, pre-reserved output ranges (parallel_radix_partition's per-thread
+// histogram + prefix scheme, radix_join.cpp:881-915, with CTAs in the role of threads).
 __global__ void __launch_bounds__(kHistThreads)
 radix_hist_smem_kernel(const uint2 *__restrict__ in, uint64_t n, uint32_t shift, uint32_t bits,
-                       uint32_t *__restrict__ ghist) {
+                       uint32_t *__restrict__ ghist, uint64_t chunk, uint32_t bits1,
+                       uint32_t *__restrict__ block_hist) {
     extern __shared__ uint32_t sh[];
     const uint32_t fan = 1u << bits, mask = fan - 1;
     for (uint32_t i = threadIdx.x; i < fan; i += kHistThreads) sh[i] = 0;
     __syncthreads();
+    const uint64_t cbeg = (uint64_t) blockIdx.x * chunk;
+    const uint64_t cend = cbeg + chunk < n ? cbeg + chunk : n;
     const uint64_t tile = (uint64_t) kHistThreads * kHistUnroll;
-    for (uint64_t base = (uint64_t) blockIdx.x * tile; base < n; base += (uint64_t) gridDim.x * tile) {
+    for (uint64_t base = cbeg; base < cend; base += tile) {
         uint2 v[kHistUnroll];
 #pragma unroll
         for (int j = 0; j < kHistUnroll; ++j) {
             uint64_t i = base + (uint64_t) j * kHistThreads + threadIdx.x;
-            if (i < n) v[j] = ld_stream_v2(in + i);
+            if (i < cend) v[j] = ld_stream_v2(in + i);
         }
 #pragma unroll
         for (int j = 0; j < kHistUnroll; ++j) {
             uint64_t i = base + (uint64_t) j * kHistThreads + threadIdx.x;
-            if (i < n) atomicAdd(&sh[(v[j].x >> shift) & mask], 1u);
+            if (i < cend) atomicAdd(&sh[(v[j].x >> shift) & mask], 1u);
         }
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < fan; i += kHistThreads) {
         uint32_t c = sh[i];
         if (c) atomicAdd(&ghist[i], c);
+    }
+    if (block_hist) {
+        const uint32_t F1 = 1u << bits1, F2 = fan >> bits1;
+        for (uint32_t p1 = threadIdx.x; p1 < F1; p1 += kHistThreads) {
+            uint32_t c = 0;
+            for (uint32_t p2 = 0; p2 < F2; ++p2) c += sh[p1 + (p2 << bits1)];
+            block_hist[(size_t) blockIdx.x * F1 + p1] = c;
+        }
     }
 }
 
@@ -69,15 +85,21 @@ radix_hist_global_kernel(const uint2 *__restrict__ in, uint64_t n, uint32_t shif
         atomicAdd(&ghist[(ld_stream_v2(in + i).x >> shift) & mask], 1u);
 }
 
+// nblocks == 0: plain histogram with a grid chosen here. nblocks > 0: exactly nblocks CTAs, CTA b
+// covering tuples [b*chunk, (b+1)*chunk), and block_hist[nblocks][2^bits1] rows are written.
 int radix_hist_device(const row_t *d_in, uint64_t n, uint32_t shift, uint32_t bits, uint32_t *d_hist,
-                      cudaStream_t st) {
-    if (n == 0) return 0;
+                      uint32_t nblocks, uint64_t chunk, uint32_t bits1, uint32_t *d_block_hist, cudaStream_t st) {
     if (bits > 24) {
         set_error("radix_hist: bits > 24 not supported");
         return -1;
     }
+    if (nblocks && bits > (uint32_t) kMaxSmemHistBits) {
+        set_error("radix_hist: per-block histograms need bits <= 15");
+        return -1;
+    }
+    if (n == 0 && !nblocks) return 0;
     const uint2 *in = reinterpret_cast<const uint2 *>(d_in);
-    if (bits <= kMaxSmemHistBits) {
+    if (bits <= (uint32_t) kMaxSmemHistBits) {
         size_t smem = sizeof(uint32_t) << bits;
         static bool attr_set = false;
         if (!attr_set) {
@@ -85,10 +107,16 @@ int radix_hist_device(const row_t *d_in, uint64_t n, uint32_t shift, uint32_t bi
                                              (int) (sizeof(uint32_t) << kMaxSmemHistBits)));
             attr_set = true;
         }
-        uint64_t tiles = (n + (uint64_t) kHistThreads * kHistUnroll - 1) / ((uint64_t) kHistThreads * kHistUnroll);
-        int per_sm = bits <= 13 ? 3 : (bits == 14 ? 2 : 1);
-        int grid = (int) (tiles < (uint64_t) kNumSMs * per_sm ? tiles : (uint64_t) kNumSMs * per_sm);
-        radix_hist_smem_kernel<<<grid, kHistThreads, smem, st>>>(in, n, shift, bits, d_hist);
+        uint32_t grid = nblocks;
+        if (!grid) {
+            const uint64_t tile = (uint64_t) kHistThreads * kHistUnroll;
+            uint64_t tiles = (n + tile - 1) / tile;
+            int per_sm = bits <= 13 ? 3 : (bits == 14 ? 2 : 1);
+            grid = (uint32_t) (tiles < (uint64_t) kNumSMs * per_sm ? tiles : (uint64_t) kNumSMs * per_sm);
+            chunk = (tiles + grid - 1) / grid * tile;
+        }
+        radix_hist_smem_kernel<<<grid, kHistThreads, smem, st>>>(in, n, shift, bits, d_hist, chunk, bits1,
+                                                                nblocks ? d_block_hist : nullptr);
     } else {
         radix_hist_global_kernel<<<kNumSMs * 4, kHistThreads, 0, st>>>(in, n, shift, bits, d_hist);
     }
@@ -151,6 +179,19 @@ __global__ void __launch_bounds__(kScanBlock) plan_offsets_kernel(PlanArgs a) {
         },
         [&](uint32_t s, uint32_t v) { r.seg_tile_start[s] = v; });
     if (threadIdx.x == 0) r.seg_tile_start[F1] = tiles;
+    // private pass-1 cursors: block b starts writing partition p1 at
+    //   part_start[p1] + sum over earlier blocks of their pass-1 histogram rows (radix_join.cpp:901-915)
+    if (r.block_hist) {
+        __syncthreads();
+        for (uint32_t p1 = threadIdx.x; p1 < F1; p1 += kScanBlock) {
+            uint32_t run = r.cursor1[p1];
+            for (uint32_t b = 0; b < a.nblocks1; ++b) {
+                uint32_t c = r.block_hist[(size_t) b * F1 + p1];
+                r.block_base[(size_t) b * F1 + p1] = run;
+                run += c;
+            }
+        }
+    }
 }
 
 int plan_offsets_device(const PlanArgs &a, cudaStream_t st) {
@@ -162,61 +203,152 @@ int plan_offsets_device(const PlanArgs &a, cudaStream_t st) {
 
 // ---------------------------------------------------------------------------------------------
 // scatter
+//
+// One CTA streams its tiles through a two-deep TMA ring: an elected thread issues 1-D bulk copies
+// (cp.async.bulk, completion on an mbarrier) for tile i+2 while the CTA works on tile i, so HBM reads
+// never wait for compute. Per tile:
+//   rank      every tuple takes a slot in its partition with a shared-memory atomicAdd
+//   reserve   warp 0 scans the tile histogram and reserves the tile's run in every partition:
+//             pass 1 from CTA-private cursors (pre-computed from per-block histograms, no atomics),
+//             pass 2 with one global atomicAdd per (tile, partition)
+//   stage     tuples are reordered in shared memory so that each partition's run is contiguous
+//   write-out the runs leave the SM as coalesced stores
 // ---------------------------------------------------------------------------------------------
-constexpr int kScatterThreads = 256;
-constexpr int kScatterItems = kScatterTile / kScatterThreads;   // 16 tuples per thread
-static_assert(kScatterItems * kScatterThreads == kScatterTile, "tile shape");
-static_assert(kScatterThreads >= kMaxFanout, "one thread per bin in the bookkeeping steps");
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// 1-D bulk copy global -> shared through the TMA unit; src/dst 16-byte aligned, bytes % 16 == 0
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 
-__global__ void __launch_bounds__(kScatterThreads, 3)
+constexpr int kScatterThreads = AQP_SCATTER_THREADS;
+constexpr int kScatterItems = kScatterTile / kScatterThreads;
+static_assert(kScatterItems * kScatterThreads == kScatterTile, "tile shape");
+constexpr int kInBufTuples = kScatterTile + 2;   // +1 leading tuple when the tile starts on an odd index, +1 to round up
+constexpr size_t kScatterSmemBytes = (size_t) (2 * kInBufTuples + kScatterTile) * sizeof(uint2);
+// 228 KiB of shared memory per SM; every CTA also pays ~6.2 KiB of static arrays + 1 KiB reserved
+constexpr int kScatterBlocksPerSMRaw = (int) (228 * 1024 / (kScatterSmemBytes + 7424));
+constexpr int kScatterBlocksPerSM = kScatterBlocksPerSMRaw < 1 ? 1 : (kScatterBlocksPerSMRaw * kScatterThreads > 2048 ? 2048 / kScatterThreads : kScatterBlocksPerSMRaw);
+
+uint32_t pass1_blocks() { return (uint32_t) kNumSMs * kScatterBlocksPerSM; }
+
+__global__ void __launch_bounds__(kScatterThreads, kScatterBlocksPerSM)
 radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
                      const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_tile_start,
-                     uint32_t nseg, uint32_t shift, uint32_t bits, uint32_t *__restrict__ cursors) {
-    __shared__ uint2 stage[kScatterTile];
+                     uint32_t nseg, uint32_t shift, uint32_t bits, uint32_t *__restrict__ cursors,
+                     const uint32_t *__restrict__ block_base, uint32_t tiles_per_block) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint2 *inbuf0 = reinterpret_cast<uint2 *>(smem_raw);
+    uint2 *inbuf1 = inbuf0 + kInBufTuples;
+    uint2 *stage = inbuf1 + kInBufTuples;
     __shared__ uint32_t cnt[kMaxFanout];     // tuples of this tile per partition
     __shared__ uint32_t lbase[kMaxFanout];   // start of the partition's run inside `stage`
     __shared__ uint32_t gdst[kMaxFanout];    // global index of stage slot s of partition d is gdst[d] + s
+    __shared__ uint32_t scur[kMaxFanout];    // CTA-private write cursors (pass 1)
     __shared__ uint32_t s_tstart[kMaxFanout + 1];
     __shared__ uint32_t s_soff[kMaxFanout + 1];
+    __shared__ __align__(8) uint64_t mbar[2];
 
     const uint32_t fan = 1u << bits, mask = fan - 1;
+    const bool priv = block_base != nullptr;
     for (uint32_t i = threadIdx.x; i <= nseg; i += kScatterThreads) {
         s_tstart[i] = seg_tile_start[i];
         s_soff[i] = seg_off[i];
     }
+    for (uint32_t i = threadIdx.x; i < fan; i += kScatterThreads) {
+        cnt[i] = 0;
+        if (priv) scur[i] = block_base[(size_t) blockIdx.x * fan + i];
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     const uint32_t ntiles = s_tstart[nseg];
+    // tiles of this CTA: a contiguous range (private cursors) or a grid-strided sequence (atomic reservation)
+    uint32_t first, step, n_my;
+    if (priv) {
+        first = blockIdx.x * tiles_per_block;
+        step = 1;
+        n_my = first < ntiles ? min(tiles_per_block, ntiles - first) : 0;
+    } else {
+        first = blockIdx.x;
+        step = gridDim.x;
+        n_my = first < ntiles ? (ntiles - first + step - 1) / step : 0;
+    }
 
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        // segment of this tile: last s with s_tstart[s] <= tile
-        uint32_t lo = 0, hi = nseg;
+    // tile -> (segment, [begin, end))
+    auto tile_range = [&](uint32_t tile, uint32_t &seg, uint32_t &begin, uint32_t &end) {
+        uint32_t lo = 0, hi = nseg;   // last s with s_tstart[s] <= tile
         while (hi - lo > 1) {
             uint32_t mid = (lo + hi) >> 1;
             if (s_tstart[mid] <= tile) lo = mid; else hi = mid;
         }
-        const uint32_t seg = lo;
-        const uint32_t begin = s_soff[seg] + (tile - s_tstart[seg]) * kScatterTile;
-        const uint32_t end = min(begin + (uint32_t) kScatterTile, s_soff[seg + 1]);
+        seg = lo;
+        begin = s_soff[lo] + (tile - s_tstart[lo]) * kScatterTile;
+        end = min(begin + (uint32_t) kScatterTile, s_soff[lo + 1]);
+    };
+    auto issue = [&](uint32_t i) {   // one thread: bulk-load tile #i of this CTA into ring slot i & 1
+        uint32_t seg, begin, end;
+        tile_range(first + i * step, seg, begin, end);
+        const uint2 *src = in + begin;
+        uint32_t skew = (uint32_t) ((reinterpret_cast<uintptr_t>(src) >> 3) & 1u);   // 16-byte alignment of the source
+        uint32_t bytes = ((end - begin + skew + 1) & ~1u) * (uint32_t) sizeof(uint2);
+        uint64_t *bar = &mbar[i & 1];
+        mbar_expect_tx(bar, bytes);
+        tma_load_1d((i & 1) ? inbuf1 : inbuf0, src - skew, bytes, bar);
+    };
+    if (threadIdx.x == 0) {
+        if (n_my > 0) issue(0);
+        if (n_my > 1) issue(1);
+    }
+
+    for (uint32_t i = 0; i < n_my; ++i) {
+        uint32_t seg, begin, end;
+        tile_range(first + i * step, seg, begin, end);
         const uint32_t ntile = end - begin;
+        const uint32_t skew = (uint32_t) ((reinterpret_cast<uintptr_t>(in + begin) >> 3) & 1u);
+        const uint2 *buf = ((i & 1) ? inbuf1 : inbuf0) + skew;
 
+        mbar_wait(&mbar[i & 1], (i >> 1) & 1);
         uint2 v[kScatterItems];
-#pragma unroll
-        for (int j = 0; j < kScatterItems; ++j) {
-            uint32_t i = begin + j * kScatterThreads + threadIdx.x;
-            if (i < end) v[j] = ld_stream_v2(in + i);
-        }
-        if (threadIdx.x < fan) cnt[threadIdx.x] = 0;
-        __syncthreads();   // (A) previous tile fully written out, counters cleared
-
         uint32_t rank[kScatterItems];
 #pragma unroll
         for (int j = 0; j < kScatterItems; ++j) {
-            uint32_t i = begin + j * kScatterThreads + threadIdx.x;
-            if (i < end) rank[j] = atomicAdd(&cnt[(v[j].x >> shift) & mask], 1u);
+            uint32_t k = j * kScatterThreads + threadIdx.x;
+            if (k < ntile) v[j] = buf[k];
         }
-        __syncthreads();   // (B) tile histogram complete
+#pragma unroll
+        for (int j = 0; j < kScatterItems; ++j) {
+            uint32_t k = j * kScatterThreads + threadIdx.x;
+            if (k < ntile) rank[j] = atomicAdd(&cnt[(v[j].x >> shift) & mask], 1u);
+        }
+        __syncthreads();   // (1) tile histogram complete; ring slot consumed; previous write-out finished
 
-        // warp 0: exclusive scan of the tile histogram, then reserve the runs globally
+        if (threadIdx.x == 0 && i + 2 < n_my) issue(i + 2);
+
+        // warp 0: exclusive scan of the tile histogram, then reserve the runs
         uint32_t my_g[kMaxFanout / 32], my_b[kMaxFanout / 32];
         if (threadIdx.x < 32) {
             const uint32_t per = (fan + 31) / 32;   // consecutive bins per lane (<= 8)
@@ -224,7 +356,9 @@ radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
 #pragma unroll
             for (int k = 0; k < kMaxFanout / 32; ++k) {
                 uint32_t d = threadIdx.x * per + k;
-                c[k] = (k < (int) per && d < fan) ? cnt[d] : 0;
+                bool ok = k < (int) per && d < fan;
+                c[k] = ok ? cnt[d] : 0;
+                if (ok) cnt[d] = 0;   // ready for the next tile
                 sum += c[k];
             }
             uint32_t run = warp_incl_scan(sum) - sum;
@@ -234,17 +368,22 @@ radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
                 my_b[k] = run;
                 if (k < (int) per && d < fan) {
                     lbase[d] = run;
-                    my_g[k] = c[k] ? atomicAdd(&cursors[(seg << bits) + d], c[k]) : 0u;
+                    if (priv) {
+                        my_g[k] = scur[d];
+                        scur[d] = my_g[k] + c[k];
+                    } else {
+                        my_g[k] = c[k] ? atomicAdd(&cursors[(seg << bits) + d], c[k]) : 0u;
+                    }
                 }
                 run += c[k];
             }
         }
-        __syncthreads();   // (C) lbase ready
+        __syncthreads();   // (2) lbase ready
 
 #pragma unroll
         for (int j = 0; j < kScatterItems; ++j) {
-            uint32_t i = begin + j * kScatterThreads + threadIdx.x;
-            if (i < end) stage[lbase[(v[j].x >> shift) & mask] + rank[j]] = v[j];
+            uint32_t k = j * kScatterThreads + threadIdx.x;
+            if (k < ntile) stage[lbase[(v[j].x >> shift) & mask] + rank[j]] = v[j];
         }
         if (threadIdx.x < 32) {
             const uint32_t per = (fan + 31) / 32;
@@ -254,7 +393,7 @@ radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
                 if (k < (int) per && d < fan) gdst[d] = my_g[k] - my_b[k];
             }
         }
-        __syncthreads();   // (D) tile reordered, destinations known
+        __syncthreads();   // (3) tile reordered, destinations known
 
         for (uint32_t s = threadIdx.x; s < ntile; s += kScatterThreads) {
             uint2 t = stage[s];
@@ -265,17 +404,34 @@ radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
 
 int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_off,
                          const uint32_t *d_seg_tile_start, uint32_t nseg, uint64_t n_total, uint32_t shift,
-                         uint32_t bits, uint32_t *d_cursors, cudaStream_t st) {
-    if (bits > kMaxFanoutBits || nseg > kMaxFanout) {
+                         uint32_t bits, uint32_t *d_cursors, const uint32_t *d_block_base, uint32_t nblocks,
+                         uint32_t tiles_per_block, cudaStream_t st) {
+    if (bits > (uint32_t) kMaxFanoutBits || nseg > (uint32_t) kMaxFanout) {
         set_error("radix_scatter: fan-out too large");
         return -1;
     }
+    if ((reinterpret_cast<uintptr_t>(d_in) & 7u) != 0) {
+        set_error("radix_scatter: relation must be 8-byte aligned");
+        return -1;
+    }
     if (n_total == 0) return 0;
-    uint64_t max_tiles = n_total / kScatterTile + nseg;
-    int grid = (int) (max_tiles < (uint64_t) kNumSMs * 3 ? max_tiles : (uint64_t) kNumSMs * 3);
-    radix_scatter_kernel<<<grid, kScatterThreads, 0, st>>>(reinterpret_cast<const uint2 *>(d_in),
-                                                          reinterpret_cast<uint2 *>(d_out), d_seg_off,
-                                                          d_seg_tile_start, nseg, shift, bits, d_cursors);
+    static bool attr_set = false;
+    if (!attr_set) {
+        AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int) kScatterSmemBytes));
+        attr_set = true;
+    }
+    uint32_t grid;
+    if (d_block_base) {
+        grid = nblocks;
+    } else {
+        uint64_t max_tiles = n_total / kScatterTile + nseg;
+        uint64_t g = (uint64_t) kNumSMs * kScatterBlocksPerSM;
+        grid = (uint32_t) (max_tiles < g ? max_tiles : g);
+    }
+    radix_scatter_kernel<<<grid, kScatterThreads, kScatterSmemBytes, st>>>(
+        reinterpret_cast<const uint2 *>(d_in), reinterpret_cast<uint2 *>(d_out), d_seg_off, d_seg_tile_start, nseg,
+        shift, bits, d_cursors, d_block_base, tiles_per_block);
     AQP_LAUNCHED();
     AQP_CUDA_OK(cudaGetLastError());
     return 0;

@@ -135,6 +135,8 @@ __device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+constexpr int kLookWidth = 2;   // predecessors inspected per thread and look-back round (window = 512 tiles)
+
 __global__ void __launch_bounds__(kScanThreads)
 index_scan_kernel(const uint4 *__restrict__ in, size_t nvec, uint64_t id_base, uint64_t *__restrict__ out,
                   uint64_t out_capacity, unsigned long long *__restrict__ count_out,
@@ -142,11 +144,13 @@ index_scan_kernel(const uint4 *__restrict__ in, size_t nvec, uint64_t id_base, u
     __shared__ __align__(8) uint16_t smask[kScanTileVec];   // 16-bit masks, one per uint4 of the tile
     __shared__ uint16_t stage[kScanTileVals];               // compacted tile-local positions
     __shared__ uint32_t wtot[kScanThreads / 32];
+    __shared__ uint32_t w_p[kScanThreads / 32], w_inv[kScanThreads / 32];
+    __shared__ unsigned long long w_sum[kScanThreads / 32];
     __shared__ uint32_t s_tile;
-    __shared__ uint64_t s_excl;
 
     const uint32_t ntiles = (uint32_t) ((nvec + kScanTileVec - 1) / kScanTileVec);
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    constexpr uint32_t kNone = 0xffffffffu;
 
     while (true) {
         if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
@@ -181,37 +185,8 @@ index_scan_kernel(const uint4 *__restrict__ in, size_t nvec, uint64_t id_base, u
             wbase += (w < (int) warp) ? t : 0;
             total += t;
         }
-
-        if (warp == 0) {   // publish the aggregate, then look back for the exclusive prefix
-            uint64_t excl = 0;
-            if (tile == 0) {
-                if (lane == 0) st_relaxed_u64(tile_state, kFlagIncl | total);
-            } else {
-                if (lane == 0) st_relaxed_u64(tile_state + tile, kFlagAgg | total);
-                int64_t look = (int64_t) tile - 1;
-                while (true) {
-                    int64_t idx = look - lane;
-                    uint64_t s;
-                    do {
-                        s = idx >= 0 ? ld_relaxed_u64(tile_state + idx) : kFlagIncl;
-                    } while (__any_sync(0xffffffffu, (s >> kFlagShift) == 0));
-                    unsigned incl_mask = __ballot_sync(0xffffffffu, (s >> kFlagShift) == 2);
-                    uint64_t val = s & kValMask;
-                    if (incl_mask) {
-                        unsigned first = __ffs(incl_mask) - 1;
-                        excl += warp_sum<unsigned long long>(lane <= first ? val : 0ull);
-                        break;
-                    }
-                    excl += warp_sum<unsigned long long>(val);
-                    look -= 32;
-                }
-                if (lane == 0) st_relaxed_u64(tile_state + tile, kFlagIncl | (excl + total));
-            }
-            if (lane == 0) {
-                s_excl = excl;
-                if (tile == ntiles - 1) *count_out = excl + total;
-            }
-        }
+        // publish this tile's aggregate as early as possible
+        if (threadIdx.x == 0) st_relaxed_u64(tile_state + tile, (tile == 0 ? kFlagIncl : kFlagAgg) | total);
 
         // compact this thread's matches into the staging buffer (tile-local positions)
         uint32_t pos = wbase + incl - cnt;
@@ -221,12 +196,65 @@ index_scan_kernel(const uint4 *__restrict__ in, size_t nvec, uint64_t id_base, u
             m &= m - 1;
             stage[pos++] = (uint16_t) (vbase + b);
         }
-        __syncthreads();
 
-        const uint64_t gbase = s_excl;
+        // Block-wide decoupled look-back: every thread inspects kLookWidth predecessors per round, so a
+        // round covers 512 tiles for the price of one memory round trip. The sum of the aggregates
+        // back to (and including) the nearest tile with a known inclusive prefix is this tile's offset.
+        unsigned long long excl = 0;
+        if (tile > 0) {
+            int64_t look = (int64_t) tile - 1;
+            while (true) {
+                uint64_t sv[kLookWidth];
+                uint32_t nearest_p, nearest_inv;
+                do {
+                    uint32_t my_p = kNone, my_inv = kNone;
+#pragma unroll
+                    for (int k = kLookWidth - 1; k >= 0; --k) {
+                        uint32_t d = k * kScanThreads + threadIdx.x;   // distance behind `look`
+                        int64_t idx = look - (int64_t) d;
+                        sv[k] = idx >= 0 ? ld_relaxed_u64(tile_state + idx) : kFlagIncl;
+                        uint32_t f = (uint32_t) (sv[k] >> kFlagShift);
+                        if (f == 2) my_p = d;
+                        if (f == 0) my_inv = d;
+                    }
+                    my_p = __reduce_min_sync(0xffffffffu, my_p);
+                    my_inv = __reduce_min_sync(0xffffffffu, my_inv);
+                    __syncthreads();   // previous round's w_p / w_inv readers are done
+                    if (lane == 0) {
+                        w_p[warp] = my_p;
+                        w_inv[warp] = my_inv;
+                    }
+                    __syncthreads();
+                    nearest_p = kNone;
+                    nearest_inv = kNone;
+#pragma unroll
+                    for (int w = 0; w < kScanThreads / 32; ++w) {
+                        nearest_p = min(nearest_p, w_p[w]);
+                        nearest_inv = min(nearest_inv, w_inv[w]);
+                    }
+                } while (nearest_inv < nearest_p);   // a tile in front of the nearest prefix has not published yet
+                unsigned long long part = 0;
+#pragma unroll
+                for (int k = 0; k < kLookWidth; ++k) {
+                    uint32_t d = k * kScanThreads + threadIdx.x;
+                    if (d <= nearest_p) part += sv[k] & kValMask;   // nearest_p == kNone: take the whole window
+                }
+                part = warp_sum(part);
+                if (lane == 0) w_sum[warp] = part;
+                __syncthreads();
+#pragma unroll
+                for (int w = 0; w < kScanThreads / 32; ++w) excl += w_sum[w];
+                if (nearest_p != kNone) break;
+                look -= (int64_t) kLookWidth * kScanThreads;
+            }
+            if (threadIdx.x == 0) st_relaxed_u64(tile_state + tile, kFlagIncl | (excl + total));
+        }
+        if (threadIdx.x == 0 && tile == ntiles - 1) *count_out = excl + total;
+        __syncthreads();   // staging complete (and w_sum consumed)
+
         const uint64_t idb = id_base + (uint64_t) tile * kScanTileVals;
         for (uint32_t s = threadIdx.x; s < total; s += kScanThreads) {
-            uint64_t g = gbase + s;
+            uint64_t g = excl + s;
             if (g < out_capacity) out[g] = idb + stage[s];
         }
     }

@@ -31,9 +31,10 @@ def test_pk_is_permutation(gpu, n):
     if n >= 1000:
         assert not np.array_equal(R["key"], np.arange(1, n + 1, dtype=np.uint32))
         assert not np.array_equal(R["key"], _gen_pk(gpu, n, 22222)["key"])     # seed matters
-        # low radix bits look uniform (what partitioning sees)
+    if n >= 100000:
+        # low radix bits of the first half look uniform (what partitioning sees)
         h = np.bincount(R["key"][: n // 2] & 15, minlength=16)
-        assert h.min() > 0.8 * (n // 2) / 16
+        assert h.min() > 0.9 * (n // 2) / 16 and h.max() < 1.1 * (n // 2) / 16
 
 
 def test_fk_blocks_are_permutations(gpu):
