@@ -204,51 +204,33 @@ int plan_offsets_device(const PlanArgs &a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 // scatter
 //
-// One CTA streams its tiles through a two-deep TMA ring: an elected thread issues 1-D bulk copies
-// (cp.async.bulk, completion on an mbarrier) for tile i+2 while the CTA works on tile i, so HBM reads
-// never wait for compute. Per tile:
+// A CTA walks its tiles with the NEXT tile's tuples already in flight into registers (software
+// pipelining: the loads are issued before the current tile is reordered and written out), so HBM
+// reads overlap everything else. Per tile:
 //   rank      every tuple takes a slot in its partition with a shared-memory atomicAdd
-//   reserve   warp 0 scans the tile histogram and reserves the tile's run in every partition:
-//             pass 1 from CTA-private cursors (pre-computed from per-block histograms, no atomics),
-//             pass 2 with one global atomicAdd per (tile, partition)
+//   scan      every warp scans the tile histogram for itself (redundant, but it saves a block barrier)
+//   reserve   warp 0 reserves the tile's run in every partition: pass 1 from CTA-private cursors
+//             (pre-computed from per-block histograms, no atomics), pass 2 with one global atomicAdd
+//             per (tile, partition) whose latency hides behind the staging step
 //   stage     tuples are reordered in shared memory so that each partition's run is contiguous
 //   write-out the runs leave the SM as coalesced stores
+// Two block barriers per tile. ncu on the first (TMA-ring) version of this kernel showed the
+// shared-memory pipe, not HBM, as the limiter (l1tex 71-82 %), so this version keeps tuples in
+// registers between load and staging instead of bouncing them through a shared-memory ring.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-// 1-D bulk copy global -> shared through the TMA unit; src/dst 16-byte aligned, bytes % 16 == 0
-__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
 constexpr int kScatterThreads = AQP_SCATTER_THREADS;
+constexpr int kScatterWarps = kScatterThreads / 32;
 constexpr int kScatterItems = kScatterTile / kScatterThreads;
 static_assert(kScatterItems * kScatterThreads == kScatterTile, "tile shape");
-constexpr int kInBufTuples = kScatterTile + 2;   // +1 leading tuple when the tile starts on an odd index, +1 to round up
-constexpr size_t kScatterSmemBytes = (size_t) (2 * kInBufTuples + kScatterTile) * sizeof(uint2);
-// 228 KiB of shared memory per SM; every CTA also pays ~6.2 KiB of static arrays + 1 KiB reserved
-constexpr int kScatterBlocksPerSMRaw = (int) (228 * 1024 / (kScatterSmemBytes + 7424));
-constexpr int kScatterBlocksPerSM = kScatterBlocksPerSMRaw < 1 ? 1 : (kScatterBlocksPerSMRaw * kScatterThreads > 2048 ? 2048 / kScatterThreads : kScatterBlocksPerSMRaw);
+constexpr int kBinsPerLane = kMaxFanout / 32;
+// 228 KiB of shared memory per SM: staging buffer + per-warp scan copies + bookkeeping per CTA
+constexpr size_t kScatterSmemApprox = (size_t) kScatterTile * 8 + (size_t) kScatterWarps * kMaxFanout * 4 + 6 * 1024;
+constexpr int kScatterBlocksBySmem = (int) (228 * 1024 / kScatterSmemApprox);
+constexpr int kScatterBlocksByThreads = 2048 / kScatterThreads;
+constexpr int kScatterBlocksByRegs = 65536 / (kScatterThreads * 64);   // kernel is held to 64 registers
+constexpr int kScatterBlocksPerSM0 = kScatterBlocksBySmem < kScatterBlocksByThreads ? kScatterBlocksBySmem : kScatterBlocksByThreads;
+constexpr int kScatterBlocksPerSM1 = kScatterBlocksPerSM0 < kScatterBlocksByRegs ? kScatterBlocksPerSM0 : kScatterBlocksByRegs;
+constexpr int kScatterBlocksPerSM = kScatterBlocksPerSM1 < 1 ? 1 : kScatterBlocksPerSM1;
 
 uint32_t pass1_blocks() { return (uint32_t) kNumSMs * kScatterBlocksPerSM; }
 
@@ -257,32 +239,26 @@ radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
                      const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_tile_start,
                      uint32_t nseg, uint32_t shift, uint32_t bits, uint32_t *__restrict__ cursors,
                      const uint32_t *__restrict__ block_base, uint32_t tiles_per_block) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint2 *inbuf0 = reinterpret_cast<uint2 *>(smem_raw);
-    uint2 *inbuf1 = inbuf0 + kInBufTuples;
-    uint2 *stage = inbuf1 + kInBufTuples;
-    __shared__ uint32_t cnt[kMaxFanout];     // tuples of this tile per partition
-    __shared__ uint32_t lbase[kMaxFanout];   // start of the partition's run inside `stage`
+    extern __shared__ __align__(16) uint2 stage[];         // kScatterTile tuples
+    __shared__ uint32_t cnt[2][kMaxFanout];                // tile histograms, double-buffered
+    __shared__ uint32_t wbase[kScatterWarps][kMaxFanout];  // per-warp copy of the exclusive scan
     __shared__ uint32_t gdst[kMaxFanout];    // global index of stage slot s of partition d is gdst[d] + s
     __shared__ uint32_t scur[kMaxFanout];    // CTA-private write cursors (pass 1)
     __shared__ uint32_t s_tstart[kMaxFanout + 1];
     __shared__ uint32_t s_soff[kMaxFanout + 1];
-    __shared__ __align__(8) uint64_t mbar[2];
 
     const uint32_t fan = 1u << bits, mask = fan - 1;
+    const uint32_t per = (fan + 31) / 32;   // consecutive bins per lane in the warp scan (<= 8)
     const bool priv = block_base != nullptr;
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     for (uint32_t i = threadIdx.x; i <= nseg; i += kScatterThreads) {
         s_tstart[i] = seg_tile_start[i];
         s_soff[i] = seg_off[i];
     }
     for (uint32_t i = threadIdx.x; i < fan; i += kScatterThreads) {
-        cnt[i] = 0;
+        cnt[0][i] = 0;
+        cnt[1][i] = 0;
         if (priv) scur[i] = block_base[(size_t) blockIdx.x * fan + i];
-    }
-    if (threadIdx.x == 0) {
-        mbar_init(&mbar[0], 1);
-        mbar_init(&mbar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     const uint32_t ntiles = s_tstart[nseg];
@@ -297,7 +273,6 @@ radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
         step = gridDim.x;
         n_my = first < ntiles ? (ntiles - first + step - 1) / step : 0;
     }
-
     // tile -> (segment, [begin, end))
     auto tile_range = [&](uint32_t tile, uint32_t &seg, uint32_t &begin, uint32_t &end) {
         uint32_t lo = 0, hi = nseg;   // last s with s_tstart[s] <= tile
@@ -309,65 +284,60 @@ radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
         begin = s_soff[lo] + (tile - s_tstart[lo]) * kScatterTile;
         end = min(begin + (uint32_t) kScatterTile, s_soff[lo + 1]);
     };
-    auto issue = [&](uint32_t i) {   // one thread: bulk-load tile #i of this CTA into ring slot i & 1
-        uint32_t seg, begin, end;
-        tile_range(first + i * step, seg, begin, end);
-        const uint2 *src = in + begin;
-        uint32_t skew = (uint32_t) ((reinterpret_cast<uintptr_t>(src) >> 3) & 1u);   // 16-byte alignment of the source
-        uint32_t bytes = ((end - begin + skew + 1) & ~1u) * (uint32_t) sizeof(uint2);
-        uint64_t *bar = &mbar[i & 1];
-        mbar_expect_tx(bar, bytes);
-        tma_load_1d((i & 1) ? inbuf1 : inbuf0, src - skew, bytes, bar);
-    };
-    if (threadIdx.x == 0) {
-        if (n_my > 0) issue(0);
-        if (n_my > 1) issue(1);
+
+    uint2 vn[kScatterItems];   // next tile, in flight
+    uint32_t seg_n = 0, begin_n = 0, end_n = 0;
+    if (n_my > 0) {
+        tile_range(first, seg_n, begin_n, end_n);
+#pragma unroll
+        for (int j = 0; j < kScatterItems; ++j) {
+            uint32_t k = begin_n + j * kScatterThreads + threadIdx.x;
+            if (k < end_n) vn[j] = ld_stream_v2(in + k);
+        }
     }
 
     for (uint32_t i = 0; i < n_my; ++i) {
-        uint32_t seg, begin, end;
-        tile_range(first + i * step, seg, begin, end);
-        const uint32_t ntile = end - begin;
-        const uint32_t skew = (uint32_t) ((reinterpret_cast<uintptr_t>(in + begin) >> 3) & 1u);
-        const uint2 *buf = ((i & 1) ? inbuf1 : inbuf0) + skew;
-
-        mbar_wait(&mbar[i & 1], (i >> 1) & 1);
+        const uint32_t seg = seg_n, ntile = end_n - begin_n;
+        uint32_t *const cn = cnt[i & 1];
         uint2 v[kScatterItems];
         uint32_t rank[kScatterItems];
 #pragma unroll
-        for (int j = 0; j < kScatterItems; ++j) {
-            uint32_t k = j * kScatterThreads + threadIdx.x;
-            if (k < ntile) v[j] = buf[k];
-        }
+        for (int j = 0; j < kScatterItems; ++j) v[j] = vn[j];
 #pragma unroll
         for (int j = 0; j < kScatterItems; ++j) {
             uint32_t k = j * kScatterThreads + threadIdx.x;
-            if (k < ntile) rank[j] = atomicAdd(&cnt[(v[j].x >> shift) & mask], 1u);
+            if (k < ntile) rank[j] = atomicAdd(&cn[(v[j].x >> shift) & mask], 1u);
         }
-        __syncthreads();   // (1) tile histogram complete; ring slot consumed; previous write-out finished
-
-        if (threadIdx.x == 0 && i + 2 < n_my) issue(i + 2);
-
-        // warp 0: exclusive scan of the tile histogram, then reserve the runs
-        uint32_t my_g[kMaxFanout / 32], my_b[kMaxFanout / 32];
-        if (threadIdx.x < 32) {
-            const uint32_t per = (fan + 31) / 32;   // consecutive bins per lane (<= 8)
-            uint32_t c[kMaxFanout / 32], sum = 0;
+        if (i + 1 < n_my) {   // put the next tile in flight before anything else happens
+            tile_range(first + (i + 1) * step, seg_n, begin_n, end_n);
 #pragma unroll
-            for (int k = 0; k < kMaxFanout / 32; ++k) {
-                uint32_t d = threadIdx.x * per + k;
-                bool ok = k < (int) per && d < fan;
-                c[k] = ok ? cnt[d] : 0;
-                if (ok) cnt[d] = 0;   // ready for the next tile
-                sum += c[k];
+            for (int j = 0; j < kScatterItems; ++j) {
+                uint32_t k = begin_n + j * kScatterThreads + threadIdx.x;
+                if (k < end_n) vn[j] = ld_stream_v2(in + k);
             }
-            uint32_t run = warp_incl_scan(sum) - sum;
+        }
+        __syncthreads();   // (1) tile histogram complete; previous tile fully written out
+
+        // every warp: exclusive scan of the tile histogram into its own copy
+        uint32_t c[kBinsPerLane], my_g[kBinsPerLane], sum = 0;
 #pragma unroll
-            for (int k = 0; k < kMaxFanout / 32; ++k) {
-                uint32_t d = threadIdx.x * per + k;
-                my_b[k] = run;
+        for (int k = 0; k < kBinsPerLane; ++k) {
+            uint32_t d = lane * per + k;
+            c[k] = (k < (int) per && d < fan) ? cn[d] : 0;
+            sum += c[k];
+        }
+        uint32_t run = warp_incl_scan(sum) - sum;
+#pragma unroll
+        for (int k = 0; k < kBinsPerLane; ++k) {
+            uint32_t d = lane * per + k;
+            if (k < (int) per && d < fan) wbase[warp][d] = run;
+            run += c[k];
+        }
+        if (warp == 0) {   // reserve the runs
+#pragma unroll
+            for (int k = 0; k < kBinsPerLane; ++k) {
+                uint32_t d = lane * per + k;
                 if (k < (int) per && d < fan) {
-                    lbase[d] = run;
                     if (priv) {
                         my_g[k] = scur[d];
                         scur[d] = my_g[k] + c[k];
@@ -375,26 +345,25 @@ radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
                         my_g[k] = c[k] ? atomicAdd(&cursors[(seg << bits) + d], c[k]) : 0u;
                     }
                 }
-                run += c[k];
             }
         }
-        __syncthreads();   // (2) lbase ready
+        __syncwarp();
 
 #pragma unroll
         for (int j = 0; j < kScatterItems; ++j) {
             uint32_t k = j * kScatterThreads + threadIdx.x;
-            if (k < ntile) stage[lbase[(v[j].x >> shift) & mask] + rank[j]] = v[j];
+            if (k < ntile) stage[wbase[warp][(v[j].x >> shift) & mask] + rank[j]] = v[j];
         }
-        if (threadIdx.x < 32) {
-            const uint32_t per = (fan + 31) / 32;
+        if (warp == 0) {
 #pragma unroll
-            for (int k = 0; k < kMaxFanout / 32; ++k) {
-                uint32_t d = threadIdx.x * per + k;
-                if (k < (int) per && d < fan) gdst[d] = my_g[k] - my_b[k];
+            for (int k = 0; k < kBinsPerLane; ++k) {
+                uint32_t d = lane * per + k;
+                if (k < (int) per && d < fan) gdst[d] = my_g[k] - wbase[0][d];
             }
         }
-        __syncthreads();   // (3) tile reordered, destinations known
+        __syncthreads();   // (2) tile reordered, destinations known
 
+        if (threadIdx.x < fan) cn[threadIdx.x] = 0;   // this buffer is used again two tiles from now
         for (uint32_t s = threadIdx.x; s < ntile; s += kScatterThreads) {
             uint2 t = stage[s];
             out[gdst[(t.x >> shift) & mask] + s] = t;
@@ -415,12 +384,6 @@ int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_
         return -1;
     }
     if (n_total == 0) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-        AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int) kScatterSmemBytes));
-        attr_set = true;
-    }
     uint32_t grid;
     if (d_block_base) {
         grid = nblocks;
@@ -429,7 +392,13 @@ int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_
         uint64_t g = (uint64_t) kNumSMs * kScatterBlocksPerSM;
         grid = (uint32_t) (max_tiles < g ? max_tiles : g);
     }
-    radix_scatter_kernel<<<grid, kScatterThreads, kScatterSmemBytes, st>>>(
+    static bool attr_set = false;
+    if (!attr_set) {
+        AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int) (kScatterTile * sizeof(uint2))));
+        attr_set = true;
+    }
+    radix_scatter_kernel<<<grid, kScatterThreads, kScatterTile * sizeof(uint2), st>>>(
         reinterpret_cast<const uint2 *>(d_in), reinterpret_cast<uint2 *>(d_out), d_seg_off, d_seg_tile_start, nseg,
         shift, bits, d_cursors, d_block_base, tiles_per_block);
     AQP_LAUNCHED();

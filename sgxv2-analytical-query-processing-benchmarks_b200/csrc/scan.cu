@@ -3,7 +3,7 @@
 // Replaces the AVX-512 loops of Scan-Micro-Benchmarks/shared_libraries/SimdScan/src/SIMD512.cpp:
 //   count                :7-32     -> scan_count_kernel
 //   bitvector_scan       :210-222  -> bitvector_scan_kernel
-//   implicit_index_scan  :225-287  -> index_scan_kernel (single pass, decoupled look-back)
+//   implicit_index_scan  :225-287  -> bitvector_scan_kernel<true> + tile_offsets_kernel + expand_rowids_kernel
 // Semantics kept: unsigned inclusive range lo <= v <= hi, only n/64 whole blocks are processed,
 // bit k of word i <-> value 64*i+k, row ids ascending uint64 positions.
 //
@@ -11,6 +11,7 @@
 // flight per thread, the byte compare done 4 values at a time with carry-free SWAR arithmetic
 // (there is no per-byte compare instruction on sm_100; __vcmpgeu4 expands to more ops).
 #include "common.cuh"
+#include "block_scan.cuh"
 
 namespace aqp {
 
@@ -57,10 +58,32 @@ static Pred make_pred(uint8_t lo, uint8_t hi) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// bitvector scan
+// bitvector scan (kCount: also emit the number of matches of every 16384-value tile)
 // ---------------------------------------------------------------------------------------------
+// L2 policy for data that is touched once: do not let the streamed column push reusable lines
+// (the row-id scan's bitvector scratch) out of the 126 MB L2
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint4 ld_stream_v4_hint(const uint4 *p, uint64_t pol) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ void st_u64_hint(uint64_t *p, uint64_t v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+}
+
+template <bool kCount>
 __global__ void __launch_bounds__(kScanThreads)
-bitvector_scan_kernel(const uint4 *__restrict__ in, size_t nvec, uint64_t *__restrict__ out, Pred p) {
+bitvector_scan_kernel(const uint4 *__restrict__ in, size_t nvec, uint64_t *__restrict__ out, Pred p,
+                      uint32_t *__restrict__ tile_counts) {
+    __shared__ uint32_t wsum[kScanThreads / 32];
+    const uint64_t pol = l2_evict_first_policy();
     const size_t ntiles = (nvec + kScanTileVec - 1) / kScanTileVec;
     for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const size_t base = tile * kScanTileVec + threadIdx.x;
@@ -68,16 +91,30 @@ bitvector_scan_kernel(const uint4 *__restrict__ in, size_t nvec, uint64_t *__res
 #pragma unroll
         for (int j = 0; j < kScanUnroll; ++j) {
             size_t q = base + (size_t) j * kScanThreads;
-            v[j] = q < nvec ? ld_stream_v4(in + q) : make_uint4(0, 0, 0, 0);
+            v[j] = q < nvec ? ld_stream_v4_hint(in + q, pol) : make_uint4(0, 0, 0, 0);
         }
+        uint32_t c = 0;
 #pragma unroll
         for (int j = 0; j < kScanUnroll; ++j) {
             size_t q = base + (size_t) j * kScanThreads;
             uint32_t m16 = range_mask16(v[j], p.lo4, p.hi4, p.lo7, p.hiH);
+            if (kCount) c += q < nvec ? __popc(m16) : 0;
             // four neighbouring lanes hold the four 16-bit quarters of one output word
             uint32_t m32 = m16 | (__shfl_down_sync(0xffffffffu, m16, 1) << 16);
             uint32_t hi = __shfl_down_sync(0xffffffffu, m32, 2);
             if ((threadIdx.x & 3) == 0 && q < nvec) out[q >> 2] = (uint64_t) m32 | ((uint64_t) hi << 32);
+        }
+        if (kCount) {
+            c = warp_sum(c);
+            __syncthreads();   // wsum of the previous tile consumed
+            if (lane_id() == 0) wsum[threadIdx.x >> 5] = c;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t t = 0;
+#pragma unroll
+                for (int w = 0; w < kScanThreads / 32; ++w) t += wsum[w];
+                tile_counts[tile] = t;
+            }
         }
     }
 }
@@ -116,146 +153,72 @@ scan_count_kernel(const uint4 *__restrict__ in, size_t nvec, unsigned long long 
 }
 
 // ---------------------------------------------------------------------------------------------
-// row-id list scan: one pass over the column; tiles are taken in ticket order and chained with
-// a decoupled look-back so every tile learns the number of matches before it without a second
-// read of the input. Matches are compacted through shared memory so the uint64 ids leave the SM
-// as fully coalesced 256-byte warp stores.
+// row-id list scan. The column is processed in chunks whose bitvector (1/8 of the chunk) fits the L2:
+//   A  bitvector_scan_kernel<true>   predicate -> bitvector scratch + matches per 16384-value tile
+//   B  tile_offsets_kernel           exclusive scan of the tile counts, carried across chunks
+//   C  expand_rowids_kernel          bitvector -> ascending uint64 row ids, written warp-cooperatively so
+//                                    that every store instruction covers one contiguous run of ids
+// The scratch bitvector is rewritten by every chunk and read back while still L2-resident, so HBM
+// traffic stays at the algorithmic 1 + 8*selectivity bytes per value and no kernel waits on another
+// CTA (a single-pass decoupled look-back variant measured 3-5x slower here: its per-tile chain of
+// ticket, load, publish, look back, write kept too few bytes in flight).
 // ---------------------------------------------------------------------------------------------
-constexpr uint64_t kFlagShift = 62;
-constexpr uint64_t kFlagAgg = 1ull << kFlagShift;   // tile aggregate available
-constexpr uint64_t kFlagIncl = 2ull << kFlagShift;  // inclusive prefix available
-constexpr uint64_t kValMask = (1ull << kFlagShift) - 1;
+constexpr size_t kIndexChunkVals = (size_t) 1 << 29;                    // 512 MiB of column -> 64 MiB bitvector
+constexpr size_t kIndexChunkTiles = kIndexChunkVals / kScanTileVals;    // 32768
 
-__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p) {
-    uint64_t v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__global__ void __launch_bounds__(kScanBlock)
+tile_offsets_kernel(const uint32_t *__restrict__ counts, uint32_t ntiles, uint64_t *__restrict__ offsets,
+                    unsigned long long *__restrict__ running) {
+    const unsigned long long base = *running;
+    uint32_t total = block_exclusive_scan(ntiles, [&](uint32_t i) { return counts[i]; },
+                                          [&](uint32_t i, uint32_t v) { offsets[i] = base + v; });
+    if (threadIdx.x == 0) *running = base + total;
 }
 
-constexpr int kLookWidth = 2;   // predecessors inspected per thread and look-back round (window = 512 tiles)
-
+// One thread loads one 64-bit word; the words' match counts are scanned across the CTA; then each
+// warp expands its 32 words one at a time with all lanes cooperating: lane l owns bits l and l+32 of
+// the word, its output slot is the word's offset plus the number of set bits below it. Consecutive
+// lanes therefore write consecutive ids — every store instruction is one contiguous run, a full
+// 256-byte line pair at 100 % selectivity — with no shared-memory staging and no bank conflicts.
 __global__ void __launch_bounds__(kScanThreads)
-index_scan_kernel(const uint4 *__restrict__ in, size_t nvec, uint64_t id_base, uint64_t *__restrict__ out,
-                  uint64_t out_capacity, unsigned long long *__restrict__ count_out,
-                  uint64_t *__restrict__ tile_state, unsigned int *__restrict__ ticket, Pred p) {
-    __shared__ __align__(8) uint16_t smask[kScanTileVec];   // 16-bit masks, one per uint4 of the tile
-    __shared__ uint16_t stage[kScanTileVals];               // compacted tile-local positions
+expand_rowids_kernel(const uint64_t *__restrict__ bv, size_t nwords, const uint64_t *__restrict__ tile_offsets,
+                     uint64_t id_base, uint64_t *__restrict__ out, uint64_t out_capacity) {
     __shared__ uint32_t wtot[kScanThreads / 32];
-    __shared__ uint32_t w_p[kScanThreads / 32], w_inv[kScanThreads / 32];
-    __shared__ unsigned long long w_sum[kScanThreads / 32];
-    __shared__ uint32_t s_tile;
-
-    const uint32_t ntiles = (uint32_t) ((nvec + kScanTileVec - 1) / kScanTileVec);
+    const uint64_t pol = l2_evict_first_policy();
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-    constexpr uint32_t kNone = 0xffffffffu;
-
-    while (true) {
-        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-        __syncthreads();   // also protects stage/smask reuse from the previous iteration
-        const uint32_t tile = s_tile;
-        if (tile >= ntiles) break;
-
-        const size_t base = (size_t) tile * kScanTileVec + threadIdx.x;
-        uint4 v[kScanUnroll];
-#pragma unroll
-        for (int j = 0; j < kScanUnroll; ++j) {
-            size_t q = base + (size_t) j * kScanThreads;
-            v[j] = q < nvec ? ld_stream_v4(in + q) : make_uint4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int j = 0; j < kScanUnroll; ++j) {
-            size_t q = base + (size_t) j * kScanThreads;
-            uint32_t m16 = q < nvec ? range_mask16(v[j], p.lo4, p.hi4, p.lo7, p.hiH) : 0u;
-            smask[j * kScanThreads + threadIdx.x] = (uint16_t) m16;
-        }
-        __syncthreads();
-        // thread t now owns the 64 consecutive values [64t, 64t+64) of the tile
-        uint64_t m = reinterpret_cast<const uint64_t *>(smask)[threadIdx.x];
+    const unsigned lt = lanemask_lt();
+    const size_t ntiles = (nwords + kScanThreads - 1) / kScanThreads;
+    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const size_t w = tile * kScanThreads + threadIdx.x;
+        const uint64_t m = w < nwords ? bv[w] : 0ull;
         const uint32_t cnt = __popcll(m);
         const uint32_t incl = warp_incl_scan(cnt);
+        __syncthreads();   // wtot of the previous tile consumed
         if (lane == 31) wtot[warp] = incl;
         __syncthreads();
-        uint32_t wbase = 0, total = 0;
+        uint32_t wbase = 0;
 #pragma unroll
-        for (int w = 0; w < kScanThreads / 32; ++w) {
-            uint32_t t = wtot[w];
-            wbase += (w < (int) warp) ? t : 0;
-            total += t;
-        }
-        // publish this tile's aggregate as early as possible
-        if (threadIdx.x == 0) st_relaxed_u64(tile_state + tile, (tile == 0 ? kFlagIncl : kFlagAgg) | total);
-
-        // compact this thread's matches into the staging buffer (tile-local positions)
-        uint32_t pos = wbase + incl - cnt;
-        const uint32_t vbase = threadIdx.x * 64;
-        while (m) {
-            uint32_t b = __ffsll((long long) m) - 1;
-            m &= m - 1;
-            stage[pos++] = (uint16_t) (vbase + b);
-        }
-
-        // Block-wide decoupled look-back: every thread inspects kLookWidth predecessors per round, so a
-        // round covers 512 tiles for the price of one memory round trip. The sum of the aggregates
-        // back to (and including) the nearest tile with a known inclusive prefix is this tile's offset.
-        unsigned long long excl = 0;
-        if (tile > 0) {
-            int64_t look = (int64_t) tile - 1;
-            while (true) {
-                uint64_t sv[kLookWidth];
-                uint32_t nearest_p, nearest_inv;
-                do {
-                    uint32_t my_p = kNone, my_inv = kNone;
-#pragma unroll
-                    for (int k = kLookWidth - 1; k >= 0; --k) {
-                        uint32_t d = k * kScanThreads + threadIdx.x;   // distance behind `look`
-                        int64_t idx = look - (int64_t) d;
-                        sv[k] = idx >= 0 ? ld_relaxed_u64(tile_state + idx) : kFlagIncl;
-                        uint32_t f = (uint32_t) (sv[k] >> kFlagShift);
-                        if (f == 2) my_p = d;
-                        if (f == 0) my_inv = d;
-                    }
-                    my_p = __reduce_min_sync(0xffffffffu, my_p);
-                    my_inv = __reduce_min_sync(0xffffffffu, my_inv);
-                    __syncthreads();   // previous round's w_p / w_inv readers are done
-                    if (lane == 0) {
-                        w_p[warp] = my_p;
-                        w_inv[warp] = my_inv;
-                    }
-                    __syncthreads();
-                    nearest_p = kNone;
-                    nearest_inv = kNone;
-#pragma unroll
-                    for (int w = 0; w < kScanThreads / 32; ++w) {
-                        nearest_p = min(nearest_p, w_p[w]);
-                        nearest_inv = min(nearest_inv, w_inv[w]);
-                    }
-                } while (nearest_inv < nearest_p);   // a tile in front of the nearest prefix has not published yet
-                unsigned long long part = 0;
-#pragma unroll
-                for (int k = 0; k < kLookWidth; ++k) {
-                    uint32_t d = k * kScanThreads + threadIdx.x;
-                    if (d <= nearest_p) part += sv[k] & kValMask;   // nearest_p == kNone: take the whole window
-                }
-                part = warp_sum(part);
-                if (lane == 0) w_sum[warp] = part;
-                __syncthreads();
-#pragma unroll
-                for (int w = 0; w < kScanThreads / 32; ++w) excl += w_sum[w];
-                if (nearest_p != kNone) break;
-                look -= (int64_t) kLookWidth * kScanThreads;
+        for (int k = 0; k < kScanThreads / 32; ++k) wbase += (k < (int) warp) ? wtot[k] : 0;
+        const uint32_t my_off = wbase + incl - cnt;   // first output slot (tile-relative) of this lane's word
+        const uint64_t gbase = tile_offsets[tile];
+        const uint64_t idb = id_base + (uint64_t) tile * kScanTileVals + (uint64_t) warp * 32 * 64;
+        const uint32_t mlo = (uint32_t) m, mhi = (uint32_t) (m >> 32);
+        unsigned nz = __ballot_sync(0xffffffffu, m != 0);
+        while (nz) {
+            const int src = __ffs(nz) - 1;
+            nz &= nz - 1;
+            const uint32_t lo = __shfl_sync(0xffffffffu, mlo, src);
+            const uint32_t hi = __shfl_sync(0xffffffffu, mhi, src);
+            const uint64_t o = gbase + __shfl_sync(0xffffffffu, my_off, src);
+            const uint64_t id0 = idb + (uint64_t) src * 64 + lane;
+            if ((lo >> lane) & 1u) {
+                uint64_t g = o + __popc(lo & lt);
+                if (g < out_capacity) st_u64_hint(out + g, id0, pol);
             }
-            if (threadIdx.x == 0) st_relaxed_u64(tile_state + tile, kFlagIncl | (excl + total));
-        }
-        if (threadIdx.x == 0 && tile == ntiles - 1) *count_out = excl + total;
-        __syncthreads();   // staging complete (and w_sum consumed)
-
-        const uint64_t idb = id_base + (uint64_t) tile * kScanTileVals;
-        for (uint32_t s = threadIdx.x; s < total; s += kScanThreads) {
-            uint64_t g = excl + s;
-            if (g < out_capacity) out[g] = idb + stage[s];
+            if ((hi >> lane) & 1u) {
+                uint64_t g = o + __popc(lo) + __popc(hi & lt);
+                if (g < out_capacity) st_u64_hint(out + g, id0 + 32, pol);
+            }
         }
     }
 }
@@ -305,8 +268,8 @@ int bitvector_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t 
     }
     size_t nvec = (n / 64) * 4;
     if (nvec == 0) return 0;
-    bitvector_scan_kernel<<<scan_grid(nvec, 8), kScanThreads, 0, st>>>(reinterpret_cast<const uint4 *>(d_data), nvec,
-                                                                      d_out, make_pred(lo, hi));
+    bitvector_scan_kernel<false><<<scan_grid(nvec, 8), kScanThreads, 0, st>>>(reinterpret_cast<const uint4 *>(d_data),
+                                                                             nvec, d_out, make_pred(lo, hi), nullptr);
     AQP_LAUNCHED();
     AQP_CUDA_OK(cudaGetLastError());
     return 0;
@@ -328,12 +291,12 @@ int scan_count_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, u
     return 0;
 }
 
-// scratch = tile_state[ntiles] (uint64) followed by one uint32 ticket; must hold
-// index_scan_scratch_bytes(n) bytes.
+// scratch layout: [bitvector of one chunk][tile counts u32][tile offsets u64][running total u64]
+static size_t align256(size_t x) { return (x + 255) & ~(size_t) 255; }
 size_t index_scan_scratch_bytes(size_t n) {
-    size_t nvec = (n / 64) * 4;
-    size_t ntiles = (nvec + kScanTileVec - 1) / kScanTileVec;
-    return (ntiles + 1) * sizeof(uint64_t);
+    size_t chunk = n < kIndexChunkVals ? n : kIndexChunkVals;
+    size_t tiles = (chunk + kScanTileVals - 1) / kScanTileVals + 1;
+    return align256(chunk / 8 + 64) + align256(tiles * 4) + align256(tiles * 8) + 256;
 }
 
 int index_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, uint64_t id_base,
@@ -342,19 +305,31 @@ int index_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, u
         set_error("index_scan: column must be 16-byte aligned");
         return -1;
     }
-    size_t nvec = (n / 64) * 4;
-    if (nvec == 0) {
-        AQP_CUDA_OK(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
-        return 0;
+    AQP_CUDA_OK(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
+    n = n / 64 * 64;
+    if (n == 0) return 0;
+    const size_t chunk_cap = n < kIndexChunkVals ? n : kIndexChunkVals;
+    const size_t tiles_cap = (chunk_cap + kScanTileVals - 1) / kScanTileVals + 1;
+    unsigned char *sb = static_cast<unsigned char *>(d_scratch);
+    uint64_t *bv = reinterpret_cast<uint64_t *>(sb);
+    uint32_t *counts = reinterpret_cast<uint32_t *>(sb + align256(chunk_cap / 8 + 64));
+    uint64_t *offsets = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(counts) + align256(tiles_cap * 4));
+    unsigned long long *running = reinterpret_cast<unsigned long long *>(d_count);
+    const Pred p = make_pred(lo, hi);
+    for (size_t begin = 0; begin < n; begin += kIndexChunkVals) {
+        const size_t len = n - begin < kIndexChunkVals ? n - begin : kIndexChunkVals;
+        const size_t nvec = len / 16, nwords = len / 64;
+        const uint32_t ntiles = (uint32_t) ((nvec + kScanTileVec - 1) / kScanTileVec);
+        bitvector_scan_kernel<true><<<scan_grid(nvec, 8), kScanThreads, 0, st>>>(
+            reinterpret_cast<const uint4 *>(d_data + begin), nvec, bv, p, counts);
+        AQP_LAUNCHED();
+        tile_offsets_kernel<<<1, kScanBlock, 0, st>>>(counts, ntiles, offsets, running);
+        AQP_LAUNCHED();
+        size_t g = (size_t) kNumSMs * 8;
+        expand_rowids_kernel<<<(unsigned) (ntiles < g ? ntiles : g), kScanThreads, 0, st>>>(bv, nwords, offsets,
+                                                                                         id_base + begin, d_out, cap);
+        AQP_LAUNCHED();
     }
-    size_t ntiles = (nvec + kScanTileVec - 1) / kScanTileVec;
-    AQP_CUDA_OK(cudaMemsetAsync(d_scratch, 0, index_scan_scratch_bytes(n), st));
-    uint64_t *tile_state = reinterpret_cast<uint64_t *>(d_scratch);
-    unsigned int *ticket = reinterpret_cast<unsigned int *>(tile_state + ntiles);
-    index_scan_kernel<<<scan_grid(nvec, 5), kScanThreads, 0, st>>>(
-        reinterpret_cast<const uint4 *>(d_data), nvec, id_base, d_out, cap,
-        reinterpret_cast<unsigned long long *>(d_count), tile_state, ticket, make_pred(lo, hi));
-    AQP_LAUNCHED();
     AQP_CUDA_OK(cudaGetLastError());
     return 0;
 }
