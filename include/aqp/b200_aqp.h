@@ -126,6 +126,33 @@ int b200_radix_scatter_device(const struct row_t *d_in, uint64_t n, uint32_t shi
                               const uint32_t *d_offsets, uint32_t *d_cursors, struct row_t *d_out,
                               void *stream);
 
+/* Sharded join across the GPUs of one box, one process per GPU. The first radix pass
+ * doubles as the shuffle: a tuple is owned by the GPU whose rank equals the low log2_gpus bits of its
+ * key, and pass 1 writes the partitions of each owner as one contiguous range, so its output is the
+ * all-to-all send buffer (the host exchanges it with NCCL; this library does no communication).
+ *
+ * b200_shard_pass1_device — on every rank, for R and for S: histogram over total_bits key bits,
+ *   pass-1 boundaries, scatter of d_in[0..n) into d_send by the ROUTED pass-1 digit
+ *       p1' = rotate_right(key & (2^bits1-1), log2_gpus) within bits1 bits,
+ *   so owner g's partitions are p1' in [g*2^bits1/G, (g+1)*2^bits1/G). Outputs: d_hist[2^total_bits]
+ *   indexed by p1' | (p2 << bits1) (to be summed over ranks by the caller) and
+ *   d_part1_off[2^bits1 + 1], the partition starts inside d_send.
+ * b200_shard_join_device — on every rank after the exchange: the received relations consist of nseg
+ *   segments (d_segoff_*[nseg+1]; segment s holds tuples of pass-1 partition group d_seg_group[s],
+ *   several segments — one per source GPU — may share a group). Pass 2 scatters every segment by key
+ *   bits [shift2, shift2+bits2) into its group's partitions, whose sizes d_hist_*[ngroups << bits2]
+ *   (order group-major) are this rank's slice of the globally summed histograms; then build/probe
+ *   with the hash on the key bits from hash_shift upward. stats receives this rank's partial
+ *   matches / checksum / keysum (the caller sums them over ranks). */
+int b200_shard_pass1_device(const struct row_t *d_in, uint64_t n, uint32_t total_bits, uint32_t bits1,
+                            uint32_t log2_gpus, struct row_t *d_send, uint32_t *d_hist, uint32_t *d_part1_off,
+                            void *stream);
+int b200_shard_join_device(const struct row_t *d_R, uint64_t nR, const uint32_t *d_segoff_R, const struct row_t *d_S,
+                           uint64_t nS, const uint32_t *d_segoff_S, const uint32_t *d_seg_group, uint32_t nseg,
+                           uint32_t ngroups, uint32_t shift2, uint32_t bits2, const uint32_t *d_hist_R,
+                           const uint32_t *d_hist_S, uint32_t hash_shift, struct b200_join_stats_t *stats,
+                           void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * 4. relation generators
  * ---------------------------------------------------------------------------------------------- */

@@ -1,0 +1,188 @@
+"""Sharded RHO join across the GPUs of one box: one process per GPU, torch.distributed for the plumbing.
+
+The reference is a single shared-memory process (no communication backend); its
+inter-thread "shuffle" is the pass-1 scatter into one shared array (radix_join.cpp:901-926). Here the
+same pass is the inter-GPU shuffle:
+
+  1. every rank holds a row range of R and S;  b200_shard_pass1_device histograms it and scatters it
+     by the ROUTED pass-1 digit, so the partitions owned by GPU g (low log2(G) key bits == g) form one
+     contiguous range of the output — the output IS the all-to-all send buffer;
+  2. two small collectives size the exchange: an all-gather of the pass-1 partition counts (who
+     sends how much of which partition to whom) and an all-reduce of the full-width histograms (final
+     partition sizes);
+  3. the 8-byte tuples move with one all-to-all per relation (NCCL over NVLink 5 / NVSwitch);
+  4. every rank finishes alone: b200_shard_join_device runs pass 2 over the received segments and the
+     shared-memory build/probe;  5. a 24-byte all-reduce sums matches / checksum / keysum.
+
+All device work goes through the C ABI (`backend`); this module only computes split sizes, segment
+tables and histogram slices (pure torch, device-agnostic — tests/test_dist_gloo.py runs it with gloo
+and a host stand-in for the kernels).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def log2_exact(x: int) -> int:
+    l = x.bit_length() - 1
+    if x <= 0 or (1 << l) != x:
+        raise ValueError(f"{x} is not a power of two")
+    return l
+
+
+def plan_bits(nR_total: int, world: int, join_plan) -> tuple[int, int, int]:
+    """Radix bits of the sharded join: the single-GPU plan for the WHOLE build side, widened so that
+    pass 1 has at least log2(world) bits to route on."""
+    bits, b1, b2 = join_plan(nR_total)
+    lg = log2_exact(world)
+    if b1 < lg:
+        b1 = lg
+        bits = max(bits, lg)
+        b2 = bits - b1
+    return bits, b1, b2
+
+
+def exchange_plan(counts_all: torch.Tensor, rank: int, world: int):
+    """counts_all[s, p] = tuples rank s holds of routed pass-1 partition p (all-gathered).
+    Returns (send_splits, recv_splits, seg_off, seg_group):
+      send_splits[g]  tuples this rank sends to g        = its partitions in g's range
+      recv_splits[s]  tuples this rank receives from s   = s's partitions in this rank's range
+      seg_off         [world * per + 1] starts of the received segments, ordered (source, partition)
+      seg_group       [world * per]     local partition index of every segment"""
+    F1 = counts_all.shape[1]
+    per = F1 // world
+    mine = counts_all[rank].view(world, per).sum(1)
+    incoming = counts_all[:, rank * per:(rank + 1) * per]            # [world, per]
+    recv = incoming.sum(1)
+    seg_len = incoming.reshape(-1)
+    seg_off = torch.zeros(seg_len.numel() + 1, dtype=torch.int64, device=counts_all.device)
+    seg_off[1:] = torch.cumsum(seg_len, 0)
+    seg_group = torch.arange(per, device=counts_all.device, dtype=torch.int32).repeat(world)
+    return mine, recv, seg_off, seg_group
+
+
+def final_hist_slice(hist_global: torch.Tensor, rank: int, world: int, b1: int, b2: int) -> torch.Tensor:
+    """hist_global is indexed by the routed full-width digit p1' | (p2 << b1). Returns this rank's slice
+    in final partition order (local pass-1 partition major, then p2): [per << b2]."""
+    F1, F2 = 1 << b1, 1 << b2
+    per = F1 // world
+    return hist_global.view(F2, F1)[:, rank * per:(rank + 1) * per].t().contiguous().view(-1)
+
+
+class CudaBackend:
+    """The product backend: libb200aqp.so through ctypes."""
+
+    def __init__(self):
+        import b200aqp as A
+        self.A = A
+        self.L = A.lib()
+
+    def stream(self):
+        return self.A._st(torch.cuda.current_stream().cuda_stream)
+
+    def shard_pass1(self, rel, n, bits, b1, lg, send, hist, part1_off):
+        self.A._check(self.L.b200_shard_pass1_device(rel.data_ptr(), n, bits, b1, lg, send.data_ptr(), hist.data_ptr(),
+                                                     part1_off.data_ptr(), self.stream()), "b200_shard_pass1_device")
+
+    def shard_join(self, R, nR, segR, S, nS, segS, seg_group, nseg, ngroups, shift2, bits2, histR, histS, hash_shift):
+        import ctypes as C
+        s = self.A.JoinStats()
+        self.A._check(self.L.b200_shard_join_device(R.data_ptr(), nR, segR.data_ptr(), S.data_ptr(), nS, segS.data_ptr(),
+                                                    seg_group.data_ptr(), nseg, ngroups, shift2, bits2, histR.data_ptr(),
+                                                    histS.data_ptr(), hash_shift, C.byref(s), self.stream()),
+                      "b200_shard_join_device")
+        return s.as_dict()
+
+    def join_plan(self, nR):
+        return self.A.join_plan(nR)
+
+
+class ShardedJoin:
+    """R and S are int32 tensors of shape [2 * n_local] (key, payload interleaved = row_t) holding this
+    rank's row range. run() returns the GLOBAL matches / checksum / keysum plus per-phase device times."""
+
+    def __init__(self, nR_total: int, nS_total: int, device, backend=None, group=None):
+        self.backend = backend or CudaBackend()
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.device = device
+        self.nR_total, self.nS_total = nR_total, nS_total
+        self.lg = log2_exact(self.world)
+        self.bits, self.b1, self.b2 = plan_bits(nR_total, self.world, self.backend.join_plan)
+        self.F1, self.P = 1 << self.b1, 1 << self.bits
+        self._bufs = {}
+
+    def _buf(self, name, numel, dtype):
+        t = self._bufs.get(name)
+        if t is None or t.numel() < numel or t.dtype != dtype:
+            t = torch.empty(max(numel, 2), dtype=dtype, device=self.device)
+            self._bufs[name] = t
+        return t
+
+    def _event(self):
+        if self.device.type != "cuda":
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def run(self, R: torch.Tensor, S: torch.Tensor) -> dict:
+        be, G, rank = self.backend, self.world, self.rank
+        nR, nS = R.numel() // 2, S.numel() // 2
+        F1, P = self.F1, self.P
+        e0 = self._event()
+        # ---- 1. local histogram + routed pass-1 scatter (output = send buffer) -----------------------
+        sendR = self._buf("sendR", 2 * nR + 4, torch.int32)
+        sendS = self._buf("sendS", 2 * nS + 4, torch.int32)
+        hist = self._buf("hist", 2 * P, torch.int32)
+        off1 = self._buf("off1", 2 * (F1 + 1), torch.int32)
+        histR, histS = hist[:P], hist[P:2 * P]
+        offR, offS = off1[:F1 + 1], off1[F1 + 1:2 * (F1 + 1)]
+        be.shard_pass1(R, nR, self.bits, self.b1, self.lg, sendR, histR, offR)
+        be.shard_pass1(S, nS, self.bits, self.b1, self.lg, sendS, histS, offS)
+        e1 = self._event()
+        # ---- 2. size the exchange ---------------------------------------------------------------------
+        counts = torch.cat([offR[1:] - offR[:-1], offS[1:] - offS[:-1]]).to(torch.int64)       # [2*F1]
+        counts_flat = torch.empty(G * 2 * F1, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(counts_flat, counts, group=self.group)
+        counts_all = counts_flat.view(G, 2 * F1)
+        hist_global = hist[:2 * P].clone()
+        dist.all_reduce(hist_global, group=self.group)
+        sR, rR, segR, seg_group = exchange_plan(counts_all[:, :F1], rank, G)
+        sS, rS, segS, _ = exchange_plan(counts_all[:, F1:], rank, G)
+        splits = torch.stack([sR, rR, sS, rS]).tolist()        # the one host sync of the exchange
+        nR_recv, nS_recv = int(sum(splits[1])), int(sum(splits[3]))
+        # ---- 3. all-to-all of the 8-byte tuples ---------------------------------------------------------
+        recvR = self._buf("recvR", 2 * nR_recv + 4, torch.int32)
+        recvS = self._buf("recvS", 2 * nS_recv + 4, torch.int32)
+        dist.all_to_all_single(recvR[:2 * nR_recv].view(torch.int64), sendR[:2 * nR].view(torch.int64),
+                               output_split_sizes=splits[1], input_split_sizes=splits[0], group=self.group)
+        dist.all_to_all_single(recvS[:2 * nS_recv].view(torch.int64), sendS[:2 * nS].view(torch.int64),
+                               output_split_sizes=splits[3], input_split_sizes=splits[2], group=self.group)
+        e2 = self._event()
+        # ---- 4. local pass 2 + build/probe ------------------------------------------------------------------
+        per = F1 // G
+        hR = final_hist_slice(hist_global[:P], rank, G, self.b1, self.b2)
+        hS = final_hist_slice(hist_global[P:], rank, G, self.b1, self.b2)
+        local = be.shard_join(recvR, nR_recv, segR.to(torch.int32), recvS, nS_recv, segS.to(torch.int32), seg_group,
+                              G * per, per, self.b1, self.b2, hR, hS, self.bits)
+        e3 = self._event()
+        # ---- 5. global result ---------------------------------------------------------------------------------
+        to_i64 = lambda v: v - (1 << 64) if v >= (1 << 63) else v
+        res = torch.tensor([local["matches"], to_i64(local["checksum"]), to_i64(local["keysum"])], dtype=torch.int64,
+                           device=self.device)
+        dist.all_reduce(res, group=self.group)
+        m, cs, ks = (int(x) for x in res.tolist())
+        out = {"matches": m, "checksum": cs % (1 << 64), "keysum": ks % (1 << 64), "radix_bits": self.bits,
+               "num_passes": 2, "bits_pass1": self.b1, "bits_pass2": self.b2, "tuples_sent": int(sum(splits[0]) + sum(splits[2])),
+               "tuples_kept": int(splits[0][rank] + splits[2][rank]), "ms_pass2": local.get("ms_pass2", 0.0),
+               "ms_join": local.get("ms_join", 0.0)}
+        if e0 is not None:
+            torch.cuda.synchronize()
+            out["ms_pass1"] = e0.elapsed_time(e1)     # histogram + pass-1 scatter
+            out["ms_hist"] = 0.0
+            out["ms_exchange"] = e1.elapsed_time(e2)   # count/histogram collectives + all-to-all
+            out["ms_total"] = e0.elapsed_time(e3)
+        return out

@@ -249,11 +249,11 @@ static int join_device_locked(const row_t *dR, uint64_t nR, const row_t *dS, uin
         const bool priv = bits <= (uint32_t) kMaxSmemHistBits && !getenv("B200_AQP_ATOMIC_PASS1");
         const uint32_t tpbR = (uint32_t) (((nR + kScatterTile - 1) / kScatterTile + NB - 1) / NB);
         const uint32_t tpbS = (uint32_t) (((nS + kScatterTile - 1) / kScatterTile + NB - 1) / NB);
-        if (radix_hist_device(dR, nR, 0, bits, u32(m.histR), priv ? NB : 0, (uint64_t) tpbR * kScatterTile, b1,
-                              u32(m.bhR), st))
+        if (radix_hist_device(dR, nR, make_digit(0, bits), bits, u32(m.histR), priv ? NB : 0,
+                              (uint64_t) tpbR * kScatterTile, b1, u32(m.bhR), st))
             return -1;
-        if (radix_hist_device(dS, nS, 0, bits, u32(m.histS), priv ? NB : 0, (uint64_t) tpbS * kScatterTile, b1,
-                              u32(m.bhS), st))
+        if (radix_hist_device(dS, nS, make_digit(0, bits), bits, u32(m.histS), priv ? NB : 0,
+                              (uint64_t) tpbS * kScatterTile, b1, u32(m.bhS), st))
             return -1;
         PlanArgs pa{};
         pa.bits1 = b1;
@@ -267,20 +267,22 @@ static int join_device_locked(const row_t *dR, uint64_t nR, const row_t *dS, uin
         AQP_CUDA_OK(cudaEventRecord(g.ev[1], st));
 
         row_t *t1R = static_cast<row_t *>(g.tmp[0].p), *t1S = static_cast<row_t *>(g.tmp[1].p);
-        if (radix_scatter_launch(dR, t1R, u32(m.seg1R), u32(m.seg1R) + 2, 1, nR, 0, b1, u32(m.cur1R),
-                                 priv ? u32(m.bbR) : nullptr, NB, tpbR, st))
+        if (radix_scatter_launch(dR, t1R, u32(m.seg1R), u32(m.seg1R) + 2, nullptr, 1, nR, make_digit(0, b1), b1,
+                                 u32(m.cur1R), priv ? u32(m.bbR) : nullptr, NB, tpbR, st))
             return -1;
-        if (radix_scatter_launch(dS, t1S, u32(m.seg1S), u32(m.seg1S) + 2, 1, nS, 0, b1, u32(m.cur1S),
-                                 priv ? u32(m.bbS) : nullptr, NB, tpbS, st))
+        if (radix_scatter_launch(dS, t1S, u32(m.seg1S), u32(m.seg1S) + 2, nullptr, 1, nS, make_digit(0, b1), b1,
+                                 u32(m.cur1S), priv ? u32(m.bbS) : nullptr, NB, tpbS, st))
             return -1;
         AQP_CUDA_OK(cudaEventRecord(g.ev[2], st));
         finR = t1R;
         finS = t1S;
         if (passes == 2) {
             row_t *t2R = static_cast<row_t *>(g.tmp[2].p), *t2S = static_cast<row_t *>(g.tmp[3].p);
-            if (radix_scatter_launch(t1R, t2R, u32(m.segR), u32(m.tileR), F1, nR, b1, b2, u32(m.cur2R), nullptr, 0, 0, st))
+            if (radix_scatter_launch(t1R, t2R, u32(m.segR), u32(m.tileR), nullptr, F1, nR, make_digit(b1, b2), b2,
+                                     u32(m.cur2R), nullptr, 0, 0, st))
                 return -1;
-            if (radix_scatter_launch(t1S, t2S, u32(m.segS), u32(m.tileS), F1, nS, b1, b2, u32(m.cur2S), nullptr, 0, 0, st))
+            if (radix_scatter_launch(t1S, t2S, u32(m.segS), u32(m.tileS), nullptr, F1, nS, make_digit(b1, b2), b2,
+                                     u32(m.cur2S), nullptr, 0, 0, st))
                 return -1;
             finR = t2R;
             finS = t2S;
@@ -641,7 +643,7 @@ int b200_radix_hist_device(const struct row_t *d_in, uint64_t n, uint32_t shift,
                            void *stream) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (ensure_init()) return -1;
-    return radix_hist_device(d_in, n, shift, bits, d_hist, 0, 0, 0, nullptr,
+    return radix_hist_device(d_in, n, make_digit(shift, bits), bits, d_hist, 0, 0, 0, nullptr,
                              stream ? static_cast<cudaStream_t>(stream) : g.stream);
 }
 
@@ -666,7 +668,106 @@ int b200_radix_scatter_device(const struct row_t *d_in, uint64_t n, uint32_t shi
     if (seg.ensure(64)) return -1;
     uint32_t *d_seg = static_cast<uint32_t *>(seg.p);
     if (single_segment_setup((uint32_t) n, d_offsets, 1u << bits, d_cursors, d_seg, st)) return -1;
-    return radix_scatter_launch(d_in, d_out, d_seg, d_seg + 2, 1, n, shift, bits, d_cursors, nullptr, 0, 0, st);
+    return radix_scatter_launch(d_in, d_out, d_seg, d_seg + 2, nullptr, 1, n, make_digit(shift, bits), bits, d_cursors,
+                                nullptr, 0, 0, st);
+}
+
+// ---- sharded (multi-GPU) join stages ----------------------------------------------------------------
+int b200_shard_pass1_device(const struct row_t *d_in, uint64_t n, uint32_t total_bits, uint32_t bits1,
+                            uint32_t log2_gpus, struct row_t *d_send, uint32_t *d_hist, uint32_t *d_part1_off,
+                            void *stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : g.stream;
+    if (total_bits < bits1 || bits1 > (uint32_t) kMaxFanoutBits || total_bits > (uint32_t) kMaxSmemHistBits ||
+        log2_gpus > bits1 || n >= 0xFFFF0000ull) {
+        set_error("b200_shard_pass1_device: need log2_gpus <= bits1 <= 8, bits1 <= total_bits <= 15, n < 2^32");
+        return -1;
+    }
+    const uint32_t NB = pass1_blocks(), F1 = 1u << bits1;
+    static DevBuf ws;   // per-CTA histogram rows, private cursors, single-segment table
+    const size_t rows = (size_t) NB * F1 * 4;
+    if (ws.ensure(2 * rows + 256)) return -1;
+    uint32_t *bh = static_cast<uint32_t *>(ws.p), *bb = bh + (size_t) NB * F1, *seg1 = bb + (size_t) NB * F1;
+    const uint32_t tpb = (uint32_t) (((n + kScatterTile - 1) / kScatterTile + NB - 1) / NB);
+    AQP_CUDA_OK(cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) << total_bits, st));
+    if (radix_hist_device(d_in, n, make_digit(0, total_bits, bits1, log2_gpus), total_bits, d_hist, NB,
+                          (uint64_t) tpb * kScatterTile, bits1, bh, st))
+        return -1;
+    if (plan_pass1_device(d_hist, bits1, total_bits - bits1, d_part1_off, seg1, bh, bb, NB, st)) return -1;
+    return radix_scatter_launch(d_in, d_send, seg1, seg1 + 2, nullptr, 1, n, make_digit(0, bits1, bits1, log2_gpus),
+                                bits1, nullptr, bb, NB, tpb, st);
+}
+
+int b200_shard_join_device(const struct row_t *d_R, uint64_t nR, const uint32_t *d_segoff_R, const struct row_t *d_S,
+                           uint64_t nS, const uint32_t *d_segoff_S, const uint32_t *d_seg_group, uint32_t nseg,
+                           uint32_t ngroups, uint32_t shift2, uint32_t bits2, const uint32_t *d_hist_R,
+                           const uint32_t *d_hist_S, uint32_t hash_shift, struct b200_join_stats_t *stats,
+                           void *stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : g.stream;
+    if (nseg == 0 || nseg > (uint32_t) kMaxFanout || bits2 > (uint32_t) kMaxFanoutBits || nR >= 0xFFFF0000ull ||
+        nS >= 0xFFFF0000ull) {
+        set_error("b200_shard_join_device: need 1 <= nseg <= 256, bits2 <= 8, relations < 2^32 tuples");
+        return -1;
+    }
+    const unsigned long long launches0 = g_kernel_launches;
+    const uint32_t P = ngroups << bits2;
+    // workspace: [result][part_off R,S][cursor2 R,S][seg_tile_start R,S][item_start][items]
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        size_t r = o;
+        o += (bytes + 255) & ~(size_t) 255;
+        return r;
+    };
+    const size_t o_res = take(sizeof(JoinResult)), o_offR = take((P + 1) * 4), o_offS = take((P + 1) * 4),
+                 o_curR = take(P * 4), o_curS = take(P * 4), o_tileR = take((nseg + 1) * 4),
+                 o_tileS = take((nseg + 1) * 4), o_istart = take((P + 1) * 4),
+                 o_items = take((nS / kProbeChunk + P + 1) * sizeof(uint2));
+    if (g.meta.ensure(o) || g.tmp[2].ensure(nR * sizeof(row_t) + 16) || g.tmp[3].ensure(nS * sizeof(row_t) + 16)) return -1;
+    unsigned char *mb = static_cast<unsigned char *>(g.meta.p);
+    auto u32 = [&](size_t off) { return reinterpret_cast<uint32_t *>(mb + off); };
+    JoinResult *d_res = reinterpret_cast<JoinResult *>(mb + o_res);
+    AQP_CUDA_OK(cudaEventRecord(g.ev[0], st));
+    AQP_CUDA_OK(cudaMemsetAsync(d_res, 0, sizeof(JoinResult), st));
+    ShardPlanArgs pa{};
+    pa.nparts = P;
+    pa.nseg = nseg;
+    pa.rel[0] = ShardRelPlan{d_hist_R, d_segoff_R, u32(o_offR), u32(o_curR), u32(o_tileR)};
+    pa.rel[1] = ShardRelPlan{d_hist_S, d_segoff_S, u32(o_offS), u32(o_curS), u32(o_tileS)};
+    if (plan_shard_device(pa, st)) return -1;
+    row_t *t2R = static_cast<row_t *>(g.tmp[2].p), *t2S = static_cast<row_t *>(g.tmp[3].p);
+    if (radix_scatter_launch(d_R, t2R, d_segoff_R, u32(o_tileR), d_seg_group, nseg, nR, make_digit(shift2, bits2), bits2,
+                             u32(o_curR), nullptr, 0, 0, st))
+        return -1;
+    if (radix_scatter_launch(d_S, t2S, d_segoff_S, u32(o_tileS), d_seg_group, nseg, nS, make_digit(shift2, bits2), bits2,
+                             u32(o_curS), nullptr, 0, 0, st))
+        return -1;
+    AQP_CUDA_OK(cudaEventRecord(g.ev[3], st));
+    uint2 *d_items = reinterpret_cast<uint2 *>(mb + o_items);
+    if (join_items_device(u32(o_offR), u32(o_offS), P, u32(o_istart), d_items, st)) return -1;
+    if (build_probe_device(t2R, u32(o_offR), t2S, u32(o_offS), u32(o_istart), d_items, P, nS / kProbeChunk + P + 1,
+                           hash_shift, d_res, nullptr, 0, st))
+        return -1;
+    AQP_CUDA_OK(cudaEventRecord(g.ev[4], st));
+    JoinResult h{};
+    AQP_CUDA_OK(cudaMemcpyAsync(&h, d_res, sizeof h, cudaMemcpyDeviceToHost, st));
+    AQP_CUDA_OK(cudaStreamSynchronize(st));
+    b200_join_stats_t s{};
+    s.matches = (int64_t) h.matches;
+    s.checksum = h.checksum;
+    s.keysum = h.keysum;
+    s.radix_bits = hash_shift;
+    s.num_passes = 2;
+    s.bits_pass2 = bits2;
+    cudaEventElapsedTime(&s.ms_pass2, g.ev[0], g.ev[3]);
+    cudaEventElapsedTime(&s.ms_join, g.ev[3], g.ev[4]);
+    cudaEventElapsedTime(&s.ms_total, g.ev[0], g.ev[4]);
+    s.kernel_launches = (uint32_t) (g_kernel_launches - launches0);
+    g.last = s;
+    if (stats) *stats = s;
+    return 0;
 }
 
 // ---- generators (device) --------------------------------------------------------------------------

@@ -14,7 +14,7 @@ constexpr int kMaxSmemHistBits = 15;              // widest shared-memory histog
 #define AQP_SCATTER_TILE 4096
 #endif
 #ifndef AQP_SCATTER_THREADS
-#define AQP_SCATTER_THREADS 512
+#define AQP_SCATTER_THREADS 256
 #endif
 constexpr int kScatterTile = AQP_SCATTER_TILE;    // tuples per scatter tile (32 KiB staging + 2 x 32 KiB TMA ring)
 
@@ -22,6 +22,31 @@ constexpr int kScatterTile = AQP_SCATTER_TILE;    // tuples per scatter tile (32
 constexpr int kBuildCap = 8192;                   // R tuples per shared-memory hash table (64 KiB)
 constexpr int kProbeChunk = 32768;                // S tuples per work item
 constexpr int kJoinThreads = 512;
+
+// Partition digit of a key: the reference's (key & MASK) >> R (radix_join.cpp:47) on `bits` key bits
+// starting at `shift`, optionally with its low `rbits` bits rotated right by `rot`. The rotation is the
+// multi-GPU routing order: with G = 2^rot GPUs the pass-1 partitions owned by one GPU (those whose low
+// rot key bits equal the GPU's rank) become a contiguous range, so the pass-1 output doubles as the
+// all-to-all send buffer. rot = 0 is the identity.
+struct DigitFn {
+    uint32_t shift, mask, m1, rot, lrot;
+#ifdef __CUDACC__
+    __device__ __forceinline__ uint32_t operator()(uint32_t key) const {
+        uint32_t d = (key >> shift) & mask;
+        uint32_t p = d & m1;
+        return (d & ~m1) | (((p >> rot) | (p << lrot)) & m1);
+    }
+#endif
+};
+inline DigitFn make_digit(uint32_t shift, uint32_t bits, uint32_t rbits = 0, uint32_t rot = 0) {
+    DigitFn f;
+    f.shift = shift;
+    f.mask = (1u << bits) - 1;
+    f.m1 = rot ? (1u << rbits) - 1 : 0;
+    f.rot = rot;
+    f.lrot = rot ? rbits - rot : 0;
+    return f;
+}
 
 struct RelPlan {
     const uint32_t *hist;       // [2^B]   raw-digit histogram
@@ -40,6 +65,18 @@ struct PlanArgs {
     uint32_t nblocks1;          // CTAs of the pass-1 scatter (= rows of block_hist)
 };
 
+struct ShardRelPlan {
+    const uint32_t *hist;       // [nparts]   this rank's slice of the global histogram, final order
+    const uint32_t *seg_off;    // [nseg+1]   received segments
+    uint32_t *part_off;         // [nparts+1]
+    uint32_t *cursor2;          // [nparts]
+    uint32_t *seg_tile_start;   // [nseg+1]
+};
+struct ShardPlanArgs {
+    ShardRelPlan rel[2];
+    uint32_t nparts, nseg;
+};
+
 struct JoinResult {              // device-side accumulators
     unsigned long long matches;
     unsigned long long checksum;
@@ -48,17 +85,24 @@ struct JoinResult {              // device-side accumulators
 };
 
 // partition.cu
-int radix_hist_device(const row_t *d_in, uint64_t n, uint32_t shift, uint32_t bits, uint32_t *d_hist, uint32_t nblocks,
+int radix_hist_device(const row_t *d_in, uint64_t n, DigitFn digit, uint32_t bits, uint32_t *d_hist, uint32_t nblocks,
                       uint64_t chunk, uint32_t bits1, uint32_t *d_block_hist, cudaStream_t st);
 int exclusive_scan_u32_device(const uint32_t *d_in, uint32_t n, uint32_t *d_out, cudaStream_t st);
 int plan_offsets_device(const PlanArgs &a, cudaStream_t st);
 // d_block_base == nullptr: runs are reserved with global atomics on d_cursors (any grid).
 // d_block_base != nullptr: exactly nblocks CTAs, CTA b owns tiles [b*tiles_per_block, ...) and writes at
 // its private cursors d_block_base[b][2^bits] (single segment only).
+// d_seg_group (or null = identity) maps an input segment to the cursor group it scatters into:
+// cursor index = (group << bits) + digit. Several segments may share a group (multi-GPU: the same
+// pass-1 partition received from different source GPUs).
 int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_off, const uint32_t *d_seg_tile_start,
-                         uint32_t nseg, uint64_t n_total, uint32_t shift, uint32_t bits, uint32_t *d_cursors,
-                         const uint32_t *d_block_base, uint32_t nblocks, uint32_t tiles_per_block, cudaStream_t st);
+                         const uint32_t *d_seg_group, uint32_t nseg, uint64_t n_total, DigitFn digit, uint32_t bits,
+                         uint32_t *d_cursors, const uint32_t *d_block_base, uint32_t nblocks, uint32_t tiles_per_block,
+                         cudaStream_t st);
 uint32_t pass1_blocks();
+int plan_pass1_device(const uint32_t *d_hist, uint32_t bits1, uint32_t bits2, uint32_t *d_part1_off, uint32_t *d_seg1,
+                      const uint32_t *d_block_hist, uint32_t *d_block_base, uint32_t nblocks, cudaStream_t st);
+int plan_shard_device(const ShardPlanArgs &a, cudaStream_t st);
 int single_segment_setup(uint32_t n, const uint32_t *d_offsets, uint32_t fan, uint32_t *d_cursors,
                          uint32_t *d_seg_tables, cudaStream_t st);
 

@@ -37,11 +37,11 @@ constexpr int kHistUnroll = 8;   // 8-byte loads in flight per thread
 // scatter block private, pre-reserved output ranges (parallel_radix_partition's per-thread
 // histogram + prefix scheme, radix_join.cpp:881-915, with CTAs in the role of threads).
 __global__ void __launch_bounds__(kHistThreads)
-radix_hist_smem_kernel(const uint2 *__restrict__ in, uint64_t n, uint32_t shift, uint32_t bits,
+radix_hist_smem_kernel(const uint2 *__restrict__ in, uint64_t n, DigitFn digit, uint32_t bits,
                        uint32_t *__restrict__ ghist, uint64_t chunk, uint32_t bits1,
                        uint32_t *__restrict__ block_hist) {
     extern __shared__ uint32_t sh[];
-    const uint32_t fan = 1u << bits, mask = fan - 1;
+    const uint32_t fan = 1u << bits;
     for (uint32_t i = threadIdx.x; i < fan; i += kHistThreads) sh[i] = 0;
     __syncthreads();
     const uint64_t cbeg = (uint64_t) blockIdx.x * chunk;
@@ -57,7 +57,7 @@ radix_hist_smem_kernel(const uint2 *__restrict__ in, uint64_t n, uint32_t shift,
 #pragma unroll
         for (int j = 0; j < kHistUnroll; ++j) {
             uint64_t i = base + (uint64_t) j * kHistThreads + threadIdx.x;
-            if (i < cend) atomicAdd(&sh[(v[j].x >> shift) & mask], 1u);
+            if (i < cend) atomicAdd(&sh[digit(v[j].x)], 1u);
         }
     }
     __syncthreads();
@@ -77,17 +77,15 @@ radix_hist_smem_kernel(const uint2 *__restrict__ in, uint64_t n, uint32_t shift,
 
 // fallback for very wide histograms: global REDs only
 __global__ void __launch_bounds__(kHistThreads)
-radix_hist_global_kernel(const uint2 *__restrict__ in, uint64_t n, uint32_t shift, uint32_t bits,
-                         uint32_t *__restrict__ ghist) {
-    const uint32_t mask = (1u << bits) - 1;
+radix_hist_global_kernel(const uint2 *__restrict__ in, uint64_t n, DigitFn digit, uint32_t *__restrict__ ghist) {
     uint64_t stride = (uint64_t) gridDim.x * kHistThreads;
     for (uint64_t i = (uint64_t) blockIdx.x * kHistThreads + threadIdx.x; i < n; i += stride)
-        atomicAdd(&ghist[(ld_stream_v2(in + i).x >> shift) & mask], 1u);
+        atomicAdd(&ghist[digit(ld_stream_v2(in + i).x)], 1u);
 }
 
 // nblocks == 0: plain histogram with a grid chosen here. nblocks > 0: exactly nblocks CTAs, CTA b
 // covering tuples [b*chunk, (b+1)*chunk), and block_hist[nblocks][2^bits1] rows are written.
-int radix_hist_device(const row_t *d_in, uint64_t n, uint32_t shift, uint32_t bits, uint32_t *d_hist,
+int radix_hist_device(const row_t *d_in, uint64_t n, DigitFn digit, uint32_t bits, uint32_t *d_hist,
                       uint32_t nblocks, uint64_t chunk, uint32_t bits1, uint32_t *d_block_hist, cudaStream_t st) {
     if (bits > 24) {
         set_error("radix_hist: bits > 24 not supported");
@@ -115,10 +113,10 @@ int radix_hist_device(const row_t *d_in, uint64_t n, uint32_t shift, uint32_t bi
             grid = (uint32_t) (tiles < (uint64_t) kNumSMs * per_sm ? tiles : (uint64_t) kNumSMs * per_sm);
             chunk = (tiles + grid - 1) / grid * tile;
         }
-        radix_hist_smem_kernel<<<grid, kHistThreads, smem, st>>>(in, n, shift, bits, d_hist, chunk, bits1,
+        radix_hist_smem_kernel<<<grid, kHistThreads, smem, st>>>(in, n, digit, bits, d_hist, chunk, bits1,
                                                                 nblocks ? d_block_hist : nullptr);
     } else {
-        radix_hist_global_kernel<<<kNumSMs * 4, kHistThreads, 0, st>>>(in, n, shift, bits, d_hist);
+        radix_hist_global_kernel<<<kNumSMs * 4, kHistThreads, 0, st>>>(in, n, digit, d_hist);
     }
     AQP_LAUNCHED();
     AQP_CUDA_OK(cudaGetLastError());
@@ -202,63 +200,166 @@ int plan_offsets_device(const PlanArgs &a, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// plans for the sharded (multi-GPU) join
+// ---------------------------------------------------------------------------------------------
+// pass 1 on one rank: partition sizes of the pass-1 digit from the full-width histogram, their
+// exclusive prefix (= layout of the send buffer) and the CTA-private cursors
+__global__ void __launch_bounds__(kScanBlock)
+plan_pass1_kernel(const uint32_t *__restrict__ hist, uint32_t bits1, uint32_t bits2, uint32_t *__restrict__ part1_off,
+                  uint32_t *__restrict__ seg1, const uint32_t *__restrict__ block_hist,
+                  uint32_t *__restrict__ block_base, uint32_t nblocks) {
+    const uint32_t F1 = 1u << bits1, F2 = 1u << bits2;
+    uint32_t total = block_exclusive_scan(
+        F1,
+        [&](uint32_t p1) {
+            uint32_t c = 0;
+            for (uint32_t p2 = 0; p2 < F2; ++p2) c += hist[p1 + (p2 << bits1)];
+            return c;
+        },
+        [&](uint32_t p1, uint32_t v) { part1_off[p1] = v; });
+    if (threadIdx.x == 0) {
+        part1_off[F1] = total;
+        seg1[0] = 0;
+        seg1[1] = total;
+        seg1[2] = 0;
+        seg1[3] = (total + kScatterTile - 1) / kScatterTile;
+    }
+    __syncthreads();
+    for (uint32_t p1 = threadIdx.x; p1 < F1; p1 += kScanBlock) {
+        uint32_t run = part1_off[p1];
+        for (uint32_t b = 0; b < nblocks; ++b) {
+            uint32_t c = block_hist[(size_t) b * F1 + p1];
+            block_base[(size_t) b * F1 + p1] = run;
+            run += c;
+        }
+    }
+}
+
+int plan_pass1_device(const uint32_t *d_hist, uint32_t bits1, uint32_t bits2, uint32_t *d_part1_off, uint32_t *d_seg1,
+                      const uint32_t *d_block_hist, uint32_t *d_block_base, uint32_t nblocks, cudaStream_t st) {
+    plan_pass1_kernel<<<1, kScanBlock, 0, st>>>(d_hist, bits1, bits2, d_part1_off, d_seg1, d_block_hist, d_block_base,
+                                                nblocks);
+    AQP_LAUNCHED();
+    AQP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// after the exchange: final partition boundaries from the (already globally reduced) histogram slice
+// of this rank in final order, and the tile table of the received segments. blockIdx.x = relation.
+__global__ void __launch_bounds__(kScanBlock) plan_shard_kernel(ShardPlanArgs a) {
+    const ShardRelPlan &r = a.rel[blockIdx.x];
+    uint32_t total = block_exclusive_scan(
+        a.nparts, [&](uint32_t f) { return r.hist[f]; },
+        [&](uint32_t f, uint32_t v) {
+            r.part_off[f] = v;
+            r.cursor2[f] = v;
+        });
+    if (threadIdx.x == 0) r.part_off[a.nparts] = total;
+    __syncthreads();
+    uint32_t tiles = block_exclusive_scan(
+        a.nseg,
+        [&](uint32_t s) {
+            uint32_t len = r.seg_off[s + 1] - r.seg_off[s];
+            return (len + kScatterTile - 1) / kScatterTile;
+        },
+        [&](uint32_t s, uint32_t v) { r.seg_tile_start[s] = v; });
+    if (threadIdx.x == 0) r.seg_tile_start[a.nseg] = tiles;
+}
+
+int plan_shard_device(const ShardPlanArgs &a, cudaStream_t st) {
+    plan_shard_kernel<<<2, kScanBlock, 0, st>>>(a);
+    AQP_LAUNCHED();
+    AQP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // scatter
 //
-// A CTA walks its tiles with the NEXT tile's tuples already in flight into registers (software
-// pipelining: the loads are issued before the current tile is reordered and written out), so HBM
-// reads overlap everything else. Per tile:
+// One CTA streams its tiles through a two-deep TMA ring: an elected thread issues 1-D bulk copies
+// (cp.async.bulk, completion on an mbarrier) for tile i+2 while the CTA works on tile i, so HBM reads
+// never wait for compute. Per tile:
 //   rank      every tuple takes a slot in its partition with a shared-memory atomicAdd
-//   scan      every warp scans the tile histogram for itself (redundant, but it saves a block barrier)
-//   reserve   warp 0 reserves the tile's run in every partition: pass 1 from CTA-private cursors
-//             (pre-computed from per-block histograms, no atomics), pass 2 with one global atomicAdd
-//             per (tile, partition) whose latency hides behind the staging step
+//   reserve   warp 0 scans the tile histogram and reserves the tile's run in every partition:
+//             pass 1 from CTA-private cursors (pre-computed from per-block histograms, no atomics),
+//             pass 2 with one global atomicAdd per (tile, partition)
 //   stage     tuples are reordered in shared memory so that each partition's run is contiguous
 //   write-out the runs leave the SM as coalesced stores
-// Two block barriers per tile. ncu on the first (TMA-ring) version of this kernel showed the
-// shared-memory pipe, not HBM, as the limiter (l1tex 71-82 %), so this version keeps tuples in
-// registers between load and staging instead of bouncing them through a shared-memory ring.
+// ncu (profiles/) shows this kernel limited by the shared-memory/L1 pipe (l1tex 71-82 %), not by HBM:
+// DRAM traffic equals the algorithmic 16 B/tuple. A variant that kept tuples in registers between an
+// LDG prefetch and the staging step (no shared-memory ring) was 25 % slower: the LDG data crosses the
+// same L1 data stage the ring reads do, while TMA writes into shared memory do not.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// 1-D bulk copy global -> shared through the TMA unit; src/dst 16-byte aligned, bytes % 16 == 0
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 constexpr int kScatterThreads = AQP_SCATTER_THREADS;
-constexpr int kScatterWarps = kScatterThreads / 32;
 constexpr int kScatterItems = kScatterTile / kScatterThreads;
 static_assert(kScatterItems * kScatterThreads == kScatterTile, "tile shape");
-constexpr int kBinsPerLane = kMaxFanout / 32;
-// 228 KiB of shared memory per SM: staging buffer + per-warp scan copies + bookkeeping per CTA
-constexpr size_t kScatterSmemApprox = (size_t) kScatterTile * 8 + (size_t) kScatterWarps * kMaxFanout * 4 + 6 * 1024;
-constexpr int kScatterBlocksBySmem = (int) (228 * 1024 / kScatterSmemApprox);
-constexpr int kScatterBlocksByThreads = 2048 / kScatterThreads;
-constexpr int kScatterBlocksByRegs = 65536 / (kScatterThreads * 64);   // kernel is held to 64 registers
-constexpr int kScatterBlocksPerSM0 = kScatterBlocksBySmem < kScatterBlocksByThreads ? kScatterBlocksBySmem : kScatterBlocksByThreads;
-constexpr int kScatterBlocksPerSM1 = kScatterBlocksPerSM0 < kScatterBlocksByRegs ? kScatterBlocksPerSM0 : kScatterBlocksByRegs;
-constexpr int kScatterBlocksPerSM = kScatterBlocksPerSM1 < 1 ? 1 : kScatterBlocksPerSM1;
+constexpr int kInBufTuples = kScatterTile + 2;   // +1 leading tuple when the tile starts on an odd index, +1 to round up
+constexpr size_t kScatterSmemBytes = (size_t) (2 * kInBufTuples + kScatterTile) * sizeof(uint2);
+// 228 KiB of shared memory per SM; every CTA also pays ~6.2 KiB of static arrays + 1 KiB reserved
+constexpr int kScatterBlocksPerSMRaw = (int) (228 * 1024 / (kScatterSmemBytes + 7424));
+constexpr int kScatterBlocksPerSM = kScatterBlocksPerSMRaw < 1 ? 1 : (kScatterBlocksPerSMRaw * kScatterThreads > 2048 ? 2048 / kScatterThreads : kScatterBlocksPerSMRaw);
 
 uint32_t pass1_blocks() { return (uint32_t) kNumSMs * kScatterBlocksPerSM; }
 
 __global__ void __launch_bounds__(kScatterThreads, kScatterBlocksPerSM)
 radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
                      const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_tile_start,
-                     uint32_t nseg, uint32_t shift, uint32_t bits, uint32_t *__restrict__ cursors,
-                     const uint32_t *__restrict__ block_base, uint32_t tiles_per_block) {
-    extern __shared__ __align__(16) uint2 stage[];         // kScatterTile tuples
-    __shared__ uint32_t cnt[2][kMaxFanout];                // tile histograms, double-buffered
-    __shared__ uint32_t wbase[kScatterWarps][kMaxFanout];  // per-warp copy of the exclusive scan
+                     const uint32_t *__restrict__ seg_group, uint32_t nseg, DigitFn digit, uint32_t bits,
+                     uint32_t *__restrict__ cursors, const uint32_t *__restrict__ block_base,
+                     uint32_t tiles_per_block) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint2 *inbuf0 = reinterpret_cast<uint2 *>(smem_raw);
+    uint2 *inbuf1 = inbuf0 + kInBufTuples;
+    uint2 *stage = inbuf1 + kInBufTuples;
+    __shared__ uint32_t cnt[kMaxFanout];     // tuples of this tile per partition
+    __shared__ uint32_t lbase[kMaxFanout];   // start of the partition's run inside `stage`
     __shared__ uint32_t gdst[kMaxFanout];    // global index of stage slot s of partition d is gdst[d] + s
     __shared__ uint32_t scur[kMaxFanout];    // CTA-private write cursors (pass 1)
     __shared__ uint32_t s_tstart[kMaxFanout + 1];
     __shared__ uint32_t s_soff[kMaxFanout + 1];
+    __shared__ __align__(8) uint64_t mbar[2];
 
-    const uint32_t fan = 1u << bits, mask = fan - 1;
-    const uint32_t per = (fan + 31) / 32;   // consecutive bins per lane in the warp scan (<= 8)
+    const uint32_t fan = 1u << bits;
     const bool priv = block_base != nullptr;
-    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     for (uint32_t i = threadIdx.x; i <= nseg; i += kScatterThreads) {
         s_tstart[i] = seg_tile_start[i];
         s_soff[i] = seg_off[i];
     }
     for (uint32_t i = threadIdx.x; i < fan; i += kScatterThreads) {
-        cnt[0][i] = 0;
-        cnt[1][i] = 0;
+        cnt[i] = 0;
         if (priv) scur[i] = block_base[(size_t) blockIdx.x * fan + i];
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     const uint32_t ntiles = s_tstart[nseg];
@@ -273,6 +374,7 @@ radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
         step = gridDim.x;
         n_my = first < ntiles ? (ntiles - first + step - 1) / step : 0;
     }
+
     // tile -> (segment, [begin, end))
     auto tile_range = [&](uint32_t tile, uint32_t &seg, uint32_t &begin, uint32_t &end) {
         uint32_t lo = 0, hi = nseg;   // last s with s_tstart[s] <= tile
@@ -284,97 +386,104 @@ radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
         begin = s_soff[lo] + (tile - s_tstart[lo]) * kScatterTile;
         end = min(begin + (uint32_t) kScatterTile, s_soff[lo + 1]);
     };
-
-    uint2 vn[kScatterItems];   // next tile, in flight
-    uint32_t seg_n = 0, begin_n = 0, end_n = 0;
-    if (n_my > 0) {
-        tile_range(first, seg_n, begin_n, end_n);
-#pragma unroll
-        for (int j = 0; j < kScatterItems; ++j) {
-            uint32_t k = begin_n + j * kScatterThreads + threadIdx.x;
-            if (k < end_n) vn[j] = ld_stream_v2(in + k);
-        }
+    auto issue = [&](uint32_t i) {   // one thread: bulk-load tile #i of this CTA into ring slot i & 1
+        uint32_t seg, begin, end;
+        tile_range(first + i * step, seg, begin, end);
+        const uint2 *src = in + begin;
+        uint32_t skew = (uint32_t) ((reinterpret_cast<uintptr_t>(src) >> 3) & 1u);   // 16-byte alignment of the source
+        uint32_t bytes = ((end - begin + skew + 1) & ~1u) * (uint32_t) sizeof(uint2);
+        uint64_t *bar = &mbar[i & 1];
+        mbar_expect_tx(bar, bytes);
+        tma_load_1d((i & 1) ? inbuf1 : inbuf0, src - skew, bytes, bar);
+    };
+    if (threadIdx.x == 0) {
+        if (n_my > 0) issue(0);
+        if (n_my > 1) issue(1);
     }
 
     for (uint32_t i = 0; i < n_my; ++i) {
-        const uint32_t seg = seg_n, ntile = end_n - begin_n;
-        uint32_t *const cn = cnt[i & 1];
+        uint32_t seg, begin, end;
+        tile_range(first + i * step, seg, begin, end);
+        const uint32_t ntile = end - begin;
+        const uint32_t group = seg_group ? seg_group[seg] : seg;
+        const uint32_t skew = (uint32_t) ((reinterpret_cast<uintptr_t>(in + begin) >> 3) & 1u);
+        const uint2 *buf = ((i & 1) ? inbuf1 : inbuf0) + skew;
+
+        mbar_wait(&mbar[i & 1], (i >> 1) & 1);
         uint2 v[kScatterItems];
         uint32_t rank[kScatterItems];
 #pragma unroll
-        for (int j = 0; j < kScatterItems; ++j) v[j] = vn[j];
+        for (int j = 0; j < kScatterItems; ++j) {
+            uint32_t k = j * kScatterThreads + threadIdx.x;
+            if (k < ntile) v[j] = buf[k];
+        }
 #pragma unroll
         for (int j = 0; j < kScatterItems; ++j) {
             uint32_t k = j * kScatterThreads + threadIdx.x;
-            if (k < ntile) rank[j] = atomicAdd(&cn[(v[j].x >> shift) & mask], 1u);
+            if (k < ntile) rank[j] = atomicAdd(&cnt[digit(v[j].x)], 1u);
         }
-        if (i + 1 < n_my) {   // put the next tile in flight before anything else happens
-            tile_range(first + (i + 1) * step, seg_n, begin_n, end_n);
-#pragma unroll
-            for (int j = 0; j < kScatterItems; ++j) {
-                uint32_t k = begin_n + j * kScatterThreads + threadIdx.x;
-                if (k < end_n) vn[j] = ld_stream_v2(in + k);
-            }
-        }
-        __syncthreads();   // (1) tile histogram complete; previous tile fully written out
+        __syncthreads();   // (1) tile histogram complete; ring slot consumed; previous write-out finished
 
-        // every warp: exclusive scan of the tile histogram into its own copy
-        uint32_t c[kBinsPerLane], my_g[kBinsPerLane], sum = 0;
+        if (threadIdx.x == 0 && i + 2 < n_my) issue(i + 2);
+
+        // warp 0: exclusive scan of the tile histogram, then reserve the runs
+        uint32_t my_g[kMaxFanout / 32], my_b[kMaxFanout / 32];
+        if (threadIdx.x < 32) {
+            const uint32_t per = (fan + 31) / 32;   // consecutive bins per lane (<= 8)
+            uint32_t c[kMaxFanout / 32], sum = 0;
 #pragma unroll
-        for (int k = 0; k < kBinsPerLane; ++k) {
-            uint32_t d = lane * per + k;
-            c[k] = (k < (int) per && d < fan) ? cn[d] : 0;
-            sum += c[k];
-        }
-        uint32_t run = warp_incl_scan(sum) - sum;
+            for (int k = 0; k < kMaxFanout / 32; ++k) {
+                uint32_t d = threadIdx.x * per + k;
+                bool ok = k < (int) per && d < fan;
+                c[k] = ok ? cnt[d] : 0;
+                if (ok) cnt[d] = 0;   // ready for the next tile
+                sum += c[k];
+            }
+            uint32_t run = warp_incl_scan(sum) - sum;
 #pragma unroll
-        for (int k = 0; k < kBinsPerLane; ++k) {
-            uint32_t d = lane * per + k;
-            if (k < (int) per && d < fan) wbase[warp][d] = run;
-            run += c[k];
-        }
-        if (warp == 0) {   // reserve the runs
-#pragma unroll
-            for (int k = 0; k < kBinsPerLane; ++k) {
-                uint32_t d = lane * per + k;
+            for (int k = 0; k < kMaxFanout / 32; ++k) {
+                uint32_t d = threadIdx.x * per + k;
+                my_b[k] = run;
                 if (k < (int) per && d < fan) {
+                    lbase[d] = run;
                     if (priv) {
                         my_g[k] = scur[d];
                         scur[d] = my_g[k] + c[k];
                     } else {
-                        my_g[k] = c[k] ? atomicAdd(&cursors[(seg << bits) + d], c[k]) : 0u;
+                        my_g[k] = c[k] ? atomicAdd(&cursors[(group << bits) + d], c[k]) : 0u;
                     }
                 }
+                run += c[k];
             }
         }
-        __syncwarp();
+        __syncthreads();   // (2) lbase ready
 
 #pragma unroll
         for (int j = 0; j < kScatterItems; ++j) {
             uint32_t k = j * kScatterThreads + threadIdx.x;
-            if (k < ntile) stage[wbase[warp][(v[j].x >> shift) & mask] + rank[j]] = v[j];
+            if (k < ntile) stage[lbase[digit(v[j].x)] + rank[j]] = v[j];
         }
-        if (warp == 0) {
+        if (threadIdx.x < 32) {
+            const uint32_t per = (fan + 31) / 32;
 #pragma unroll
-            for (int k = 0; k < kBinsPerLane; ++k) {
-                uint32_t d = lane * per + k;
-                if (k < (int) per && d < fan) gdst[d] = my_g[k] - wbase[0][d];
+            for (int k = 0; k < kMaxFanout / 32; ++k) {
+                uint32_t d = threadIdx.x * per + k;
+                if (k < (int) per && d < fan) gdst[d] = my_g[k] - my_b[k];
             }
         }
-        __syncthreads();   // (2) tile reordered, destinations known
+        __syncthreads();   // (3) tile reordered, destinations known
 
-        if (threadIdx.x < fan) cn[threadIdx.x] = 0;   // this buffer is used again two tiles from now
         for (uint32_t s = threadIdx.x; s < ntile; s += kScatterThreads) {
             uint2 t = stage[s];
-            out[gdst[(t.x >> shift) & mask] + s] = t;
+            out[gdst[digit(t.x)] + s] = t;
         }
     }
 }
 
 int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_off,
-                         const uint32_t *d_seg_tile_start, uint32_t nseg, uint64_t n_total, uint32_t shift,
-                         uint32_t bits, uint32_t *d_cursors, const uint32_t *d_block_base, uint32_t nblocks,
-                         uint32_t tiles_per_block, cudaStream_t st) {
+                         const uint32_t *d_seg_tile_start, const uint32_t *d_seg_group, uint32_t nseg, uint64_t n_total,
+                         DigitFn digit, uint32_t bits, uint32_t *d_cursors, const uint32_t *d_block_base,
+                         uint32_t nblocks, uint32_t tiles_per_block, cudaStream_t st) {
     if (bits > (uint32_t) kMaxFanoutBits || nseg > (uint32_t) kMaxFanout) {
         set_error("radix_scatter: fan-out too large");
         return -1;
@@ -384,6 +493,12 @@ int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_
         return -1;
     }
     if (n_total == 0) return 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int) kScatterSmemBytes));
+        attr_set = true;
+    }
     uint32_t grid;
     if (d_block_base) {
         grid = nblocks;
@@ -392,15 +507,9 @@ int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_
         uint64_t g = (uint64_t) kNumSMs * kScatterBlocksPerSM;
         grid = (uint32_t) (max_tiles < g ? max_tiles : g);
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int) (kScatterTile * sizeof(uint2))));
-        attr_set = true;
-    }
-    radix_scatter_kernel<<<grid, kScatterThreads, kScatterTile * sizeof(uint2), st>>>(
-        reinterpret_cast<const uint2 *>(d_in), reinterpret_cast<uint2 *>(d_out), d_seg_off, d_seg_tile_start, nseg,
-        shift, bits, d_cursors, d_block_base, tiles_per_block);
+    radix_scatter_kernel<<<grid, kScatterThreads, kScatterSmemBytes, st>>>(
+        reinterpret_cast<const uint2 *>(d_in), reinterpret_cast<uint2 *>(d_out), d_seg_off, d_seg_tile_start,
+        d_seg_group, nseg, digit, bits, d_cursors, d_block_base, tiles_per_block);
     AQP_LAUNCHED();
     AQP_CUDA_OK(cudaGetLastError());
     return 0;

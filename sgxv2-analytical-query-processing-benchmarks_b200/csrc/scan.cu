@@ -19,6 +19,10 @@ constexpr int kScanThreads = 256;
 constexpr int kScanUnroll = 4;                                  // uint4 loads in flight per thread
 constexpr int kScanTileVec = kScanThreads * kScanUnroll;        // 1024 uint4 = 16 KiB per tile
 constexpr int kScanTileVals = kScanTileVec * 16;                // 16384 values per tile
+constexpr int kExpandWordsPerThread = 4;                        // row-id expansion: 64-bit bitvector words per thread
+constexpr int kExpandTileWords = kScanThreads * kExpandWordsPerThread;   // 1024 words
+constexpr int kExpandTileVals = kExpandTileWords * 64;          // 65536 values per expansion tile
+constexpr int kExpandScanTiles = kExpandTileVals / kScanTileVals;   // = 4 scan tiles per expansion tile
 
 // bit 7 of every byte of the result is set iff lo <= byte <= hi (unsigned). lo7 = lo4 & 0x7f7f7f7f,
 // hiH = hi4 | 0x80808080 are loop invariants. Per byte: (x|0x80) - lo_low never borrows across
@@ -82,7 +86,6 @@ template <bool kCount>
 __global__ void __launch_bounds__(kScanThreads)
 bitvector_scan_kernel(const uint4 *__restrict__ in, size_t nvec, uint64_t *__restrict__ out, Pred p,
                       uint32_t *__restrict__ tile_counts) {
-    __shared__ uint32_t wsum[kScanThreads / 32];
     const uint64_t pol = l2_evict_first_policy();
     const size_t ntiles = (nvec + kScanTileVec - 1) / kScanTileVec;
     for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -104,17 +107,9 @@ bitvector_scan_kernel(const uint4 *__restrict__ in, size_t nvec, uint64_t *__res
             uint32_t hi = __shfl_down_sync(0xffffffffu, m32, 2);
             if ((threadIdx.x & 3) == 0 && q < nvec) out[q >> 2] = (uint64_t) m32 | ((uint64_t) hi << 32);
         }
-        if (kCount) {
+        if (kCount) {   // one reduction-add per warp into the counter of the enclosing expansion tile
             c = warp_sum(c);
-            __syncthreads();   // wsum of the previous tile consumed
-            if (lane_id() == 0) wsum[threadIdx.x >> 5] = c;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                uint32_t t = 0;
-#pragma unroll
-                for (int w = 0; w < kScanThreads / 32; ++w) t += wsum[w];
-                tile_counts[tile] = t;
-            }
+            if (lane_id() == 0 && c) atomicAdd(&tile_counts[tile / kExpandScanTiles], c);
         }
     }
 }
@@ -164,7 +159,7 @@ scan_count_kernel(const uint4 *__restrict__ in, size_t nvec, unsigned long long 
 // ticket, load, publish, look back, write kept too few bytes in flight).
 // ---------------------------------------------------------------------------------------------
 constexpr size_t kIndexChunkVals = (size_t) 1 << 29;                    // 512 MiB of column -> 64 MiB bitvector
-constexpr size_t kIndexChunkTiles = kIndexChunkVals / kScanTileVals;    // 32768
+constexpr size_t kIndexChunkTiles = kIndexChunkVals / kExpandTileVals;  // 8192 expansion tiles per chunk
 
 __global__ void __launch_bounds__(kScanBlock)
 tile_offsets_kernel(const uint32_t *__restrict__ counts, uint32_t ntiles, uint64_t *__restrict__ offsets,
@@ -175,11 +170,14 @@ tile_offsets_kernel(const uint32_t *__restrict__ counts, uint32_t ntiles, uint64
     if (threadIdx.x == 0) *running = base + total;
 }
 
-// One thread loads one 64-bit word; the words' match counts are scanned across the CTA; then each
-// warp expands its 32 words one at a time with all lanes cooperating: lane l owns bits l and l+32 of
-// the word, its output slot is the word's offset plus the number of set bits below it. Consecutive
-// lanes therefore write consecutive ids — every store instruction is one contiguous run, a full
-// 256-byte line pair at 100 % selectivity — with no shared-memory staging and no bank conflicts.
+// A thread loads kExpandWordsPerThread consecutive 64-bit words; the match counts are scanned across
+// the CTA. Words with few matches are written by their owning thread. Dense words are expanded by the
+// whole warp: lane l owns bits l and l+32 of the broadcast word and its output slot is the word's
+// offset plus the number of set bits below it, so consecutive lanes write consecutive ids — every
+// store instruction covers one contiguous run, a full 256-byte line pair at 100 % selectivity — with
+// no shared-memory staging and no bank conflicts. (Broadcasting every word cost 9 shuffles per lane
+// and made the kernel shuffle-bound at low selectivity: 162 us per 512 MiB chunk in ncu.)
+constexpr int kDenseWord = 8;
 __global__ void __launch_bounds__(kScanThreads)
 expand_rowids_kernel(const uint64_t *__restrict__ bv, size_t nwords, const uint64_t *__restrict__ tile_offsets,
                      uint64_t id_base, uint64_t *__restrict__ out, uint64_t out_capacity) {
@@ -187,11 +185,21 @@ expand_rowids_kernel(const uint64_t *__restrict__ bv, size_t nwords, const uint6
     const uint64_t pol = l2_evict_first_policy();
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     const unsigned lt = lanemask_lt();
-    const size_t ntiles = (nwords + kScanThreads - 1) / kScanThreads;
+    const size_t ntiles = (nwords + kExpandTileWords - 1) / kExpandTileWords;
     for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const size_t w = tile * kScanThreads + threadIdx.x;
-        const uint64_t m = w < nwords ? bv[w] : 0ull;
-        const uint32_t cnt = __popcll(m);
+        const size_t w0 = tile * kExpandTileWords + (size_t) threadIdx.x * kExpandWordsPerThread;
+        uint64_t m[kExpandWordsPerThread];
+        if (w0 + kExpandWordsPerThread <= nwords) {
+            const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(bv + w0);
+            const ulonglong2 b = *reinterpret_cast<const ulonglong2 *>(bv + w0 + 2);
+            m[0] = a.x; m[1] = a.y; m[2] = b.x; m[3] = b.y;
+        } else {
+#pragma unroll
+            for (int k = 0; k < kExpandWordsPerThread; ++k) m[k] = w0 + k < nwords ? bv[w0 + k] : 0ull;
+        }
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int k = 0; k < kExpandWordsPerThread; ++k) cnt += __popcll(m[k]);
         const uint32_t incl = warp_incl_scan(cnt);
         __syncthreads();   // wtot of the previous tile consumed
         if (lane == 31) wtot[warp] = incl;
@@ -199,25 +207,52 @@ expand_rowids_kernel(const uint64_t *__restrict__ bv, size_t nwords, const uint6
         uint32_t wbase = 0;
 #pragma unroll
         for (int k = 0; k < kScanThreads / 32; ++k) wbase += (k < (int) warp) ? wtot[k] : 0;
-        const uint32_t my_off = wbase + incl - cnt;   // first output slot (tile-relative) of this lane's word
+        const uint32_t my_off = wbase + incl - cnt;   // first output slot (tile-relative) of this thread's words
         const uint64_t gbase = tile_offsets[tile];
-        const uint64_t idb = id_base + (uint64_t) tile * kScanTileVals + (uint64_t) warp * 32 * 64;
-        const uint32_t mlo = (uint32_t) m, mhi = (uint32_t) (m >> 32);
-        unsigned nz = __ballot_sync(0xffffffffu, m != 0);
-        while (nz) {
-            const int src = __ffs(nz) - 1;
-            nz &= nz - 1;
-            const uint32_t lo = __shfl_sync(0xffffffffu, mlo, src);
-            const uint32_t hi = __shfl_sync(0xffffffffu, mhi, src);
-            const uint64_t o = gbase + __shfl_sync(0xffffffffu, my_off, src);
-            const uint64_t id0 = idb + (uint64_t) src * 64 + lane;
-            if ((lo >> lane) & 1u) {
-                uint64_t g = o + __popc(lo & lt);
-                if (g < out_capacity) st_u64_hint(out + g, id0, pol);
+        const uint64_t idb = id_base + (uint64_t) tile * kExpandTileVals + (uint64_t) warp * 32 * kExpandWordsPerThread * 64;
+        // sparse words (< kDenseWord matches): the owning thread writes its few ids itself
+        uint32_t off[kExpandWordsPerThread];
+        {
+            uint32_t run = my_off;
+#pragma unroll
+            for (int k = 0; k < kExpandWordsPerThread; ++k) {
+                off[k] = run;
+                run += __popcll(m[k]);
             }
-            if ((hi >> lane) & 1u) {
-                uint64_t g = o + __popc(lo) + __popc(hi & lt);
-                if (g < out_capacity) st_u64_hint(out + g, id0 + 32, pol);
+        }
+        const uint64_t idt = idb + (uint64_t) lane * kExpandWordsPerThread * 64;
+#pragma unroll
+        for (int k = 0; k < kExpandWordsPerThread; ++k) {
+            uint64_t mm = m[k];
+            if (mm != 0 && __popcll(mm) < kDenseWord) {
+                uint64_t g = gbase + off[k];
+                while (mm) {
+                    uint32_t b = __ffsll((long long) mm) - 1;
+                    mm &= mm - 1;
+                    if (g < out_capacity) st_u64_hint(out + g, idt + (uint64_t) k * 64 + b, pol);
+                    ++g;
+                }
+            }
+        }
+        // dense words: the whole warp expands one word at a time (3 shuffles per word)
+#pragma unroll
+        for (int k = 0; k < kExpandWordsPerThread; ++k) {
+            unsigned dm = __ballot_sync(0xffffffffu, __popcll(m[k]) >= kDenseWord);
+            while (dm) {
+                const int src = __ffs(dm) - 1;
+                dm &= dm - 1;
+                const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t) m[k], src);
+                const uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t) (m[k] >> 32), src);
+                const uint64_t o = gbase + __shfl_sync(0xffffffffu, off[k], src);
+                const uint64_t id0 = idb + (uint64_t) (src * kExpandWordsPerThread + k) * 64 + lane;
+                if ((lo >> lane) & 1u) {
+                    uint64_t g = o + __popc(lo & lt);
+                    if (g < out_capacity) st_u64_hint(out + g, id0, pol);
+                }
+                if ((hi >> lane) & 1u) {
+                    uint64_t g = o + __popc(lo) + __popc(hi & lt);
+                    if (g < out_capacity) st_u64_hint(out + g, id0 + 32, pol);
+                }
             }
         }
     }
@@ -295,7 +330,7 @@ int scan_count_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, u
 static size_t align256(size_t x) { return (x + 255) & ~(size_t) 255; }
 size_t index_scan_scratch_bytes(size_t n) {
     size_t chunk = n < kIndexChunkVals ? n : kIndexChunkVals;
-    size_t tiles = (chunk + kScanTileVals - 1) / kScanTileVals + 1;
+    size_t tiles = (chunk + kExpandTileVals - 1) / kExpandTileVals + 1;
     return align256(chunk / 8 + 64) + align256(tiles * 4) + align256(tiles * 8) + 256;
 }
 
@@ -309,7 +344,7 @@ int index_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, u
     n = n / 64 * 64;
     if (n == 0) return 0;
     const size_t chunk_cap = n < kIndexChunkVals ? n : kIndexChunkVals;
-    const size_t tiles_cap = (chunk_cap + kScanTileVals - 1) / kScanTileVals + 1;
+    const size_t tiles_cap = (chunk_cap + kExpandTileVals - 1) / kExpandTileVals + 1;
     unsigned char *sb = static_cast<unsigned char *>(d_scratch);
     uint64_t *bv = reinterpret_cast<uint64_t *>(sb);
     uint32_t *counts = reinterpret_cast<uint32_t *>(sb + align256(chunk_cap / 8 + 64));
@@ -319,7 +354,8 @@ int index_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, u
     for (size_t begin = 0; begin < n; begin += kIndexChunkVals) {
         const size_t len = n - begin < kIndexChunkVals ? n - begin : kIndexChunkVals;
         const size_t nvec = len / 16, nwords = len / 64;
-        const uint32_t ntiles = (uint32_t) ((nvec + kScanTileVec - 1) / kScanTileVec);
+        const uint32_t ntiles = (uint32_t) ((nwords + kExpandTileWords - 1) / kExpandTileWords);
+        AQP_CUDA_OK(cudaMemsetAsync(counts, 0, (size_t) ntiles * 4, st));
         bitvector_scan_kernel<true><<<scan_grid(nvec, 8), kScanThreads, 0, st>>>(
             reinterpret_cast<const uint4 *>(d_data + begin), nvec, bv, p, counts);
         AQP_LAUNCHED();

@@ -1,0 +1,85 @@
+"""GPU parity of the sharded-join stage kernels (b200_shard_pass1_device / b200_shard_join_device).
+The G ranks are emulated one after another on ONE GPU — the exchange is done with tensor slicing instead
+of NCCL — so this runs in the single-GPU tier; tests/test_gpu_dist.py covers the real NCCL path."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _emulate(gpu, oracle, R, S, G, plan=None):
+    import torch
+    import b200aqp.dist as D
+    dev = torch.device("cuda:0")
+    be = D.CudaBackend()
+    nR, nS = len(R), len(S)
+    bits, b1, b2 = D.plan_bits(nR, G, (lambda n: plan) if plan else be.join_plan)
+    lg = D.log2_exact(G)
+    F1, P = 1 << b1, 1 << bits
+    send, offs, hists = [], [], []
+    for r in range(G):
+        per_rank = []
+        for rel, n in ((R, nR), (S, nS)):
+            lo, hi = r * n // G, (r + 1) * n // G
+            t = torch.from_numpy(rel[lo:hi].copy().view(np.int32)).to(dev)
+            out = torch.empty(2 * (hi - lo) + 4, dtype=torch.int32, device=dev)
+            hist = torch.zeros(P, dtype=torch.int32, device=dev)
+            off = torch.zeros(F1 + 1, dtype=torch.int32, device=dev)
+            be.shard_pass1(t, hi - lo, bits, b1, lg, out, hist, off)
+            torch.cuda.synchronize()
+            # pass-1 parity on this shard: partition p holds exactly the tuples with routed digit p
+            o = out[:2 * (hi - lo)].cpu().numpy().view(oracle.ROW)
+            offn = off.cpu().numpy().astype(np.int64)
+            key = rel[lo:hi]["key"]
+            p1 = key & (F1 - 1)
+            routed = ((p1 >> lg) | (p1 << (b1 - lg))) & (F1 - 1) if lg else p1
+            assert np.array_equal(np.diff(offn), np.bincount(routed, minlength=F1))
+            got_p1 = o["key"] & (F1 - 1)
+            got_routed = ((got_p1 >> lg) | (got_p1 << (b1 - lg))) & (F1 - 1) if lg else got_p1
+            assert np.array_equal(got_routed, np.repeat(np.arange(F1), np.diff(offn)))
+            assert np.array_equal(np.sort(o, order=["key", "payload"]), np.sort(rel[lo:hi], order=["key", "payload"]))
+            per_rank.append((out, off, hist, hi - lo))
+        send.append(per_rank)
+    tot = {"matches": 0, "checksum": 0, "keysum": 0}
+    for r in range(G):
+        args = []
+        for k in (0, 1):
+            counts_all = torch.stack([(send[s][k][1][1:] - send[s][k][1][:-1]).to(torch.int64) for s in range(G)])
+            hist_global = sum(send[s][k][2].to(torch.int64) for s in range(G)).to(torch.int32)
+            _, recv, seg_off, seg_group = D.exchange_plan(counts_all, r, G)
+            per = F1 // G
+            parts = []
+            for s in range(G):   # what the all-to-all would deliver from source s
+                o = send[s][k][1].to(torch.int64)
+                a, b = int(o[r * per]), int(o[(r + 1) * per])
+                parts.append(send[s][k][0][2 * a:2 * b])
+            buf = torch.cat(parts + [torch.zeros(4, dtype=torch.int32, device=dev)])
+            assert int(recv.sum()) == (buf.numel() - 4) // 2
+            args.append((buf, int(recv.sum()), seg_off.to(torch.int32), D.final_hist_slice(hist_global, r, G, b1, b2)))
+        st = be.shard_join(args[0][0], args[0][1], args[0][2], args[1][0], args[1][1], args[1][2], seg_group, G * per,
+                           per, b1, b2, args[0][3], args[1][3], bits)
+        for k in tot:
+            tot[k] += st[k]
+    exp = oracle.rho(R, S)
+    assert (tot["matches"], tot["checksum"] % (1 << 64), tot["keysum"] % (1 << 64)) == \
+        (exp["matches"], exp["checksum"], exp["keysum"])
+
+
+@pytest.mark.parametrize("G", [1, 2, 4, 8])
+def test_sharded_stages_uniform(gpu, oracle, G):
+    R = oracle.set_rowid_payload(oracle.gen_pk(1 << 18, 11111))
+    S = oracle.set_rowid_payload(oracle.gen_fk(1 << 20, 1 << 18, 22222))
+    _emulate(gpu, oracle, R, S, G)
+
+
+@pytest.mark.parametrize("G,plan", [(2, (6, 3, 3)), (4, (9, 4, 5)), (8, (3, 3, 0)), (2, (0, 0, 0)), (4, (14, 7, 7))])
+def test_sharded_stages_plans_and_ragged_sizes(gpu, oracle, G, plan):
+    R = oracle.set_rowid_payload(oracle.gen_pk(100003, 11111))
+    S = oracle.set_rowid_payload(oracle.gen_fk(400009, 100003, 22222))
+    _emulate(gpu, oracle, R, S, G, plan)
+
+
+def test_sharded_stages_skew_and_misses(gpu, oracle):
+    R = oracle.set_rowid_payload(oracle.gen_pk(1 << 16, 11111))
+    S = oracle.set_rowid_payload(oracle.gen_zipf(1 << 19, 1 << 17, 1.0, seed=3))   # half of the key domain misses R
+    _emulate(gpu, oracle, R, S, 4)
