@@ -36,6 +36,11 @@ struct DigitFn {
         uint32_t p = d & m1;
         return (d & ~m1) | (((p >> rot) | (p << lrot)) & m1);
     }
+    // kRot = false: the plain single-GPU digit, two instructions on the hot loops
+    template <bool kRot>
+    __device__ __forceinline__ uint32_t get(uint32_t key) const {
+        return kRot ? (*this)(key) : ((key >> shift) & mask);
+    }
 #endif
 };
 inline DigitFn make_digit(uint32_t shift, uint32_t bits, uint32_t rbits = 0, uint32_t rot = 0) {

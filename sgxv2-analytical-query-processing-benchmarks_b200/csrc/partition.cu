@@ -36,6 +36,7 @@ constexpr int kHistUnroll = 8;   // 8-byte loads in flight per thread
 // pass-1 histogram row block_hist[b][p1] (p1 = low bits1 of the digit). Those rows give every
 // scatter block private, pre-reserved output ranges (parallel_radix_partition's per-thread
 // histogram + prefix scheme, radix_join.cpp:881-915, with CTAs in the role of threads).
+template <bool kRot>
 __global__ void __launch_bounds__(kHistThreads)
 radix_hist_smem_kernel(const uint2 *__restrict__ in, uint64_t n, DigitFn digit, uint32_t bits,
                        uint32_t *__restrict__ ghist, uint64_t chunk, uint32_t bits1,
@@ -57,7 +58,7 @@ radix_hist_smem_kernel(const uint2 *__restrict__ in, uint64_t n, DigitFn digit, 
 #pragma unroll
         for (int j = 0; j < kHistUnroll; ++j) {
             uint64_t i = base + (uint64_t) j * kHistThreads + threadIdx.x;
-            if (i < cend) atomicAdd(&sh[digit(v[j].x)], 1u);
+            if (i < cend) atomicAdd(&sh[digit.template get<kRot>(v[j].x)], 1u);
         }
     }
     __syncthreads();
@@ -101,7 +102,9 @@ int radix_hist_device(const row_t *d_in, uint64_t n, DigitFn digit, uint32_t bit
         size_t smem = sizeof(uint32_t) << bits;
         static bool attr_set = false;
         if (!attr_set) {
-            AQP_CUDA_OK(cudaFuncSetAttribute(radix_hist_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            AQP_CUDA_OK(cudaFuncSetAttribute(radix_hist_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int) (sizeof(uint32_t) << kMaxSmemHistBits)));
+            AQP_CUDA_OK(cudaFuncSetAttribute(radix_hist_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int) (sizeof(uint32_t) << kMaxSmemHistBits)));
             attr_set = true;
         }
@@ -113,8 +116,12 @@ int radix_hist_device(const row_t *d_in, uint64_t n, DigitFn digit, uint32_t bit
             grid = (uint32_t) (tiles < (uint64_t) kNumSMs * per_sm ? tiles : (uint64_t) kNumSMs * per_sm);
             chunk = (tiles + grid - 1) / grid * tile;
         }
-        radix_hist_smem_kernel<<<grid, kHistThreads, smem, st>>>(in, n, digit, bits, d_hist, chunk, bits1,
-                                                                nblocks ? d_block_hist : nullptr);
+        if (digit.rot)
+            radix_hist_smem_kernel<true><<<grid, kHistThreads, smem, st>>>(in, n, digit, bits, d_hist, chunk, bits1,
+                                                                          nblocks ? d_block_hist : nullptr);
+        else
+            radix_hist_smem_kernel<false><<<grid, kHistThreads, smem, st>>>(in, n, digit, bits, d_hist, chunk, bits1,
+                                                                           nblocks ? d_block_hist : nullptr);
     } else {
         radix_hist_global_kernel<<<kNumSMs * 4, kHistThreads, 0, st>>>(in, n, digit, d_hist);
     }
@@ -328,6 +335,7 @@ constexpr int kScatterBlocksPerSM = kScatterBlocksPerSMRaw < 1 ? 1 : (kScatterBl
 
 uint32_t pass1_blocks() { return (uint32_t) kNumSMs * kScatterBlocksPerSM; }
 
+template <bool kRot>
 __global__ void __launch_bounds__(kScatterThreads, kScatterBlocksPerSM)
 radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
                      const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_tile_start,
@@ -420,7 +428,7 @@ radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
 #pragma unroll
         for (int j = 0; j < kScatterItems; ++j) {
             uint32_t k = j * kScatterThreads + threadIdx.x;
-            if (k < ntile) rank[j] = atomicAdd(&cnt[digit(v[j].x)], 1u);
+            if (k < ntile) rank[j] = atomicAdd(&cnt[digit.template get<kRot>(v[j].x)], 1u);
         }
         __syncthreads();   // (1) tile histogram complete; ring slot consumed; previous write-out finished
 
@@ -461,7 +469,7 @@ radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
 #pragma unroll
         for (int j = 0; j < kScatterItems; ++j) {
             uint32_t k = j * kScatterThreads + threadIdx.x;
-            if (k < ntile) stage[lbase[digit(v[j].x)] + rank[j]] = v[j];
+            if (k < ntile) stage[lbase[digit.template get<kRot>(v[j].x)] + rank[j]] = v[j];
         }
         if (threadIdx.x < 32) {
             const uint32_t per = (fan + 31) / 32;
@@ -475,7 +483,7 @@ radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
 
         for (uint32_t s = threadIdx.x; s < ntile; s += kScatterThreads) {
             uint2 t = stage[s];
-            out[gdst[digit(t.x)] + s] = t;
+            out[gdst[digit.template get<kRot>(t.x)] + s] = t;
         }
     }
 }
@@ -495,7 +503,9 @@ int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_
     if (n_total == 0) return 0;
     static bool attr_set = false;
     if (!attr_set) {
-        AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int) kScatterSmemBytes));
+        AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int) kScatterSmemBytes));
         attr_set = true;
     }
@@ -507,9 +517,14 @@ int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_
         uint64_t g = (uint64_t) kNumSMs * kScatterBlocksPerSM;
         grid = (uint32_t) (max_tiles < g ? max_tiles : g);
     }
-    radix_scatter_kernel<<<grid, kScatterThreads, kScatterSmemBytes, st>>>(
-        reinterpret_cast<const uint2 *>(d_in), reinterpret_cast<uint2 *>(d_out), d_seg_off, d_seg_tile_start,
-        d_seg_group, nseg, digit, bits, d_cursors, d_block_base, tiles_per_block);
+    if (digit.rot)
+        radix_scatter_kernel<true><<<grid, kScatterThreads, kScatterSmemBytes, st>>>(
+            reinterpret_cast<const uint2 *>(d_in), reinterpret_cast<uint2 *>(d_out), d_seg_off, d_seg_tile_start,
+            d_seg_group, nseg, digit, bits, d_cursors, d_block_base, tiles_per_block);
+    else
+        radix_scatter_kernel<false><<<grid, kScatterThreads, kScatterSmemBytes, st>>>(
+            reinterpret_cast<const uint2 *>(d_in), reinterpret_cast<uint2 *>(d_out), d_seg_off, d_seg_tile_start,
+            d_seg_group, nseg, digit, bits, d_cursors, d_block_base, tiles_per_block);
     AQP_LAUNCHED();
     AQP_CUDA_OK(cudaGetLastError());
     return 0;

@@ -78,9 +78,6 @@ __device__ __forceinline__ uint4 ld_stream_v4_hint(const uint4 *p, uint64_t pol)
                  : "l"(p), "l"(pol));
     return r;
 }
-__device__ __forceinline__ void st_u64_hint(uint64_t *p, uint64_t v, uint64_t pol) {
-    asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
-}
 
 template <bool kCount>
 __global__ void __launch_bounds__(kScanThreads)
@@ -182,7 +179,6 @@ __global__ void __launch_bounds__(kScanThreads)
 expand_rowids_kernel(const uint64_t *__restrict__ bv, size_t nwords, const uint64_t *__restrict__ tile_offsets,
                      uint64_t id_base, uint64_t *__restrict__ out, uint64_t out_capacity) {
     __shared__ uint32_t wtot[kScanThreads / 32];
-    const uint64_t pol = l2_evict_first_policy();
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     const unsigned lt = lanemask_lt();
     const size_t ntiles = (nwords + kExpandTileWords - 1) / kExpandTileWords;
@@ -229,29 +225,36 @@ expand_rowids_kernel(const uint64_t *__restrict__ bv, size_t nwords, const uint6
                 while (mm) {
                     uint32_t b = __ffsll((long long) mm) - 1;
                     mm &= mm - 1;
-                    if (g < out_capacity) st_u64_hint(out + g, idt + (uint64_t) k * 64 + b, pol);
+                    if (g < out_capacity) out[g] = idt + (uint64_t) k * 64 + b;
                     ++g;
                 }
             }
         }
-        // dense words: the whole warp expands one word at a time (3 shuffles per word)
+        // dense words: the whole warp expands one word at a time (3 shuffles per word), walking the
+        // source lanes in order so the warp's output is written front to back
+        unsigned dmk[kExpandWordsPerThread], any_dense = 0;
 #pragma unroll
         for (int k = 0; k < kExpandWordsPerThread; ++k) {
-            unsigned dm = __ballot_sync(0xffffffffu, __popcll(m[k]) >= kDenseWord);
-            while (dm) {
-                const int src = __ffs(dm) - 1;
-                dm &= dm - 1;
+            dmk[k] = __ballot_sync(0xffffffffu, __popcll(m[k]) >= kDenseWord);
+            any_dense |= dmk[k];
+        }
+        while (any_dense) {
+            const int src = __ffs(any_dense) - 1;
+            any_dense &= any_dense - 1;
+#pragma unroll
+            for (int k = 0; k < kExpandWordsPerThread; ++k) {
+                if (!((dmk[k] >> src) & 1u)) continue;   // warp-uniform
                 const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t) m[k], src);
                 const uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t) (m[k] >> 32), src);
                 const uint64_t o = gbase + __shfl_sync(0xffffffffu, off[k], src);
                 const uint64_t id0 = idb + (uint64_t) (src * kExpandWordsPerThread + k) * 64 + lane;
                 if ((lo >> lane) & 1u) {
                     uint64_t g = o + __popc(lo & lt);
-                    if (g < out_capacity) st_u64_hint(out + g, id0, pol);
+                    if (g < out_capacity) out[g] = id0;
                 }
                 if ((hi >> lane) & 1u) {
                     uint64_t g = o + __popc(lo) + __popc(hi & lt);
-                    if (g < out_capacity) st_u64_hint(out + g, id0 + 32, pol);
+                    if (g < out_capacity) out[g] = id0 + 32;
                 }
             }
         }
