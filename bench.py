@@ -276,7 +276,10 @@ def run_b200_arm(args):
         def step():
             return A.join_device(R.data_ptr(), nR, S.data_ptr(), nS, stream=st)
     else:
-        plan = D.ShardedJoin(nR, nS, dev)
+        # headline: scatter kernel fused with the exchange over NVLink peer memory; the NCCL all-to-all
+        # variant is timed beside it as the baseline (B200_AQP_EXCHANGE=nccl makes it the headline)
+        fused = os.environ.get("B200_AQP_EXCHANGE", "p2p") != "nccl"
+        plan = (D.FusedShardedJoin if fused else D.ShardedJoin)(nR, nS, dev)
 
         def step():
             return plan.run(R, S)
@@ -322,6 +325,34 @@ def run_b200_arm(args):
     join_roof = {"bound": "hbm", "bytes_per_tuple": JOIN_BYTES_PER_TUPLE, "achieved": join_bytes / ms_step / 1e6,
                  "peak": peak, "unit": "GB/s", "frac": join_bytes / ms_step / 1e6 / peak,
                  "actual_bytes_per_tuple": 48, "note": "the pass-2 histogram read is avoided: one full-width histogram serves both passes"}
+
+    # ---- multi-GPU: NVLink traffic of the shuffle, and the NCCL all-to-all variant as the baseline -------
+    exchange = None
+    if world > 1:
+        sent = 8 * ((nR_loc + nS_loc) - s.get("tuples_kept", 0))
+        ms_x = phase["ms_pass1"] if s.get("exchange") == "p2p-fused" else phase["ms_exchange"]
+        exchange = {"kind": s.get("exchange", "nccl all_to_all_single"), "bytes_sent_per_gpu": sent,
+                    "ms": ms_x, "busbw_gbs": sent / ms_x / 1e6 if ms_x else None,
+                    "note": "p2p-fused: ms covers the sizing collectives, the fused scatter+exchange kernel and the "
+                            "barrier; reference peaks: 770 GB/s measured peer copy, 900 GB/s nominal per direction"}
+        if s.get("exchange") == "p2p-fused":
+            base = D.ShardedJoin(nR, nS, dev)
+            for _ in range(2):
+                sb = base.run(R, S)
+            assert sb["matches"] == nS
+            barrier()
+            e0.record()
+            xb = 0.0
+            for _ in range(args.steps):
+                sb = base.run(R, S)
+                xb += sb["ms_exchange"]
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            exchange["nccl_baseline"] = {"ms_per_step": float(t.item()), "value": (nR + nS) / float(t.item()) / 1e3,
+                                         "unit": UNIT, "ms_exchange": xb / args.steps}
+            del base
 
     # ---- e2e through run_join() with pinned host relations (N=1 path of the drop-in API) ----------
     e2e = None
@@ -382,6 +413,7 @@ def run_b200_arm(args):
                            "cache": "inputs (5 GiB) exceed the 126 MB L2; no flush between steps",
                            "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: pass-1 routes by low key bits, NCCL all-to-all"},
                 "phases_ms": phase, "roofline": roof, "join_roofline": join_roof, "cpu_baseline": cpu, "e2e": e2e,
+                "exchange": exchange,
                 "gpu_launches": launches_timed, "gpu_launches_total": A.kernel_launch_count() - launches0,
                 "clocks": clocks, "scan": scan}
         print(json.dumps(line))

@@ -147,6 +147,28 @@ int b200_radix_scatter_device(const struct row_t *d_in, uint64_t n, uint32_t shi
 int b200_shard_pass1_device(const struct row_t *d_in, uint64_t n, uint32_t total_bits, uint32_t bits1,
                             uint32_t log2_gpus, struct row_t *d_send, uint32_t *d_hist, uint32_t *d_part1_off,
                             void *stream);
+/* Fused scatter + exchange (the B200 form of the shuffle): instead of writing a send buffer and handing
+ * it to NCCL, the pass-1 scatter kernel stores every run directly into the receive buffer of the GPU
+ * that owns the partition — peer memory mapped over NVLink 5 / NVSwitch — so the transfer overlaps the
+ * partitioning tile by tile and the send buffer's HBM write + read disappear.
+ *   b200_shard_hist_device    histogram of d_in[0..n) (as in b200_shard_pass1_device) + d_counts1[2^bits1],
+ *                             this rank's size of every routed pass-1 partition. slot (0 = R, 1 = S) names
+ *                             the workspace that carries per-CTA histogram rows to the scatter call.
+ *   (host: all-gather the counts, derive d_dest_off[p] = where this rank's segment of partition p starts
+ *    inside its owner's receive buffer)
+ *   b200_shard_scatter_device scatters d_in into dest_bufs[owner(p)] + d_dest_off[p]; dest_bufs is a HOST
+ *                             array of 2^log2_gpus device pointers (this GPU's own buffer and peers' buffers
+ *                             opened with b200_ipc_open). The caller separates it from the readers of the
+ *                             destination buffers with a cross-GPU barrier on the same stream.
+ *   b200_ipc_*                export / open / close a buffer from b200_device_alloc across processes
+ *                             (cudaIpc*; handle = 64 bytes). */
+int b200_shard_hist_device(const struct row_t *d_in, uint64_t n, uint32_t total_bits, uint32_t bits1,
+                           uint32_t log2_gpus, uint32_t *d_hist, uint32_t *d_counts1, int slot, void *stream);
+int b200_shard_scatter_device(const struct row_t *d_in, uint64_t n, const uint32_t *d_dest_off, void *const *dest_bufs,
+                              int slot, void *stream);
+int b200_ipc_export(void *d_ptr, unsigned char *handle_out /* 64 bytes */);
+int b200_ipc_open(const unsigned char *handle /* 64 bytes */, void **d_ptr_out);
+int b200_ipc_close(void *d_ptr);
 int b200_shard_join_device(const struct row_t *d_R, uint64_t nR, const uint32_t *d_segoff_R, const struct row_t *d_S,
                            uint64_t nS, const uint32_t *d_segoff_S, const uint32_t *d_seg_group, uint32_t nseg,
                            uint32_t ngroups, uint32_t shift2, uint32_t bits2, const uint32_t *d_hist_R,

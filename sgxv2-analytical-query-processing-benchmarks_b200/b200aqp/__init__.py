@@ -86,6 +86,11 @@ SYMBOLS = {
     "b200_shard_pass1_device": (_int, [_vp, _u64, _u32, _u32, _u32, _vp, _vp, _vp, _vp]),
     "b200_shard_join_device": (_int, [_vp, _u64, _vp, _vp, _u64, _vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _u32,
                                       C.POINTER(JoinStats), _vp]),
+    "b200_shard_hist_device": (_int, [_vp, _u64, _u32, _u32, _u32, _vp, _vp, _int, _vp]),
+    "b200_shard_scatter_device": (_int, [_vp, _u64, _vp, C.POINTER(_vp), _int, _vp]),
+    "b200_ipc_export": (_int, [_vp, _vp]),
+    "b200_ipc_open": (_int, [_vp, C.POINTER(_vp)]),
+    "b200_ipc_close": (_int, [_vp]),
     "seed_generator": (None, [C.c_uint]),
     "create_relation_pk": (_int, [C.POINTER(Table), _u64, _int]),
     "create_relation_fk": (_int, [C.POINTER(Table), _u64, C.c_int64, _int]),

@@ -62,6 +62,20 @@ def exchange_plan(counts_all: torch.Tensor, rank: int, world: int):
     return mine, recv, seg_off, seg_group
 
 
+def dest_offsets(counts_all: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    """Fused exchange: dest_off[p] = tuple index inside the receive buffer of partition p's owner at which
+    THIS rank's segment of p starts. Every owner lays its buffer out by (source rank, local partition),
+    the same order exchange_plan() reports as seg_off on the receiving side."""
+    F1 = counts_all.shape[1]
+    per = F1 // world
+    c = counts_all.view(world, world, per)                       # [source, owner, local partition]
+    per_src_owner = c.sum(2)                                     # tuples source s sends to owner g
+    before = torch.cumsum(per_src_owner, 0) - per_src_owner      # sent to g by lower-ranked sources
+    mine = c[rank]                                               # [owner, per]
+    within = torch.cumsum(mine, 1) - mine
+    return (before[rank].unsqueeze(1) + within).reshape(-1)
+
+
 def final_hist_slice(hist_global: torch.Tensor, rank: int, world: int, b1: int, b2: int) -> torch.Tensor:
     """hist_global is indexed by the routed full-width digit p1' | (p2 << b1). Returns this rank's slice
     in final partition order (local pass-1 partition major, then p2): [per << b2]."""
@@ -96,6 +110,32 @@ class CudaBackend:
 
     def join_plan(self, nR):
         return self.A.join_plan(nR)
+
+    # ---- fused scatter + exchange over peer memory ---------------------------------------------------
+    def shard_hist(self, rel, n, bits, b1, lg, hist, counts1, slot):
+        self.A._check(self.L.b200_shard_hist_device(rel.data_ptr(), n, bits, b1, lg, hist.data_ptr(), counts1.data_ptr(),
+                                                    slot, self.stream()), "b200_shard_hist_device")
+
+    def shard_scatter(self, rel, n, dest_off, dest_ptrs, slot):
+        import ctypes as C
+        arr = (C.c_void_p * len(dest_ptrs))(*dest_ptrs)
+        self.A._check(self.L.b200_shard_scatter_device(rel.data_ptr(), n, dest_off.data_ptr(), arr, slot, self.stream()),
+                      "b200_shard_scatter_device")
+
+    def alloc_shared(self, nbytes):
+        """(buffer, 64-byte IPC handle as a uint8 tensor)"""
+        import ctypes as C
+        buf = self.A.DeviceBuffer(nbytes)
+        h = (C.c_ubyte * 64)()
+        self.A._check(self.L.b200_ipc_export(buf.ptr, h), "b200_ipc_export")
+        return buf, torch.tensor(list(h), dtype=torch.uint8)
+
+    def open_shared(self, handle: torch.Tensor) -> int:
+        import ctypes as C
+        h = (C.c_ubyte * 64)(*handle.tolist())
+        p = C.c_void_p()
+        self.A._check(self.L.b200_ipc_open(h, C.byref(p)), "b200_ipc_open")
+        return p.value
 
 
 class ShardedJoin:
@@ -184,5 +224,103 @@ class ShardedJoin:
             out["ms_pass1"] = e0.elapsed_time(e1)     # histogram + pass-1 scatter
             out["ms_hist"] = 0.0
             out["ms_exchange"] = e1.elapsed_time(e2)   # count/histogram collectives + all-to-all
+            out["ms_total"] = e0.elapsed_time(e3)
+        return out
+
+
+class _RawBuffer:
+    """Pointer + size with the .data_ptr() face the backends expect (memory owned by the C library)."""
+
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def data_ptr(self):
+        return self.ptr
+
+
+class FusedShardedJoin(ShardedJoin):
+    """Same join, but the shuffle is fused into the pass-1 scatter kernel: every rank maps its peers'
+    receive buffers (CUDA IPC over NVLink 5 / NVSwitch peer memory) and the kernel stores each tile's runs
+    straight into the owner's buffer. No send buffer, no NCCL all-to-all; NCCL only carries the two small
+    sizing collectives, one barrier and the final 24-byte all-reduce.
+
+    capacity_factor sizes the receive buffers relative to a perfectly even split; if a run would
+    overflow them (heavy skew) that run falls back to the NCCL path of the base class."""
+
+    def __init__(self, nR_total, nS_total, device, backend=None, group=None, capacity_factor: float = 1.5):
+        super().__init__(nR_total, nS_total, device, backend, group)
+        be, G = self.backend, self.world
+        self.capR = int(nR_total / G * capacity_factor) + 4096
+        self.capS = int(nS_total / G * capacity_factor) + 4096
+        self.peerR, self.peerS = [], []
+        self._own = []
+        for cap, peers in ((self.capR, self.peerR), (self.capS, self.peerS)):
+            buf, handle = be.alloc_shared(cap * 8 + 64)
+            self._own.append(buf)
+            hs = torch.empty(G * 64, dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(hs, handle.to(device), group=self.group)
+            hs = hs.cpu().view(G, 64)
+            for g in range(G):
+                peers.append(buf.ptr if g == self.rank else be.open_shared(hs[g]))
+        self.fallbacks = 0
+
+    def run(self, R: torch.Tensor, S: torch.Tensor) -> dict:
+        be, G, rank = self.backend, self.world, self.rank
+        nR, nS = R.numel() // 2, S.numel() // 2
+        F1, P = self.F1, self.P
+        e0 = self._event()
+        # ---- 1. local histograms (per-CTA rows stay inside the library for the scatter) --------------
+        hist = self._buf("hist", 2 * P, torch.int32)
+        cnt1 = self._buf("cnt1", 2 * F1, torch.int32)
+        be.shard_hist(R, nR, self.bits, self.b1, self.lg, hist[:P], cnt1[:F1], 0)
+        be.shard_hist(S, nS, self.bits, self.b1, self.lg, hist[P:2 * P], cnt1[F1:2 * F1], 1)
+        eh = self._event()
+        # ---- 2. size the exchange -------------------------------------------------------------------------
+        counts_flat = torch.empty(G * 2 * F1, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(counts_flat, cnt1[:2 * F1].to(torch.int64), group=self.group)
+        counts_all = counts_flat.view(G, 2 * F1)
+        hist_global = hist[:2 * P].clone()
+        dist.all_reduce(hist_global, group=self.group)
+        _, rR, segR, seg_group = exchange_plan(counts_all[:, :F1], rank, G)
+        _, rS, segS, _ = exchange_plan(counts_all[:, F1:], rank, G)
+        dR = dest_offsets(counts_all[:, :F1], rank, G).to(torch.int32)
+        dS = dest_offsets(counts_all[:, F1:], rank, G).to(torch.int32)
+        # every rank must take the same path: compare the largest receive sizes anywhere with the capacities
+        per = F1 // G
+        worst = torch.stack([counts_all[:, :F1].view(G, G, per).sum((0, 2)).max(),
+                             counts_all[:, F1:].view(G, G, per).sum((0, 2)).max(), rR.sum(), rS.sum()]).tolist()
+        if worst[0] > self.capR or worst[1] > self.capS:
+            self.fallbacks += 1
+            out = super().run(R, S)
+            out["exchange"] = "nccl-fallback"
+            return out
+        nR_recv, nS_recv = int(worst[2]), int(worst[3])
+        # ---- 3. fused scatter + exchange: stores go to the owners' buffers over NVLink ------------------
+        be.shard_scatter(R, nR, dR, self.peerR, 0)
+        be.shard_scatter(S, nS, dS, self.peerS, 1)
+        flag = self._buf("flag", 2, torch.int32)
+        dist.all_reduce(flag[:1], group=self.group)    # barrier: every rank's stores have landed
+        e2 = self._event()
+        # ---- 4. local pass 2 + build/probe -------------------------------------------------------------------
+        hR = final_hist_slice(hist_global[:P], rank, G, self.b1, self.b2)
+        hS = final_hist_slice(hist_global[P:], rank, G, self.b1, self.b2)
+        local = be.shard_join(_RawBuffer(self.peerR[rank]), nR_recv, segR.to(torch.int32), _RawBuffer(self.peerS[rank]),
+                              nS_recv, segS.to(torch.int32), seg_group, G * per, per, self.b1, self.b2, hR, hS, self.bits)
+        e3 = self._event()
+        to_i64 = lambda v: v - (1 << 64) if v >= (1 << 63) else v
+        res = torch.tensor([local["matches"], to_i64(local["checksum"]), to_i64(local["keysum"])], dtype=torch.int64,
+                           device=self.device)
+        dist.all_reduce(res, group=self.group)
+        m, cs, ks = (int(x) for x in res.tolist())
+        kept = int(counts_all[rank, rank * per:(rank + 1) * per].sum() + counts_all[rank, F1 + rank * per:F1 + (rank + 1) * per].sum())
+        out = {"matches": m, "checksum": cs % (1 << 64), "keysum": ks % (1 << 64), "radix_bits": self.bits,
+               "num_passes": 2, "bits_pass1": self.b1, "bits_pass2": self.b2, "tuples_sent": nR + nS,
+               "tuples_kept": kept, "ms_pass2": local.get("ms_pass2", 0.0), "ms_join": local.get("ms_join", 0.0),
+               "exchange": "p2p-fused"}
+        if e0 is not None:
+            torch.cuda.synchronize()
+            out["ms_hist"] = e0.elapsed_time(eh)
+            out["ms_pass1"] = eh.elapsed_time(e2)      # sizing collectives + fused scatter/exchange + barrier
+            out["ms_exchange"] = 0.0                   # no separate exchange step
             out["ms_total"] = e0.elapsed_time(e3)
         return out

@@ -699,6 +699,84 @@ int b200_shard_pass1_device(const struct row_t *d_in, uint64_t n, uint32_t total
                                 bits1, nullptr, bb, NB, tpb, st);
 }
 
+// per-relation workspace of the fused path: per-CTA histogram rows survive from the histogram call to
+// the scatter call (slot 0 = R, 1 = S)
+struct ShardSlot {
+    DevBuf ws;
+    uint32_t tpb = 0, bits1 = 0, lg = 0;
+    uint64_t n = 0;
+};
+static ShardSlot g_shard[2];
+
+int b200_shard_hist_device(const struct row_t *d_in, uint64_t n, uint32_t total_bits, uint32_t bits1,
+                           uint32_t log2_gpus, uint32_t *d_hist, uint32_t *d_counts1, int slot, void *stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : g.stream;
+    if (slot < 0 || slot > 1 || total_bits < bits1 || bits1 > (uint32_t) kMaxFanoutBits ||
+        total_bits > (uint32_t) kMaxSmemHistBits || log2_gpus > bits1 || log2_gpus > 3 || n >= 0xFFFF0000ull) {
+        set_error("b200_shard_hist_device: need slot in {0,1}, log2_gpus <= min(bits1,3), bits1 <= 8, total_bits <= 15");
+        return -1;
+    }
+    ShardSlot &sl = g_shard[slot];
+    const uint32_t NB = pass1_blocks(), F1 = 1u << bits1;
+    if (sl.ws.ensure(2 * (size_t) NB * F1 * 4 + 256)) return -1;
+    uint32_t *bh = static_cast<uint32_t *>(sl.ws.p);
+    sl.tpb = (uint32_t) (((n + kScatterTile - 1) / kScatterTile + NB - 1) / NB);
+    sl.bits1 = bits1;
+    sl.lg = log2_gpus;
+    sl.n = n;
+    AQP_CUDA_OK(cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) << total_bits, st));
+    if (radix_hist_device(d_in, n, make_digit(0, total_bits, bits1, log2_gpus), total_bits, d_hist, NB,
+                          (uint64_t) sl.tpb * kScatterTile, bits1, bh, st))
+        return -1;
+    return block_base_device(bh, nullptr, F1, NB, nullptr, d_counts1, nullptr, 0, st);
+}
+
+int b200_shard_scatter_device(const struct row_t *d_in, uint64_t n, const uint32_t *d_dest_off, void *const *dest_bufs,
+                              int slot, void *stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : g.stream;
+    if (slot < 0 || slot > 1 || g_shard[slot].n != n || !g_shard[slot].ws.p) {
+        set_error("b200_shard_scatter_device: call b200_shard_hist_device on the same relation and slot first");
+        return -1;
+    }
+    ShardSlot &sl = g_shard[slot];
+    const uint32_t NB = pass1_blocks(), F1 = 1u << sl.bits1;
+    uint32_t *bh = static_cast<uint32_t *>(sl.ws.p), *bb = bh + (size_t) NB * F1, *seg1 = bb + (size_t) NB * F1;
+    if (block_base_device(bh, d_dest_off, F1, NB, bb, nullptr, seg1, (uint32_t) n, st)) return -1;
+    PeerTable pt{};
+    pt.n = 1u << sl.lg;
+    pt.per_shift = sl.bits1 - sl.lg;
+    for (uint32_t i = 0; i < pt.n; ++i) pt.base[i] = static_cast<uint2 *>(dest_bufs[i]);
+    return radix_scatter_launch(d_in, nullptr, seg1, seg1 + 2, nullptr, 1, n, make_digit(0, sl.bits1, sl.bits1, sl.lg),
+                                sl.bits1, nullptr, bb, NB, sl.tpb, st, &pt);
+}
+
+int b200_ipc_export(void *d_ptr, unsigned char *handle_out) {
+    if (ensure_init()) return -1;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    cudaIpcMemHandle_t h;
+    AQP_CUDA_OK(cudaIpcGetMemHandle(&h, d_ptr));
+    memcpy(handle_out, &h, sizeof h);
+    return 0;
+}
+
+int b200_ipc_open(const unsigned char *handle, void **d_ptr_out) {
+    if (ensure_init()) return -1;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    AQP_CUDA_OK(cudaIpcOpenMemHandle(d_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int b200_ipc_close(void *d_ptr) {
+    if (ensure_init()) return -1;
+    AQP_CUDA_OK(cudaIpcCloseMemHandle(d_ptr));
+    return 0;
+}
+
 int b200_shard_join_device(const struct row_t *d_R, uint64_t nR, const uint32_t *d_segoff_R, const struct row_t *d_S,
                            uint64_t nS, const uint32_t *d_segoff_S, const uint32_t *d_seg_group, uint32_t nseg,
                            uint32_t ngroups, uint32_t shift2, uint32_t bits2, const uint32_t *d_hist_R,

@@ -53,6 +53,15 @@ inline DigitFn make_digit(uint32_t shift, uint32_t bits, uint32_t rbits = 0, uin
     return f;
 }
 
+// Destination buffers of the fused scatter+exchange: partition d of the routed pass-1 digit is written
+// into base[d >> per_shift], the receive buffer of the GPU that owns it (a peer-mapped pointer, or this
+// GPU's own buffer). n == 0 means "no peer table": write to the kernel's `out` argument.
+struct PeerTable {
+    uint2 *base[8];
+    uint32_t per_shift;
+    uint32_t n;
+};
+
 struct RelPlan {
     const uint32_t *hist;       // [2^B]   raw-digit histogram
     uint32_t *part_off;         // [2^B+1] final partition starts, order f = p1*F2 + p2
@@ -103,7 +112,9 @@ int plan_offsets_device(const PlanArgs &a, cudaStream_t st);
 int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_off, const uint32_t *d_seg_tile_start,
                          const uint32_t *d_seg_group, uint32_t nseg, uint64_t n_total, DigitFn digit, uint32_t bits,
                          uint32_t *d_cursors, const uint32_t *d_block_base, uint32_t nblocks, uint32_t tiles_per_block,
-                         cudaStream_t st);
+                         cudaStream_t st, const PeerTable *peers = nullptr);
+int block_base_device(const uint32_t *d_block_hist, const uint32_t *d_part_start, uint32_t fan, uint32_t nblocks,
+                      uint32_t *d_block_base, uint32_t *d_counts, uint32_t *d_seg1, uint32_t n, cudaStream_t st);
 uint32_t pass1_blocks();
 int plan_pass1_device(const uint32_t *d_hist, uint32_t bits1, uint32_t bits2, uint32_t *d_part1_off, uint32_t *d_seg1,
                       const uint32_t *d_block_hist, uint32_t *d_block_base, uint32_t nblocks, cudaStream_t st);

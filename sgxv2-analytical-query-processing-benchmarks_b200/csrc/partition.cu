@@ -251,6 +251,39 @@ int plan_pass1_device(const uint32_t *d_hist, uint32_t bits1, uint32_t bits2, ui
     return 0;
 }
 
+// fused exchange: CTA-private cursors that point INTO the owners' receive buffers. part_start[p] is
+// where this rank's segment of routed partition p begins in its owner's buffer (computed by the host
+// from the all-gathered counts); counts[p] (optional) receives this rank's size of partition p.
+__global__ void __launch_bounds__(256)
+block_base_kernel(const uint32_t *__restrict__ block_hist, const uint32_t *__restrict__ part_start, uint32_t fan,
+                  uint32_t nblocks, uint32_t *__restrict__ block_base, uint32_t *__restrict__ counts,
+                  uint32_t *__restrict__ seg1, uint32_t n) {
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < fan; p += gridDim.x * blockDim.x) {
+        uint32_t run = part_start ? part_start[p] : 0u, tot = 0;
+        for (uint32_t b = 0; b < nblocks; ++b) {
+            uint32_t c = block_hist[(size_t) b * fan + p];
+            if (block_base) block_base[(size_t) b * fan + p] = run;
+            run += c;
+            tot += c;
+        }
+        if (counts) counts[p] = tot;
+    }
+    if (seg1 && blockIdx.x == 0 && threadIdx.x == 0) {
+        seg1[0] = 0;
+        seg1[1] = n;
+        seg1[2] = 0;
+        seg1[3] = (n + kScatterTile - 1) / kScatterTile;
+    }
+}
+
+int block_base_device(const uint32_t *d_block_hist, const uint32_t *d_part_start, uint32_t fan, uint32_t nblocks,
+                      uint32_t *d_block_base, uint32_t *d_counts, uint32_t *d_seg1, uint32_t n, cudaStream_t st) {
+    block_base_kernel<<<1, 256, 0, st>>>(d_block_hist, d_part_start, fan, nblocks, d_block_base, d_counts, d_seg1, n);
+    AQP_LAUNCHED();
+    AQP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 // after the exchange: final partition boundaries from the (already globally reduced) histogram slice
 // of this rank in final order, and the tile table of the received segments. blockIdx.x = relation.
 __global__ void __launch_bounds__(kScanBlock) plan_shard_kernel(ShardPlanArgs a) {
@@ -335,13 +368,13 @@ constexpr int kScatterBlocksPerSM = kScatterBlocksPerSMRaw < 1 ? 1 : (kScatterBl
 
 uint32_t pass1_blocks() { return (uint32_t) kNumSMs * kScatterBlocksPerSM; }
 
-template <bool kRot>
+template <bool kRot, bool kPeer>
 __global__ void __launch_bounds__(kScatterThreads, kScatterBlocksPerSM)
 radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
                      const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_tile_start,
                      const uint32_t *__restrict__ seg_group, uint32_t nseg, DigitFn digit, uint32_t bits,
                      uint32_t *__restrict__ cursors, const uint32_t *__restrict__ block_base,
-                     uint32_t tiles_per_block) {
+                     uint32_t tiles_per_block, PeerTable peers) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint2 *inbuf0 = reinterpret_cast<uint2 *>(smem_raw);
     uint2 *inbuf1 = inbuf0 + kInBufTuples;
@@ -483,7 +516,11 @@ radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
 
         for (uint32_t s = threadIdx.x; s < ntile; s += kScatterThreads) {
             uint2 t = stage[s];
-            out[gdst[digit.template get<kRot>(t.x)] + s] = t;
+            const uint32_t d = digit.template get<kRot>(t.x);
+            if (kPeer)   // fused exchange: the run goes straight into its owner's receive buffer over NVLink
+                peers.base[d >> peers.per_shift][gdst[d] + s] = t;
+            else
+                out[gdst[d] + s] = t;
         }
     }
 }
@@ -491,7 +528,7 @@ radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
 int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_off,
                          const uint32_t *d_seg_tile_start, const uint32_t *d_seg_group, uint32_t nseg, uint64_t n_total,
                          DigitFn digit, uint32_t bits, uint32_t *d_cursors, const uint32_t *d_block_base,
-                         uint32_t nblocks, uint32_t tiles_per_block, cudaStream_t st) {
+                         uint32_t nblocks, uint32_t tiles_per_block, cudaStream_t st, const PeerTable *peers) {
     if (bits > (uint32_t) kMaxFanoutBits || nseg > (uint32_t) kMaxFanout) {
         set_error("radix_scatter: fan-out too large");
         return -1;
@@ -503,9 +540,11 @@ int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_
     if (n_total == 0) return 0;
     static bool attr_set = false;
     if (!attr_set) {
-        AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int) kScatterSmemBytes));
-        AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int) kScatterSmemBytes));
+        AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int) kScatterSmemBytes));
         attr_set = true;
     }
@@ -517,14 +556,21 @@ int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_
         uint64_t g = (uint64_t) kNumSMs * kScatterBlocksPerSM;
         grid = (uint32_t) (max_tiles < g ? max_tiles : g);
     }
-    if (digit.rot)
-        radix_scatter_kernel<true><<<grid, kScatterThreads, kScatterSmemBytes, st>>>(
-            reinterpret_cast<const uint2 *>(d_in), reinterpret_cast<uint2 *>(d_out), d_seg_off, d_seg_tile_start,
-            d_seg_group, nseg, digit, bits, d_cursors, d_block_base, tiles_per_block);
+    PeerTable none{};
+    const uint2 *in = reinterpret_cast<const uint2 *>(d_in);
+    uint2 *out = reinterpret_cast<uint2 *>(d_out);
+    if (peers && peers->n)
+        radix_scatter_kernel<true, true><<<grid, kScatterThreads, kScatterSmemBytes, st>>>(
+            in, out, d_seg_off, d_seg_tile_start, d_seg_group, nseg, digit, bits, d_cursors, d_block_base,
+            tiles_per_block, *peers);
+    else if (digit.rot)
+        radix_scatter_kernel<true, false><<<grid, kScatterThreads, kScatterSmemBytes, st>>>(
+            in, out, d_seg_off, d_seg_tile_start, d_seg_group, nseg, digit, bits, d_cursors, d_block_base,
+            tiles_per_block, none);
     else
-        radix_scatter_kernel<false><<<grid, kScatterThreads, kScatterSmemBytes, st>>>(
-            reinterpret_cast<const uint2 *>(d_in), reinterpret_cast<uint2 *>(d_out), d_seg_off, d_seg_tile_start,
-            d_seg_group, nseg, digit, bits, d_cursors, d_block_base, tiles_per_block);
+        radix_scatter_kernel<false, false><<<grid, kScatterThreads, kScatterSmemBytes, st>>>(
+            in, out, d_seg_off, d_seg_tile_start, d_seg_group, nseg, digit, bits, d_cursors, d_block_base,
+            tiles_per_block, none);
     AQP_LAUNCHED();
     AQP_CUDA_OK(cudaGetLastError());
     return 0;

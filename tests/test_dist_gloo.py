@@ -119,6 +119,13 @@ def test_exchange_plan_and_hist_slice():
     assert recv.tolist() == [26, 260]                  # and receives partitions 4-7 from both
     assert seg_off.tolist() == [0, 5, 11, 18, 26, 76, 136, 206, 286]
     assert seg_group.tolist() == [0, 1, 2, 3, 0, 1, 2, 3]
+    # fused exchange: where each rank's segments start inside the owners' buffers = the owners' seg_off
+    assert D.dest_offsets(counts, 0, 2).tolist() == [0, 1, 3, 6, 0, 5, 11, 18]
+    assert D.dest_offsets(counts, 1, 2).tolist() == [10, 20, 40, 70, 26, 76, 136, 206]
+    for owner in (0, 1):
+        seg = D.exchange_plan(counts, owner, 2)[2].tolist()
+        for src in (0, 1):
+            assert D.dest_offsets(counts, src, 2).view(2, 4)[owner].tolist() == seg[src * 4:src * 4 + 4]
     h = torch.arange(16)                               # b1 = 2, b2 = 2: index = p1 | p2 << 2
     assert D.final_hist_slice(h, rank=1, world=2, b1=2, b2=2).tolist() == [2, 6, 10, 14, 3, 7, 11, 15]
     assert D.plan_bits(1 << 27, 8, lambda n: (14, 7, 7)) == (14, 7, 7)

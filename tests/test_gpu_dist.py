@@ -24,14 +24,16 @@ for logR, logS in ((20, 22), (24, 26)):
     R = torch.empty(2 * nRl, dtype=torch.int32, device=dev); S = torch.empty(2 * nSl, dtype=torch.int32, device=dev)
     st = torch.cuda.current_stream().cuda_stream
     A.gen_pk_device(R.data_ptr(), nR, 11111, rank * nRl, nRl, st); A.gen_fk_device(S.data_ptr(), nS, nR, 22222, rank * nSl, nSl, st)
-    sj = D.ShardedJoin(nR, nS, dev)
-    for _ in range(3):
-        o = sj.run(R, S)
     rep = nS // nR
-    assert o["matches"] == nS, o
-    assert o["keysum"] == rep * nR * (nR + 1) // 2, o
-    assert o["checksum"] == rep * (nR * (nR - 1) // 2) + nS * (nS - 1) // 2, o
-    if rank == 0: print("OK", logR, logS, {k: round(v, 3) if isinstance(v, float) else v for k, v in o.items()})
+    for cls in (D.ShardedJoin, D.FusedShardedJoin):
+        sj = cls(nR, nS, dev)
+        for _ in range(3):
+            o = sj.run(R, S)
+        assert o["matches"] == nS, o
+        assert o["keysum"] == rep * nR * (nR + 1) // 2, o
+        assert o["checksum"] == rep * (nR * (nR - 1) // 2) + nS * (nS - 1) // 2, o
+        if rank == 0: print("OK", cls.__name__, logR, logS, {k: round(v, 3) if isinstance(v, float) else v for k, v in o.items()})
+        del sj
 dist.destroy_process_group()
 '''
 
@@ -49,4 +51,4 @@ def test_nccl_sharded_join(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29517", str(script)], env=env,
                        capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
-    assert p.stdout.count("OK") == 2
+    assert p.stdout.count("OK") == 4

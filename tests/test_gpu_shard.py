@@ -83,3 +83,61 @@ def test_sharded_stages_skew_and_misses(gpu, oracle):
     R = oracle.set_rowid_payload(oracle.gen_pk(1 << 16, 11111))
     S = oracle.set_rowid_payload(oracle.gen_zipf(1 << 19, 1 << 17, 1.0, seed=3))   # half of the key domain misses R
     _emulate(gpu, oracle, R, S, 4)
+
+
+def _emulate_fused(gpu, oracle, R, S, G):
+    """The fused scatter+exchange path with all G 'peer' receive buffers living on this one GPU."""
+    import torch
+    import b200aqp.dist as D
+    dev = torch.device("cuda:0")
+    be = D.CudaBackend()
+    nR, nS = len(R), len(S)
+    bits, b1, b2 = D.plan_bits(nR, G, be.join_plan)
+    lg = D.log2_exact(G)
+    F1, P = 1 << b1, 1 << bits
+    per = F1 // G
+    shards = [[torch.from_numpy(rel[r * n // G:(r + 1) * n // G].copy().view(np.int32)).to(dev)
+               for rel, n in ((R, nR), (S, nS))] for r in range(G)]
+    counts = [[None, None] for _ in range(G)]
+    hists = [[None, None] for _ in range(G)]
+    for r in range(G):
+        for k in (0, 1):
+            h = torch.zeros(P, dtype=torch.int32, device=dev)
+            c = torch.zeros(F1, dtype=torch.int32, device=dev)
+            be.shard_hist(shards[r][k], shards[r][k].numel() // 2, bits, b1, lg, h, c, k)
+            torch.cuda.synchronize()
+            counts[r][k], hists[r][k] = c.to(torch.int64), h
+    recv = [[torch.zeros(2 * (n + 64), dtype=torch.int32, device=dev) for n in (nR, nS)] for _ in range(G)]
+    for r in range(G):
+        for k in (0, 1):
+            counts_all = torch.stack([counts[s][k] for s in range(G)])
+            h = torch.zeros(P, dtype=torch.int32, device=dev)
+            c = torch.zeros(F1, dtype=torch.int32, device=dev)
+            be.shard_hist(shards[r][k], shards[r][k].numel() // 2, bits, b1, lg, h, c, k)   # re-arm the slot for rank r
+            be.shard_scatter(shards[r][k], shards[r][k].numel() // 2, D.dest_offsets(counts_all, r, G).to(torch.int32),
+                             [recv[g][k].data_ptr() for g in range(G)], k)
+    torch.cuda.synchronize()
+    tot = {"matches": 0, "checksum": 0, "keysum": 0}
+    for r in range(G):
+        args = []
+        for k in (0, 1):
+            counts_all = torch.stack([counts[s][k] for s in range(G)])
+            hist_global = sum(hists[s][k].to(torch.int64) for s in range(G)).to(torch.int32)
+            _, rc, seg_off, seg_group = D.exchange_plan(counts_all, r, G)
+            args.append((recv[r][k], int(rc.sum()), seg_off.to(torch.int32), D.final_hist_slice(hist_global, r, G, b1, b2)))
+        st = be.shard_join(args[0][0], args[0][1], args[0][2], args[1][0], args[1][1], args[1][2], seg_group, G * per,
+                           per, b1, b2, args[0][3], args[1][3], bits)
+        for k in tot:
+            tot[k] += st[k]
+    exp = oracle.rho(R, S)
+    assert (tot["matches"], tot["checksum"] % (1 << 64), tot["keysum"] % (1 << 64)) == \
+        (exp["matches"], exp["checksum"], exp["keysum"])
+
+
+@pytest.mark.parametrize("G", [1, 2, 4, 8])
+def test_fused_scatter_exchange(gpu, oracle, G):
+    R = oracle.set_rowid_payload(oracle.gen_pk(100003, 11111))
+    S = oracle.set_rowid_payload(oracle.gen_fk(1 << 20, 100003, 22222))
+    _emulate_fused(gpu, oracle, R, S, G)
+    Sz = oracle.set_rowid_payload(oracle.gen_zipf(400009, 100003, 1.0, seed=5))
+    _emulate_fused(gpu, oracle, R, Sz, G)
