@@ -292,7 +292,8 @@ def run_b200_arm(args):
 
     sampler = ClockSampler(local_rank)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    phase = {"ms_hist": 0.0, "ms_pass1": 0.0, "ms_pass2": 0.0, "ms_join": 0.0, "ms_total": 0.0, "ms_exchange": 0.0}
+    phase = {"ms_hist": 0.0, "ms_pass1": 0.0, "ms_pass2": 0.0, "ms_join": 0.0, "ms_total": 0.0, "ms_exchange": 0.0,
+             "ms_sizing": 0.0, "ms_scatter_kernels": 0.0, "ms_barrier": 0.0}
     l_before = A.kernel_launch_count()
     barrier()
     sampler.start()

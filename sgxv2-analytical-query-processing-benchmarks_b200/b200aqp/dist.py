@@ -295,9 +295,11 @@ class FusedShardedJoin(ShardedJoin):
             out["exchange"] = "nccl-fallback"
             return out
         nR_recv, nS_recv = int(worst[2]), int(worst[3])
+        es = self._event()
         # ---- 3. fused scatter + exchange: stores go to the owners' buffers over NVLink ------------------
         be.shard_scatter(R, nR, dR, self.peerR, 0)
         be.shard_scatter(S, nS, dS, self.peerS, 1)
+        ex = self._event()
         flag = self._buf("flag", 2, torch.int32)
         dist.all_reduce(flag[:1], group=self.group)    # barrier: every rank's stores have landed
         e2 = self._event()
@@ -321,6 +323,9 @@ class FusedShardedJoin(ShardedJoin):
             torch.cuda.synchronize()
             out["ms_hist"] = e0.elapsed_time(eh)
             out["ms_pass1"] = eh.elapsed_time(e2)      # sizing collectives + fused scatter/exchange + barrier
+            out["ms_sizing"] = eh.elapsed_time(es)     # all-gather + all-reduce + offset arithmetic + host sync
+            out["ms_scatter_kernels"] = es.elapsed_time(ex)
+            out["ms_barrier"] = ex.elapsed_time(e2)
             out["ms_exchange"] = 0.0                   # no separate exchange step
             out["ms_total"] = e0.elapsed_time(e3)
         return out
