@@ -368,9 +368,7 @@ constexpr int kScatterBlocksPerSM = kScatterBlocksPerSMRaw < 1 ? 1 : (kScatterBl
 
 uint32_t pass1_blocks() { return (uint32_t) kNumSMs * kScatterBlocksPerSM; }
 
-constexpr uint32_t kLongRun = 512;   // runs longer than this are written by the whole CTA
-
-template <bool kRot, bool kPeer, bool kAligned>
+template <bool kRot, bool kPeer>
 __global__ void __launch_bounds__(kScatterThreads, kScatterBlocksPerSM)
 radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
                      const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_tile_start,
@@ -385,7 +383,6 @@ radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
     __shared__ uint32_t lbase[kMaxFanout];   // start of the partition's run inside `stage`
     __shared__ uint32_t gdst[kMaxFanout];    // global index of stage slot s of partition d is gdst[d] + s
     __shared__ uint32_t scur[kMaxFanout];    // CTA-private write cursors (pass 1)
-    __shared__ uint32_t rlen[kMaxFanout];    // run length of every partition in this tile (aligned write-out)
     __shared__ uint2 *s_peer[8];             // receive buffers of the owners (fused exchange)
     __shared__ uint32_t s_tstart[kMaxFanout + 1];
     __shared__ uint32_t s_soff[kMaxFanout + 1];
@@ -492,7 +489,6 @@ radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
                 my_b[k] = run;
                 if (k < (int) per && d < fan) {
                     lbase[d] = run;
-                    if (kAligned) rlen[d] = c[k];
                     if (priv) {
                         my_g[k] = scur[d];
                         scur[d] = my_g[k] + c[k];
@@ -520,47 +516,13 @@ radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
         }
         __syncthreads();   // (3) tile reordered, destinations known
 
-        if (!kAligned) {
-            for (uint32_t s = threadIdx.x; s < ntile; s += kScatterThreads) {
-                uint2 t = stage[s];
-                const uint32_t d = digit.template get<kRot>(t.x);
-                if (kPeer)   // fused exchange: the run goes straight into its owner's receive buffer over NVLink
-                    s_peer[d >> peers.per_shift][gdst[d] + s] = t;
-                else
-                    out[gdst[d] + s] = t;
-            }
-        } else {
-            // Destination-aligned write-out: a warp takes whole runs and walks each one in windows aligned
-            // to 256 bytes of the DESTINATION, so every store instruction covers whole 128-byte lines except
-            // at the two ends of a run (p2pbench: 710 vs 535 GB/s to a peer, 5.4 vs 4.1 TB/s locally).
-            const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-            bool any_long = false;
-            for (uint32_t d = warp; d < fan; d += kScatterThreads / 32) {
-                const uint32_t len = rlen[d];
-                if (len == 0) continue;
-                if (len > kLongRun) {
-                    any_long = true;
-                    continue;
-                }
-                const uint32_t src0 = lbase[d], g0 = gdst[d] + src0, g1 = g0 + len;
-                uint2 *dst = kPeer ? s_peer[d >> peers.per_shift] : out;
-                for (uint32_t w = g0 & ~31u; w < g1; w += 32) {
-                    const uint32_t idx = w + lane;
-                    if (idx >= g0 && idx < g1) dst[idx] = stage[src0 + (idx - g0)];
-                }
-            }
-            if (__syncthreads_or(any_long)) {   // skewed tile: long runs are written by all threads together
-                for (uint32_t d = 0; d < fan; ++d) {
-                    const uint32_t len = rlen[d];
-                    if (len <= kLongRun) continue;
-                    const uint32_t src0 = lbase[d], g0 = gdst[d] + src0, g1 = g0 + len;
-                    uint2 *dst = kPeer ? s_peer[d >> peers.per_shift] : out;
-                    for (uint32_t w = (g0 & ~31u) + warp * 32; w < g1; w += kScatterThreads) {
-                        const uint32_t idx = w + lane;
-                        if (idx >= g0 && idx < g1) dst[idx] = stage[src0 + (idx - g0)];
-                    }
-                }
-            }
+        for (uint32_t s = threadIdx.x; s < ntile; s += kScatterThreads) {
+            uint2 t = stage[s];
+            const uint32_t d = digit.template get<kRot>(t.x);
+            if (kPeer)   // fused exchange: the run goes straight into its owner's receive buffer over NVLink
+                s_peer[d >> peers.per_shift][gdst[d] + s] = t;
+            else
+                out[gdst[d] + s] = t;
         }
     }
 }
@@ -580,16 +542,12 @@ int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_
     if (n_total == 0) return 0;
     static bool attr_set = false;
     if (!attr_set) {
-        AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_kernel<false, false, false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kScatterSmemBytes));
-        AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_kernel<false, false, true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kScatterSmemBytes));
-        AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_kernel<true, false, false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kScatterSmemBytes));
-        AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_kernel<true, true, false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kScatterSmemBytes));
-        AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_kernel<true, true, true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kScatterSmemBytes));
+        AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int) kScatterSmemBytes));
+        AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int) kScatterSmemBytes));
+        AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int) kScatterSmemBytes));
         attr_set = true;
     }
     uint32_t grid;
@@ -603,20 +561,17 @@ int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_
     PeerTable none{};
     const uint2 *in = reinterpret_cast<const uint2 *>(d_in);
     uint2 *out = reinterpret_cast<uint2 *>(d_out);
-    static const int aligned_env = getenv("B200_AQP_ALIGNED") ? atoi(getenv("B200_AQP_ALIGNED")) : -1;
     const bool peer = peers && peers->n;
-    const bool aligned = aligned_env >= 0 ? aligned_env != 0 : peer;   // default: aligned for NVLink stores only
-#define AQP_SCATTER_LAUNCH(ROT, PEER, AL)                                                                          \
-    radix_scatter_kernel<ROT, PEER, AL><<<grid, kScatterThreads, kScatterSmemBytes, st>>>(                          \
+#define AQP_SCATTER_LAUNCH(ROT, PEER)                                                                              \
+    radix_scatter_kernel<ROT, PEER><<<grid, kScatterThreads, kScatterSmemBytes, st>>>(                              \
         in, out, d_seg_off, d_seg_tile_start, d_seg_group, nseg, digit, bits, d_cursors, d_block_base, tiles_per_block, \
         peer ? *peers : none)
-    if (peer) {
-        if (aligned) AQP_SCATTER_LAUNCH(true, true, true); else AQP_SCATTER_LAUNCH(true, true, false);
-    } else if (digit.rot) {
-        AQP_SCATTER_LAUNCH(true, false, false);
-    } else {
-        if (aligned) AQP_SCATTER_LAUNCH(false, false, true); else AQP_SCATTER_LAUNCH(false, false, false);
-    }
+    if (peer)
+        AQP_SCATTER_LAUNCH(true, true);
+    else if (digit.rot)
+        AQP_SCATTER_LAUNCH(true, false);
+    else
+        AQP_SCATTER_LAUNCH(false, false);
 #undef AQP_SCATTER_LAUNCH
     AQP_LAUNCHED();
     AQP_CUDA_OK(cudaGetLastError());
