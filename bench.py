@@ -327,6 +327,25 @@ def run_b200_arm(args):
                  "peak": peak, "unit": "GB/s", "frac": join_bytes / ms_step / 1e6 / peak,
                  "actual_bytes_per_tuple": 48, "note": "the pass-2 histogram read is avoided: one full-width histogram serves both passes"}
 
+    # ---- BASELINE config 4: Zipf-skewed S (z = 0.5, 1.0), same sizes, 1 GPU ----------------------------
+    skew = None
+    if world == 1:
+        skew = {}
+        for z in (0.5, 1.0):
+            A.gen_zipf_device(S.data_ptr(), nS, nR, z, 22222, 0, st)
+            torch.cuda.synchronize()
+            for _ in range(2):
+                sz = A.join_device(R.data_ptr(), nR, S.data_ptr(), nS, stream=st)
+            assert sz["matches"] == nS
+            tz = []
+            for _ in range(max(3, args.steps // 2)):
+                tz.append(A.join_device(R.data_ptr(), nR, S.data_ptr(), nS, stream=st)["ms_total"])
+            ms = sum(tz) / len(tz)
+            skew[f"z{z}"] = {"ms": ms, "value": (nR + nS) / ms / 1e3, "unit": UNIT,
+                             "join_roofline_frac": JOIN_BYTES_PER_TUPLE * (nR + nS) / ms / 1e6 / peak}
+        A.gen_fk_device(S.data_ptr(), nS, nR, 22222, 0, nS, st)   # restore the uniform S for the e2e leg
+        torch.cuda.synchronize()
+
     # ---- multi-GPU: NVLink traffic of the shuffle, and the NCCL all-to-all variant as the baseline -------
     exchange = None
     if world > 1:
@@ -414,7 +433,7 @@ def run_b200_arm(args):
                            "cache": "inputs (5 GiB) exceed the 126 MB L2; no flush between steps",
                            "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: pass-1 routes by low key bits, NCCL all-to-all"},
                 "phases_ms": phase, "roofline": roof, "join_roofline": join_roof, "cpu_baseline": cpu, "e2e": e2e,
-                "exchange": exchange,
+                "exchange": exchange, "skew": skew,
                 "gpu_launches": launches_timed, "gpu_launches_total": A.kernel_launch_count() - launches0,
                 "clocks": clocks, "scan": scan}
         print(json.dumps(line))

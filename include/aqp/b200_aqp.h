@@ -202,6 +202,12 @@ int b200_gen_pk_device(struct row_t *d_rel, uint64_t n_total, uint64_t row_begin
                        uint64_t seed, void *stream);
 int b200_gen_fk_device(struct row_t *d_rel, uint64_t n_total, uint64_t maxid, uint64_t row_begin, uint64_t n,
                        uint64_t seed, void *stream);
+/* Zipf-skewed foreign keys (create_relation_zipf, generator.cpp:638-660 -> gen_zipf, genzipf.cpp:87-144):
+ * keys drawn from a random permutation ("alphabet") of 1..maxid with probability proportional to
+ * rank^-zipf_param, by binary search in the cumulative table the reference builds. The table (8*maxid
+ * bytes, temporary) is computed on the device; rows [row_begin, row_begin+n) of the stream are written. */
+int b200_gen_zipf_device(struct row_t *d_rel, uint64_t maxid, double zipf_param, uint64_t row_begin, uint64_t n,
+                         uint64_t seed, void *stream);
 /* payload[i] = row_begin + i for an existing device relation (TPC-H loader convention,
  * Join-Benchmarks/App/TpcH/TpcHCommons.cpp:332,:413) */
 int b200_set_rowid_payload_device(struct row_t *d_rel, uint64_t row_begin, uint64_t n, void *stream);

@@ -99,6 +99,7 @@ SYMBOLS = {
     "delete_relation": (None, [C.POINTER(Table)]),
     "b200_gen_pk_device": (_int, [_vp, _u64, _u64, _u64, _u64, _vp]),
     "b200_gen_fk_device": (_int, [_vp, _u64, _u64, _u64, _u64, _u64, _vp]),
+    "b200_gen_zipf_device": (_int, [_vp, _u64, C.c_double, _u64, _u64, _u64, _vp]),
     "b200_set_rowid_payload_device": (_int, [_vp, _u64, _u64, _vp]),
     "b200_bitvector_scan_user": (None, [_u8, _u8, _vp, _sz, _vp, C.POINTER(_u64), _sz, _sz, _int]),
     "b200_index_scan_user": (None, [_u8, _u8, _vp, _sz, _vp, _sz, C.POINTER(_sz), C.POINTER(_u64), _sz, _sz, _int]),
@@ -306,6 +307,10 @@ def gen_fk_device(d_rel: int, n_total: int, maxid: int, seed: int, row_begin: in
                   stream=None):
     _check(lib().b200_gen_fk_device(d_rel, n_total, maxid, row_begin, n_total if n is None else n, seed,
                                     _st(stream)), "b200_gen_fk_device")
+
+
+def gen_zipf_device(d_rel: int, n: int, maxid: int, z: float, seed: int, row_begin: int = 0, stream=None):
+    _check(lib().b200_gen_zipf_device(d_rel, maxid, z, row_begin, n, seed, _st(stream)), "b200_gen_zipf_device")
 
 
 # ---- scans -------------------------------------------------------------------------------------------------

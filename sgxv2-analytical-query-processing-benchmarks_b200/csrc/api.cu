@@ -861,6 +861,13 @@ int b200_gen_fk_device(struct row_t *d_rel, uint64_t n_total, uint64_t maxid, ui
     if (ensure_init()) return -1;
     return gen_fk_device(d_rel, n_total, maxid, row_begin, n, seed, stream ? static_cast<cudaStream_t>(stream) : g.stream);
 }
+int b200_gen_zipf_device(struct row_t *d_rel, uint64_t maxid, double zipf_param, uint64_t row_begin, uint64_t n,
+                         uint64_t seed, void *stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    return gen_zipf_device(d_rel, maxid, zipf_param, row_begin, n, seed,
+                           stream ? static_cast<cudaStream_t>(stream) : g.stream);
+}
 int b200_set_rowid_payload_device(struct row_t *d_rel, uint64_t row_begin, uint64_t n, void *stream) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (ensure_init()) return -1;

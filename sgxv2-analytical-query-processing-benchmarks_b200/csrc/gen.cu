@@ -76,6 +76,96 @@ __global__ void set_rowid_payload_kernel(uint2 *rel, uint64_t row_begin, uint64_
         rel[i].y = (uint32_t) (row_begin + i);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Zipf (Join-Benchmarks/lib/AppUtilities/src/genzipf.cpp): alphabet = random permutation of 1..maxid
+// (:33-51, here the keyed bijection), cumulative distribution table lut[i] = sum_{k<=i+1} k^-z / total
+// (:58-83), per tuple a uniform r in [0,1) and a binary search for the first lut[pos] >= r (:113-137).
+// The table is built on the device with a three-phase fp64 scan (block sums, scan of sums, rescan).
+// ---------------------------------------------------------------------------------------------
+constexpr int kLutBlock = 256, kLutPerThread = 16, kLutChunk = kLutBlock * kLutPerThread;
+
+__device__ __forceinline__ double block_sum_f64(double v, double *sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0;
+    for (int w = 0; w < kLutBlock / 32; ++w) t += sh[w];
+    __syncthreads();
+    return t;
+}
+
+__global__ void __launch_bounds__(kLutBlock) zipf_chunk_sums_kernel(uint64_t n, double z, double *sums) {
+    __shared__ double sh[kLutBlock / 32];
+    uint64_t base = (uint64_t) blockIdx.x * kLutChunk + (uint64_t) threadIdx.x * kLutPerThread;
+    double v = 0;
+    for (int k = 0; k < kLutPerThread; ++k)
+        if (base + k < n) v += 1.0 / pow((double) (base + k + 1), z);
+    double t = block_sum_f64(v, sh);
+    if (threadIdx.x == 0) sums[blockIdx.x] = t;
+}
+
+__global__ void zipf_scan_sums_kernel(double *sums, uint32_t nchunks, double *total) {   // one thread: <= 2^15 chunks
+    double run = 0;
+    for (uint32_t i = 0; i < nchunks; ++i) {
+        double c = sums[i];
+        sums[i] = run;
+        run += c;
+    }
+    *total = run;
+}
+
+__global__ void __launch_bounds__(kLutBlock)
+zipf_lut_kernel(uint64_t n, double z, const double *sums, const double *total, double *lut) {
+    __shared__ double sh[kLutBlock / 32];
+    __shared__ double wsum[kLutBlock / 32];
+    uint64_t base = (uint64_t) blockIdx.x * kLutChunk + (uint64_t) threadIdx.x * kLutPerThread;
+    double w[kLutPerThread], v = 0;
+    for (int k = 0; k < kLutPerThread; ++k) {
+        w[k] = base + k < n ? 1.0 / pow((double) (base + k + 1), z) : 0.0;
+        v += w[k];
+    }
+    // exclusive prefix of the per-thread sums inside the block
+    double incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= o) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    double before = 0;
+    for (int k = 0; k < (int) (threadIdx.x >> 5); ++k) before += wsum[k];
+    (void) sh;
+    double run = sums[blockIdx.x] + before + incl - v;
+    const double inv = 1.0 / *total;
+    for (int k = 0; k < kLutPerThread; ++k) {
+        run += w[k];
+        if (base + k < n) lut[base + k] = run * inv;
+    }
+}
+
+__global__ void gen_zipf_kernel(uint2 *rel, const double *__restrict__ lut, uint64_t maxid, uint32_t b,
+                                uint64_t row_begin, uint64_t n, uint64_t seed, uint64_t alpha_key) {
+    uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t row = row_begin + i;
+        double r = (double) (mix64(seed ^ mix64(row)) >> 11) * (1.0 / 9007199254740992.0);   // [0,1), 53 bits
+        uint64_t pos;
+        if (lut[0] >= r) {
+            pos = 0;
+        } else {
+            uint64_t left = 0, right = maxid - 1;
+            while (right - left > 1) {
+                uint64_t m = (left + right) / 2;
+                if (lut[m] < r) left = m; else right = m;
+            }
+            pos = right;
+        }
+        rel[i] = make_uint2((uint32_t) (permute(pos, maxid, b, alpha_key) + 1), (uint32_t) row);
+    }
+}
+
 static uint64_t host_mix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ull;
     x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -108,6 +198,32 @@ int gen_fk_device(row_t *d_rel, uint64_t n_total, uint64_t maxid, uint64_t row_b
                                               ceil_log2(rem ? rem : 1), row_begin, n, seed);
     AQP_LAUNCHED();
     AQP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int gen_zipf_device(row_t *d_rel, uint64_t maxid, double z, uint64_t row_begin, uint64_t n, uint64_t seed,
+                    cudaStream_t st) {
+    if (n == 0) return 0;
+    if (maxid == 0 || maxid > 0xFFFFFFFFull || maxid > ((uint64_t) 1 << 15) * kLutChunk) {
+        set_error("gen_zipf: maxid must be in [1, 2^27]");
+        return -1;
+    }
+    const uint32_t nchunks = (uint32_t) ((maxid + kLutChunk - 1) / kLutChunk);
+    double *lut = nullptr, *sums = nullptr;
+    AQP_CUDA_OK(cudaMallocAsync(&lut, maxid * sizeof(double), st));
+    AQP_CUDA_OK(cudaMallocAsync(&sums, ((size_t) nchunks + 1) * sizeof(double), st));
+    zipf_chunk_sums_kernel<<<nchunks, kLutBlock, 0, st>>>(maxid, z, sums);
+    AQP_LAUNCHED();
+    zipf_scan_sums_kernel<<<1, 1, 0, st>>>(sums, nchunks, sums + nchunks);
+    AQP_LAUNCHED();
+    zipf_lut_kernel<<<nchunks, kLutBlock, 0, st>>>(maxid, z, sums, sums + nchunks, lut);
+    AQP_LAUNCHED();
+    gen_zipf_kernel<<<kNumSMs * 8, 256, 0, st>>>(reinterpret_cast<uint2 *>(d_rel), lut, maxid, ceil_log2(maxid), row_begin,
+                                                n, seed, host_mix64(seed ^ 0x5a17f00dull));
+    AQP_LAUNCHED();
+    AQP_CUDA_OK(cudaGetLastError());
+    AQP_CUDA_OK(cudaFreeAsync(lut, st));
+    AQP_CUDA_OK(cudaFreeAsync(sums, st));
     return 0;
 }
 

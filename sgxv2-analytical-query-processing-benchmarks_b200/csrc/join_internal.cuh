@@ -134,6 +134,8 @@ int build_probe_device(const row_t *d_R, const uint32_t *d_offR, const row_t *d_
 int gen_pk_device(row_t *d_rel, uint64_t n_total, uint64_t row_begin, uint64_t n, uint64_t seed, cudaStream_t st);
 int gen_fk_device(row_t *d_rel, uint64_t n_total, uint64_t maxid, uint64_t row_begin, uint64_t n, uint64_t seed,
                   cudaStream_t st);
+int gen_zipf_device(row_t *d_rel, uint64_t maxid, double z, uint64_t row_begin, uint64_t n, uint64_t seed,
+                    cudaStream_t st);
 int set_rowid_payload_device(row_t *d_rel, uint64_t row_begin, uint64_t n, cudaStream_t st);
 
 // scan.cu

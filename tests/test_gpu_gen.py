@@ -55,3 +55,31 @@ def test_row_ranges_compose(gpu):
     whole = _gen_fk(gpu, n, 30011, 6)
     parts = [_gen_fk(gpu, n, 30011, 6, b, min(40000, n - b)) for b in range(0, n, 40000)]
     assert np.array_equal(np.concatenate(parts), whole)
+
+
+def test_zipf_device_distribution_and_join(gpu, oracle):
+    maxid, n = 1 << 12, 1 << 20
+    for z in (0.5, 1.0):
+        buf = gpu.DeviceBuffer(8 * n)
+        gpu.gen_zipf_device(buf.ptr, n, maxid, z, seed=7)
+        gpu.lib().b200_device_sync()
+        S = buf.download(gpu.ROW, n)
+        assert S["key"].min() >= 1 and S["key"].max() <= maxid
+        assert np.array_equal(S["payload"], np.arange(n, dtype=np.uint32))
+        # frequencies follow rank^-z: compare the sorted empirical frequencies with the reference's table
+        lut = np.empty(maxid)
+        oracle.lib().oracle_zipf_lut(lut.ctypes.data, maxid, z)
+        p = np.diff(np.concatenate([[0.0], lut]))
+        freq = np.sort(np.bincount(S["key"], minlength=maxid + 1)[1:])[::-1] / n
+        assert abs(freq[0] - p[0]) < 0.1 * p[0] + 3e-4            # tolerance: sampling noise of n = 2^20 draws
+        assert abs(freq[:16].sum() - p[:16].sum()) < 0.05 * p[:16].sum() + 1e-3
+        # row ranges compose and the relation joins like the oracle says
+        half = gpu.DeviceBuffer(8 * (n // 2))
+        gpu.gen_zipf_device(half.ptr, n // 2, maxid, z, seed=7, row_begin=n // 2)
+        gpu.lib().b200_device_sync()
+        assert np.array_equal(half.download(gpu.ROW, n // 2), S[n // 2:])
+        R = oracle.set_rowid_payload(oracle.gen_pk(maxid, 11111))
+        o = oracle.rho(R, S)
+        g = gpu.run_join(R, S)
+        assert (g["matches"], g["checksum"], g["keysum"]) == (o["matches"], o["checksum"], o["keysum"])
+        assert g["matches"] == n

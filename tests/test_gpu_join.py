@@ -175,3 +175,28 @@ def test_full_size_device_generated(gpu, logR, logS):
     assert s["checksum"] == rep * (nR * (nR - 1) // 2) + nS * (nS - 1) // 2
     s2 = gpu.join_device(R.data_ptr(), nR, S.data_ptr(), nS)   # idempotent, inputs untouched
     assert (s2["matches"], s2["checksum"], s2["keysum"]) == (s["matches"], s["checksum"], s["keysum"])
+
+
+@pytest.mark.parametrize("z", [0.5, 1.0])
+def test_full_size_zipf(gpu, z):
+    """BASELINE config 4: |R|=2^27, Zipf-skewed |S|=2^29 generated on the device. R is a primary key, so
+    every S tuple matches exactly once; checksum and keysum are re-derived with torch from the relations."""
+    import torch
+    nR, nS = 1 << 27, 1 << 29
+    dev = torch.device("cuda:0")
+    R = torch.empty(nR * 2, dtype=torch.int32, device=dev)
+    S = torch.empty(nS * 2, dtype=torch.int32, device=dev)
+    gpu.gen_pk_device(R.data_ptr(), nR, seed=11111)
+    gpu.gen_zipf_device(S.data_ptr(), nS, nR, z, seed=22222)
+    gpu.lib().b200_device_sync()
+    s = gpu.join_device(R.data_ptr(), nR, S.data_ptr(), nS)
+    assert s["matches"] == nS
+    Rk, Rp = R.view(nR, 2)[:, 0].long(), R.view(nR, 2)[:, 1].long()
+    inv = torch.empty(nR + 1, dtype=torch.int64, device=dev)
+    inv[Rk] = Rp
+    Sk, Sp = S.view(nS, 2)[:, 0].long(), S.view(nS, 2)[:, 1].long()
+    assert int(Sk.min()) >= 1 and int(Sk.max()) <= nR
+    assert s["keysum"] == int(Sk.sum())
+    assert s["checksum"] == int(inv[Sk].sum() + Sp.sum())
+    hot = int(torch.bincount(Sk[: 1 << 24].int()).max())
+    assert hot > (1 << 24) * (0.03 if z == 1.0 else 1e-5)      # the skew is really there
