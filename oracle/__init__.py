@@ -27,7 +27,7 @@ _f64p = C.POINTER(C.c_double)
 def build(force: bool = False) -> str:
     """Compile the C restatement (and, when /root/reference is present, oracle/_ref)."""
     so = os.path.join(HERE, "liboracle.so")
-    srcs = [os.path.join(HERE, f) for f in ("oracle_gen.c", "oracle_join.c", "oracle_scan.c", "oracle.h")]
+    srcs = [os.path.join(HERE, f) for f in ("oracle_gen.c", "oracle_join.c", "oracle_scan.c", "oracle_tpch.c", "oracle.h")]
     stale = force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if stale:
         subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
@@ -187,7 +187,8 @@ def host_has_avx512() -> bool:
 
 def have_ref() -> bool:
     return host_has_avx512() and all(
-        os.path.exists(os.path.join(REF_DIR, f)) for f in ("libref_join.so", "libref_join_1p.so", "libref_scan.so"))
+        os.path.exists(os.path.join(REF_DIR, f))
+        for f in ("libref_join.so", "libref_join_1p.so", "libref_scan.so", "libref_tpch.so"))
 
 
 _ref_join = {}
@@ -320,3 +321,170 @@ def ref_index_scan_self_alloc(lo, hi, data):
     out = np.zeros(cap, dtype=np.uint64)
     c = ref_scan().ref_index_scan_self_alloc(lo, hi, _ptr(data), data.shape[0], _ptr(out), cap)
     return out[:c]
+
+
+# ----------------------------------------------------------------------------- TPC-H-style pipelines
+class _LineItem(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("l_orderkey", C.c_void_p), ("l_shipdate", C.c_void_p), ("l_commitdate", C.c_void_p),
+                ("l_receiptdate", C.c_void_p), ("l_shipmode", C.c_void_p), ("l_partkey", C.c_void_p),
+                ("l_quantity", C.c_void_p), ("l_shipinstruct", C.c_void_p), ("l_returnflag", C.c_void_p)]
+
+
+class _Orders(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("o_orderkey", C.c_void_p), ("o_orderdate", C.c_void_p), ("o_custkey", C.c_void_p)]
+
+
+class _Customer(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("c_custkey", C.c_void_p), ("c_mktsegment", C.c_void_p), ("c_nationkey", C.c_void_p)]
+
+
+class _Part(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("p_partkey", C.c_void_p), ("p_brand", C.c_void_p), ("p_size", C.c_void_p),
+                ("p_container", C.c_void_p)]
+
+
+_TPCH_DTYPES = {
+    "lineitem": [("l_orderkey", ROW), ("l_shipdate", np.uint64), ("l_commitdate", np.uint64), ("l_receiptdate", np.uint64),
+                 ("l_shipmode", np.uint8), ("l_partkey", np.uint32), ("l_quantity", np.float32),
+                 ("l_shipinstruct", np.uint8), ("l_returnflag", np.int8)],
+    "orders": [("o_orderkey", ROW), ("o_orderdate", np.uint64), ("o_custkey", np.uint32)],
+    "customer": [("c_custkey", ROW), ("c_mktsegment", np.uint8), ("c_nationkey", np.uint32)],
+    "part": [("p_partkey", ROW), ("p_brand", np.uint8), ("p_size", np.uint32), ("p_container", np.uint8)],
+}
+_TPCH_STRUCT = {"lineitem": _LineItem, "orders": _Orders, "customer": _Customer, "part": _Part}
+
+
+def tpch_struct(name: str, cols: dict):
+    """ctypes struct (layout of TpcHTypes.hpp) over a dict of numpy columns; 64-byte aligned copies are made
+    because the reference's AVX-512 filters use aligned stream loads (Q12Predicates.hpp:63-70)."""
+    keep = {}
+    st = _TPCH_STRUCT[name]()
+    n = None
+    for col, dt in _TPCH_DTYPES[name]:
+        a = cols[col]
+        n = len(a) if n is None else n
+        assert len(a) == n and a.dtype == np.dtype(dt), (col, a.dtype)
+        raw = np.empty(a.nbytes + 128, dtype=np.uint8)
+        off = (-raw.ctypes.data) % 64
+        al = raw[off:off + a.nbytes].view(a.dtype)
+        al[:] = a
+        keep[col] = (raw, al)
+        setattr(st, col, al.ctypes.data)
+    st.n = n
+    st._keep = keep
+    return st
+
+
+def synth_tpch(sf: float, seed: int = 1) -> dict:
+    """numpy TPC-H-like tables with the encodings of the reference's loader (dictionary codes, epoch-second
+    dates, sparse order keys). For CPU tests only; the GPU generator (b200_tpch_generate_device) has the same
+    distributions but other random numbers."""
+    rng = np.random.default_rng(seed)
+    nc, no, np_ = max(3, int(150000 * sf)), max(1, int(1500000 * sf)), max(1, int(200000 * sf))
+    nl = no * 4
+    day = 86400
+    t = {}
+    ck = np.zeros(nc, dtype=ROW)
+    ck["key"] = np.arange(1, nc + 1)
+    ck["payload"] = np.arange(nc)
+    t["customer"] = {"c_custkey": ck, "c_mktsegment": (rng.integers(0, 5, nc) == 0).astype(np.uint8),
+                     "c_nationkey": rng.integers(0, 25, nc).astype(np.uint32)}
+    ok = np.zeros(no, dtype=ROW)
+    i = np.arange(no, dtype=np.uint64)
+    ok["key"] = ((i >> 3) * 32 + (i & 7) + 1).astype(np.uint32)
+    ok["payload"] = i.astype(np.uint32)
+    od = (694224000 + day * rng.integers(0, 2406, no)).astype(np.uint64)
+    k = rng.integers(0, nc - nc // 3, no)
+    t["orders"] = {"o_orderkey": ok, "o_orderdate": od, "o_custkey": (k + k // 2 + 1).astype(np.uint32)}
+    lk = np.zeros(nl, dtype=ROW)
+    lk["key"] = np.repeat(ok["key"], 4)
+    lk["payload"] = np.arange(nl)
+    odl = np.repeat(od, 4)
+    sd = odl + (day * rng.integers(1, 122, nl)).astype(np.uint64)
+    mode = rng.integers(0, 7, nl)
+    t["lineitem"] = {"l_orderkey": lk, "l_shipdate": sd,
+                     "l_commitdate": odl + (day * rng.integers(30, 91, nl)).astype(np.uint64),
+                     "l_receiptdate": sd + (day * rng.integers(1, 31, nl)).astype(np.uint64),
+                     "l_shipmode": np.select([mode == 5, mode == 3, mode == 1], [1, 2, 3], 0).astype(np.uint8),
+                     "l_partkey": rng.integers(1, np_ + 1, nl).astype(np.uint32),
+                     "l_quantity": rng.integers(1, 51, nl).astype(np.float32),
+                     "l_shipinstruct": (rng.integers(0, 4, nl) == 0).astype(np.uint8),
+                     "l_returnflag": rng.choice(np.array([ord("R"), ord("A"), ord("N")], dtype=np.int8), nl)}
+    pk = np.zeros(np_, dtype=ROW)
+    pk["key"] = np.arange(1, np_ + 1)
+    pk["payload"] = np.arange(np_)
+    mn = rng.integers(1, 6, np_) * 10 + rng.integers(1, 6, np_)
+    s1, s2 = rng.integers(0, 5, np_), rng.integers(0, 8, np_)
+    cont = np.zeros(np_, dtype=np.uint8)
+    for code, (a, b) in enumerate([(0, 0), (0, 1), (0, 5), (0, 4), (2, 2), (2, 1), (2, 4), (2, 5), (1, 0), (1, 1), (1, 5), (1, 4)], 1):
+        cont[(s1 == a) & (s2 == b)] = code
+    t["part"] = {"p_partkey": pk, "p_brand": np.select([mn == 12, mn == 23, mn == 34], [1, 2, 3], 0).astype(np.uint8),
+                 "p_size": rng.integers(1, 51, np_).astype(np.uint32), "p_container": cont}
+    return t
+
+
+def _tpch_lib_setup(L):
+    if getattr(L, "_tpch_ready", False):
+        return
+    L.oracle_tpch_q12.argtypes = [C.c_void_p, C.c_void_p, _u64p]
+    L.oracle_tpch_q12.restype = C.c_int64
+    L.oracle_tpch_q3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _u64p, _u64p]
+    L.oracle_tpch_q3.restype = C.c_int64
+    L.oracle_tpch_q19.argtypes = [C.c_void_p, C.c_void_p, _u64p, _u64p]
+    L.oracle_tpch_q19.restype = C.c_int64
+    L._tpch_ready = True
+
+
+def tpch_query(q: int, tables: dict) -> dict:
+    """Run the oracle restatement of Q3 / Q12 / Q19 on a dict of tables (dicts of numpy columns)."""
+    L = lib()
+    _tpch_lib_setup(L)
+    st = {k: tpch_struct(k, v) for k, v in tables.items()}
+    f = (C.c_uint64 * 3)()
+    j1 = C.c_uint64(0)
+    if q == 12:
+        r = L.oracle_tpch_q12(C.byref(st["lineitem"]), C.byref(st["orders"]), f)
+    elif q == 3:
+        r = L.oracle_tpch_q3(C.byref(st["customer"]), C.byref(st["orders"]), C.byref(st["lineitem"]), f, C.byref(j1))
+    elif q == 19:
+        r = L.oracle_tpch_q19(C.byref(st["lineitem"]), C.byref(st["part"]), f, C.byref(j1))
+    else:
+        raise ValueError(q)
+    return {"result_rows": int(r), "filtered": [int(x) for x in f], "join1_rows": int(j1.value)}
+
+
+_ref_tpch = None
+
+
+def ref_tpch():
+    global _ref_tpch
+    if _ref_tpch is None:
+        L = C.CDLL(os.path.join(REF_DIR, "libref_tpch.so"))
+        L.ref_tpch_q3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, _f64p]
+        L.ref_tpch_q3.restype = C.c_longlong
+        L.ref_tpch_q12.argtypes = [C.c_void_p, C.c_void_p, C.c_int, _f64p]
+        L.ref_tpch_q12.restype = C.c_longlong
+        L.ref_tpch_q19.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_longlong), _f64p]
+        L.ref_tpch_q19.restype = C.c_longlong
+        _ref_tpch = L
+    return _ref_tpch
+
+
+def ref_tpch_query(q: int, tables: dict, nthreads: int = 4) -> dict:
+    """The unmodified reference pipeline (oracle/_ref/libref_tpch.so) on the same tables."""
+    L = ref_tpch()
+    st = {k: tpch_struct(k, v) for k, v in tables.items()}
+    sec = C.c_double(0)
+    out = {}
+    if q == 12:
+        r = L.ref_tpch_q12(C.byref(st["lineitem"]), C.byref(st["orders"]), nthreads, C.byref(sec))
+    elif q == 3:
+        r = L.ref_tpch_q3(C.byref(st["customer"]), C.byref(st["orders"]), C.byref(st["lineitem"]), nthreads, C.byref(sec))
+    elif q == 19:
+        j = C.c_longlong(0)
+        r = L.ref_tpch_q19(C.byref(st["lineitem"]), C.byref(st["part"]), nthreads, C.byref(j), C.byref(sec))
+        out["join1_rows"] = int(j.value)
+    else:
+        raise ValueError(q)
+    out.update(result_rows=int(r), seconds=sec.value)
+    return out

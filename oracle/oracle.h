@@ -70,6 +70,20 @@ uint64_t oracle_scalar_index_scan(uint8_t lo, uint8_t hi, const uint8_t *in, siz
 /* shared_libraries/SharedHeaders/include/Allocator.hpp:95-109: v[i] = i mod 256 */
 void     oracle_fill_tiled_column(uint8_t *data, size_t n);
 
+/* ---- TPC-H-style pipelines (Join-Benchmarks/lib/TPCH-Queries/src/tpch.cpp) ---------------------- */
+/* column tables, byte-compatible with Join-Benchmarks/lib/SharedHeaders/include/TpcHTypes.hpp:50-83 */
+typedef struct { uint64_t n; oracle_row_t *l_orderkey; uint64_t *l_shipdate, *l_commitdate, *l_receiptdate;
+                 uint8_t *l_shipmode; uint32_t *l_partkey; float *l_quantity; uint8_t *l_shipinstruct;
+                 char *l_returnflag; } oracle_lineitem_t;
+typedef struct { uint64_t n; oracle_row_t *o_orderkey; uint64_t *o_orderdate; uint32_t *o_custkey; } oracle_orders_t;
+typedef struct { uint64_t n; oracle_row_t *c_custkey; uint8_t *c_mktsegment; uint32_t *c_nationkey; } oracle_customer_t;
+typedef struct { uint64_t n; oracle_row_t *p_partkey; uint8_t *p_brand; uint32_t *p_size; uint8_t *p_container; } oracle_part_t;
+/* row counts, like the reference; filtered[] receives the selection cardinalities (3 entries) */
+int64_t oracle_tpch_q12(const oracle_lineitem_t *l, const oracle_orders_t *o, uint64_t *filtered);                 /* :219-253 */
+int64_t oracle_tpch_q3(const oracle_customer_t *c, const oracle_orders_t *o, const oracle_lineitem_t *l,
+                       uint64_t *filtered, uint64_t *join1_rows);                                                    /* :37-117  */
+int64_t oracle_tpch_q19(const oracle_lineitem_t *l, const oracle_part_t *p, uint64_t *filtered, uint64_t *join1_rows); /* :255-309 */
+
 #ifdef __cplusplus
 }
 #endif

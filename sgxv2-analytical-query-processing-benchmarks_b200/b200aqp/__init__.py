@@ -46,6 +46,38 @@ class JoinConfig(C.Structure):     # struct joinconfig_t
                 ("ALLOC_CORE", C.c_int)]
 
 
+class TpchStats(C.Structure):      # struct b200_tpch_stats_t
+    _fields_ = [("result_rows", C.c_uint64), ("input_rows", C.c_uint64), ("filtered", C.c_uint64 * 3),
+                ("join1_rows", C.c_uint64), ("ms_total", C.c_float), ("ms_filter", C.c_float), ("ms_join", C.c_float),
+                ("ms_other", C.c_float), ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32)]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k not in ("reserved", "filtered")}
+        d["filtered"] = list(self.filtered)
+        return d
+
+
+class LineItemTable(C.Structure):  # TpcHTypes.hpp:50-61
+    _fields_ = [("numTuples", C.c_uint64), ("l_orderkey", C.c_void_p), ("l_shipdate", C.c_void_p),
+                ("l_commitdate", C.c_void_p), ("l_receiptdate", C.c_void_p), ("l_shipmode", C.c_void_p),
+                ("l_partkey", C.c_void_p), ("l_quantity", C.c_void_p), ("l_shipinstruct", C.c_void_p),
+                ("l_returnflag", C.c_void_p)]
+
+
+class OrdersTable(C.Structure):    # TpcHTypes.hpp:63-68
+    _fields_ = [("numTuples", C.c_uint64), ("o_orderkey", C.c_void_p), ("o_orderdate", C.c_void_p), ("o_custkey", C.c_void_p)]
+
+
+class CustomerTable(C.Structure):  # TpcHTypes.hpp:70-75
+    _fields_ = [("numTuples", C.c_uint64), ("c_custkey", C.c_void_p), ("c_mktsegment", C.c_void_p),
+                ("c_nationkey", C.c_void_p)]
+
+
+class PartTable(C.Structure):      # TpcHTypes.hpp:77-83
+    _fields_ = [("numTuples", C.c_uint64), ("p_partkey", C.c_void_p), ("p_brand", C.c_void_p), ("p_size", C.c_void_p),
+                ("p_container", C.c_void_p)]
+
+
 class JoinStats(C.Structure):      # struct b200_join_stats_t
     _fields_ = [("matches", C.c_int64), ("checksum", C.c_uint64), ("keysum", C.c_uint64), ("radix_bits", C.c_uint32),
                 ("num_passes", C.c_uint32), ("bits_pass1", C.c_uint32), ("bits_pass2", C.c_uint32),
@@ -110,6 +142,24 @@ SYMBOLS = {
     "b200_fill_tiled_column_device": (_int, [_vp, _sz, _u64, _vp]),
     "b200_fill_skewed_column_device": (_int, [_vp, _sz, _u64, _u32, _u64, _vp]),
     "b200_kernel_launch_count": (_u64, []),
+    # include/aqp/b200_tpch.h
+    "tpch_q3": (None, [C.POINTER(Result), C.POINTER(CustomerTable), C.POINTER(OrdersTable), C.POINTER(LineItemTable),
+                       C.c_char_p, C.POINTER(JoinConfig)]),
+    "tpch_q12": (None, [C.POINTER(Result), C.POINTER(LineItemTable), C.POINTER(OrdersTable), C.c_char_p,
+                        C.POINTER(JoinConfig)]),
+    "tpch_q19": (None, [C.POINTER(Result), C.POINTER(LineItemTable), C.POINTER(PartTable), C.c_char_p,
+                        C.POINTER(JoinConfig)]),
+    "b200_tpch_generate_device": (_int, [C.c_double, _u64]),
+    "b200_tpch_upload": (_int, [C.POINTER(LineItemTable), C.POINTER(OrdersTable), C.POINTER(CustomerTable),
+                                C.POINTER(PartTable)]),
+    "b200_tpch_download": (_int, [C.POINTER(LineItemTable), C.POINTER(OrdersTable), C.POINTER(CustomerTable),
+                                  C.POINTER(PartTable)]),
+    "b200_tpch_free_host": (None, [C.POINTER(LineItemTable), C.POINTER(OrdersTable), C.POINTER(CustomerTable),
+                                   C.POINTER(PartTable)]),
+    "b200_tpch_free_device": (None, []),
+    "b200_tpch_q3_device": (_int, [C.POINTER(TpchStats)]),
+    "b200_tpch_q12_device": (_int, [C.POINTER(TpchStats)]),
+    "b200_tpch_q19_device": (_int, [C.POINTER(TpchStats)]),
 }
 
 _lib = None
@@ -353,3 +403,84 @@ def index_scan_device(lo, hi, d_data, n, d_out, capacity, d_count, id_base=0, st
 
 def kernel_launch_count() -> int:
     return int(lib().b200_kernel_launch_count())
+
+
+# ---- TPC-H-style pipelines (include/aqp/b200_tpch.h) ---------------------------------------------------------
+_TPCH_COLS = {
+    "lineitem": (LineItemTable, [("l_orderkey", ROW), ("l_shipdate", np.uint64), ("l_commitdate", np.uint64),
+                                 ("l_receiptdate", np.uint64), ("l_shipmode", np.uint8), ("l_partkey", np.uint32),
+                                 ("l_quantity", np.float32), ("l_shipinstruct", np.uint8), ("l_returnflag", np.int8)]),
+    "orders": (OrdersTable, [("o_orderkey", ROW), ("o_orderdate", np.uint64), ("o_custkey", np.uint32)]),
+    "customer": (CustomerTable, [("c_custkey", ROW), ("c_mktsegment", np.uint8), ("c_nationkey", np.uint32)]),
+    "part": (PartTable, [("p_partkey", ROW), ("p_brand", np.uint8), ("p_size", np.uint32), ("p_container", np.uint8)]),
+}
+
+
+def tpch_generate_device(scale_factor: float, seed: int = 1):
+    init()
+    _check(lib().b200_tpch_generate_device(scale_factor, seed), "b200_tpch_generate_device")
+
+
+def tpch_download() -> dict:
+    """Device tables -> dict of dicts of numpy columns (copies)."""
+    st = {k: cls() for k, (cls, _) in _TPCH_COLS.items()}
+    _check(lib().b200_tpch_download(C.byref(st["lineitem"]), C.byref(st["orders"]), C.byref(st["customer"]),
+                                    C.byref(st["part"])), "b200_tpch_download")
+    out = {}
+    for name, (cls, cols) in _TPCH_COLS.items():
+        n = st[name].numTuples
+        out[name] = {}
+        for col, dt in cols:
+            dt = np.dtype(dt)
+            buf = (C.c_uint8 * (n * dt.itemsize)).from_address(getattr(st[name], col)) if n else b""
+            out[name][col] = np.frombuffer(buf, dtype=dt).copy()
+    lib().b200_tpch_free_host(C.byref(st["lineitem"]), C.byref(st["orders"]), C.byref(st["customer"]), C.byref(st["part"]))
+    return out
+
+
+def tpch_host_struct(name: str, cols: dict):
+    cls, spec = _TPCH_COLS[name]
+    st = cls()
+    st._keep = []
+    n = None
+    for col, dt in spec:
+        a = np.ascontiguousarray(cols[col])
+        assert a.dtype == np.dtype(dt), (col, a.dtype)
+        n = len(a) if n is None else n
+        st._keep.append(a)
+        setattr(st, col, a.ctypes.data)
+    st.numTuples = n
+    return st
+
+
+def tpch_upload(tables: dict):
+    st = {k: tpch_host_struct(k, v) for k, v in tables.items()}
+    g = lambda k: C.byref(st[k]) if k in st else None
+    _check(lib().b200_tpch_upload(g("lineitem"), g("orders"), g("customer"), g("part")), "b200_tpch_upload")
+
+
+def tpch_query_device(q: int) -> dict:
+    s = TpchStats()
+    f = {3: lib().b200_tpch_q3_device, 12: lib().b200_tpch_q12_device, 19: lib().b200_tpch_q19_device}[q]
+    _check(f(C.byref(s)), f"b200_tpch_q{q}_device")
+    return s.as_dict()
+
+
+def tpch_query_host(q: int, tables: dict, nthreads: int = 1) -> dict:
+    """The drop-in host entry points tpch_q3 / tpch_q12 / tpch_q19 (tpch.hpp:7-21) on host tables."""
+    st = {k: tpch_host_struct(k, v) for k, v in tables.items()}
+    res, cfg = Result(), JoinConfig()
+    cfg.NTHREADS = nthreads
+    if q == 3:
+        lib().tpch_q3(C.byref(res), C.byref(st["customer"]), C.byref(st["orders"]), C.byref(st["lineitem"]), b"RHO", C.byref(cfg))
+    elif q == 12:
+        lib().tpch_q12(C.byref(res), C.byref(st["lineitem"]), C.byref(st["orders"]), b"RHO", C.byref(cfg))
+    elif q == 19:
+        lib().tpch_q19(C.byref(res), C.byref(st["lineitem"]), C.byref(st["part"]), b"RHO", C.byref(cfg))
+    else:
+        raise ValueError(q)
+    out = {"result_rows": int(res.totalresults), "result_type": res.result_type, "throughput": res.throughput}
+    ct = C.cast(res.result, C.POINTER(ChunkedTable))
+    lib().destroy_table(ct)
+    C.CDLL(None).free(C.c_void_p(res.result))
+    return out

@@ -31,27 +31,6 @@ static double now_s() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-// grow-only device buffer
-struct DevBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    int ensure(size_t bytes) {
-        if (bytes <= cap) return 0;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        size_t want = bytes + (bytes >> 4) + 256;   // a little slack so near-equal sizes do not re-allocate
-        AQP_CUDA_OK(cudaMalloc(&p, want));
-        cap = want;
-        return 0;
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-};
-
 struct Ctx {
     bool inited = false;
     int device = -1;
@@ -318,6 +297,18 @@ static int join_device_locked(const row_t *dR, uint64_t nR, const row_t *dS, uin
     g.last = s;
     if (stats) *stats = s;
     return 0;
+}
+
+// entry for the library's other translation units (tpch.cu): same lock, same workspace
+int join_device_internal(const row_t *dR, uint64_t nR, const row_t *dS, uint64_t nS, output_triple_t *d_out,
+                         uint64_t out_cap, b200_join_stats_t *stats, cudaStream_t st) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    return join_device_locked(dR, nR, dS, nS, d_out, out_cap, stats, st ? st : g.stream, false);
+}
+cudaStream_t library_stream() {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    return ensure_init() ? nullptr : g.stream;
 }
 
 // re-run only build/probe on the partitions left in the workspace by the last join (used when the

@@ -6,6 +6,27 @@
 
 namespace aqp {
 
+// grow-only device buffer
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + (bytes >> 4) + 256;   // a little slack so near-equal sizes do not re-allocate
+        AQP_CUDA_OK(cudaMalloc(&p, want));
+        cap = want;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
 // ---- partitioning geometry ---------------------------------------------------------------------
 constexpr int kMaxFanoutBits = 8;                 // bits per pass
 constexpr int kMaxFanout = 1 << kMaxFanoutBits;
@@ -97,6 +118,11 @@ struct JoinResult {              // device-side accumulators
     unsigned long long keysum;
     unsigned long long out_count;   // triples reserved in the output buffer
 };
+
+// api.cu
+int join_device_internal(const row_t *dR, uint64_t nR, const row_t *dS, uint64_t nS, output_triple_t *d_out,
+                         uint64_t out_cap, b200_join_stats_t *stats, cudaStream_t st);
+cudaStream_t library_stream();
 
 // partition.cu
 int radix_hist_device(const row_t *d_in, uint64_t n, DigitFn digit, uint32_t bits, uint32_t *d_hist, uint32_t nblocks,

@@ -27,30 +27,14 @@ constexpr int kExpandScanTiles = kExpandTileVals / kScanTileVals;   // = 4 scan 
 // bit 7 of every byte of the result is set iff lo <= byte <= hi (unsigned). lo7 = lo4 & 0x7f7f7f7f,
 // hiH = hi4 | 0x80808080 are loop invariants. Per byte: (x|0x80) - lo_low never borrows across
 // bytes and its bit 7 says x_low >= lo_low; x >= lo  <=>  x7 > lo7 or (x7 == lo7 and that bit).
-__device__ __forceinline__ uint32_t inrange_msb(uint32_t x, uint32_t lo4, uint32_t hi4, uint32_t lo7,
-                                                uint32_t hiH) {
-    const uint32_t H = 0x80808080u;
-    uint32_t t = (x | H) - lo7;
-    uint32_t ge = (x & ~lo4) | (~(x ^ lo4) & t);
-    uint32_t u = hiH - (x & ~H);
-    uint32_t le = (hi4 & ~x) | (~(hi4 ^ x) & u);
-    return ge & le & H;
-}
-
-// 16-bit mask of the 16 bytes of v (bit i <-> byte i in memory order). The multiply gathers the
-// four bit-7 flags of a word into its top nibble (bit 7+8k lands on 28+k, no carries collide).
-__device__ __forceinline__ uint32_t range_mask16(uint4 v, uint32_t lo4, uint32_t hi4, uint32_t lo7,
-                                                 uint32_t hiH) {
-    const uint32_t M = 0x00204081u;
-    uint32_t p0 = inrange_msb(v.x, lo4, hi4, lo7, hiH) * M;
-    uint32_t p1 = inrange_msb(v.y, lo4, hi4, lo7, hiH) * M;
-    uint32_t p2 = inrange_msb(v.z, lo4, hi4, lo7, hiH) * M;
-    uint32_t p3 = inrange_msb(v.w, lo4, hi4, lo7, hiH) * M;
-    return (p0 >> 28) | ((p1 >> 24) & 0xF0u) | ((p2 >> 20) & 0xF00u) | ((p3 >> 16) & 0xF000u);
-}
-
+//
+// Pipe balance (ncu, profiles/r01_ncu_scan_kernels.md): LOP3/IADD/SHF all issue on the half-rate ALU
+// pipe and the first version of this predicate (36 ALU ops per 16 bytes) stalled on math-pipe throttle
+// at 5.1 TB/s. The two subtractions and the four combine shifts are therefore expressed as multiply-adds
+// (a - b = b * (0 - one) + a with `one` a runtime 1 the compiler cannot fold; x >> s = umulhi(x, 2^(32-s))),
+// which ptxas places on the FMA pipe: 23 LOP3 + 20 IMAD per 16 bytes.
 struct Pred {
-    uint32_t lo4, hi4, lo7, hiH;
+    uint32_t lo4, hi4, lo7, hiH, neg_one;
 };
 static Pred make_pred(uint8_t lo, uint8_t hi) {
     Pred p;
@@ -58,7 +42,35 @@ static Pred make_pred(uint8_t lo, uint8_t hi) {
     p.hi4 = 0x01010101u * hi;
     p.lo7 = p.lo4 & 0x7f7f7f7fu;
     p.hiH = p.hi4 | 0x80808080u;
+    p.neg_one = 0xffffffffu;
     return p;
+}
+
+__device__ __forceinline__ uint32_t sub_fma(uint32_t a, uint32_t b, uint32_t neg_one) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(neg_one), "r"(a));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t inrange_msb(uint32_t x, const Pred &p) {
+    const uint32_t H = 0x80808080u;
+    uint32_t t = sub_fma(x | H, p.lo7, p.neg_one);
+    uint32_t ge = (x & ~p.lo4) | (~(x ^ p.lo4) & t);
+    uint32_t u = sub_fma(p.hiH, x & ~H, p.neg_one);
+    uint32_t le = (p.hi4 & ~x) | (~(p.hi4 ^ x) & u);
+    return ge & le & H;
+}
+
+// 16-bit mask of the 16 bytes of v (bit i <-> byte i in memory order). The multiply gathers the
+// four bit-7 flags of a word into its top nibble (bit 7+8k lands on 28+k, no carries collide).
+__device__ __forceinline__ uint32_t range_mask16(uint4 v, const Pred &p) {
+    const uint32_t M = 0x00204081u;
+    uint32_t p0 = inrange_msb(v.x, p) * M;
+    uint32_t p1 = inrange_msb(v.y, p) * M;
+    uint32_t p2 = inrange_msb(v.z, p) * M;
+    uint32_t p3 = inrange_msb(v.w, p) * M;
+    return __umulhi(p0, 1u << 4) | (__umulhi(p1, 1u << 8) & 0xF0u) | (__umulhi(p2, 1u << 12) & 0xF00u) |
+           (__umulhi(p3, 1u << 16) & 0xF000u);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -97,7 +109,7 @@ bitvector_scan_kernel(const uint4 *__restrict__ in, size_t nvec, uint64_t *__res
 #pragma unroll
         for (int j = 0; j < kScanUnroll; ++j) {
             size_t q = base + (size_t) j * kScanThreads;
-            uint32_t m16 = range_mask16(v[j], p.lo4, p.hi4, p.lo7, p.hiH);
+            uint32_t m16 = range_mask16(v[j], p);
             if (kCount) c += q < nvec ? __popc(m16) : 0;
             // four neighbouring lanes hold the four 16-bit quarters of one output word
             uint32_t m32 = m16 | (__shfl_down_sync(0xffffffffu, m16, 1) << 16);
@@ -129,7 +141,7 @@ scan_count_kernel(const uint4 *__restrict__ in, size_t nvec, unsigned long long 
 #pragma unroll
         for (int j = 0; j < kScanUnroll; ++j) {
             size_t q = base + (size_t) j * kScanThreads;
-            uint32_t m16 = range_mask16(v[j], p.lo4, p.hi4, p.lo7, p.hiH);
+            uint32_t m16 = range_mask16(v[j], p);
             c += q < nvec ? __popc(m16) : 0;
         }
     }

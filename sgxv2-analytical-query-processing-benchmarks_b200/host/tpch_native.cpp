@@ -1,0 +1,90 @@
+// tpch_native.cpp — the TPC-H benchmark driver, GPU edition.
+//
+// Host-side mirror of Join-Benchmarks/App/TpcH/TpcHNative.cpp:12-102 with the flags of
+// TpcHCommons.cpp:105 (-q query, -s scale, -a algorithm, -n threads; -b / -p accepted and ignored). The
+// reference loads dbgen columns from ../data/scaleNNN (TpcHCommons.cpp:235-295); this driver synthesises
+// the tables in HBM (b200_tpch_generate_device) and prints the lines the scripts scrape
+// (Join-Benchmarks/lib/TPCH-Queries/src/time_print.cpp:19-35: QueryTimeTotal, QueryTimeSelection,
+// QueryTimeJoin, QueryThroughput). Extra flag --reps N repeats the query.
+#include <getopt.h>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "aqp/b200_aqp.h"
+#include "aqp/b200_tpch.h"
+
+static double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static double g_t0;
+static void info(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    printf("[%8.4f][ INFO] %s\n", now_s() - g_t0, buf);
+}
+
+int main(int argc, char **argv) {
+    g_t0 = now_s();
+    info("************* TPC-H APP (B200) *************");
+    int query = 12, threads = 1, reps = 1;
+    double scale = 1;
+    char alg[128] = "RHO";
+    static option long_opts[] = {{"reps", required_argument, nullptr, 'R'}, {nullptr, 0, nullptr, 0}};
+    int c;
+    while ((c = getopt_long(argc, argv, "a:b:m:n:q:s:p", long_opts, nullptr)) != -1) {
+        switch (c) {
+            case 'a': strncpy(alg, optarg, sizeof alg - 1); break;
+            case 'n': threads = atoi(optarg); break;
+            case 'q': query = atoi(optarg); break;
+            case 's': scale = atof(optarg); break;
+            case 'R': reps = atoi(optarg); break;
+            default: break;
+        }
+    }
+    if (strcmp(alg, "RHO") != 0) {
+        fprintf(stderr, "[ERROR] Algorithm not found: %s (this build serves RHO only)\n", alg);
+        return EXIT_FAILURE;
+    }
+    info("Run Q%d (scale %g) with join algorithm %s (%d threads)", query, scale, alg, threads);
+    if (b200_init(-1) != 0) {
+        fprintf(stderr, "[ERROR] %s\n", b200_last_error());
+        return EXIT_FAILURE;
+    }
+    info("Generating tables in device memory.");
+    if (b200_tpch_generate_device(scale, 1)) {
+        fprintf(stderr, "[ERROR] %s\n", b200_last_error());
+        return EXIT_FAILURE;
+    }
+    info("Done.");
+    for (int r = 0; r < reps; ++r) {
+        b200_tpch_stats_t s{};
+        int rc = query == 3 ? b200_tpch_q3_device(&s) : query == 12 ? b200_tpch_q12_device(&s)
+                 : query == 19 ? b200_tpch_q19_device(&s) : -2;
+        if (rc == -2) {
+            fprintf(stderr, "[ERROR] TPC-H Q%d is not supported\n", query);
+            return EXIT_FAILURE;
+        }
+        if (rc) {
+            fprintf(stderr, "[ERROR] %s\n", b200_last_error());
+            return EXIT_FAILURE;
+        }
+        const double us = s.ms_total * 1e3;
+        info("QueryTimeTotal (us)         : %u", (unsigned) us);
+        info("QueryTimeSelection (us)     : %u (%.2lf%%)", (unsigned) (s.ms_filter * 1e3), 100.0 * s.ms_filter / s.ms_total);
+        info("QueryTimeJoin (us)          : %u (%.2lf%%)", (unsigned) (s.ms_join * 1e3), 100.0 * s.ms_join / s.ms_total);
+        info("QueryTimeCopy (us)          : %u (%.2lf%%)", (unsigned) (s.ms_other * 1e3), 100.0 * s.ms_other / s.ms_total);
+        info("QueryThroughput (M rec/s)   : %.4lf", (double) s.input_rows / us);
+        info("Selections: %lu %lu %lu  join 1: %lu  result rows: %lu", (unsigned long) s.filtered[0],
+             (unsigned long) s.filtered[1], (unsigned long) s.filtered[2], (unsigned long) s.join1_rows,
+             (unsigned long) s.result_rows);
+    }
+    info("Query completed");
+    b200_tpch_free_device();
+    return 0;
+}

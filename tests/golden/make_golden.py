@@ -11,6 +11,7 @@ What is recorded (the reference ships no join/scan KATs of its own, SURVEY.md §
   * zipf: a small reference-generated Zipf relation is stored verbatim (it is not reproducible,
     genzipf.cpp:44-45) together with the reference join result on it
   * scan: popcounts and sha256 of bitvector / row-id outputs of SIMD512 on the tiled column
+  * tpch: row counts of the reference's tpch_q3 / tpch_q12 / tpch_q19 on oracle.synth_tpch(sf, seed) tables
 """
 import hashlib
 import json
@@ -34,7 +35,7 @@ def sorted_triples(t):
 
 def main():
     assert O.have_ref(), "build oracle/_ref first: make -C oracle ref"
-    g = {"generator": [], "join": [], "scan": []}
+    g = {"generator": [], "join": [], "scan": [], "tpch": []}
 
     gen_cases = [("pk", 1 << 10, None, 11111), ("pk", 1 << 20, None, 11111), ("pk", 100003, None, 12345),
                  ("pk", 1 << 24, None, 11111),
@@ -88,6 +89,15 @@ def main():
             ids = O.ref_index_scan(lo, hi, data)
             g["scan"].append({"column": name, "n": n, "lo": lo, "hi": hi, "count": O.ref_scan_count(lo, hi, data),
                               "sha256_bitvector": sha(bv), "sha256_rowids": sha(ids)})
+
+    # TPC-H-style pipelines: the reference's tpch_q3 / q12 / q19 (SIMD filters + RHO) on seeded numpy tables
+    for sf, seed in ((0.02, 5), (0.05, 3)):
+        t = O.synth_tpch(sf, seed)
+        entry = {"sf": sf, "seed": seed}
+        for q in (3, 12, 19):
+            r = O.ref_tpch_query(q, t, nthreads=4)
+            entry[f"q{q}"] = {k: v for k, v in r.items() if k != "seconds"}
+        g["tpch"].append(entry)
 
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(g, f, indent=1)

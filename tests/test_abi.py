@@ -12,11 +12,11 @@ import pytest
 from conftest import PKG, ROOT
 from helpers import sha
 
-HEADER = os.path.join(ROOT, "include", "aqp", "b200_aqp.h")
+HEADERS = [os.path.join(ROOT, "include", "aqp", h) for h in ("b200_aqp.h", "b200_tpch.h")]
 
 
 def _declared_functions():
-    src = open(HEADER).read()
+    src = "\n".join(open(h).read() for h in HEADERS)
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     names = re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{}]*\)\s*;", src)
     return sorted(set(n for n in names if n not in ("defined",)))
