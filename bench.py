@@ -412,6 +412,39 @@ def run_b200_arm(args):
                 n_tot = 1 << SCAN_LOG_N
                 v["input_gbs"] = n_tot / v["ms"] / 1e6
 
+    # ---- BASELINE config 5: TPC-H-style Q3 / Q12 / Q19 at SF100 on device-generated columns (1 GPU) -------
+    tpch = None
+    if world == 1 and not args.no_tpch:
+        sf = float(os.environ.get("B200_AQP_TPCH_SF", "100"))
+        A.tpch_generate_device(sf, 1)
+        published_ms = {3: 730.0, 12: 225.0, 19: 120.0}   # reference, 16 threads, SF100, other hardware
+        tpch = {"scale_factor": sf, "data": "synthetic, generated in HBM (include/aqp/b200_tpch.h)"}
+        for q in (3, 12, 19):
+            for _ in range(2):
+                r = A.tpch_query_device(q)
+            runs = [A.tpch_query_device(q) for _ in range(3)]
+            ms = sum(x["ms_total"] for x in runs) / len(runs)
+            tpch[f"q{q}"] = {"ms": ms, "mrows_per_s": r["input_rows"] / ms / 1e3, "result_rows": r["result_rows"],
+                             "ms_filter": runs[-1]["ms_filter"], "ms_join": runs[-1]["ms_join"],
+                             "reference_published_ms_sf100": published_ms[q]}
+        if not args.no_cpu_baseline:
+            try:   # the reference's own pipelines on the host cores, bounded sample: the same generator at SF1
+                import oracle as O
+                if O.have_ref():
+                    A.tpch_generate_device(1.0, 1)
+                    t = A.tpch_download()
+                    tpch["cpu_reference_sf1"] = {"cores": os.cpu_count(), "kind": "reference"}
+                    for q in (3, 12, 19):
+                        g = A.tpch_query_device(q)
+                        c = O.ref_tpch_query(q, t, nthreads=os.cpu_count())
+                        assert c["result_rows"] == g["result_rows"], (q, c, g)
+                        tpch["cpu_reference_sf1"][f"q{q}"] = {"ms": c["seconds"] * 1e3, "gpu_ms": g["ms_total"],
+                                                              "result_rows": c["result_rows"]}
+                    del t
+            except Exception as ex:
+                tpch["cpu_reference_sf1"] = {"failed": str(ex)}
+        A.lib().b200_tpch_free_device()
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -433,7 +466,7 @@ def run_b200_arm(args):
                            "cache": "inputs (5 GiB) exceed the 126 MB L2; no flush between steps",
                            "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: pass-1 routes by low key bits, NCCL all-to-all"},
                 "phases_ms": phase, "roofline": roof, "join_roofline": join_roof, "cpu_baseline": cpu, "e2e": e2e,
-                "exchange": exchange, "skew": skew,
+                "exchange": exchange, "skew": skew, "tpch": tpch,
                 "gpu_launches": launches_timed, "gpu_launches_total": A.kernel_launch_count() - launches0,
                 "clocks": clocks, "scan": scan}
         print(json.dumps(line))
@@ -448,6 +481,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tpch", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
