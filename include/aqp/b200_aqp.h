@@ -166,6 +166,9 @@ int b200_shard_hist_device(const struct row_t *d_in, uint64_t n, uint32_t total_
                            uint32_t log2_gpus, uint32_t *d_hist, uint32_t *d_counts1, int slot, void *stream);
 int b200_shard_scatter_device(const struct row_t *d_in, uint64_t n, const uint32_t *d_dest_off, void *const *dest_bufs,
                               int slot, void *stream);
+/* asynchronous device-to-device copy on `stream` (cudaMemcpyAsync, cudaMemcpyDefault): with a peer pointer
+ * from b200_ipc_open as dst this is a copy-engine transfer over NVLink — the DMA form of the exchange */
+int b200_copy_async(void *dst, const void *src, size_t bytes, void *stream);
 int b200_ipc_export(void *d_ptr, unsigned char *handle_out /* 64 bytes */);
 int b200_ipc_open(const unsigned char *handle /* 64 bytes */, void **d_ptr_out);
 int b200_ipc_close(void *d_ptr);

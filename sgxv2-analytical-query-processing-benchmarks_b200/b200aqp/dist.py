@@ -122,6 +122,9 @@ class CudaBackend:
         self.A._check(self.L.b200_shard_scatter_device(rel.data_ptr(), n, dest_off.data_ptr(), arr, slot, self.stream()),
                       "b200_shard_scatter_device")
 
+    def copy_async(self, dst_ptr, src_ptr, nbytes, stream):
+        self.A._check(self.L.b200_copy_async(dst_ptr, src_ptr, nbytes, self.A._st(stream)), "b200_copy_async")
+
     def alloc_shared(self, nbytes):
         """(buffer, 64-byte IPC handle as a uint8 tensor)"""
         import ctypes as C
@@ -327,5 +330,104 @@ class FusedShardedJoin(ShardedJoin):
             out["ms_scatter_kernels"] = es.elapsed_time(ex)
             out["ms_barrier"] = ex.elapsed_time(e2)
             out["ms_exchange"] = 0.0                   # no separate exchange step
+            out["ms_total"] = e0.elapsed_time(e3)
+        return out
+
+
+class DmaShardedJoin(FusedShardedJoin):
+    """Third exchange variant: local pass 1 into a send buffer laid out by destination (as in ShardedJoin),
+    then one copy-engine transfer per (relation, destination) straight into the peers' IPC-mapped receive
+    buffers. Copy engines move large contiguous blocks at the full NVLink rate (774 GB/s measured peer copy,
+    profiles/r01_p2pbench_2gpu.txt) where SM-issued 256-byte runs reach 300-435 GB/s; the price is the send
+    buffer's extra HBM write + read. The sizing collectives run on a side stream under the pass-1 scatter."""
+
+    def __init__(self, nR_total, nS_total, device, backend=None, group=None, capacity_factor: float = 1.5):
+        super().__init__(nR_total, nS_total, device, backend, group, capacity_factor)
+        self.copy_streams = [torch.cuda.Stream(device=device) for _ in range(2 * self.world)]
+
+    def run(self, R: torch.Tensor, S: torch.Tensor) -> dict:
+        be, G, rank = self.backend, self.world, self.rank
+        nR, nS = R.numel() // 2, S.numel() // 2
+        F1, P = self.F1, self.P
+        per = F1 // G
+        main = torch.cuda.current_stream()
+        e0 = self._event()
+        sendR = self._buf("sendR", 2 * nR + 4, torch.int32)
+        sendS = self._buf("sendS", 2 * nS + 4, torch.int32)
+        hist = self._buf("hist", 2 * P, torch.int32)
+        off1 = self._buf("off1", 2 * (F1 + 1), torch.int32)
+        offR, offS = off1[:F1 + 1], off1[F1 + 1:2 * (F1 + 1)]
+        # ---- 1. local histogram + routed pass-1 scatter into the send buffers --------------------------
+        be.shard_pass1(R, nR, self.bits, self.b1, self.lg, sendR, hist[:P], offR)
+        be.shard_pass1(S, nS, self.bits, self.b1, self.lg, sendS, hist[P:2 * P], offS)
+        e1 = self._event()
+        # ---- 2. size the exchange ------------------------------------------------------------------------
+        counts = torch.cat([offR[1:] - offR[:-1], offS[1:] - offS[:-1]]).to(torch.int64)
+        counts_flat = torch.empty(G * 2 * F1, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(counts_flat, counts, group=self.group)
+        counts_all = counts_flat.view(G, 2 * F1)
+        hist_global = hist[:2 * P].clone()
+        dist.all_reduce(hist_global, group=self.group)
+        sR, rR, segR, seg_group = exchange_plan(counts_all[:, :F1], rank, G)
+        sS, rS, segS, _ = exchange_plan(counts_all[:, F1:], rank, G)
+        # where my block for destination g starts inside g's receive buffer = tuples sent to g by lower ranks
+        toR = counts_all[:, :F1].view(G, G, per).sum(2)          # [source, owner]
+        toS = counts_all[:, F1:].view(G, G, per).sum(2)
+        dstR = (torch.cumsum(toR, 0) - toR)[rank]
+        dstS = (torch.cumsum(toS, 0) - toS)[rank]
+        worst = torch.stack([toR.sum(0).max(), toS.sum(0).max(), rR.sum(), rS.sum()])
+        host = torch.cat([worst, sR, sS, dstR, dstS]).tolist()    # the one host sync of the exchange
+        if host[0] > self.capR or host[1] > self.capS:
+            self.fallbacks += 1
+            out = ShardedJoin.run(self, R, S)
+            out["exchange"] = "nccl-fallback"
+            return out
+        nR_recv, nS_recv = int(host[2]), int(host[3])
+        sendsR, sendsS = host[4:4 + G], host[4 + G:4 + 2 * G]
+        dR, dS = host[4 + 2 * G:4 + 3 * G], host[4 + 3 * G:4 + 4 * G]
+        es = self._event()
+        # ---- 3. DMA exchange: 2G copy-engine transfers into the peers' buffers -------------------------------
+        offs_r, offs_s, a, b = [], [], 0, 0
+        for g in range(G):
+            offs_r.append(a)
+            offs_s.append(b)
+            a += int(sendsR[g])
+            b += int(sendsS[g])
+        for k in range(G):
+            g = (rank + k) % G
+            for which, (peers, send, offs, sends, dsts) in enumerate(((self.peerR, sendR, offs_r, sendsR, dR),
+                                                                      (self.peerS, sendS, offs_s, sendsS, dS))):
+                st = self.copy_streams[2 * k + which]
+                st.wait_stream(main)
+                be.copy_async(peers[g] + 8 * int(dsts[g]), send.data_ptr() + 8 * offs[g], 8 * int(sends[g]), st.cuda_stream)
+        for st in self.copy_streams:
+            main.wait_stream(st)
+        ex = self._event()
+        flag = self._buf("flag", 2, torch.int32)
+        dist.all_reduce(flag[:1], group=self.group)    # barrier: every rank's copies have landed
+        e2 = self._event()
+        # ---- 4. local pass 2 + build/probe -------------------------------------------------------------------
+        hR = final_hist_slice(hist_global[:P], rank, G, self.b1, self.b2)
+        hS = final_hist_slice(hist_global[P:], rank, G, self.b1, self.b2)
+        local = be.shard_join(_RawBuffer(self.peerR[rank]), nR_recv, segR.to(torch.int32), _RawBuffer(self.peerS[rank]),
+                              nS_recv, segS.to(torch.int32), seg_group, G * per, per, self.b1, self.b2, hR, hS, self.bits)
+        e3 = self._event()
+        to_i64 = lambda v: v - (1 << 64) if v >= (1 << 63) else v
+        res = torch.tensor([local["matches"], to_i64(local["checksum"]), to_i64(local["keysum"])], dtype=torch.int64,
+                           device=self.device)
+        dist.all_reduce(res, group=self.group)
+        m, cs, ks = (int(x) for x in res.tolist())
+        out = {"matches": m, "checksum": cs % (1 << 64), "keysum": ks % (1 << 64), "radix_bits": self.bits,
+               "num_passes": 2, "bits_pass1": self.b1, "bits_pass2": self.b2, "tuples_sent": nR + nS,
+               "tuples_kept": int(sendsR[rank] + sendsS[rank]), "ms_pass2": local.get("ms_pass2", 0.0),
+               "ms_join": local.get("ms_join", 0.0), "exchange": "p2p-dma"}
+        if e0 is not None:
+            torch.cuda.synchronize()
+            out["ms_hist"] = 0.0
+            out["ms_pass1"] = e0.elapsed_time(e1)      # histogram + local routed pass-1 scatter
+            out["ms_sizing"] = e1.elapsed_time(es)
+            out["ms_scatter_kernels"] = 0.0
+            out["ms_exchange"] = es.elapsed_time(e2)   # copy-engine transfers + barrier
+            out["ms_barrier"] = ex.elapsed_time(e2)
             out["ms_total"] = e0.elapsed_time(e3)
         return out

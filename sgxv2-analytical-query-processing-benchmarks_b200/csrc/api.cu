@@ -745,6 +745,13 @@ int b200_shard_scatter_device(const struct row_t *d_in, uint64_t n, const uint32
                                 sl.bits1, nullptr, bb, NB, sl.tpb, st, &pt);
 }
 
+int b200_copy_async(void *dst, const void *src, size_t bytes, void *stream) {
+    if (ensure_init()) return -1;
+    if (bytes == 0) return 0;
+    AQP_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream ? static_cast<cudaStream_t>(stream) : g.stream));
+    return 0;
+}
+
 int b200_ipc_export(void *d_ptr, unsigned char *handle_out) {
     if (ensure_init()) return -1;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");

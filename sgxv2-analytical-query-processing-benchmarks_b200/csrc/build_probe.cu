@@ -48,7 +48,7 @@ int join_items_device(const uint32_t *d_offR, const uint32_t *d_offS, uint32_t n
 // ---------------------------------------------------------------------------------------------
 // build + probe
 // ---------------------------------------------------------------------------------------------
-constexpr int kProbeUnroll = 8;
+constexpr int kProbeUnroll = 4;   // S tuples per thread and round; two rounds are in flight (double buffering)
 constexpr uint32_t kChainFlag = 0x80000000u;   // set in a bucket head when its chain holds more than one tuple
 constexpr size_t kJoinSmemBytes = (size_t) kBuildCap * (sizeof(uint2) + sizeof(uint32_t) + sizeof(uint16_t));
 
@@ -73,37 +73,58 @@ build_probe_kernel(const uint2 *__restrict__ R, const uint32_t *__restrict__ off
         const uint32_t sbeg = offS[p] + item.y * kProbeChunk;
         const uint32_t send = min(sbeg + (uint32_t) kProbeChunk, offS[p + 1]);
 
+        constexpr uint32_t kRound = kJoinThreads * kProbeUnroll;
+        auto load_round = [&](uint32_t base, uint2 (&dst)[kProbeUnroll]) {
+#pragma unroll
+            for (int j = 0; j < kProbeUnroll; ++j) {
+                uint32_t i = base + j * kJoinThreads + threadIdx.x;
+                if (i < send) dst[j] = ld_stream_v2(S + i);
+            }
+        };
+
         for (uint32_t rb = rbeg; rb < rend; rb += kBuildCap) {
             const uint32_t nr = min((uint32_t) kBuildCap, rend - rb);
             uint32_t N = 1;
             while (N < nr) N <<= 1;
             const uint32_t hmask = N - 1;
+            // the first round of S tuples is put in flight BEFORE the build so its latency hides behind it
+            uint2 sn[kProbeUnroll];
+            load_round(sbeg, sn);
+            // all R tuples of this thread are requested up front, then inserted
+            constexpr int kBuildPerThread = kBuildCap / kJoinThreads;
+            uint2 rv[kBuildPerThread];
+#pragma unroll
+            for (int k = 0; k < kBuildPerThread; ++k) {
+                uint32_t i = k * kJoinThreads + threadIdx.x;
+                if (i < nr) rv[k] = R[rb + i];
+            }
             __syncthreads();   // previous round's probe done before the table is cleared
             for (uint32_t i = threadIdx.x; i < N; i += kJoinThreads) bucket[i] = 0;
             __syncthreads();
-            for (uint32_t i = threadIdx.x; i < nr; i += kJoinThreads) {
-                uint2 t = R[rb + i];
-                rt[i] = t;
-                uint32_t *b = &bucket[(t.x >> hash_shift) & hmask];
-                uint32_t old = atomicExch(b, i + 1);
-                next[i] = (uint16_t) old;             // low 16 bits: previous head (0 = end of chain)
-                if (old) atomicOr(b, kChainFlag);     // whoever is head in the end carries the flag
+#pragma unroll
+            for (int k = 0; k < kBuildPerThread; ++k) {
+                uint32_t i = k * kJoinThreads + threadIdx.x;
+                if (i < nr) {
+                    rt[i] = rv[k];
+                    uint32_t *b = &bucket[(rv[k].x >> hash_shift) & hmask];
+                    uint32_t old = atomicExch(b, i + 1);
+                    next[i] = (uint16_t) old;             // low 16 bits: previous head (0 = end of chain)
+                    if (old) atomicOr(b, kChainFlag);     // whoever is head in the end carries the flag
+                }
             }
             __syncthreads();
 
-            // uniform trip count so the materialising variant can use warp-wide primitives
-            for (uint32_t base = sbeg; base < send; base += kJoinThreads * kProbeUnroll) {
+            // uniform trip count so the materialising variant can use warp-wide primitives; the next round's
+            // loads are issued before the current round is probed (register double buffering)
+            for (uint32_t base = sbeg; base < send; base += kRound) {
                 uint2 s[kProbeUnroll];
-                bool valid[kProbeUnroll];
+#pragma unroll
+                for (int j = 0; j < kProbeUnroll; ++j) s[j] = sn[j];
+                if (base + kRound < send) load_round(base + kRound, sn);
 #pragma unroll
                 for (int j = 0; j < kProbeUnroll; ++j) {
-                    uint32_t i = base + j * kJoinThreads + threadIdx.x;
-                    valid[j] = i < send;
-                    if (valid[j]) s[j] = ld_stream_v2(S + i);
-                }
-#pragma unroll
-                for (int j = 0; j < kProbeUnroll; ++j) {
-                    const uint32_t head = valid[j] ? bucket[(s[j].x >> hash_shift) & hmask] : 0u;
+                    const bool valid = base + j * kJoinThreads + threadIdx.x < send;
+                    const uint32_t head = valid ? bucket[(s[j].x >> hash_shift) & hmask] : 0u;
                     uint32_t hit = head & 0xFFFFu;
                     if (!kMaterialize) {
                         if (!(head & kChainFlag)) {
