@@ -42,6 +42,7 @@ LOG_R, LOG_S = 27, 29          # BASELINE config 3
 SCAN_LOG_N = 30                # BASELINE config 2
 JOIN_BYTES_PER_TUPLE = 56      # 8 * (3 P + 1) with P = 2 passes
 SCATTER_BYTES_PER_TUPLE = 16   # read 8 + write 8
+DEFAULT_EXCHANGE = "dma"       # multi-GPU shuffle: "dma" (copy engines), "p2p" (fused peer stores), "nccl"
 METRIC = "rho_join_throughput"
 UNIT = "Mtuples/s"
 
@@ -278,8 +279,8 @@ def run_b200_arm(args):
     else:
         # headline: scatter kernel fused with the exchange over NVLink peer memory; the NCCL all-to-all
         # variant is timed beside it as the baseline (B200_AQP_EXCHANGE=nccl makes it the headline)
-        fused = os.environ.get("B200_AQP_EXCHANGE", "p2p") != "nccl"
-        plan = (D.FusedShardedJoin if fused else D.ShardedJoin)(nR, nS, dev)
+        variants = {"p2p": D.FusedShardedJoin, "dma": D.DmaShardedJoin, "nccl": D.ShardedJoin}
+        plan = variants[os.environ.get("B200_AQP_EXCHANGE", DEFAULT_EXCHANGE)](nR, nS, dev)
 
         def step():
             return plan.run(R, S)
@@ -350,34 +351,38 @@ def run_b200_arm(args):
     exchange = None
     if world > 1:
         sent = 8 * ((nR_loc + nS_loc) - s.get("tuples_kept", 0))
-        ms_x = phase["ms_pass1"] if s.get("exchange") == "p2p-fused" else phase["ms_exchange"]
-        exchange = {"kind": s.get("exchange", "nccl all_to_all_single"), "bytes_sent_per_gpu": sent,
-                    "ms": ms_x, "busbw_gbs": sent / ms_x / 1e6 if ms_x else None,
-                    "note": "p2p-fused: ms covers the sizing collectives, the fused scatter+exchange kernel and the "
-                            "barrier; reference peaks: 770 GB/s measured peer copy, 900 GB/s nominal per direction"}
-        if s.get("exchange") == "p2p-fused":
-            base = D.ShardedJoin(nR, nS, dev)
+        kind = s.get("exchange", "nccl all_to_all_single")
+        ms_x = phase["ms_exchange"] if kind.startswith("nccl") else phase["ms_pass1"]
+        exchange = {"kind": kind, "bytes_sent_per_gpu": sent, "ms": ms_x, "busbw_gbs": sent / ms_x / 1e6 if ms_x else None,
+                    "note": "p2p-fused: ms = sizing collectives + fused scatter/exchange kernel + barrier; p2p-dma: ms = local "
+                            "pass-1 scatter (sizing hidden underneath) + copy-engine transfers + barrier; nccl: sizing + "
+                            "all_to_all_single. Reference peaks: 770 GB/s measured peer copy, 900 GB/s nominal per direction",
+                    "variants": {}}
+        # the other exchange implementations timed beside the headline one (same inputs, same step count)
+        for name, cls in variants.items():
+            if cls is type(plan):
+                continue
+            other = cls(nR, nS, dev)
             for _ in range(2):
-                sb = base.run(R, S)
+                sb = other.run(R, S)
             assert sb["matches"] == nS
             barrier()
             e0.record()
             xb = 0.0
             for _ in range(args.steps):
-                sb = base.run(R, S)
-                xb += sb["ms_exchange"]
+                sb = other.run(R, S)
+                xb += sb["ms_exchange"] if name == "nccl" else sb["ms_pass1"]
             e1.record()
             barrier()
             t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            exchange["nccl_baseline"] = {"ms_per_step": float(t.item()), "value": (nR + nS) / float(t.item()) / 1e3,
-                                         "unit": UNIT, "ms_exchange": xb / args.steps}
-            del base
+            exchange["variants"][name] = {"ms_per_step": float(t.item()), "value": (nR + nS) / float(t.item()) / 1e3,
+                                          "unit": UNIT, "ms_exchange": xb / args.steps}
+            del other
 
     # ---- e2e through run_join() with pinned host relations (N=1 path of the drop-in API) ----------
     e2e = None
     if world == 1:
-        import numpy as np
         hR = torch.empty(nR * 2, dtype=torch.int32).pin_memory()
         hS = torch.empty(nS * 2, dtype=torch.int32).pin_memory()
         hR.copy_(R)
@@ -399,6 +404,36 @@ def run_b200_arm(args):
                "d2h_bytes_per_step": 32, "ms_per_step": dt * 1e3, "steps": e2e_steps,
                "api": "run_join(result_t*, R, S, \"RHO\", joinconfig_t*) on pinned host relations"}
         del hR, hS, npR, npS
+    else:
+        # N > 1: every rank keeps its row-range shard in pinned host memory; a step = H2D of the shard over this
+        # GPU's own PCIe link + the sharded join (whose result read-back is the final 24-byte all-reduce)
+        hR = torch.empty(nR_loc * 2, dtype=torch.int32).pin_memory()
+        hS = torch.empty(nS_loc * 2, dtype=torch.int32).pin_memory()
+        hR.copy_(R)
+        hS.copy_(S)
+        torch.cuda.synchronize()
+        e2e_steps = max(1, min(args.steps, 5))
+
+        def e2e_step():
+            R.copy_(hR, non_blocking=True)
+            S.copy_(hS, non_blocking=True)
+            return plan.run(R, S)
+
+        for _ in range(2):
+            g = e2e_step()
+        assert g["matches"] == nS
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            g = e2e_step()
+        barrier()
+        t = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        e2e = {"value": (nR + nS) / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": 8 * (nR + nS),
+               "d2h_bytes_per_step": 24 * world, "ms_per_step": dt * 1e3, "steps": e2e_steps,
+               "api": f"{type(plan).__name__}.run on pinned host row-range shards, one H2D stream per GPU"}
+        del hR, hS
     del R, S
     torch.cuda.empty_cache()
 

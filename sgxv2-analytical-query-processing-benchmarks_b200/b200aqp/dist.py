@@ -335,36 +335,27 @@ class FusedShardedJoin(ShardedJoin):
 
 
 class DmaShardedJoin(FusedShardedJoin):
-    """Third exchange variant: local pass 1 into a send buffer laid out by destination (as in ShardedJoin),
-    then one copy-engine transfer per (relation, destination) straight into the peers' IPC-mapped receive
-    buffers. Copy engines move large contiguous blocks at the full NVLink rate (774 GB/s measured peer copy,
-    profiles/r01_p2pbench_2gpu.txt) where SM-issued 256-byte runs reach 300-435 GB/s; the price is the send
-    buffer's extra HBM write + read. The sizing collectives run on a side stream under the pass-1 scatter."""
+    """Third exchange variant: pass 1 scatters into a LOCAL send buffer laid out by destination, then one
+    copy-engine transfer per (relation, destination) moves each block straight into the peer's IPC-mapped
+    receive buffer. Copy engines move large contiguous blocks at the full NVLink rate (774 GB/s measured peer
+    copy, profiles/r01_p2pbench_2gpu.txt) where SM-issued 256-byte runs reach 300-435 GB/s; the price is the
+    send buffer's extra HBM write + read. Overlap: the sizing collectives and the plan arithmetic run on a side
+    stream under the pass-1 scatter (the send-buffer layout needs only local counts), and R's transfers run
+    under S's scatter."""
 
     def __init__(self, nR_total, nS_total, device, backend=None, group=None, capacity_factor: float = 1.5):
         super().__init__(nR_total, nS_total, device, backend, group, capacity_factor)
-        self.copy_streams = [torch.cuda.Stream(device=device) for _ in range(2 * self.world)]
+        cuda = device.type == "cuda"
+        self.side = torch.cuda.Stream(device=device) if cuda else None
+        self.copy_streams = [torch.cuda.Stream(device=device) for _ in range(2 * self.world)] if cuda else []
 
-    def run(self, R: torch.Tensor, S: torch.Tensor) -> dict:
-        be, G, rank = self.backend, self.world, self.rank
-        nR, nS = R.numel() // 2, S.numel() // 2
-        F1, P = self.F1, self.P
+    def _plan(self, cnt1, hist):
+        """sizing collectives + plan arithmetic (device tensors only); returns the plan and ONE flat int64
+        tensor with everything the host needs to issue the transfers"""
+        G, rank, F1, P = self.world, self.rank, self.F1, self.P
         per = F1 // G
-        main = torch.cuda.current_stream()
-        e0 = self._event()
-        sendR = self._buf("sendR", 2 * nR + 4, torch.int32)
-        sendS = self._buf("sendS", 2 * nS + 4, torch.int32)
-        hist = self._buf("hist", 2 * P, torch.int32)
-        off1 = self._buf("off1", 2 * (F1 + 1), torch.int32)
-        offR, offS = off1[:F1 + 1], off1[F1 + 1:2 * (F1 + 1)]
-        # ---- 1. local histogram + routed pass-1 scatter into the send buffers --------------------------
-        be.shard_pass1(R, nR, self.bits, self.b1, self.lg, sendR, hist[:P], offR)
-        be.shard_pass1(S, nS, self.bits, self.b1, self.lg, sendS, hist[P:2 * P], offS)
-        e1 = self._event()
-        # ---- 2. size the exchange ------------------------------------------------------------------------
-        counts = torch.cat([offR[1:] - offR[:-1], offS[1:] - offS[:-1]]).to(torch.int64)
         counts_flat = torch.empty(G * 2 * F1, dtype=torch.int64, device=self.device)
-        dist.all_gather_into_tensor(counts_flat, counts, group=self.group)
+        dist.all_gather_into_tensor(counts_flat, cnt1[:2 * F1].to(torch.int64), group=self.group)
         counts_all = counts_flat.view(G, 2 * F1)
         hist_global = hist[:2 * P].clone()
         dist.all_reduce(hist_global, group=self.group)
@@ -376,41 +367,81 @@ class DmaShardedJoin(FusedShardedJoin):
         dstR = (torch.cumsum(toR, 0) - toR)[rank]
         dstS = (torch.cumsum(toS, 0) - toS)[rank]
         worst = torch.stack([toR.sum(0).max(), toS.sum(0).max(), rR.sum(), rS.sum()])
-        host = torch.cat([worst, sR, sS, dstR, dstS]).tolist()    # the one host sync of the exchange
+        hv = torch.cat([worst, sR, sS, dstR, dstS])
+        hR = final_hist_slice(hist_global[:P], rank, G, self.b1, self.b2)
+        hS = final_hist_slice(hist_global[P:], rank, G, self.b1, self.b2)
+        return hv, segR.to(torch.int32), segS.to(torch.int32), seg_group, hR, hS
+
+    def run(self, R: torch.Tensor, S: torch.Tensor) -> dict:
+        be, G, rank = self.backend, self.world, self.rank
+        nR, nS = R.numel() // 2, S.numel() // 2
+        F1, P = self.F1, self.P
+        per = F1 // G
+        cuda = self.device.type == "cuda"
+        main = torch.cuda.current_stream() if cuda else None
+        e0 = self._event()
+        sendR = self._buf("sendR", 2 * nR + 4, torch.int32)
+        sendS = self._buf("sendS", 2 * nS + 4, torch.int32)
+        hist = self._buf("hist", 2 * P, torch.int32)
+        cnt1 = self._buf("cnt1", 2 * F1, torch.int32)
+        # ---- 1. local histograms --------------------------------------------------------------------------
+        be.shard_hist(R, nR, self.bits, self.b1, self.lg, hist[:P], cnt1[:F1], 0)
+        be.shard_hist(S, nS, self.bits, self.b1, self.lg, hist[P:2 * P], cnt1[F1:2 * F1], 1)
+        eh = self._event()
+        # ---- 2. sizing on the side stream, under ... ------------------------------------------------------
+        if cuda:
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                hv, segR, segS, seg_group, hR, hS = self._plan(cnt1, hist)
+                hv_host = hv.to("cpu", non_blocking=True)
+                side_done = torch.cuda.Event()
+                side_done.record()
+        else:
+            hv, segR, segS, seg_group, hR, hS = self._plan(cnt1, hist)
+            hv_host = hv
+        # ---- 3. ... the routed pass-1 scatter into the send buffers (layout = local exclusive prefix) ------
+        c = cnt1[:2 * F1].view(2, F1).to(torch.int64)
+        loc = (torch.cumsum(c, 1) - c).to(torch.int32)
+        be.shard_scatter(R, nR, loc[0], [sendR.data_ptr()] * G, 0)
+        eR = self._event()
+        be.shard_scatter(S, nS, loc[1], [sendS.data_ptr()] * G, 1)
+        eS = self._event()
+        if cuda:
+            side_done.synchronize()            # the one host sync of the exchange
+        host = [int(x) for x in hv_host.tolist()]
         if host[0] > self.capR or host[1] > self.capS:
             self.fallbacks += 1
+            if cuda:
+                main.wait_stream(self.side)
             out = ShardedJoin.run(self, R, S)
             out["exchange"] = "nccl-fallback"
             return out
-        nR_recv, nS_recv = int(host[2]), int(host[3])
+        nR_recv, nS_recv = host[2], host[3]
         sendsR, sendsS = host[4:4 + G], host[4 + G:4 + 2 * G]
         dR, dS = host[4 + 2 * G:4 + 3 * G], host[4 + 3 * G:4 + 4 * G]
-        es = self._event()
-        # ---- 3. DMA exchange: 2G copy-engine transfers into the peers' buffers -------------------------------
+        # ---- 4. DMA exchange: 2G copy-engine transfers into the owners' buffers ------------------------------
         offs_r, offs_s, a, b = [], [], 0, 0
         for g in range(G):
             offs_r.append(a)
             offs_s.append(b)
-            a += int(sendsR[g])
-            b += int(sendsS[g])
+            a += sendsR[g]
+            b += sendsS[g]
         for k in range(G):
-            g = (rank + k) % G
-            for which, (peers, send, offs, sends, dsts) in enumerate(((self.peerR, sendR, offs_r, sendsR, dR),
-                                                                      (self.peerS, sendS, offs_s, sendsS, dS))):
-                st = self.copy_streams[2 * k + which]
-                st.wait_stream(main)
-                be.copy_async(peers[g] + 8 * int(dsts[g]), send.data_ptr() + 8 * offs[g], 8 * int(sends[g]), st.cuda_stream)
-        for st in self.copy_streams:
-            main.wait_stream(st)
+            g = (rank + k) % G                 # start with the local block, then walk the ring
+            for which, (peers, send, offs, sends, dsts, ev) in enumerate(
+                    ((self.peerR, sendR, offs_r, sendsR, dR, eR), (self.peerS, sendS, offs_s, sendsS, dS, eS))):
+                self.exchange_copy(peers[g] + 8 * dsts[g], send.data_ptr() + 8 * offs[g], 8 * sends[g], 2 * k + which, ev)
+        if cuda:
+            for st in self.copy_streams:
+                main.wait_stream(st)
+            main.wait_stream(self.side)
         ex = self._event()
         flag = self._buf("flag", 2, torch.int32)
-        dist.all_reduce(flag[:1], group=self.group)    # barrier: every rank's copies have landed
+        dist.all_reduce(flag[:1], group=self.group)    # barrier: every rank's transfers have landed
         e2 = self._event()
-        # ---- 4. local pass 2 + build/probe -------------------------------------------------------------------
-        hR = final_hist_slice(hist_global[:P], rank, G, self.b1, self.b2)
-        hS = final_hist_slice(hist_global[P:], rank, G, self.b1, self.b2)
-        local = be.shard_join(_RawBuffer(self.peerR[rank]), nR_recv, segR.to(torch.int32), _RawBuffer(self.peerS[rank]),
-                              nS_recv, segS.to(torch.int32), seg_group, G * per, per, self.b1, self.b2, hR, hS, self.bits)
+        # ---- 5. local pass 2 + build/probe -------------------------------------------------------------------
+        local = be.shard_join(_RawBuffer(self.peerR[rank]), nR_recv, segR, _RawBuffer(self.peerS[rank]),
+                              nS_recv, segS, seg_group, G * per, per, self.b1, self.b2, hR, hS, self.bits)
         e3 = self._event()
         to_i64 = lambda v: v - (1 << 64) if v >= (1 << 63) else v
         res = torch.tensor([local["matches"], to_i64(local["checksum"]), to_i64(local["keysum"])], dtype=torch.int64,
@@ -423,11 +454,20 @@ class DmaShardedJoin(FusedShardedJoin):
                "ms_join": local.get("ms_join", 0.0), "exchange": "p2p-dma"}
         if e0 is not None:
             torch.cuda.synchronize()
-            out["ms_hist"] = 0.0
-            out["ms_pass1"] = e0.elapsed_time(e1)      # histogram + local routed pass-1 scatter
-            out["ms_sizing"] = e1.elapsed_time(es)
-            out["ms_scatter_kernels"] = 0.0
-            out["ms_exchange"] = es.elapsed_time(e2)   # copy-engine transfers + barrier
+            out["ms_hist"] = e0.elapsed_time(eh)
+            out["ms_pass1"] = eh.elapsed_time(e2)      # scatter (sizing underneath) + transfers + barrier
+            out["ms_sizing"] = 0.0                     # hidden under the scatter
+            out["ms_scatter_kernels"] = eh.elapsed_time(eS)
+            out["ms_exchange"] = eS.elapsed_time(e2)   # the part of the transfers not hidden under S's scatter
             out["ms_barrier"] = ex.elapsed_time(e2)
             out["ms_total"] = e0.elapsed_time(e3)
         return out
+
+    def exchange_copy(self, dst_ptr, src_ptr, nbytes, lane, after):
+        """one transfer of the exchange on copy stream `lane`, ordered after event `after`"""
+        if not self.copy_streams:               # host stand-in backend (tests): synchronous copy
+            self.backend.copy_async(dst_ptr, src_ptr, nbytes, None)
+            return
+        st = self.copy_streams[lane]
+        st.wait_event(after)
+        self.backend.copy_async(dst_ptr, src_ptr, nbytes, st.cuda_stream)

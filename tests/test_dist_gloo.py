@@ -73,6 +73,124 @@ class NumpyBackend:
         return {"matches": o["matches"], "checksum": o["checksum"], "keysum": o["keysum"]}
 
 
+class _ShmBuffer:
+    def __init__(self, shm):
+        import ctypes as C
+        self.shm = shm
+        self.ptr = C.addressof(C.c_char.from_buffer(shm.buf))
+
+
+class SharedNumpyBackend(NumpyBackend):
+    """Adds host stand-ins for the peer-memory stage calls (b200_shard_hist_device, b200_shard_scatter_device,
+    b200_copy_async, b200_ipc_export/open): receive buffers are POSIX shared memory mapped by every rank, the
+    'device pointers' are this process's addresses of those mappings."""
+
+    def __init__(self, oracle, plan):
+        super().__init__(oracle, plan)
+        self._slots = {}
+        self._maps = []
+
+    @staticmethod
+    def _view(ptr, n):
+        import ctypes as C
+        return np.ctypeslib.as_array((C.c_int32 * (2 * n)).from_address(ptr))
+
+    def alloc_shared(self, nbytes):
+        from multiprocessing import shared_memory
+        shm = shared_memory.SharedMemory(create=True, size=nbytes)
+        name = shm.name.encode()
+        assert len(name) < 64
+        h = torch.zeros(64, dtype=torch.uint8)
+        h[:len(name)] = torch.tensor(list(name), dtype=torch.uint8)
+        self._maps.append(shm)
+        return _ShmBuffer(shm), h
+
+    def open_shared(self, handle):
+        from multiprocessing import shared_memory
+        name = bytes(handle.tolist()).rstrip(b"\0").decode()
+        shm = shared_memory.SharedMemory(name=name)
+        self._maps.append(shm)
+        return _ShmBuffer(shm).ptr
+
+    def close(self, unlink_own):
+        for i, m in enumerate(self._maps):
+            m.close()
+        for m in unlink_own:
+            m.unlink()
+
+    def shard_hist(self, rel, n, bits, b1, lg, hist, counts1, slot):
+        a = rel.numpy()[:2 * n].view(self.O.ROW)
+        d = a["key"] & ((1 << bits) - 1)
+        p1 = self._rot(d & ((1 << b1) - 1), b1, lg)
+        routed = (d & ~np.uint32((1 << b1) - 1)) | p1
+        hist.numpy()[:1 << bits] = np.bincount(routed, minlength=1 << bits).astype(np.int32)
+        counts1.numpy()[:1 << b1] = np.bincount(p1, minlength=1 << b1).astype(np.int32)
+        self._slots[slot] = (p1, b1, lg)
+
+    def shard_scatter(self, rel, n, dest_off, dest_ptrs, slot):
+        p1, b1, lg = self._slots[slot]
+        a = rel.numpy()[:2 * n].view(np.int64)
+        per_shift = b1 - lg
+        off = dest_off.numpy()
+        for p in np.unique(p1):
+            rows = a[p1 == p]
+            dst = self._view(dest_ptrs[int(p) >> per_shift] + 8 * int(off[p]), len(rows)).view(np.int64)
+            dst[:] = rows
+
+    def copy_async(self, dst_ptr, src_ptr, nbytes, stream):
+        import ctypes as C
+        C.memmove(dst_ptr, src_ptr, nbytes)
+
+    def shard_join(self, R, nR, segR, S, nS, segS, *rest):
+        wrap = lambda b, n: torch.from_numpy(self._view(b.data_ptr(), n).copy()) if not isinstance(b, torch.Tensor) else b
+        return super().shard_join(wrap(R, nR), nR, segR, wrap(S, nS), nS, segS, *rest)
+
+
+def _peer_worker(rank, world, port, nR, nS, plan, cls_name, ret):
+    for p in (ROOT, PKG):
+        sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle as O
+    import b200aqp.dist as D
+    R = O.set_rowid_payload(O.gen_pk(nR, 11111))
+    S = O.set_rowid_payload(O.gen_fk(nS, nR, 22222))
+    exp = O.rho(R, S)
+    be = SharedNumpyBackend(O, plan)
+    be.rank, be.lg = rank, D.log2_exact(world)
+    lo_r, hi_r = rank * nR // world, (rank + 1) * nR // world
+    lo_s, hi_s = rank * nS // world, (rank + 1) * nS // world
+    Rl = torch.from_numpy(R[lo_r:hi_r].copy().view(np.int32))
+    Sl = torch.from_numpy(S[lo_s:hi_s].copy().view(np.int32))
+    sj = getattr(D, cls_name)(nR, nS, torch.device("cpu"), backend=be)
+    own = [b.shm for b in sj._own]
+    try:
+        for _ in range(2):                                          # buffers are reused across runs
+            out = sj.run(Rl, Sl)
+            assert (out["matches"], out["checksum"], out["keysum"]) == (exp["matches"], exp["checksum"], exp["keysum"]), out
+            assert out["exchange"] == ("p2p-dma" if cls_name == "DmaShardedJoin" else "p2p-fused")
+            dist.barrier()                                          # nobody overwrites a buffer a peer still reads
+        # a capacity too small for the data must take the NCCL path on every rank, with the same answer
+        sj.capR = sj.capS = 1
+        out = sj.run(Rl, Sl)
+        assert out["exchange"] == "nccl-fallback" and out["matches"] == exp["matches"] and sj.fallbacks == 1
+        ret[rank] = out["matches"]
+        dist.barrier()
+    finally:
+        del sj
+        be.close(own)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cls_name", ["FusedShardedJoin", "DmaShardedJoin"])
+@pytest.mark.parametrize("world,nR,nS,plan", [(2, 20011, 100003, (6, 3, 3)), (4, 30000, 120001, (7, 3, 4))])
+def test_peer_memory_exchange_host_logic(cls_name, world, nR, nS, plan):
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_peer_worker, args=(world, port, nR, nS, plan, cls_name, ret), nprocs=world, join=True)
+    assert len(ret) == world and len(set(ret.values())) == 1
+
+
 def _worker(rank, world, port, nR, nS, plan, ret):
     for p in (ROOT, PKG):
         sys.path.insert(0, p)

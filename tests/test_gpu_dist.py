@@ -25,7 +25,7 @@ for logR, logS in ((20, 22), (24, 26)):
     st = torch.cuda.current_stream().cuda_stream
     A.gen_pk_device(R.data_ptr(), nR, 11111, rank * nRl, nRl, st); A.gen_fk_device(S.data_ptr(), nS, nR, 22222, rank * nSl, nSl, st)
     rep = nS // nR
-    for cls in (D.ShardedJoin, D.FusedShardedJoin):
+    for cls in (D.ShardedJoin, D.FusedShardedJoin, D.DmaShardedJoin):
         sj = cls(nR, nS, dev)
         for _ in range(3):
             o = sj.run(R, S)
@@ -51,4 +51,4 @@ def test_nccl_sharded_join(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29517", str(script)], env=env,
                        capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
-    assert p.stdout.count("OK") == 4
+    assert p.stdout.count("OK") == 6
