@@ -32,12 +32,12 @@ constexpr int kMaxFanoutBits = 8;                 // bits per pass
 constexpr int kMaxFanout = 1 << kMaxFanoutBits;
 constexpr int kMaxSmemHistBits = 15;              // widest shared-memory histogram (128 KiB)
 #ifndef AQP_SCATTER_TILE
-#define AQP_SCATTER_TILE 2048
+#define AQP_SCATTER_TILE 4096
 #endif
 #ifndef AQP_SCATTER_THREADS
 #define AQP_SCATTER_THREADS 256
 #endif
-constexpr int kScatterTile = AQP_SCATTER_TILE;    // tuples per scatter tile (one TMA bulk load; 2-deep input ring)
+constexpr int kScatterTile = AQP_SCATTER_TILE;    // tuples per scatter tile (32 KiB staging + 2 x 32 KiB TMA ring)
 
 // ---- build/probe geometry ------------------------------------------------------------------------
 constexpr int kBuildCap = 8192;                   // R tuples per shared-memory hash table (64 KiB)

@@ -21,7 +21,6 @@
 #include "common.cuh"
 #include "join_internal.cuh"
 #include "block_scan.cuh"
-#include <cstring>
 
 namespace aqp {
 
@@ -367,6 +366,7 @@ constexpr size_t kScatterSmemBytes = (size_t) (2 * kInBufTuples + kScatterTile) 
 constexpr int kScatterBlocksPerSMRaw = (int) (228 * 1024 / (kScatterSmemBytes + 7424));
 constexpr int kScatterBlocksPerSM = kScatterBlocksPerSMRaw < 1 ? 1 : (kScatterBlocksPerSMRaw * kScatterThreads > 2048 ? 2048 / kScatterThreads : kScatterBlocksPerSMRaw);
 
+uint32_t pass1_blocks() { return (uint32_t) kNumSMs * kScatterBlocksPerSM; }
 
 template <bool kRot, bool kPeer>
 __global__ void __launch_bounds__(kScatterThreads, kScatterBlocksPerSM)
@@ -527,272 +527,6 @@ radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// scatter, write-combining ring variant (the default for fan-outs >= 16)
-//
-// Every partition owns a ring of Bp = 8192 / fan tuple slots in shared memory (64 KiB per CTA) that
-// lives ACROSS tiles. One packed shared-memory atomicAdd per tuple returns both the tuple's position
-// in its partition's stream (high half) and the ring's fill (low half); the slot is pos mod Bp, so the
-// producer step is ONE atomic + ONE store — no per-tile scan, no offset look-ups. After the tile's
-// barrier each warp flushes its own partitions: whole 16-tuple blocks (one 128-byte line) leave the
-// ring as coalesced stores, the tail (< 16 tuples) stays for the next tile. In pass 1 positions are
-// kept congruent to the destination index, so every flushed block is a full, ALIGNED 128-byte line
-// (what both HBM and NVLink peers like best); the destination comes from the CTA-private cursor.
-// In pass 2 the warp reserves each partition's flush with one global atomicAdd.
-// A partition that receives more than its ring holds in one tile (skew) flushes the whole ring and its
-// late tuples are stored directly from registers behind it — correct for any distribution.
-// Shared-memory wavefronts per 32 tuples: ~15 (ring read 2, atomic ~3.5, ring store ~6, flush 2+2)
-// against ~20 for the staged kernel (which adds two random look-ups and a serial scan per tile).
-// ---------------------------------------------------------------------------------------------
-#ifndef AQP_RING_THREADS
-#define AQP_RING_THREADS 512
-#endif
-constexpr int kRingThreads = AQP_RING_THREADS;
-constexpr int kRingWarps = kRingThreads / 32;
-constexpr int kRingItems = kScatterTile / kRingThreads;
-static_assert(kRingItems * kRingThreads == kScatterTile && kRingItems <= 32, "ring tile shape");
-constexpr int kRingSlotsLog = 13;                 // 8192 tuple slots = 64 KiB per CTA
-constexpr int kRingMinBits = 4;                   // narrower fan-outs use the staged kernel
-#ifndef AQP_RING_TMA
-#define AQP_RING_TMA 0      // 1: tiles arrive through a 2-deep TMA ring in shared memory; 0: LDG into registers, one tile ahead
-#endif
-constexpr bool kRingTma = AQP_RING_TMA != 0;
-constexpr size_t kRingSmemBytes = (size_t) ((kRingTma ? 2 * kInBufTuples : 0) + (1 << kRingSlotsLog)) * sizeof(uint2);
-constexpr int kRingBlocksPerSMRaw = (int) (228 * 1024 / (kRingSmemBytes + 8192));
-constexpr int kRingBlocksPerSM = kRingBlocksPerSMRaw < 1 ? 1 : (kRingBlocksPerSMRaw * kRingThreads > 2048 ? 2048 / kRingThreads : kRingBlocksPerSMRaw);
-
-// pass-1 geometry (histogram rows = scatter CTAs): one resident wave of the ring kernel
-uint32_t pass1_blocks() { return (uint32_t) kNumSMs * (kRingBlocksPerSM < kScatterBlocksPerSM ? kRingBlocksPerSM : kScatterBlocksPerSM); }
-
-template <bool kRot, bool kPeer, bool kPriv>
-__global__ void __launch_bounds__(kRingThreads, kRingBlocksPerSM)
-radix_scatter_ring_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
-                          const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_tile_start,
-                          const uint32_t *__restrict__ seg_group, uint32_t nseg, DigitFn digit, uint32_t bits,
-                          uint32_t *__restrict__ cursors, const uint32_t *__restrict__ block_base,
-                          uint32_t tiles_per_block, PeerTable peers) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint2 *inbuf0 = reinterpret_cast<uint2 *>(smem_raw);
-    uint2 *inbuf1 = inbuf0 + (kRingTma ? kInBufTuples : 0);
-    uint2 *ring = inbuf1 + (kRingTma ? kInBufTuples : 0);
-    __shared__ uint32_t w[kMaxFanout];      // (position in the partition's stream) << 16 | tuples in the ring
-    __shared__ uint32_t scur[kMaxFanout];   // pass 1: CTA-private destination cursor of the ring's oldest tuple
-    __shared__ uint32_t gst[kMaxFanout];    // overflow path: destination of the ring's oldest tuple ...
-    __shared__ uint32_t spos[kMaxFanout];   //                ... and its stream position
-    __shared__ uint2 *s_peer[8];
-    __shared__ uint32_t s_tstart[kMaxFanout + 1];
-    __shared__ uint32_t s_soff[kMaxFanout + 1];
-    __shared__ uint32_t s_ovf[2];
-    __shared__ __align__(8) uint64_t mbar[2];
-
-    const uint32_t fan = 1u << bits;
-    const uint32_t lgBp = kRingSlotsLog - bits, Bp = 1u << lgBp, pmask = Bp - 1;
-    const uint32_t bmask = Bp >= 64 ? 31u : 15u;   // flush granularity: 32 tuples (256 B), 16 for the widest fan-out
-    for (uint32_t i = threadIdx.x; i <= nseg; i += kRingThreads) {
-        s_tstart[i] = seg_tile_start[i];
-        s_soff[i] = seg_off[i];
-    }
-    for (uint32_t i = threadIdx.x; i < fan; i += kRingThreads) {
-        uint32_t base = kPriv ? block_base[(size_t) blockIdx.x * fan + i] : 0u;
-        scur[i] = base;
-        w[i] = base << 16;   // position == destination index (mod 2^16): flushed blocks are aligned lines
-    }
-    if (kPeer && threadIdx.x < 8) s_peer[threadIdx.x] = peers.base[threadIdx.x];
-    if (threadIdx.x == 0) {
-        s_ovf[0] = s_ovf[1] = 0;
-        mbar_init(&mbar[0], 1);
-        mbar_init(&mbar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const uint32_t ntiles = s_tstart[nseg];
-    // every CTA owns a contiguous range of tiles (its partitions' rings carry over from tile to tile)
-    const uint32_t tpb = kPriv ? tiles_per_block : (ntiles + gridDim.x - 1) / gridDim.x;
-    const uint32_t first = blockIdx.x * tpb;
-    const uint32_t n_my = first < ntiles ? min(tpb, ntiles - first) : 0;
-    if (n_my == 0) return;
-
-    // tiles are visited in increasing order, so the segment of a tile is found by walking forward
-    auto advance = [&](uint32_t &seg, uint32_t tile) {
-        while (seg + 1 < nseg && s_tstart[seg + 1] <= tile) ++seg;
-    };
-    auto tile_bounds = [&](uint32_t seg, uint32_t tile, uint32_t &begin, uint32_t &end) {
-        begin = s_soff[seg] + (tile - s_tstart[seg]) * kScatterTile;
-        end = min(begin + (uint32_t) kScatterTile, s_soff[seg + 1]);
-    };
-    uint32_t seg = 0;
-    {   // first segment of this CTA: binary search once
-        uint32_t lo = 0, hi = nseg;
-        while (hi - lo > 1) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (s_tstart[mid] <= first) lo = mid; else hi = mid;
-        }
-        seg = lo;
-    }
-    uint32_t iseg = seg;   // thread 0: segment of the next tile to load
-    auto issue = [&](uint32_t i) {   // one thread: bulk-load tile #i of this CTA into input slot i & 1
-        uint32_t begin, end;
-        advance(iseg, first + i);
-        tile_bounds(iseg, first + i, begin, end);
-        const uint2 *src = in + begin;
-        uint32_t skew = (uint32_t) ((reinterpret_cast<uintptr_t>(src) >> 3) & 1u);
-        uint32_t bytes = ((end - begin + skew + 1) & ~1u) * (uint32_t) sizeof(uint2);
-        uint64_t *bar = &mbar[i & 1];
-        mbar_expect_tx(bar, bytes);
-        tma_load_1d((i & 1) ? inbuf1 : inbuf0, src - skew, bytes, bar);
-    };
-    if (kRingTma && threadIdx.x == 0) {
-        issue(0);
-        if (n_my > 1) issue(1);
-    }
-    // register path: every thread loads its tuples of the NEXT tile while the current one is processed
-    uint2 nv[kRingItems];
-    auto prefetch = [&](uint32_t i) {
-        uint32_t begin, end;
-        advance(iseg, first + i);
-        tile_bounds(iseg, first + i, begin, end);
-        const uint32_t nt = end - begin;
-#pragma unroll
-        for (int j = 0; j < kRingItems; ++j) {
-            uint32_t k = j * kRingThreads + threadIdx.x;
-            if (k < nt) nv[j] = ld_stream_v2(in + begin + k);
-        }
-    };
-    if (!kRingTma) prefetch(0);
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint32_t ppw = (fan + kRingWarps - 1) / kRingWarps;   // partitions flushed by each warp (<= 32)
-    const uint32_t my_d = warp * ppw + lane;
-    const bool keeper = lane < ppw && my_d < fan;               // this lane keeps the books of partition my_d
-
-    for (uint32_t i = 0; i < n_my; ++i) {
-        uint32_t begin, end;
-        advance(seg, first + i);
-        tile_bounds(seg, first + i, begin, end);
-        const uint32_t ntile = end - begin;
-        const uint32_t group = seg_group ? seg_group[seg] : seg;
-        bool flush_all = i + 1 == n_my;
-        if (!kPriv && !flush_all) {   // the rings are emptied before the CTA moves on to another cursor group
-            uint32_t seg2 = seg;
-            advance(seg2, first + i + 1);
-            flush_all = seg2 != seg && (seg_group ? seg_group[seg2] : seg2) != group;
-        }
-        const uint32_t skew = (uint32_t) ((reinterpret_cast<uintptr_t>(in + begin) >> 3) & 1u);
-        const uint2 *buf = ((i & 1) ? inbuf1 : inbuf0) + skew;
-
-        uint2 v[kRingItems];
-        uint32_t posr[kRingItems];
-        uint32_t ovf_bits = 0;
-        if (kRingTma) {
-            mbar_wait(&mbar[i & 1], (i >> 1) & 1);
-        } else {
-#pragma unroll
-            for (int j = 0; j < kRingItems; ++j) v[j] = nv[j];
-            if (i + 1 < n_my) prefetch(i + 1);
-        }
-        if (ntile == (uint32_t) kScatterTile) {
-            if (kRingTma) {
-#pragma unroll
-                for (int j = 0; j < kRingItems; ++j) v[j] = buf[j * kRingThreads + threadIdx.x];
-            }
-#pragma unroll
-            for (int j = 0; j < kRingItems; ++j) {
-                const uint32_t d = digit.template get<kRot>(v[j].x);
-                const uint32_t old = atomicAdd(&w[d], 0x10001u);
-                posr[j] = old >> 16;
-                if ((old & 0xFFFFu) < Bp)
-                    ring[(d << lgBp) | (posr[j] & pmask)] = v[j];
-                else
-                    ovf_bits |= 1u << j;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < kRingItems; ++j) {
-                uint32_t k = j * kRingThreads + threadIdx.x;
-                if (k < ntile) {
-                    if (kRingTma) v[j] = buf[k];
-                    const uint32_t d = digit.template get<kRot>(v[j].x);
-                    const uint32_t old = atomicAdd(&w[d], 0x10001u);
-                    posr[j] = old >> 16;
-                    if ((old & 0xFFFFu) < Bp)
-                        ring[(d << lgBp) | (posr[j] & pmask)] = v[j];
-                    else
-                        ovf_bits |= 1u << j;
-                }
-            }
-        }
-        if (ovf_bits) s_ovf[i & 1] = 1;
-        __syncthreads();   // (A) every tuple of the tile has its position and the in-window ones are in the ring
-
-        if (threadIdx.x == 0) {
-            if (kRingTma && i + 2 < n_my) issue(i + 2);
-            s_ovf[(i + 1) & 1] = 0;
-        }
-        // ---- flush: the keeper lane decides what leaves partition my_d's ring, the warp copies it ----
-        uint32_t f_start = 0, f_end = 0, f_goff = 0;   // positions [f_start, f_end) go to dst[f_goff + position]
-        if (keeper) {
-            const uint32_t wd = w[my_d];
-            const uint32_t fill = wd & 0xFFFFu, pos_end = wd >> 16;
-            const uint32_t start = (pos_end - fill) & 0xFFFFu;
-            uint32_t n, nres;
-            if (fill > Bp) {            // skewed tile: the whole ring goes, late tuples follow it from registers
-                n = Bp;
-                nres = fill;
-            } else {
-                const uint32_t left = flush_all ? 0u : (pos_end & bmask);
-                n = fill > left ? fill - left : 0u;
-                nres = n;
-            }
-            if (nres) {
-                uint32_t g;
-                if (kPriv) {
-                    g = scur[my_d];
-                    scur[my_d] = g + nres;
-                } else {
-                    g = atomicAdd(&cursors[(group << bits) + my_d], nres);
-                }
-                w[my_d] = (pos_end << 16) | (fill - nres);
-                if (fill > Bp) {
-                    gst[my_d] = g;
-                    spos[my_d] = start;
-                }
-                f_start = start;
-                f_end = start + n;
-                f_goff = g - start;
-            }
-        }
-        for (uint32_t b = 0;; ++b) {   // round b: every partition's b-th 32-position block, one block per step
-            const uint32_t bpos = (f_start & ~31u) + 32u * b;
-            uint32_t m = __ballot_sync(0xffffffffu, bpos < f_end);
-            if (!m) break;
-            do {
-                const uint32_t src = __ffs(m) - 1;
-                m &= m - 1;
-                const uint32_t s_ = __shfl_sync(0xffffffffu, f_start, src);
-                const uint32_t e_ = __shfl_sync(0xffffffffu, f_end, src);
-                const uint32_t go = __shfl_sync(0xffffffffu, f_goff, src);
-                const uint32_t d = warp * ppw + src;
-                const uint32_t pnt = (s_ & ~31u) + 32u * b + lane;
-                if (pnt >= s_ && pnt < e_) {
-                    uint2 *dst = kPeer ? s_peer[d >> peers.per_shift] : out;
-                    dst[go + pnt] = ring[(d << lgBp) | (pnt & pmask)];
-                }
-            } while (m);
-        }
-        __syncthreads();   // (C) flushed slots are free again; overflow destinations are published
-
-        if (s_ovf[i & 1]) {
-#pragma unroll
-            for (int j = 0; j < kRingItems; ++j) {
-                if (ovf_bits & (1u << j)) {
-                    const uint32_t d = digit.template get<kRot>(v[j].x);
-                    uint2 *dst = kPeer ? s_peer[d >> peers.per_shift] : out;
-                    dst[gst[d] + ((posr[j] - spos[d]) & 0xFFFFu)] = v[j];
-                }
-            }
-        }
-    }
-}
-
 int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_off,
                          const uint32_t *d_seg_tile_start, const uint32_t *d_seg_group, uint32_t nseg, uint64_t n_total,
                          DigitFn digit, uint32_t bits, uint32_t *d_cursors, const uint32_t *d_block_base,
@@ -828,49 +562,6 @@ int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_
     const uint2 *in = reinterpret_cast<const uint2 *>(d_in);
     uint2 *out = reinterpret_cast<uint2 *>(d_out);
     const bool peer = peers && peers->n;
-    static const bool force_staged = getenv("B200_AQP_SCATTER") && !strcmp(getenv("B200_AQP_SCATTER"), "staged");
-    if (bits >= (uint32_t) kRingMinBits && !force_staged) {
-        static bool ring_attr_set = false;
-        if (!ring_attr_set) {
-#define AQP_RING_ATTR(ROT, PEER, PRIV)                                                                                 \
-    AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_ring_kernel<ROT, PEER, PRIV>,                                        \
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kRingSmemBytes))
-            AQP_RING_ATTR(false, false, false);
-            AQP_RING_ATTR(false, false, true);
-            AQP_RING_ATTR(true, false, false);
-            AQP_RING_ATTR(true, false, true);
-            AQP_RING_ATTR(true, true, true);
-#undef AQP_RING_ATTR
-            ring_attr_set = true;
-        }
-        uint32_t rgrid;
-        if (d_block_base) {
-            rgrid = nblocks;
-        } else {
-            uint64_t max_tiles = n_total / kScatterTile + nseg;
-            uint64_t gmax = (uint64_t) kNumSMs * kRingBlocksPerSM;
-            rgrid = (uint32_t) (max_tiles < gmax ? max_tiles : gmax);
-        }
-#define AQP_RING_LAUNCH(ROT, PEER, PRIV)                                                                               \
-    radix_scatter_ring_kernel<ROT, PEER, PRIV><<<rgrid, kRingThreads, kRingSmemBytes, st>>>(                            \
-        in, out, d_seg_off, d_seg_tile_start, d_seg_group, nseg, digit, bits, d_cursors, d_block_base, tiles_per_block, \
-        peer ? *peers : none)
-        if (peer) {
-            if (!d_block_base) {
-                set_error("radix_scatter: the peer variant needs CTA-private cursors");
-                return -1;
-            }
-            AQP_RING_LAUNCH(true, true, true);
-        } else if (digit.rot) {
-            if (d_block_base) AQP_RING_LAUNCH(true, false, true); else AQP_RING_LAUNCH(true, false, false);
-        } else {
-            if (d_block_base) AQP_RING_LAUNCH(false, false, true); else AQP_RING_LAUNCH(false, false, false);
-        }
-#undef AQP_RING_LAUNCH
-        AQP_LAUNCHED();
-        AQP_CUDA_OK(cudaGetLastError());
-        return 0;
-    }
 #define AQP_SCATTER_LAUNCH(ROT, PEER)                                                                              \
     radix_scatter_kernel<ROT, PEER><<<grid, kScatterThreads, kScatterSmemBytes, st>>>(                              \
         in, out, d_seg_off, d_seg_tile_start, d_seg_group, nseg, digit, bits, d_cursors, d_block_base, tiles_per_block, \
