@@ -57,6 +57,20 @@ def measured_peaks():
         return 6650.0, "fallback"   # B200_PROFILING.md fallback
 
 
+def ncu_traffic(kernel_prefix: str):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/traffic.json, written by tools/ncu_traffic.py); None if there is no capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        for name, e in t.items():
+            if name.startswith(kernel_prefix):
+                return e["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -323,7 +337,8 @@ def run_b200_arm(args):
     scatter_ms = (phase["ms_pass1"] + phase["ms_pass2"]) / 4
     scatter_bytes = SCATTER_BYTES_PER_TUPLE * (nR_loc + nS_loc) * 2 / 4
     roof = {"bound": "hbm", "kernel": "radix_scatter_kernel", "achieved": scatter_bytes / scatter_ms / 1e6 if scatter_ms else None,
-            "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": None,
+            "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+            "traffic": ncu_traffic("radix_scatter_kernel") if world == 1 else None,
             "bytes_per_launch": scatter_bytes, "ms_per_launch": scatter_ms}
     roof["frac"] = roof["achieved"] / peak if roof["achieved"] else None
     join_bytes = JOIN_BYTES_PER_TUPLE * (nR + nS) / world
