@@ -42,9 +42,10 @@ LOG_R, LOG_S = 27, 29          # BASELINE config 3
 SCAN_LOG_N = 30                # BASELINE config 2
 JOIN_BYTES_PER_TUPLE = 56      # 8 * (3 P + 1) with P = 2 passes
 SCATTER_BYTES_PER_TUPLE = 16   # read 8 + write 8
-# multi-GPU shuffle per world size: "p2p" (scatter fused with peer stores), "dma" (local scatter + copy engines),
-# "nccl" (all_to_all_single). Measured at 2 GPUs: p2p 6.13 ms, dma 6.60 ms, nccl 9.46 ms (profiles/)
-DEFAULT_EXCHANGE = {2: "p2p"}
+# multi-GPU shuffle: "p2p" (scatter fused with peer stores over NVLink), "dma" (local scatter + copy engines),
+# "nccl" (all_to_all_single). Measured ms per join at 2 / 4 / 8 GPUs (profiles/r01_bench_{2,4,8}gpu_*.json):
+# p2p 6.13 / 4.25 / 2.90, dma 6.60 / 4.95 / 3.68, nccl 9.46 / 5.02 / 5.99 -> p2p everywhere
+DEFAULT_EXCHANGE = {}
 METRIC = "rho_join_throughput"
 UNIT = "Mtuples/s"
 
@@ -296,7 +297,7 @@ def run_b200_arm(args):
         # headline: scatter kernel fused with the exchange over NVLink peer memory; the NCCL all-to-all
         # variant is timed beside it as the baseline (B200_AQP_EXCHANGE=nccl makes it the headline)
         variants = {"p2p": D.FusedShardedJoin, "dma": D.DmaShardedJoin, "nccl": D.ShardedJoin}
-        default = DEFAULT_EXCHANGE.get(world, "dma")
+        default = DEFAULT_EXCHANGE.get(world, "p2p")
         plan = variants[os.environ.get("B200_AQP_EXCHANGE", default)](nR, nS, dev)
 
         def step():
