@@ -15,6 +15,9 @@
 
 namespace aqp {
 
+#ifndef AQP_INDEX_CHUNK_LOG
+#define AQP_INDEX_CHUNK_LOG 30
+#endif
 constexpr int kScanThreads = 256;
 constexpr int kScanUnroll = 4;                                  // uint4 loads in flight per thread
 constexpr int kScanTileVec = kScanThreads * kScanUnroll;        // 1024 uint4 = 16 KiB per tile
@@ -117,7 +120,7 @@ bitvector_scan_kernel(const uint4 *__restrict__ in, size_t nvec, uint64_t *__res
             if ((threadIdx.x & 3) == 0 && q < nvec) out[q >> 2] = (uint64_t) m32 | ((uint64_t) hi << 32);
         }
         if (kCount) {   // one reduction-add per warp into the counter of the enclosing expansion tile
-            c = warp_sum(c);
+            c = __reduce_add_sync(0xffffffffu, c);   // one REDUX instead of a 5-step shuffle tree
             if (lane_id() == 0 && c) atomicAdd(&tile_counts[tile / kExpandScanTiles], c);
         }
     }
@@ -167,43 +170,218 @@ scan_count_kernel(const uint4 *__restrict__ in, size_t nvec, unsigned long long 
 // CTA (a single-pass decoupled look-back variant measured 3-5x slower here: its per-tile chain of
 // ticket, load, publish, look back, write kept too few bytes in flight).
 // ---------------------------------------------------------------------------------------------
-constexpr size_t kIndexChunkVals = (size_t) 1 << 29;                    // 512 MiB of column -> 64 MiB bitvector
+constexpr size_t kIndexChunkVals = (size_t) 1 << AQP_INDEX_CHUNK_LOG;                    // 1 GiB of column -> 128 MiB bitvector
 constexpr size_t kIndexChunkTiles = kIndexChunkVals / kExpandTileVals;  // 8192 expansion tiles per chunk
 
+constexpr int kExpandDenseTile = kExpandTileVals / 4 * 3;   // tiles at least this full take the whole-warp path
+
+// Exclusive scan of the per-tile match counts of one chunk (<= 16384 tiles) by ONE CTA, entirely in shared
+// memory: coalesced load, 16 consecutive counts per thread (index skewed by i/32 against bank conflicts), warp and
+// block scan, coalesced write of the 64-bit tile offsets. The same pass sorts the non-empty tiles into the
+// "window" and "dense" lists the two expansion kernels walk (warp-aggregated appends).
+// lists[0] = number of window tiles, lists[1] = number of dense tiles, then the two tile-id lists
+// (window tiles from lists + 2, dense tiles from lists + 2 + ntiles_cap); empty tiles are in neither.
+constexpr uint32_t kPlanMaxTiles = 16384;
+constexpr size_t kPlanSmemBytes = (kPlanMaxTiles + kPlanMaxTiles / 32 + 32) * sizeof(uint32_t);
 __global__ void __launch_bounds__(kScanBlock)
 tile_offsets_kernel(const uint32_t *__restrict__ counts, uint32_t ntiles, uint64_t *__restrict__ offsets,
-                    unsigned long long *__restrict__ running) {
+                    unsigned long long *__restrict__ running, uint32_t *__restrict__ lists, uint32_t ntiles_cap) {
+    extern __shared__ uint32_t sc[];
+    __shared__ uint32_t wsum[kScanBlock / 32];
+    __shared__ uint32_t nclass[2];
+    auto at = [](uint32_t i) { return i + (i >> 5); };
+    if (threadIdx.x < 2) nclass[threadIdx.x] = 0;
+    for (uint32_t i = threadIdx.x; i < ntiles; i += kScanBlock) sc[at(i)] = counts[i];
+    __syncthreads();
+    const uint32_t per = (ntiles + kScanBlock - 1) / kScanBlock;
+    const uint32_t b = threadIdx.x * per, e = min(ntiles, b + per);
+    uint32_t local = 0;
+    for (uint32_t i = b; i < e; ++i) local += sc[at(i)];
+    const uint32_t incl = warp_incl_scan(local);
+    if (lane_id() == 31) wsum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const uint32_t w = wsum[threadIdx.x];
+        const uint32_t wi = warp_incl_scan(w);
+        wsum[threadIdx.x] = wi - w;
+        if (threadIdx.x == 31) sc[at(kPlanMaxTiles)] = wi;   // grand total behind the counts
+    }
+    __syncthreads();
+    uint32_t run = wsum[threadIdx.x >> 5] + incl - local;
+    for (uint32_t i = b; i < e; ++i) {   // counts -> exclusive prefixes, in place
+        const uint32_t v = sc[at(i)];
+        sc[at(i)] = run;
+        run += v;
+    }
+    __syncthreads();
     const unsigned long long base = *running;
-    uint32_t total = block_exclusive_scan(ntiles, [&](uint32_t i) { return counts[i]; },
-                                          [&](uint32_t i, uint32_t v) { offsets[i] = base + v; });
+    const uint32_t total = sc[at(kPlanMaxTiles)];
+    for (uint32_t i0 = 0; i0 < ntiles; i0 += kScanBlock) {
+        const uint32_t i = i0 + threadIdx.x;
+        uint32_t c = 0;
+        if (i < ntiles) {
+            offsets[i] = base + sc[at(i)];
+            c = counts[i];
+        }
+#pragma unroll
+        for (uint32_t cls = 0; cls < 2; ++cls) {
+            const bool in = c != 0 && (c >= (uint32_t) kExpandDenseTile) == (cls == 1);
+            const unsigned m = __ballot_sync(0xffffffffu, in);
+            if (m) {
+                uint32_t pos = 0;
+                if (lane_id() == (unsigned) (__ffs(m) - 1)) pos = atomicAdd(&nclass[cls], (uint32_t) __popc(m));
+                pos = __shfl_sync(0xffffffffu, pos, __ffs(m) - 1);
+                if (in) lists[2 + cls * ntiles_cap + pos + __popc(m & lanemask_lt())] = i;
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) lists[threadIdx.x] = nclass[threadIdx.x];
     if (threadIdx.x == 0) *running = base + total;
 }
 
-// A thread loads kExpandWordsPerThread consecutive 64-bit words; the match counts are scanned across
-// the CTA. Words with few matches are written by their owning thread. Dense words are expanded by the
-// whole warp: lane l owns bits l and l+32 of the broadcast word and its output slot is the word's
-// offset plus the number of set bits below it, so consecutive lanes write consecutive ids — every
-// store instruction covers one contiguous run, a full 256-byte line pair at 100 % selectivity — with
-// no shared-memory staging and no bank conflicts. (Broadcasting every word cost 9 shuffles per lane
-// and made the kernel shuffle-bound at low selectivity: 162 us per 512 MiB chunk in ncu.)
-constexpr int kDenseWord = 8;
+// A thread loads kExpandWordsPerThread consecutive 64-bit words; the match counts are scanned across the
+// CTA, which gives every thread the first output slot of its words. Expansion goes through a shared-memory
+// window of kExpandWindow tile-relative ids: each thread walks the set bits of its own words (two 32-bit
+// halves per word, FLO + clear-lowest per id) and drops the ids into its slots of the window; then the CTA
+// copies the window out front to back, so every store instruction writes 32 consecutive uint64 ids.
+// The earlier per-word warp broadcast spent 47 instructions per 27-id word at 10 % selectivity and was
+// issue-bound (profiles/r01_ncu_scan_expand_v1.md); it survives only for tiles that are at least 3/4 full,
+// where a word yields ~64 ids and the window's extra shared-memory round trip costs more than it saves.
+// Slots are XOR-swizzled so that equal per-thread match counts (64 at 100 %) do not map all lanes of a warp
+// to one bank.
+constexpr int kExpandWindow = 8192;   // ids per window: 32 KiB of shared memory
+__device__ __forceinline__ void st_stream_u64(uint64_t *p, uint64_t v) {
+    asm volatile("st.global.cs.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t expand_phys(uint32_t slot) { return slot ^ ((slot >> 5) & 31u); }
+
 __global__ void __launch_bounds__(kScanThreads)
 expand_rowids_kernel(const uint64_t *__restrict__ bv, size_t nwords, const uint64_t *__restrict__ tile_offsets,
-                     uint64_t id_base, uint64_t *__restrict__ out, uint64_t out_capacity) {
+                     const uint32_t *__restrict__ tile_list, const uint32_t *__restrict__ tile_list_len, uint64_t id_base,
+                     uint64_t *__restrict__ out, uint64_t out_capacity) {
+    __shared__ uint32_t stage[kExpandWindow];
+    __shared__ uint32_t wtot[kScanThreads / 32];
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    const size_t ntiles = (nwords + kExpandTileWords - 1) / kExpandTileWords;
+    // the words of the NEXT tile are requested before the current tile is expanded
+    auto load_words = [&](size_t tile, uint64_t (&dst)[kExpandWordsPerThread]) {
+        const size_t w0 = tile * kExpandTileWords + (size_t) threadIdx.x * kExpandWordsPerThread;
+        if (w0 + kExpandWordsPerThread <= nwords) {
+            const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(bv + w0);
+            const ulonglong2 b = *reinterpret_cast<const ulonglong2 *>(bv + w0 + 2);
+            dst[0] = a.x; dst[1] = a.y; dst[2] = b.x; dst[3] = b.y;
+        } else {
+#pragma unroll
+            for (int k = 0; k < kExpandWordsPerThread; ++k) dst[k] = w0 + k < nwords ? bv[w0 + k] : 0ull;
+        }
+    };
+    // this kernel walks the list of tiles that are less than 3/4 full (built by tile_offsets_kernel); the words
+    // of the next list entry are requested before the current tile is expanded
+    uint64_t mn[kExpandWordsPerThread];
+    const uint32_t nlist = *tile_list_len;
+    uint32_t tile_n = 0;
+    uint64_t gbase_n = 0;
+    if (blockIdx.x < nlist) {
+        tile_n = tile_list[blockIdx.x];
+        load_words(tile_n, mn);
+        gbase_n = tile_offsets[tile_n];
+    }
+    for (uint32_t li = blockIdx.x; li < nlist; li += gridDim.x) {
+        const size_t tile = tile_n;
+        const uint64_t gbase = gbase_n;
+        uint32_t piece[2 * kExpandWordsPerThread];   // remaining bits, 32 per piece
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int k = 0; k < kExpandWordsPerThread; ++k) {
+            piece[2 * k] = (uint32_t) mn[k];
+            piece[2 * k + 1] = (uint32_t) (mn[k] >> 32);
+            cnt += __popcll(mn[k]);
+        }
+        if (li + gridDim.x < nlist) {
+            tile_n = tile_list[li + gridDim.x];
+            load_words(tile_n, mn);
+            gbase_n = tile_offsets[tile_n];
+        }
+        const uint32_t incl = warp_incl_scan(cnt);
+        __syncthreads();   // wtot and the window of the previous tile are consumed
+        if (lane == 31) wtot[warp] = incl;
+        __syncthreads();
+        uint32_t wbase = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < kScanThreads / 32; ++k) {
+            wbase += (k < (int) warp) ? wtot[k] : 0;
+            total += wtot[k];
+        }
+        uint32_t slot = wbase + incl - cnt;                                  // next output slot of this thread
+        const uint32_t rel0 = threadIdx.x * kExpandWordsPerThread * 64;     // tile-relative id of my first bit
+        const uint64_t idb = id_base + (uint64_t) tile * kExpandTileVals;
+        for (uint32_t wlo = 0; wlo < total; wlo += kExpandWindow) {
+            const uint32_t whi = wlo + kExpandWindow;
+#pragma unroll
+            for (int q = 0; q < 2 * kExpandWordsPerThread; ++q) {
+                uint32_t bits = piece[q];
+                while (bits && slot < whi) {
+                    const uint32_t b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    stage[expand_phys(slot - wlo)] = rel0 + q * 32 + b;
+                    ++slot;
+                }
+                piece[q] = bits;
+            }
+            __syncthreads();
+            const uint32_t nwin = min((uint32_t) kExpandWindow, total - wlo);
+            const uint64_t g0 = gbase + wlo;
+            const uint32_t nok = g0 >= out_capacity ? 0u : (uint32_t) min((uint64_t) nwin, out_capacity - g0);
+            for (uint32_t t = threadIdx.x; t < nok; t += kScanThreads)
+                st_stream_u64(out + g0 + t, idb + stage[expand_phys(t)]);
+            if (whi < total) __syncthreads();   // the window is reused
+        }
+    }
+}
+
+// Tiles that are at least 3/4 full: whole-warp expansion, one word at a time, straight from registers. Lane l
+// owns bits l and l+32 of the broadcast word; its slot is the word's offset plus the set bits below it, so each
+// store instruction writes one contiguous run (a full 256-byte line pair for a full word).
+__global__ void __launch_bounds__(kScanThreads)
+expand_dense_rowids_kernel(const uint64_t *__restrict__ bv, size_t nwords, const uint64_t *__restrict__ tile_offsets,
+                           const uint32_t *__restrict__ tile_list, const uint32_t *__restrict__ tile_list_len, uint64_t id_base,
+                           uint64_t *__restrict__ out, uint64_t out_capacity) {
     __shared__ uint32_t wtot[kScanThreads / 32];
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     const unsigned lt = lanemask_lt();
     const size_t ntiles = (nwords + kExpandTileWords - 1) / kExpandTileWords;
-    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    auto load_words = [&](size_t tile, uint64_t (&dst)[kExpandWordsPerThread]) {
         const size_t w0 = tile * kExpandTileWords + (size_t) threadIdx.x * kExpandWordsPerThread;
-        uint64_t m[kExpandWordsPerThread];
         if (w0 + kExpandWordsPerThread <= nwords) {
             const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(bv + w0);
             const ulonglong2 b = *reinterpret_cast<const ulonglong2 *>(bv + w0 + 2);
-            m[0] = a.x; m[1] = a.y; m[2] = b.x; m[3] = b.y;
+            dst[0] = a.x; dst[1] = a.y; dst[2] = b.x; dst[3] = b.y;
         } else {
 #pragma unroll
-            for (int k = 0; k < kExpandWordsPerThread; ++k) m[k] = w0 + k < nwords ? bv[w0 + k] : 0ull;
+            for (int k = 0; k < kExpandWordsPerThread; ++k) dst[k] = w0 + k < nwords ? bv[w0 + k] : 0ull;
+        }
+    };
+    // this kernel walks the list of tiles that are at least 3/4 full
+    uint64_t mn[kExpandWordsPerThread];
+    const uint32_t nlist = *tile_list_len;
+    uint32_t tile_n = 0;
+    uint64_t gbase_n = 0;
+    if (blockIdx.x < nlist) {
+        tile_n = tile_list[blockIdx.x];
+        load_words(tile_n, mn);
+        gbase_n = tile_offsets[tile_n];
+    }
+    for (uint32_t li = blockIdx.x; li < nlist; li += gridDim.x) {
+        const size_t tile = tile_n;
+        const uint64_t gbase = gbase_n;
+        uint64_t m[kExpandWordsPerThread];
+#pragma unroll
+        for (int k = 0; k < kExpandWordsPerThread; ++k) m[k] = mn[k];
+        if (li + gridDim.x < nlist) {
+            tile_n = tile_list[li + gridDim.x];
+            load_words(tile_n, mn);
+            gbase_n = tile_offsets[tile_n];
         }
         uint32_t cnt = 0;
 #pragma unroll
@@ -215,58 +393,36 @@ expand_rowids_kernel(const uint64_t *__restrict__ bv, size_t nwords, const uint6
         uint32_t wbase = 0;
 #pragma unroll
         for (int k = 0; k < kScanThreads / 32; ++k) wbase += (k < (int) warp) ? wtot[k] : 0;
-        const uint32_t my_off = wbase + incl - cnt;   // first output slot (tile-relative) of this thread's words
-        const uint64_t gbase = tile_offsets[tile];
-        const uint64_t idb = id_base + (uint64_t) tile * kExpandTileVals + (uint64_t) warp * 32 * kExpandWordsPerThread * 64;
-        // sparse words (< kDenseWord matches): the owning thread writes its few ids itself
         uint32_t off[kExpandWordsPerThread];
+        unsigned nz[kExpandWordsPerThread], any = 0;
         {
-            uint32_t run = my_off;
+            uint32_t run = wbase + incl - cnt;
 #pragma unroll
             for (int k = 0; k < kExpandWordsPerThread; ++k) {
                 off[k] = run;
                 run += __popcll(m[k]);
+                nz[k] = __ballot_sync(0xffffffffu, m[k] != 0);
+                any |= nz[k];
             }
         }
-        const uint64_t idt = idb + (uint64_t) lane * kExpandWordsPerThread * 64;
-#pragma unroll
-        for (int k = 0; k < kExpandWordsPerThread; ++k) {
-            uint64_t mm = m[k];
-            if (mm != 0 && __popcll(mm) < kDenseWord) {
-                uint64_t g = gbase + off[k];
-                while (mm) {
-                    uint32_t b = __ffsll((long long) mm) - 1;
-                    mm &= mm - 1;
-                    if (g < out_capacity) out[g] = idt + (uint64_t) k * 64 + b;
-                    ++g;
-                }
-            }
-        }
-        // dense words: the whole warp expands one word at a time (3 shuffles per word), walking the
-        // source lanes in order so the warp's output is written front to back
-        unsigned dmk[kExpandWordsPerThread], any_dense = 0;
-#pragma unroll
-        for (int k = 0; k < kExpandWordsPerThread; ++k) {
-            dmk[k] = __ballot_sync(0xffffffffu, __popcll(m[k]) >= kDenseWord);
-            any_dense |= dmk[k];
-        }
-        while (any_dense) {
-            const int src = __ffs(any_dense) - 1;
-            any_dense &= any_dense - 1;
+        const uint64_t idw = id_base + (uint64_t) tile * kExpandTileVals + (uint64_t) warp * 32 * kExpandWordsPerThread * 64;
+        while (any) {
+            const int src = __ffs(any) - 1;
+            any &= any - 1;
 #pragma unroll
             for (int k = 0; k < kExpandWordsPerThread; ++k) {
-                if (!((dmk[k] >> src) & 1u)) continue;   // warp-uniform
+                if (!((nz[k] >> src) & 1u)) continue;   // warp-uniform
                 const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t) m[k], src);
                 const uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t) (m[k] >> 32), src);
                 const uint64_t o = gbase + __shfl_sync(0xffffffffu, off[k], src);
-                const uint64_t id0 = idb + (uint64_t) (src * kExpandWordsPerThread + k) * 64 + lane;
+                const uint64_t id0 = idw + (uint64_t) (src * kExpandWordsPerThread + k) * 64 + lane;
                 if ((lo >> lane) & 1u) {
                     uint64_t g = o + __popc(lo & lt);
-                    if (g < out_capacity) out[g] = id0;
+                    if (g < out_capacity) st_stream_u64(out + g, id0);
                 }
                 if ((hi >> lane) & 1u) {
                     uint64_t g = o + __popc(lo) + __popc(hi & lt);
-                    if (g < out_capacity) out[g] = id0 + 32;
+                    if (g < out_capacity) st_stream_u64(out + g, id0 + 32);
                 }
             }
         }
@@ -341,12 +497,12 @@ int scan_count_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, u
     return 0;
 }
 
-// scratch layout: [bitvector of one chunk][tile counts u32][tile offsets u64][running total u64]
+// scratch layout: [bitvector of one chunk][tile counts u32][tile offsets u64][tile lists: 2 lengths + 2 lists u32]
 static size_t align256(size_t x) { return (x + 255) & ~(size_t) 255; }
 size_t index_scan_scratch_bytes(size_t n) {
     size_t chunk = n < kIndexChunkVals ? n : kIndexChunkVals;
     size_t tiles = (chunk + kExpandTileVals - 1) / kExpandTileVals + 1;
-    return align256(chunk / 8 + 64) + align256(tiles * 4) + align256(tiles * 8) + 256;
+    return align256(chunk / 8 + 64) + align256(tiles * 4) + align256(tiles * 8) + align256((2 * tiles + 2) * 4) + 256;
 }
 
 int index_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, uint64_t id_base,
@@ -364,8 +520,16 @@ int index_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, u
     uint64_t *bv = reinterpret_cast<uint64_t *>(sb);
     uint32_t *counts = reinterpret_cast<uint32_t *>(sb + align256(chunk_cap / 8 + 64));
     uint64_t *offsets = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(counts) + align256(tiles_cap * 4));
+    uint32_t *lists = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(offsets) + align256(tiles_cap * 8));
     unsigned long long *running = reinterpret_cast<unsigned long long *>(d_count);
     const Pred p = make_pred(lo, hi);
+    static_assert(kIndexChunkVals / kExpandTileVals <= kPlanMaxTiles, "one planning CTA per chunk");
+    static bool attr_set = false;
+    if (!attr_set) {
+        AQP_CUDA_OK(cudaFuncSetAttribute(tile_offsets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int) kPlanSmemBytes));
+        attr_set = true;
+    }
     for (size_t begin = 0; begin < n; begin += kIndexChunkVals) {
         const size_t len = n - begin < kIndexChunkVals ? n - begin : kIndexChunkVals;
         const size_t nvec = len / 16, nwords = len / 64;
@@ -374,11 +538,16 @@ int index_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, u
         bitvector_scan_kernel<true><<<scan_grid(nvec, 8), kScanThreads, 0, st>>>(
             reinterpret_cast<const uint4 *>(d_data + begin), nvec, bv, p, counts);
         AQP_LAUNCHED();
-        tile_offsets_kernel<<<1, kScanBlock, 0, st>>>(counts, ntiles, offsets, running);
+        tile_offsets_kernel<<<1, kScanBlock, kPlanSmemBytes, st>>>(counts, ntiles, offsets, running, lists,
+                                                                   (uint32_t) tiles_cap);
         AQP_LAUNCHED();
-        size_t g = (size_t) kNumSMs * 8;
-        expand_rowids_kernel<<<(unsigned) (ntiles < g ? ntiles : g), kScanThreads, 0, st>>>(bv, nwords, offsets,
-                                                                                         id_base + begin, d_out, cap);
+        size_t g = (size_t) kNumSMs * 6;   // 6 CTAs/SM resident (32 KiB window each)
+        expand_rowids_kernel<<<(unsigned) (ntiles < g ? ntiles : g), kScanThreads, 0, st>>>(
+            bv, nwords, offsets, lists + 2, lists, id_base + begin, d_out, cap);
+        AQP_LAUNCHED();
+        g = (size_t) kNumSMs * 8;
+        expand_dense_rowids_kernel<<<(unsigned) (ntiles < g ? ntiles : g), kScanThreads, 0, st>>>(
+            bv, nwords, offsets, lists + 2 + tiles_cap, lists + 1, id_base + begin, d_out, cap);
         AQP_LAUNCHED();
     }
     AQP_CUDA_OK(cudaGetLastError());

@@ -64,6 +64,28 @@ def test_random_ranges_and_sparse_columns(gpu, oracle):
     assert 100 < cnt < 500
 
 
+def test_mixed_density_tiles(gpu, oracle):
+    """Row-id expansion picks a kernel per 65536-value tile (empty: none, < 3/4 full: shared-memory window,
+    otherwise whole-warp): one column with every kind side by side, in an order that makes the lists ragged,
+    plus a capacity that cuts through a dense tile."""
+    rng = np.random.default_rng(23)
+    T = 1 << 16
+    kinds = [0.0, 1.0, 0.8, 0.3, 0.0, 1.0, 1e-5, 0.74, 0.76, 0.5, 1.0, 0.0, 0.02, 0.999, 0.25, 1.0, 0.6]
+    parts = []
+    for dens in kinds:
+        hit = rng.random(T) < dens
+        parts.append(np.where(hit, rng.integers(10, 20, T), rng.integers(100, 256, T)).astype(np.uint8))
+    col = np.concatenate(parts + [parts[2][:64 * 37]])           # ragged tail tile
+    exp = oracle.index_scan(10, 19, col)
+    ids, cnt, _ = gpu.index_scan_user(10, 19, col)
+    assert cnt == len(exp) and np.array_equal(ids, exp)
+    bv, _ = gpu.bitvector_scan_user(10, 19, col)
+    assert np.array_equal(bv, oracle.bitvector_scan(10, 19, col))
+    cut = int(np.searchsorted(exp, 5 * T + 1000))                  # inside the second full tile
+    ids, cnt, _ = gpu.index_scan_user(10, 19, col, capacity=cut)
+    assert cnt == len(exp) and np.array_equal(ids, exp[:cut])
+
+
 def test_index_scan_capacity_clamp(gpu, oracle):
     col = oracle.tiled_column(1 << 16)
     ids, cnt, _ = gpu.index_scan_user(0, 127, col, capacity=1000)
