@@ -146,12 +146,91 @@ int exclusive_scan_u32_device(const uint32_t *d_in, uint32_t n, uint32_t *d_out,
     return 0;
 }
 
+// CTA-private pass-1 cursors: block_base[b][p] = start[p] + sum of block_hist[b'][p] over b' < b. One WARP per
+// partition column p: the lanes take blocks lane, lane + 32, ... (128 loads of a column in flight at once) and a
+// warp scan with a carry turns them into prefixes; columns are spread over many small CTAs. The first version
+// walked each column with one thread and nblocks dependent iterations inside a single CTA: 57-93 us under ncu
+// on the critical path of every join (and four times per multi-GPU join).
+// Returns the column total to every lane.
+__device__ __forceinline__ uint32_t block_base_column(const uint32_t *__restrict__ block_hist, uint32_t start,
+                                                      uint32_t p, uint32_t fan, uint32_t nblocks,
+                                                      uint32_t *__restrict__ block_base) {
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t run = start;
+    for (uint32_t b0 = 0; b0 < nblocks; b0 += 128) {
+        uint32_t c[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t b = b0 + k * 32 + lane;
+            c[k] = b < nblocks ? block_hist[(size_t) b * fan + p] : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t b = b0 + k * 32 + lane;
+            const uint32_t incl = warp_incl_scan(c[k]);
+            if (block_base && b < nblocks) block_base[(size_t) b * fan + p] = run + incl - c[k];
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    return run - start;
+}
+
+constexpr int kBlockBaseWarps = 4;   // columns per CTA of block_base_kernel
+
+// CTA-private cursors of `nrel` relations in one launch (blockIdx.y = relation). part_start[p] is where the
+// relation's partition p begins in its destination: the local pass-1 output (single GPU), the send buffer, or —
+// fused exchange — the owner's receive buffer (computed by the host from the all-gathered counts); null = 0.
+// counts[p] (optional) receives the relation's size of partition p, seg1 (optional) the single-segment tile table.
+struct BlockBaseRel {
+    const uint32_t *block_hist;
+    const uint32_t *part_start;
+    uint32_t *block_base;
+    uint32_t *counts;
+    uint32_t *seg1;
+    uint32_t n;
+};
+struct BlockBaseArgs {
+    BlockBaseRel rel[2];
+};
+__global__ void __launch_bounds__(kBlockBaseWarps * 32)
+block_base_kernel(BlockBaseArgs a, uint32_t fan, uint32_t nblocks) {
+    const BlockBaseRel &r = a.rel[blockIdx.y];
+    const uint32_t p = blockIdx.x * kBlockBaseWarps + (threadIdx.x >> 5);
+    if (p < fan) {
+        const uint32_t start = r.part_start ? r.part_start[p] : 0u;
+        const uint32_t tot = block_base_column(r.block_hist, start, p, fan, nblocks, r.block_base);
+        if (r.counts && (threadIdx.x & 31u) == 0) r.counts[p] = tot;
+    }
+    if (r.seg1 && blockIdx.x == 0 && threadIdx.x == 0) {
+        r.seg1[0] = 0;
+        r.seg1[1] = r.n;
+        r.seg1[2] = 0;
+        r.seg1[3] = (r.n + kScatterTile - 1) / kScatterTile;
+    }
+}
+
+static int block_base_launch(const BlockBaseArgs &a, uint32_t nrel, uint32_t fan, uint32_t nblocks, cudaStream_t st) {
+    dim3 grid((fan + kBlockBaseWarps - 1) / kBlockBaseWarps, nrel);
+    block_base_kernel<<<grid, kBlockBaseWarps * 32, 0, st>>>(a, fan, nblocks);
+    AQP_LAUNCHED();
+    AQP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int block_base_device(const uint32_t *d_block_hist, const uint32_t *d_part_start, uint32_t fan, uint32_t nblocks,
+                      uint32_t *d_block_base, uint32_t *d_counts, uint32_t *d_seg1, uint32_t n, cudaStream_t st) {
+    BlockBaseArgs a{};
+    a.rel[0] = BlockBaseRel{d_block_hist, d_part_start, d_block_base, d_counts, d_seg1, n};
+    return block_base_launch(a, 1, fan, nblocks, st);
+}
+
 // ---------------------------------------------------------------------------------------------
 // plan: all partition boundaries of both passes from the full-width histogram.
 //   hist is indexed by the raw digit D = key & (2^B-1) = p1 | (p2 << b1)
 //   final partitions are ordered by f = p1 * F2 + p2 (pass-1 partition major)
 // blockIdx.x selects the relation (0 = R, 1 = S).
 // ---------------------------------------------------------------------------------------------
+
 __global__ void __launch_bounds__(kScanBlock) plan_offsets_kernel(PlanArgs a) {
     const RelPlan &r = a.rel[blockIdx.x];
     const uint32_t b1 = a.bits1, F2 = 1u << a.bits2, P = 1u << (a.bits1 + a.bits2), F1 = 1u << a.bits1;
@@ -186,23 +265,18 @@ __global__ void __launch_bounds__(kScanBlock) plan_offsets_kernel(PlanArgs a) {
     if (threadIdx.x == 0) r.seg_tile_start[F1] = tiles;
     // private pass-1 cursors: block b starts writing partition p1 at
     //   part_start[p1] + sum over earlier blocks of their pass-1 histogram rows (radix_join.cpp:901-915)
-    if (r.block_hist) {
-        __syncthreads();
-        for (uint32_t p1 = threadIdx.x; p1 < F1; p1 += kScanBlock) {
-            uint32_t run = r.cursor1[p1];
-            for (uint32_t b = 0; b < a.nblocks1; ++b) {
-                uint32_t c = r.block_hist[(size_t) b * F1 + p1];
-                r.block_base[(size_t) b * F1 + p1] = run;
-                run += c;
-            }
-        }
-    }
 }
 
 int plan_offsets_device(const PlanArgs &a, cudaStream_t st) {
     plan_offsets_kernel<<<2, kScanBlock, 0, st>>>(a);
     AQP_LAUNCHED();
     AQP_CUDA_OK(cudaGetLastError());
+    if (a.rel[0].block_hist) {   // CTA-private pass-1 cursors from the per-CTA histogram rows
+        BlockBaseArgs b{};
+        for (int i = 0; i < 2; ++i)
+            b.rel[i] = BlockBaseRel{a.rel[i].block_hist, a.rel[i].cursor1, a.rel[i].block_base, nullptr, nullptr, 0};
+        return block_base_launch(b, 2, 1u << a.bits1, a.nblocks1, st);
+    }
     return 0;
 }
 
@@ -231,15 +305,6 @@ plan_pass1_kernel(const uint32_t *__restrict__ hist, uint32_t bits1, uint32_t bi
         seg1[2] = 0;
         seg1[3] = (total + kScatterTile - 1) / kScatterTile;
     }
-    __syncthreads();
-    for (uint32_t p1 = threadIdx.x; p1 < F1; p1 += kScanBlock) {
-        uint32_t run = part1_off[p1];
-        for (uint32_t b = 0; b < nblocks; ++b) {
-            uint32_t c = block_hist[(size_t) b * F1 + p1];
-            block_base[(size_t) b * F1 + p1] = run;
-            run += c;
-        }
-    }
 }
 
 int plan_pass1_device(const uint32_t *d_hist, uint32_t bits1, uint32_t bits2, uint32_t *d_part1_off, uint32_t *d_seg1,
@@ -248,40 +313,7 @@ int plan_pass1_device(const uint32_t *d_hist, uint32_t bits1, uint32_t bits2, ui
                                                 nblocks);
     AQP_LAUNCHED();
     AQP_CUDA_OK(cudaGetLastError());
-    return 0;
-}
-
-// fused exchange: CTA-private cursors that point INTO the owners' receive buffers. part_start[p] is
-// where this rank's segment of routed partition p begins in its owner's buffer (computed by the host
-// from the all-gathered counts); counts[p] (optional) receives this rank's size of partition p.
-__global__ void __launch_bounds__(256)
-block_base_kernel(const uint32_t *__restrict__ block_hist, const uint32_t *__restrict__ part_start, uint32_t fan,
-                  uint32_t nblocks, uint32_t *__restrict__ block_base, uint32_t *__restrict__ counts,
-                  uint32_t *__restrict__ seg1, uint32_t n) {
-    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < fan; p += gridDim.x * blockDim.x) {
-        uint32_t run = part_start ? part_start[p] : 0u, tot = 0;
-        for (uint32_t b = 0; b < nblocks; ++b) {
-            uint32_t c = block_hist[(size_t) b * fan + p];
-            if (block_base) block_base[(size_t) b * fan + p] = run;
-            run += c;
-            tot += c;
-        }
-        if (counts) counts[p] = tot;
-    }
-    if (seg1 && blockIdx.x == 0 && threadIdx.x == 0) {
-        seg1[0] = 0;
-        seg1[1] = n;
-        seg1[2] = 0;
-        seg1[3] = (n + kScatterTile - 1) / kScatterTile;
-    }
-}
-
-int block_base_device(const uint32_t *d_block_hist, const uint32_t *d_part_start, uint32_t fan, uint32_t nblocks,
-                      uint32_t *d_block_base, uint32_t *d_counts, uint32_t *d_seg1, uint32_t n, cudaStream_t st) {
-    block_base_kernel<<<1, 256, 0, st>>>(d_block_hist, d_part_start, fan, nblocks, d_block_base, d_counts, d_seg1, n);
-    AQP_LAUNCHED();
-    AQP_CUDA_OK(cudaGetLastError());
-    return 0;
+    return block_base_device(d_block_hist, d_part1_off, 1u << bits1, nblocks, d_block_base, nullptr, nullptr, 0, st);
 }
 
 // after the exchange: final partition boundaries from the (already globally reduced) histogram slice
