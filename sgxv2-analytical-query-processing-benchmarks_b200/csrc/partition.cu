@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "join_internal.cuh"
 #include "block_scan.cuh"
+#include <cstdlib>
 
 namespace aqp {
 
@@ -393,14 +394,34 @@ constexpr int kScatterThreads = AQP_SCATTER_THREADS;
 constexpr int kScatterItems = kScatterTile / kScatterThreads;
 static_assert(kScatterItems * kScatterThreads == kScatterTile, "tile shape");
 constexpr int kInBufTuples = kScatterTile + 2;   // +1 leading tuple when the tile starts on an odd index, +1 to round up
-constexpr size_t kScatterSmemBytes = (size_t) (2 * kInBufTuples + kScatterTile) * sizeof(uint2);
+constexpr int kStageTuples = kScatterTile + 3 * kMaxFanout;   // bulk write-out: carried tuple + parity pad + round-up per run
+constexpr size_t kScatterSmemBytes = (size_t) (2 * kInBufTuples + kStageTuples) * sizeof(uint2);
 // 228 KiB of shared memory per SM; every CTA also pays ~6.2 KiB of static arrays + 1 KiB reserved
 constexpr int kScatterBlocksPerSMRaw = (int) (228 * 1024 / (kScatterSmemBytes + 7424));
 constexpr int kScatterBlocksPerSM = kScatterBlocksPerSMRaw < 1 ? 1 : (kScatterBlocksPerSMRaw * kScatterThreads > 2048 ? 2048 / kScatterThreads : kScatterBlocksPerSMRaw);
 
 uint32_t pass1_blocks() { return (uint32_t) kNumSMs * kScatterBlocksPerSM; }
 
-template <bool kRot, bool kPeer>
+// 1-D bulk copy shared -> global through the TMA unit (src/dst 16-byte aligned, bytes % 16 == 0), tracked by the
+// thread's bulk async-group
+__device__ __forceinline__ void tma_store_1d(void *gdst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+// kBulk (CTA-private cursors only): every partition's run of a tile leaves shared memory as ONE TMA bulk store
+// issued by the partition's own thread, instead of the CTA's threads copying the staging buffer with 8-byte stores.
+// The write-out then costs no LSU instructions and — more important — runs asynchronously under the next tile's
+// rank/scan phases (the CTA only waits, before it overwrites the staging buffer, until the bulk group has READ it).
+// Bulk stores need 16-byte aligned source, destination and size; runs are 8-byte granular, so
+//   * a run is staged at a slot whose parity equals the parity of its destination index,
+//   * an odd destination start is fixed once per (CTA, partition) with one scalar store of the first tuple,
+//   * an odd run length keeps its last tuple in shared memory (carry[d]) as the first tuple of the partition's
+//     next run; the carries are flushed with scalar stores when the CTA is done.
+// bulkbench (profiles/r01_bulkbench.txt): 256-byte bulk stores sustain 5.9 TB/s into local HBM and 714 GB/s to an
+// NVLink peer (the link rate), far above what the scatter needs.
+template <bool kRot, bool kPeer, bool kBulk>
 __global__ void __launch_bounds__(kScatterThreads, kScatterBlocksPerSM)
 radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
                      const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_tile_start,
@@ -416,6 +437,8 @@ radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
     __shared__ uint32_t gdst[kMaxFanout];    // global index of stage slot s of partition d is gdst[d] + s
     __shared__ uint32_t scur[kMaxFanout];    // CTA-private write cursors (pass 1)
     __shared__ uint2 *s_peer[8];             // receive buffers of the owners (fused exchange)
+    __shared__ uint2 carry[kBulk ? kMaxFanout : 1];        // kBulk: the odd tuple a run left behind
+    __shared__ uint32_t runlen[kBulk ? kMaxFanout : 1];    // kBulk: tuples in the run incl. the carried one | carried << 31
     __shared__ uint32_t s_tstart[kMaxFanout + 1];
     __shared__ uint32_t s_soff[kMaxFanout + 1];
     __shared__ __align__(8) uint64_t mbar[2];
@@ -429,6 +452,7 @@ radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
     for (uint32_t i = threadIdx.x; i < fan; i += kScatterThreads) {
         cnt[i] = 0;
         if (priv) scur[i] = block_base[(size_t) blockIdx.x * fan + i];
+        if (kBulk) runlen[i] = 0;
     }
     if (kPeer && threadIdx.x < 8) s_peer[threadIdx.x] = peers.base[threadIdx.x];
     if (threadIdx.x == 0) {
@@ -506,30 +530,62 @@ radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
         if (threadIdx.x < 32) {
             const uint32_t per = (fan + 31) / 32;   // consecutive bins per lane (<= 8)
             uint32_t c[kMaxFanout / 32], sum = 0;
+            if (kBulk) {
+                // run d occupies an even-sized region of the staging buffer that starts on an even slot; inside it the
+                // run starts at the parity of its destination index: [pad?][carried tuple?][new tuples by rank]
+                uint32_t hc[kMaxFanout / 32], par[kMaxFanout / 32];
 #pragma unroll
-            for (int k = 0; k < kMaxFanout / 32; ++k) {
-                uint32_t d = threadIdx.x * per + k;
-                bool ok = k < (int) per && d < fan;
-                c[k] = ok ? cnt[d] : 0;
-                if (ok) cnt[d] = 0;   // ready for the next tile
-                sum += c[k];
-            }
-            uint32_t run = warp_incl_scan(sum) - sum;
-#pragma unroll
-            for (int k = 0; k < kMaxFanout / 32; ++k) {
-                uint32_t d = threadIdx.x * per + k;
-                my_b[k] = run;
-                if (k < (int) per && d < fan) {
-                    lbase[d] = run;
-                    if (priv) {
-                        my_g[k] = scur[d];
-                        scur[d] = my_g[k] + c[k];
-                    } else {
-                        my_g[k] = c[k] ? atomicAdd(&cursors[(group << bits) + d], c[k]) : 0u;
-                    }
+                for (int k = 0; k < kMaxFanout / 32; ++k) {
+                    uint32_t d = threadIdx.x * per + k;
+                    bool ok = k < (int) per && d < fan;
+                    c[k] = ok ? cnt[d] : 0;
+                    hc[k] = ok ? runlen[d] >> 31 : 0;
+                    par[k] = ok ? (scur[d] & 1u) : 0;
+                    if (ok) cnt[d] = 0;
+                    sum += (c[k] + hc[k] + par[k] + 1u) & ~1u;
                 }
-                run += c[k];
+                uint32_t run = warp_incl_scan(sum) - sum;
+#pragma unroll
+                for (int k = 0; k < kMaxFanout / 32; ++k) {
+                    uint32_t d = threadIdx.x * per + k;
+                    if (k < (int) per && d < fan) {
+                        const uint32_t n = c[k] + hc[k];          // tuples of the run, carried one first
+                        lbase[d] = run + par[k] + hc[k];           // where the new tuples go (rank 0)
+                        gdst[d] = run + par[k];                    // where the run starts in the staging buffer
+                        runlen[d] = n | (hc[k] << 31);
+                    }
+                    run += (c[k] + hc[k] + par[k] + 1u) & ~1u;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < kMaxFanout / 32; ++k) {
+                    uint32_t d = threadIdx.x * per + k;
+                    bool ok = k < (int) per && d < fan;
+                    c[k] = ok ? cnt[d] : 0;
+                    if (ok) cnt[d] = 0;   // ready for the next tile
+                    sum += c[k];
+                }
+                uint32_t run = warp_incl_scan(sum) - sum;
+#pragma unroll
+                for (int k = 0; k < kMaxFanout / 32; ++k) {
+                    uint32_t d = threadIdx.x * per + k;
+                    my_b[k] = run;
+                    if (k < (int) per && d < fan) {
+                        lbase[d] = run;
+                        if (priv) {
+                            my_g[k] = scur[d];
+                            scur[d] = my_g[k] + c[k];
+                        } else {
+                            my_g[k] = c[k] ? atomicAdd(&cursors[(group << bits) + d], c[k]) : 0u;
+                        }
+                    }
+                    run += c[k];
+                }
             }
+        }
+        if (kBulk && threadIdx.x < fan) {
+            // the previous tile's bulk stores must have read the staging buffer before it is overwritten
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
         __syncthreads();   // (2) lbase ready
 
@@ -538,23 +594,69 @@ radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
             uint32_t k = j * kScatterThreads + threadIdx.x;
             if (k < ntile) stage[lbase[digit.template get<kRot>(v[j].x)] + rank[j]] = v[j];
         }
-        if (threadIdx.x < 32) {
-            const uint32_t per = (fan + 31) / 32;
+        if (kBulk) {
+            // the partition's own thread: carried tuple to the front of the run, then (after the barrier) head fix,
+            // bulk store of the even body, new carry
+            const uint32_t d = threadIdx.x;
+            uint32_t n = 0, sb = 0;
+            if (d < fan) {
+                const uint32_t rl = runlen[d];
+                n = rl & 0x7FFFFFFFu;
+                sb = gdst[d];
+                if (rl >> 31) stage[sb] = carry[d];
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged tuples visible to the TMA unit
+            __syncthreads();   // (3) tile reordered
+            if (d < fan) {
+                uint32_t left = 0;
+                if (n) {
+                    uint2 *dst = kPeer ? s_peer[d >> peers.per_shift] : out;
+                    uint32_t g = scur[d];
+                    if (g & 1u) {   // odd destination start: once per (CTA, partition)
+                        dst[g] = stage[sb];
+                        ++g;
+                        ++sb;
+                        --n;
+                    }
+                    const uint32_t body = n & ~1u;
+                    if (body) tma_store_1d(dst + g, stage + sb, body * (uint32_t) sizeof(uint2));
+                    left = n & 1u;
+                    if (left) carry[d] = stage[sb + body];
+                    scur[d] = g + body;
+                }
+                runlen[d] = left << 31;
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else {
+            if (threadIdx.x < 32) {
+                const uint32_t per = (fan + 31) / 32;
 #pragma unroll
-            for (int k = 0; k < kMaxFanout / 32; ++k) {
-                uint32_t d = threadIdx.x * per + k;
-                if (k < (int) per && d < fan) gdst[d] = my_g[k] - my_b[k];
+                for (int k = 0; k < kMaxFanout / 32; ++k) {
+                    uint32_t d = threadIdx.x * per + k;
+                    if (k < (int) per && d < fan) gdst[d] = my_g[k] - my_b[k];
+                }
+            }
+            __syncthreads();   // (3) tile reordered, destinations known
+
+            for (uint32_t s = threadIdx.x; s < ntile; s += kScatterThreads) {
+                uint2 t = stage[s];
+                const uint32_t d = digit.template get<kRot>(t.x);
+                if (kPeer)   // fused exchange: the run goes straight into its owner's receive buffer over NVLink
+                    s_peer[d >> peers.per_shift][gdst[d] + s] = t;
+                else
+                    out[gdst[d] + s] = t;
             }
         }
-        __syncthreads();   // (3) tile reordered, destinations known
-
-        for (uint32_t s = threadIdx.x; s < ntile; s += kScatterThreads) {
-            uint2 t = stage[s];
-            const uint32_t d = digit.template get<kRot>(t.x);
-            if (kPeer)   // fused exchange: the run goes straight into its owner's receive buffer over NVLink
-                s_peer[d >> peers.per_shift][gdst[d] + s] = t;
-            else
-                out[gdst[d] + s] = t;
+    }
+    if (kBulk) {
+        // flush the carried tuples, and do not leave before the TMA unit has finished reading shared memory
+        const uint32_t d = threadIdx.x;
+        if (d < fan) {
+            if (runlen[d] >> 31) {
+                uint2 *dst = kPeer ? s_peer[d >> peers.per_shift] : out;
+                dst[scur[d]] = carry[d];
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
     }
 }
@@ -574,12 +676,16 @@ int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_
     if (n_total == 0) return 0;
     static bool attr_set = false;
     if (!attr_set) {
-        AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int) kScatterSmemBytes));
-        AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int) kScatterSmemBytes));
-        AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int) kScatterSmemBytes));
+#define AQP_SCATTER_ATTR(ROT, PEER, BULK)                                                                             \
+    AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_kernel<ROT, PEER, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int) kScatterSmemBytes))
+        AQP_SCATTER_ATTR(false, false, false);
+        AQP_SCATTER_ATTR(false, false, true);
+        AQP_SCATTER_ATTR(true, false, false);
+        AQP_SCATTER_ATTR(true, false, true);
+        AQP_SCATTER_ATTR(true, true, false);
+        AQP_SCATTER_ATTR(true, true, true);
+#undef AQP_SCATTER_ATTR
         attr_set = true;
     }
     uint32_t grid;
@@ -594,10 +700,25 @@ int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_
     const uint2 *in = reinterpret_cast<const uint2 *>(d_in);
     uint2 *out = reinterpret_cast<uint2 *>(d_out);
     const bool peer = peers && peers->n;
+    // bulk write-out needs CTA-private cursors (the destination parity must be known when the tile is staged) and a
+    // 16-byte aligned destination buffer; B200_AQP_SCATTER_BULK=0 keeps the SM-store write-out (A/B measurements)
+    static const bool bulk_off = getenv("B200_AQP_SCATTER_BULK") && atoi(getenv("B200_AQP_SCATTER_BULK")) == 0;
+    bool bulk = d_block_base && !bulk_off && kMaxFanout <= kScatterThreads;
+    if (bulk && !peer && (reinterpret_cast<uintptr_t>(d_out) & 15u)) bulk = false;
+    if (bulk && peer)
+        for (uint32_t i = 0; i < peers->n; ++i)
+            if (reinterpret_cast<uintptr_t>(peers->base[i]) & 15u) bulk = false;
 #define AQP_SCATTER_LAUNCH(ROT, PEER)                                                                              \
-    radix_scatter_kernel<ROT, PEER><<<grid, kScatterThreads, kScatterSmemBytes, st>>>(                              \
-        in, out, d_seg_off, d_seg_tile_start, d_seg_group, nseg, digit, bits, d_cursors, d_block_base, tiles_per_block, \
-        peer ? *peers : none)
+    do {                                                                                                           \
+        if (bulk)                                                                                                  \
+            radix_scatter_kernel<ROT, PEER, true><<<grid, kScatterThreads, kScatterSmemBytes, st>>>(               \
+                in, out, d_seg_off, d_seg_tile_start, d_seg_group, nseg, digit, bits, d_cursors, d_block_base,     \
+                tiles_per_block, peer ? *peers : none);                                                            \
+        else                                                                                                       \
+            radix_scatter_kernel<ROT, PEER, false><<<grid, kScatterThreads, kScatterSmemBytes, st>>>(              \
+                in, out, d_seg_off, d_seg_tile_start, d_seg_group, nseg, digit, bits, d_cursors, d_block_base,     \
+                tiles_per_block, peer ? *peers : none);                                                            \
+    } while (0)
     if (peer)
         AQP_SCATTER_LAUNCH(true, true);
     else if (digit.rot)
