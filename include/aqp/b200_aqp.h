@@ -177,6 +177,25 @@ int b200_shard_join_device(const struct row_t *d_R, uint64_t nR, const uint32_t 
                            uint32_t ngroups, uint32_t shift2, uint32_t bits2, const uint32_t *d_hist_R,
                            const uint32_t *d_hist_S, uint32_t hash_shift, struct b200_join_stats_t *stats,
                            void *stream);
+/* Latency-trimmed forms for the fused exchange (the per-join fixed cost is what limits strong scaling at 8 GPUs):
+ *   b200_exchange_plan_device     everything a rank derives from the two sizing collectives, in one launch.
+ *       d_counts_all[world][2][2^bits1]  all-gathered d_counts1 of R and S;  d_hist_global[2][2^(bits1+bits2)] the
+ *       all-reduced histograms. Outputs: d_seg_off[2][world*per+1] (per = 2^bits1/world; received segments ordered
+ *       (source, local partition)), d_dest_off[2][2^bits1] (argument of b200_shard_scatter_device),
+ *       d_hist_slice[2][per << bits2] (d_hist_R / d_hist_S of b200_shard_join_device) and d_host_vals[6] =
+ *       {largest receive size of any rank R, S; this rank's receive sizes R, S; tuples this rank keeps R, S}.
+ *   b200_shard_join_async_device  b200_shard_join_device without the host round trip: d_result3[3] receives
+ *       {matches, checksum, keysum} on the device, in stream order; no synchronisation.
+ *   b200_shard_join_times         phase times of the last (async) shard join; waits for its last event. */
+int b200_exchange_plan_device(const uint32_t *d_counts_all, uint32_t world, uint32_t rank, uint32_t bits1,
+                              uint32_t bits2, const uint32_t *d_hist_global, uint32_t *d_seg_off, uint32_t *d_dest_off,
+                              uint32_t *d_hist_slice, uint64_t *d_host_vals, void *stream);
+int b200_shard_join_async_device(const struct row_t *d_R, uint64_t nR, const uint32_t *d_segoff_R,
+                                 const struct row_t *d_S, uint64_t nS, const uint32_t *d_segoff_S,
+                                 const uint32_t *d_seg_group, uint32_t nseg, uint32_t ngroups, uint32_t shift2,
+                                 uint32_t bits2, const uint32_t *d_hist_R, const uint32_t *d_hist_S, uint32_t hash_shift,
+                                 uint64_t *d_result3, void *stream);
+int b200_shard_join_times(struct b200_join_stats_t *stats);
 
 /* ------------------------------------------------------------------------------------------------
  * 4. relation generators

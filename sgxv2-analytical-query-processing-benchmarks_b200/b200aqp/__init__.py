@@ -121,6 +121,10 @@ SYMBOLS = {
     "b200_shard_hist_device": (_int, [_vp, _u64, _u32, _u32, _u32, _vp, _vp, _int, _vp]),
     "b200_shard_scatter_device": (_int, [_vp, _u64, _vp, C.POINTER(_vp), _int, _vp]),
     "b200_copy_async": (_int, [_vp, _vp, _sz, _vp]),
+    "b200_exchange_plan_device": (_int, [_vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200_shard_join_async_device": (_int, [_vp, _u64, _vp, _vp, _u64, _vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _u32,
+                                            _vp, _vp]),
+    "b200_shard_join_times": (_int, [C.POINTER(JoinStats)]),
     "b200_ipc_export": (_int, [_vp, _vp]),
     "b200_ipc_open": (_int, [_vp, C.POINTER(_vp)]),
     "b200_ipc_close": (_int, [_vp]),

@@ -122,6 +122,24 @@ class CudaBackend:
         self.A._check(self.L.b200_shard_scatter_device(rel.data_ptr(), n, dest_off.data_ptr(), arr, slot, self.stream()),
                       "b200_shard_scatter_device")
 
+    def exchange_plan(self, counts_all, world, rank, b1, b2, hist_global, seg_off, dest_off, hist_slice, host_vals):
+        self.A._check(self.L.b200_exchange_plan_device(counts_all.data_ptr(), world, rank, b1, b2, hist_global.data_ptr(),
+                                                       seg_off.data_ptr(), dest_off.data_ptr(), hist_slice.data_ptr(),
+                                                       host_vals.data_ptr(), self.stream()), "b200_exchange_plan_device")
+
+    def shard_join_async(self, R, nR, segR, S, nS, segS, seg_group, nseg, ngroups, shift2, bits2, histR, histS, hash_shift,
+                         result3):
+        self.A._check(self.L.b200_shard_join_async_device(R.data_ptr(), nR, segR.data_ptr(), S.data_ptr(), nS,
+                                                          segS.data_ptr(), seg_group.data_ptr(), nseg, ngroups, shift2,
+                                                          bits2, histR.data_ptr(), histS.data_ptr(), hash_shift,
+                                                          result3.data_ptr(), self.stream()),
+                      "b200_shard_join_async_device")
+
+    def shard_join_times(self):
+        s = self.A.JoinStats()
+        self.A._check(self.L.b200_shard_join_times(s), "b200_shard_join_times")
+        return s.as_dict()
+
     def copy_async(self, dst_ptr, src_ptr, nbytes, stream):
         self.A._check(self.L.b200_copy_async(dst_ptr, src_ptr, nbytes, self.A._st(stream)), "b200_copy_async")
 
@@ -266,6 +284,69 @@ class FusedShardedJoin(ShardedJoin):
             for g in range(G):
                 peers.append(buf.ptr if g == self.rank else be.open_shared(hs[g]))
         self.fallbacks = 0
+        self._seg_group = None
+
+    def _sizing(self, cnt1, hist):
+        """The two sizing collectives and everything derived from them. Returns (host, segR, segS, dR, dS, hR, hS,
+        seg_group) with host = [largest receive size anywhere R, S; my receive sizes R, S; tuples I keep R, S] — reading
+        it is the one host sync of the exchange. On the CUDA backend the derivation is ONE kernel
+        (b200_exchange_plan_device); other backends (CPU tests) use the tensor formulation above."""
+        be, G, rank, F1, P = self.backend, self.world, self.rank, self.F1, self.P
+        per = F1 // G
+        fast = hasattr(be, "exchange_plan")
+        counts_flat = self._buf("counts_all", G * 2 * F1, torch.int32 if fast else torch.int64)
+        dist.all_gather_into_tensor(counts_flat[:G * 2 * F1], cnt1[:2 * F1] if fast else cnt1[:2 * F1].to(torch.int64),
+                                    group=self.group)
+        dist.all_reduce(hist[:2 * P], group=self.group)          # in place: shard_hist re-zeroes it next run
+        if self._seg_group is None:
+            self._seg_group = torch.arange(per, device=self.device, dtype=torch.int32).repeat(G)
+        if fast:
+            nseg = G * per
+            seg = self._buf("seg_off", 2 * (nseg + 1), torch.int32)
+            dest = self._buf("dest_off", 2 * F1, torch.int32)
+            hsl = self._buf("hist_slice", 2 * (per << self.b2), torch.int32)
+            hv = self._buf("host_vals", 6, torch.int64)
+            be.exchange_plan(counts_flat, G, rank, self.b1, self.b2, hist, seg, dest, hsl, hv)
+            host = hv[:6].tolist()
+            n2 = per << self.b2
+            return (host, seg[:nseg + 1], seg[nseg + 1:2 * (nseg + 1)], dest[:F1], dest[F1:2 * F1], hsl[:n2],
+                    hsl[n2:2 * n2], self._seg_group)
+        counts_all = counts_flat[:G * 2 * F1].view(G, 2 * F1)
+        _, rR, segR, _ = exchange_plan(counts_all[:, :F1], rank, G)
+        _, rS, segS, _ = exchange_plan(counts_all[:, F1:], rank, G)
+        dR = dest_offsets(counts_all[:, :F1], rank, G).to(torch.int32)
+        dS = dest_offsets(counts_all[:, F1:], rank, G).to(torch.int32)
+        # every rank must take the same path: the largest receive sizes anywhere are compared with the capacities
+        host = torch.stack([counts_all[:, :F1].view(G, G, per).sum((0, 2)).max(),
+                            counts_all[:, F1:].view(G, G, per).sum((0, 2)).max(), rR.sum(), rS.sum(),
+                            counts_all[rank, rank * per:(rank + 1) * per].sum(),
+                            counts_all[rank, F1 + rank * per:F1 + (rank + 1) * per].sum()]).tolist()
+        hR = final_hist_slice(hist[:P], rank, G, self.b1, self.b2)
+        hS = final_hist_slice(hist[P:2 * P], rank, G, self.b1, self.b2)
+        return host, segR.to(torch.int32), segS.to(torch.int32), dR, dS, hR, hS, self._seg_group
+
+    def _finish(self, nR_recv, segR, nS_recv, segS, seg_group, hR, hS):
+        """Local pass 2 + build/probe on the received segments and the global sum of the result.
+        Returns (matches, checksum, keysum, phase times of the local stage)."""
+        be, G, rank = self.backend, self.world, self.rank
+        per = self.F1 // G
+        bufR, bufS = _RawBuffer(self.peerR[rank]), _RawBuffer(self.peerS[rank])
+        if hasattr(be, "shard_join_async"):
+            res = self._buf("result3", 4, torch.int64)
+            be.shard_join_async(bufR, nR_recv, segR, bufS, nS_recv, segS, seg_group, G * per, per, self.b1, self.b2,
+                                hR, hS, self.bits, res)
+            dist.all_reduce(res[:3], group=self.group)
+            m, cs, ks = (int(x) for x in res[:3].tolist())       # the sync that ends the join
+            local = be.shard_join_times()
+        else:
+            local = be.shard_join(bufR, nR_recv, segR, bufS, nS_recv, segS, seg_group, G * per, per, self.b1, self.b2,
+                                  hR, hS, self.bits)
+            to_i64 = lambda v: v - (1 << 64) if v >= (1 << 63) else v
+            res = torch.tensor([local["matches"], to_i64(local["checksum"]), to_i64(local["keysum"])], dtype=torch.int64,
+                               device=self.device)
+            dist.all_reduce(res, group=self.group)
+            m, cs, ks = (int(x) for x in res.tolist())
+        return m, cs % (1 << 64), ks % (1 << 64), local
 
     def run(self, R: torch.Tensor, S: torch.Tensor) -> dict:
         be, G, rank = self.backend, self.world, self.rank
@@ -279,25 +360,13 @@ class FusedShardedJoin(ShardedJoin):
         be.shard_hist(S, nS, self.bits, self.b1, self.lg, hist[P:2 * P], cnt1[F1:2 * F1], 1)
         eh = self._event()
         # ---- 2. size the exchange -------------------------------------------------------------------------
-        counts_flat = torch.empty(G * 2 * F1, dtype=torch.int64, device=self.device)
-        dist.all_gather_into_tensor(counts_flat, cnt1[:2 * F1].to(torch.int64), group=self.group)
-        counts_all = counts_flat.view(G, 2 * F1)
-        hist_global = hist[:2 * P].clone()
-        dist.all_reduce(hist_global, group=self.group)
-        _, rR, segR, seg_group = exchange_plan(counts_all[:, :F1], rank, G)
-        _, rS, segS, _ = exchange_plan(counts_all[:, F1:], rank, G)
-        dR = dest_offsets(counts_all[:, :F1], rank, G).to(torch.int32)
-        dS = dest_offsets(counts_all[:, F1:], rank, G).to(torch.int32)
-        # every rank must take the same path: compare the largest receive sizes anywhere with the capacities
-        per = F1 // G
-        worst = torch.stack([counts_all[:, :F1].view(G, G, per).sum((0, 2)).max(),
-                             counts_all[:, F1:].view(G, G, per).sum((0, 2)).max(), rR.sum(), rS.sum()]).tolist()
-        if worst[0] > self.capR or worst[1] > self.capS:
+        host, segR, segS, dR, dS, hR, hS, seg_group = self._sizing(cnt1, hist)
+        if host[0] > self.capR or host[1] > self.capS:
             self.fallbacks += 1
-            out = super().run(R, S)
+            out = ShardedJoin.run(self, R, S)
             out["exchange"] = "nccl-fallback"
             return out
-        nR_recv, nS_recv = int(worst[2]), int(worst[3])
+        nR_recv, nS_recv = int(host[2]), int(host[3])
         es = self._event()
         # ---- 3. fused scatter + exchange: stores go to the owners' buffers over NVLink ------------------
         be.shard_scatter(R, nR, dR, self.peerR, 0)
@@ -306,31 +375,22 @@ class FusedShardedJoin(ShardedJoin):
         flag = self._buf("flag", 2, torch.int32)
         dist.all_reduce(flag[:1], group=self.group)    # barrier: every rank's stores have landed
         e2 = self._event()
-        # ---- 4. local pass 2 + build/probe -------------------------------------------------------------------
-        hR = final_hist_slice(hist_global[:P], rank, G, self.b1, self.b2)
-        hS = final_hist_slice(hist_global[P:], rank, G, self.b1, self.b2)
-        local = be.shard_join(_RawBuffer(self.peerR[rank]), nR_recv, segR.to(torch.int32), _RawBuffer(self.peerS[rank]),
-                              nS_recv, segS.to(torch.int32), seg_group, G * per, per, self.b1, self.b2, hR, hS, self.bits)
+        # ---- 4. local pass 2 + build/probe, global result ----------------------------------------------------
+        m, cs, ks, local = self._finish(nR_recv, segR, nS_recv, segS, seg_group, hR, hS)
         e3 = self._event()
-        to_i64 = lambda v: v - (1 << 64) if v >= (1 << 63) else v
-        res = torch.tensor([local["matches"], to_i64(local["checksum"]), to_i64(local["keysum"])], dtype=torch.int64,
-                           device=self.device)
-        dist.all_reduce(res, group=self.group)
-        m, cs, ks = (int(x) for x in res.tolist())
-        kept = int(counts_all[rank, rank * per:(rank + 1) * per].sum() + counts_all[rank, F1 + rank * per:F1 + (rank + 1) * per].sum())
-        out = {"matches": m, "checksum": cs % (1 << 64), "keysum": ks % (1 << 64), "radix_bits": self.bits,
+        out = {"matches": m, "checksum": cs, "keysum": ks, "radix_bits": self.bits,
                "num_passes": 2, "bits_pass1": self.b1, "bits_pass2": self.b2, "tuples_sent": nR + nS,
-               "tuples_kept": kept, "ms_pass2": local.get("ms_pass2", 0.0), "ms_join": local.get("ms_join", 0.0),
-               "exchange": "p2p-fused"}
+               "tuples_kept": int(host[4] + host[5]), "ms_pass2": local.get("ms_pass2", 0.0),
+               "ms_join": local.get("ms_join", 0.0), "exchange": "p2p-fused"}
         if e0 is not None:
             torch.cuda.synchronize()
             out["ms_hist"] = e0.elapsed_time(eh)
             out["ms_pass1"] = eh.elapsed_time(e2)      # sizing collectives + fused scatter/exchange + barrier
-            out["ms_sizing"] = eh.elapsed_time(es)     # all-gather + all-reduce + offset arithmetic + host sync
+            out["ms_sizing"] = eh.elapsed_time(es)     # all-gather + all-reduce + plan kernel + host sync
             out["ms_scatter_kernels"] = es.elapsed_time(ex)
             out["ms_barrier"] = ex.elapsed_time(e2)
             out["ms_exchange"] = 0.0                   # no separate exchange step
-            out["ms_total"] = e0.elapsed_time(e3)
+            out["ms_total"] = e0.elapsed_time(e3)      # up to the global result
         return out
 
 

@@ -7,6 +7,7 @@
 // (Scan-Micro-Benchmarks/microbenchmarks/SimdScanMulti/Enclave/Enclave.cpp:100-133,:270-299).
 // The reference's threads, barriers and task queues have no equivalent here: a phase is one kernel
 // launch on one stream and stream order is the barrier.
+#include <cstddef>
 #include <chrono>
 #include <cstdarg>
 #include <cstring>
@@ -775,11 +776,66 @@ int b200_ipc_close(void *d_ptr) {
     return 0;
 }
 
+int b200_exchange_plan_device(const uint32_t *d_counts_all, uint32_t world, uint32_t rank, uint32_t bits1,
+                              uint32_t bits2, const uint32_t *d_hist_global, uint32_t *d_seg_off, uint32_t *d_dest_off,
+                              uint32_t *d_hist_slice, uint64_t *d_host_vals, void *stream) {
+    if (ensure_init()) return -1;
+    if (world == 0 || world > 8 || (world & (world - 1)) || rank >= world || bits1 > (uint32_t) kMaxFanoutBits ||
+        (1u << bits1) < world || bits2 > (uint32_t) kMaxFanoutBits) {
+        set_error("b200_exchange_plan_device: need world in {1,2,4,8}, rank < world, world <= 2^bits1, bits <= 8 per pass");
+        return -1;
+    }
+    return exchange_plan_device(d_counts_all, world, rank, bits1, bits2, d_hist_global, d_seg_off, d_dest_off, d_hist_slice,
+                                reinterpret_cast<unsigned long long *>(d_host_vals),
+                                stream ? static_cast<cudaStream_t>(stream) : g.stream);
+}
+
+static int shard_join_locked(const struct row_t *d_R, uint64_t nR, const uint32_t *d_segoff_R, const struct row_t *d_S,
+                             uint64_t nS, const uint32_t *d_segoff_S, const uint32_t *d_seg_group, uint32_t nseg,
+                             uint32_t ngroups, uint32_t shift2, uint32_t bits2, const uint32_t *d_hist_R,
+                             const uint32_t *d_hist_S, uint32_t hash_shift, struct b200_join_stats_t *stats,
+                             uint64_t *d_result3, void *stream);
+
 int b200_shard_join_device(const struct row_t *d_R, uint64_t nR, const uint32_t *d_segoff_R, const struct row_t *d_S,
                            uint64_t nS, const uint32_t *d_segoff_S, const uint32_t *d_seg_group, uint32_t nseg,
                            uint32_t ngroups, uint32_t shift2, uint32_t bits2, const uint32_t *d_hist_R,
                            const uint32_t *d_hist_S, uint32_t hash_shift, struct b200_join_stats_t *stats,
                            void *stream) {
+    return shard_join_locked(d_R, nR, d_segoff_R, d_S, nS, d_segoff_S, d_seg_group, nseg, ngroups, shift2, bits2, d_hist_R,
+                             d_hist_S, hash_shift, stats, nullptr, stream);
+}
+
+int b200_shard_join_async_device(const struct row_t *d_R, uint64_t nR, const uint32_t *d_segoff_R,
+                                 const struct row_t *d_S, uint64_t nS, const uint32_t *d_segoff_S,
+                                 const uint32_t *d_seg_group, uint32_t nseg, uint32_t ngroups, uint32_t shift2,
+                                 uint32_t bits2, const uint32_t *d_hist_R, const uint32_t *d_hist_S, uint32_t hash_shift,
+                                 uint64_t *d_result3, void *stream) {
+    if (!d_result3) {
+        set_error("b200_shard_join_async_device: d_result3 must not be null");
+        return -1;
+    }
+    return shard_join_locked(d_R, nR, d_segoff_R, d_S, nS, d_segoff_S, d_seg_group, nseg, ngroups, shift2, bits2, d_hist_R,
+                             d_hist_S, hash_shift, nullptr, d_result3, stream);
+}
+
+int b200_shard_join_times(struct b200_join_stats_t *stats) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init() || !stats) return -1;
+    b200_join_stats_t s = g.last;
+    AQP_CUDA_OK(cudaEventSynchronize(g.ev[4]));
+    cudaEventElapsedTime(&s.ms_pass2, g.ev[0], g.ev[3]);
+    cudaEventElapsedTime(&s.ms_join, g.ev[3], g.ev[4]);
+    cudaEventElapsedTime(&s.ms_total, g.ev[0], g.ev[4]);
+    g.last = s;
+    *stats = s;
+    return 0;
+}
+
+static int shard_join_locked(const struct row_t *d_R, uint64_t nR, const uint32_t *d_segoff_R, const struct row_t *d_S,
+                             uint64_t nS, const uint32_t *d_segoff_S, const uint32_t *d_seg_group, uint32_t nseg,
+                             uint32_t ngroups, uint32_t shift2, uint32_t bits2, const uint32_t *d_hist_R,
+                             const uint32_t *d_hist_S, uint32_t hash_shift, struct b200_join_stats_t *stats,
+                             uint64_t *d_result3, void *stream) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (ensure_init()) return -1;
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : g.stream;
@@ -827,6 +883,19 @@ int b200_shard_join_device(const struct row_t *d_R, uint64_t nR, const uint32_t 
                            hash_shift, d_res, nullptr, 0, st))
         return -1;
     AQP_CUDA_OK(cudaEventRecord(g.ev[4], st));
+    if (d_result3) {
+        // asynchronous form: {matches, checksum, keysum} stay on the device (the caller all-reduces them there);
+        // nothing here waits for the GPU. Phase times: b200_shard_join_times() after the caller's own sync.
+        static_assert(offsetof(JoinResult, matches) == 0 && offsetof(JoinResult, keysum) == 16, "JoinResult layout");
+        AQP_CUDA_OK(cudaMemcpyAsync(d_result3, d_res, 3 * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+        b200_join_stats_t s{};
+        s.radix_bits = hash_shift;
+        s.num_passes = 2;
+        s.bits_pass2 = bits2;
+        s.kernel_launches = (uint32_t) (g_kernel_launches - launches0);
+        g.last = s;
+        return 0;
+    }
     JoinResult h{};
     AQP_CUDA_OK(cudaMemcpyAsync(&h, d_res, sizeof h, cudaMemcpyDeviceToHost, st));
     AQP_CUDA_OK(cudaStreamSynchronize(st));

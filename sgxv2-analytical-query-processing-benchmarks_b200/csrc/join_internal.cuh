@@ -145,6 +145,9 @@ uint32_t pass1_blocks();
 int plan_pass1_device(const uint32_t *d_hist, uint32_t bits1, uint32_t bits2, uint32_t *d_part1_off, uint32_t *d_seg1,
                       const uint32_t *d_block_hist, uint32_t *d_block_base, uint32_t nblocks, cudaStream_t st);
 int plan_shard_device(const ShardPlanArgs &a, cudaStream_t st);
+int exchange_plan_device(const uint32_t *d_counts_all, uint32_t world, uint32_t rank, uint32_t bits1, uint32_t bits2,
+                         const uint32_t *d_hist_global, uint32_t *d_seg_off, uint32_t *d_dest_off, uint32_t *d_hist_slice,
+                         unsigned long long *d_host_vals, cudaStream_t st);
 int single_segment_setup(uint32_t n, const uint32_t *d_offsets, uint32_t fan, uint32_t *d_cursors,
                          uint32_t *d_seg_tables, cudaStream_t st);
 

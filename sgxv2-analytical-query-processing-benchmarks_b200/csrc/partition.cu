@@ -317,6 +317,82 @@ int plan_pass1_device(const uint32_t *d_hist, uint32_t bits1, uint32_t bits2, ui
     return block_base_device(d_block_hist, d_part1_off, 1u << bits1, nblocks, d_block_base, nullptr, nullptr, 0, st);
 }
 
+// Everything a rank derives from the two sizing collectives of the fused exchange, in ONE launch (the host side
+// used ~45 small tensor kernels for this, 0.2 ms of launch latency per join):
+//   counts_all[s][rel][p]  tuples source rank s holds of routed pass-1 partition p of relation rel (all-gathered)
+//   hist_global[rel][D]    full-width histograms summed over ranks, D = p1' | (p2 << bits1)
+// ->
+//   seg_off[rel][world*per + 1]   starts of the segments this rank receives, ordered (source, local partition)
+//   dest_off[rel][F1]             where THIS rank's segment of partition p starts inside its owner's buffer
+//   hist_slice[rel][per << bits2] this rank's final partition sizes, order (local partition, p2)
+//   host_vals[6]                  largest receive size of any rank for R, for S; this rank's receive sizes R, S;
+//                                 tuples this rank keeps (R, S)
+__global__ void __launch_bounds__(256)
+exchange_plan_kernel(const uint32_t *__restrict__ counts_all, uint32_t world, uint32_t rank, uint32_t bits1,
+                     uint32_t bits2, const uint32_t *__restrict__ hist_global, uint32_t *__restrict__ seg_off,
+                     uint32_t *__restrict__ dest_off, uint32_t *__restrict__ hist_slice,
+                     unsigned long long *__restrict__ host_vals) {
+    __shared__ uint32_t tot[2][8][8];   // [rel][source][owner]
+    const uint32_t F1 = 1u << bits1, F2 = 1u << bits2, P = F1 << bits2, per = F1 / world, nseg = world * per;
+    auto cnt = [&](uint32_t s, uint32_t rel, uint32_t p) { return counts_all[((size_t) s * 2 + rel) * F1 + p]; };
+    for (uint32_t t = threadIdx.x; t < 2 * world * world; t += blockDim.x) {
+        const uint32_t rel = t / (world * world), s = (t / world) % world, g = t % world;
+        uint32_t a = 0;
+        for (uint32_t j = 0; j < per; ++j) a += cnt(s, rel, g * per + j);
+        tot[rel][s][g] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {   // sizes for the host
+        const uint32_t rel = threadIdx.x;
+        unsigned long long worst = 0, mine = 0;
+        for (uint32_t g = 0; g < world; ++g) {
+            unsigned long long r = 0;
+            for (uint32_t s = 0; s < world; ++s) r += tot[rel][s][g];
+            worst = r > worst ? r : worst;
+            if (g == rank) mine = r;
+        }
+        host_vals[rel] = worst;
+        host_vals[2 + rel] = mine;
+        host_vals[4 + rel] = tot[rel][rank][rank];
+    }
+    for (uint32_t t = threadIdx.x; t < 2 * world; t += blockDim.x) {   // dest_off: one thread per (relation, owner)
+        const uint32_t rel = t / world, g = t % world;
+        uint32_t run = 0;
+        for (uint32_t s = 0; s < rank; ++s) run += tot[rel][s][g];
+        for (uint32_t j = 0; j < per; ++j) {
+            dest_off[rel * F1 + g * per + j] = run;
+            run += cnt(rank, rel, g * per + j);
+        }
+    }
+    // seg_off: exclusive prefix over (source, local partition); one warp per relation
+    if (threadIdx.x < 64) {
+        const uint32_t rel = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+        uint32_t run = 0;
+        for (uint32_t i0 = 0; i0 < nseg; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            const uint32_t v = i < nseg ? cnt(i / per, rel, rank * per + i % per) : 0u;
+            const uint32_t incl = warp_incl_scan(v);
+            if (i < nseg) seg_off[rel * (nseg + 1) + i] = run + incl - v;
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) seg_off[rel * (nseg + 1) + nseg] = run;
+    }
+    for (uint32_t t = threadIdx.x; t < 2 * (per << bits2); t += blockDim.x) {
+        const uint32_t rel = t / (per << bits2), f = t % (per << bits2), j = f >> bits2, p2 = f & (F2 - 1);
+        hist_slice[t] = hist_global[(size_t) rel * P + ((size_t) p2 << bits1) + rank * per + j];
+    }
+}
+
+int exchange_plan_device(const uint32_t *d_counts_all, uint32_t world, uint32_t rank, uint32_t bits1, uint32_t bits2,
+                         const uint32_t *d_hist_global, uint32_t *d_seg_off, uint32_t *d_dest_off, uint32_t *d_hist_slice,
+                         unsigned long long *d_host_vals, cudaStream_t st) {
+    exchange_plan_kernel<<<1, 256, 0, st>>>(d_counts_all, world, rank, bits1, bits2, d_hist_global, d_seg_off, d_dest_off,
+                                            d_hist_slice, d_host_vals);
+    AQP_LAUNCHED();
+    AQP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 // after the exchange: final partition boundaries from the (already globally reduced) histogram slice
 // of this rank in final order, and the tile table of the received segments. blockIdx.x = relation.
 __global__ void __launch_bounds__(kScanBlock) plan_shard_kernel(ShardPlanArgs a) {

@@ -141,3 +141,40 @@ def test_fused_scatter_exchange(gpu, oracle, G):
     _emulate_fused(gpu, oracle, R, S, G)
     Sz = oracle.set_rowid_payload(oracle.gen_zipf(400009, 100003, 1.0, seed=5))
     _emulate_fused(gpu, oracle, R, Sz, G)
+
+
+@pytest.mark.parametrize("G,b1,b2", [(2, 3, 3), (4, 7, 7), (8, 7, 7), (8, 3, 0), (1, 5, 6), (2, 8, 8)])
+def test_exchange_plan_kernel_matches_tensor_formulation(gpu, G, b1, b2):
+    """b200_exchange_plan_device (one launch) against the tensor formulation in b200aqp.dist that the CPU tests pin:
+    received-segment tables, destination offsets, histogram slices and the sizes the host reads, for every rank."""
+    import torch
+    import b200aqp.dist as D
+    dev = torch.device("cuda:0")
+    be = D.CudaBackend()
+    F1, P = 1 << b1, 1 << (b1 + b2)
+    per = F1 // G
+    gen = torch.Generator().manual_seed(1000 * G + b1)
+    counts = torch.randint(0, 5000, (G, 2, F1), generator=gen, dtype=torch.int32)
+    counts[0, 0, :per] = 0                                           # empty partitions too
+    hist = torch.randint(0, 1 << 20, (2, P), generator=gen, dtype=torch.int32)
+    c_dev, h_dev = counts.to(dev).contiguous(), hist.to(dev).contiguous()
+    for rank in range(G):
+        nseg = G * per
+        seg = torch.full((2 * (nseg + 1),), -1, dtype=torch.int32, device=dev)
+        dest = torch.full((2 * F1,), -1, dtype=torch.int32, device=dev)
+        hsl = torch.full((2 * (per << b2),), -1, dtype=torch.int32, device=dev)
+        hv = torch.zeros(6, dtype=torch.int64, device=dev)
+        be.exchange_plan(c_dev, G, rank, b1, b2, h_dev, seg, dest, hsl, hv)
+        torch.cuda.synchronize()
+        c64 = counts.to(torch.int64)
+        for rel in range(2):
+            ca = c64[:, rel, :]
+            _, recv, seg_off, _ = D.exchange_plan(ca, rank, G)
+            assert seg[rel * (nseg + 1):(rel + 1) * (nseg + 1)].cpu().tolist() == seg_off.tolist()
+            assert dest[rel * F1:(rel + 1) * F1].cpu().tolist() == D.dest_offsets(ca, rank, G).tolist()
+            exp_h = D.final_hist_slice(hist[rel], rank, G, b1, b2)
+            n2 = per << b2
+            assert torch.equal(hsl[rel * n2:(rel + 1) * n2].cpu(), exp_h)
+            assert int(hv[rel]) == int(ca.view(G, G, per).sum((0, 2)).max())
+            assert int(hv[2 + rel]) == int(recv.sum())
+            assert int(hv[4 + rel]) == int(ca[rank, rank * per:(rank + 1) * per].sum())
