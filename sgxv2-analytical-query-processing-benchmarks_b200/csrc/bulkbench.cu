@@ -21,17 +21,20 @@ __device__ __forceinline__ uint32_t mix(uint32_t x) {
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 
 template <bool kBulk>
-__global__ void __launch_bounds__(kThreads, 2) k_runs(unsigned char *out, size_t out_bytes, int run_bytes, int iters) {
+__global__ void __launch_bounds__(kThreads, 2) k_runs(unsigned char *out, size_t out_bytes, int run_bytes, int iters,
+                                                      int misalign) {
     extern __shared__ __align__(128) unsigned char stage[];
     for (int i = threadIdx.x; i < kStageBytes / 8; i += kThreads) reinterpret_cast<uint2 *>(stage)[i] = make_uint2(i, blockIdx.x);
     __syncthreads();
     const int nruns = kStageBytes / run_bytes;
-    const size_t nslots = out_bytes / run_bytes;
+    const size_t nslots = out_bytes / run_bytes - 1;
+    // misalign: every run starts 16..112 bytes into a 128-byte line (what the scatter's 8-byte granular runs look like)
+    auto shift = [&](uint32_t r) { return misalign ? 16u * (1u + (mix(r * 2246822519u) % 7u)) : 0u; };
     for (int it = 0; it < iters; ++it) {
         if (kBulk) {
             for (int r = threadIdx.x; r < nruns; r += kThreads) {
                 size_t slot = mix((uint32_t) (it * 1315423911u) ^ (blockIdx.x * 2654435761u) ^ (uint32_t) r * 40503u) % nslots;
-                unsigned char *dst = out + slot * (size_t) run_bytes;
+                unsigned char *dst = out + slot * (size_t) run_bytes + shift((uint32_t) r + it);
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
                              "r"(smem_u32(stage + (size_t) r * run_bytes)), "r"(run_bytes) : "memory");
             }
@@ -43,7 +46,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_runs(unsigned char *out, size_t
             for (int s = threadIdx.x; s < kStageBytes / 8; s += kThreads) {
                 int r = s / per_run, o = s % per_run;
                 size_t slot = mix((uint32_t) (it * 1315423911u) ^ (blockIdx.x * 2654435761u) ^ (uint32_t) r * 40503u) % nslots;
-                reinterpret_cast<uint2 *>(out + slot * (size_t) run_bytes)[o] = reinterpret_cast<uint2 *>(stage)[s];
+                reinterpret_cast<uint2 *>(out + slot * (size_t) run_bytes + shift((uint32_t) r + it))[o] = reinterpret_cast<uint2 *>(stage)[s];
             }
             __syncthreads();
         }
@@ -71,13 +74,14 @@ int main(int argc, char **argv) {
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
     const int grid = 148 * 2, iters = peer >= 0 ? 200 : 1000;
+    for (int misalign = 0; misalign < 2; ++misalign)
     for (int run_bytes : {128, 256, 512, 1024, 2048}) {
         float ms[2];
         for (int v = 0; v < 2; ++v) {
             for (int rep = 0; rep < 2; ++rep) {
                 CK(cudaEventRecord(e0));
-                if (v) k_runs<true><<<grid, kThreads, kStageBytes>>>(out, out_bytes, run_bytes, iters);
-                else k_runs<false><<<grid, kThreads, kStageBytes>>>(out, out_bytes, run_bytes, iters);
+                if (v) k_runs<true><<<grid, kThreads, kStageBytes>>>(out, out_bytes, run_bytes, iters, misalign);
+                else k_runs<false><<<grid, kThreads, kStageBytes>>>(out, out_bytes, run_bytes, iters, misalign);
                 CK(cudaEventRecord(e1));
                 CK(cudaEventSynchronize(e1));
                 CK(cudaGetLastError());
@@ -85,7 +89,7 @@ int main(int argc, char **argv) {
             }
         }
         double bytes = (double) grid * iters * kStageBytes;
-        printf("run %4d B: SM stores %7.1f GB/s   TMA bulk stores %7.1f GB/s\n", run_bytes, bytes / ms[0] / 1e6, bytes / ms[1] / 1e6);
+        printf("%s run %4d B: SM stores %7.1f GB/s   TMA bulk stores %7.1f GB/s\n", misalign ? "16B-aligned " : "line-aligned", run_bytes, bytes / ms[0] / 1e6, bytes / ms[1] / 1e6);
     }
     return 0;
 }
