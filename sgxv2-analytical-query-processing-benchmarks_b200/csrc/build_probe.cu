@@ -52,6 +52,18 @@ constexpr int kProbeUnroll = 4;   // S tuples per thread and round; two rounds a
 constexpr uint32_t kChainFlag = 0x80000000u;   // set in a bucket head when its chain holds more than one tuple
 constexpr size_t kJoinSmemBytes = (size_t) kBuildCap * (sizeof(uint2) + sizeof(uint32_t) + sizeof(uint16_t));
 
+// pull a 128-byte line into L2 ahead of the loads that will use it: the registers only cover two S rounds in flight,
+// the L2 prefetch turns the HBM latency of the rounds after those (and of the next item's R side) into L2 latency
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+#ifndef AQP_NO_PROBE_PREFETCH
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
+#ifndef AQP_PROBE_PREFETCH_ROUNDS
+#define AQP_PROBE_PREFETCH_ROUNDS 3
+#endif
+constexpr uint32_t kPrefetchRounds = AQP_PROBE_PREFETCH_ROUNDS;   // S rounds (16 KiB each) prefetched ahead of the register pipeline
+
 template <bool kMaterialize>
 __global__ void __launch_bounds__(kJoinThreads, 2)
 build_probe_kernel(const uint2 *__restrict__ R, const uint32_t *__restrict__ offR, const uint2 *__restrict__ S,
@@ -63,6 +75,7 @@ build_probe_kernel(const uint2 *__restrict__ R, const uint32_t *__restrict__ off
     uint32_t *bucket = reinterpret_cast<uint32_t *>(rt + kBuildCap);                     // chain heads (1-based)
     uint16_t *next = reinterpret_cast<uint16_t *>(bucket + kBuildCap);                   // chain links (1-based)
 
+    __shared__ uint32_t s_collisions;
     const uint32_t nitems = item_start[nparts];
     unsigned long long matches = 0, checksum = 0, keysum = 0;
 
@@ -74,6 +87,18 @@ build_probe_kernel(const uint2 *__restrict__ R, const uint32_t *__restrict__ off
         const uint32_t send = min(sbeg + (uint32_t) kProbeChunk, offS[p + 1]);
 
         constexpr uint32_t kRound = kJoinThreads * kProbeUnroll;
+        // lines of S round `base` .. : 16 tuples per line, kRound / 16 lines per round
+        auto prefetch_round = [&](uint32_t base) {
+            if (threadIdx.x < kRound / 16) {
+                const uint32_t i = base + threadIdx.x * 16;
+                if (i < send) prefetch_l2(S + i);
+            }
+        };
+        if (it + gridDim.x < nitems) {   // the next item's R side (one line per thread covers 8192 tuples)
+            const uint2 nx = items[it + gridDim.x];
+            const uint32_t nrb = offR[nx.x], nre = offR[nx.x + 1];
+            for (uint32_t i = nrb + threadIdx.x * 16; i < nre && i < nrb + kBuildCap; i += kJoinThreads * 16) prefetch_l2(R + i);
+        }
         auto load_round = [&](uint32_t base, uint2 (&dst)[kProbeUnroll]) {
 #pragma unroll
             for (int j = 0; j < kProbeUnroll; ++j) {
@@ -90,6 +115,8 @@ build_probe_kernel(const uint2 *__restrict__ R, const uint32_t *__restrict__ off
             // the first round of S tuples is put in flight BEFORE the build so its latency hides behind it
             uint2 sn[kProbeUnroll];
             load_round(sbeg, sn);
+#pragma unroll
+            for (uint32_t r = 1; r <= kPrefetchRounds; ++r) prefetch_round(sbeg + r * kRound);
             // all R tuples of this thread are requested up front, then inserted
             constexpr int kBuildPerThread = kBuildCap / kJoinThreads;
             uint2 rv[kBuildPerThread];
@@ -99,6 +126,55 @@ build_probe_kernel(const uint2 *__restrict__ R, const uint32_t *__restrict__ off
                 if (i < nr) rv[k] = R[rb + i];
             }
             __syncthreads();   // previous round's probe done before the table is cleared
+            constexpr uint32_t kRoundS = kJoinThreads * kProbeUnroll;
+            if (!kMaterialize && N >= 2) {
+                // ---- collision-free fast path (what a dense primary key gives: every R tuple of the co-partition
+                // hashes to its own bucket). The table is direct-mapped: tuple -> rt[hash]; an empty slot holds a key
+                // of ANOTHER bucket, which no probe key of this bucket can equal, so the probe is ONE 8-byte
+                // shared-memory load and a compare — no chain head, no link (9.5 -> 6 wavefronts per 32 probes on
+                // the shared-memory pipe that bounds this kernel, profiles/r01_ncu_join_kernels_final.md).
+                // Any collision during the build sends the round to the chained path below.
+                if (threadIdx.x == 0) s_collisions = 0;
+                for (uint32_t i = threadIdx.x; i < N; i += kJoinThreads) rt[i].x = (i ^ 1u) << hash_shift;
+                __syncthreads();
+                bool clash = false;
+#pragma unroll
+                for (int k = 0; k < kBuildPerThread; ++k) {
+                    uint32_t i = k * kJoinThreads + threadIdx.x;
+                    if (i < nr) {
+                        const uint32_t h = (rv[k].x >> hash_shift) & hmask;
+                        const uint32_t empty = (h ^ 1u) << hash_shift;
+                        if (atomicCAS(&rt[h].x, empty, rv[k].x) == empty)
+                            rt[h].y = rv[k].y;
+                        else
+                            clash = true;
+                    }
+                }
+                if (clash) s_collisions = 1;
+                __syncthreads();
+                if (s_collisions == 0) {
+                    for (uint32_t base = sbeg; base < send; base += kRoundS) {
+                        uint2 s[kProbeUnroll];
+#pragma unroll
+                        for (int j = 0; j < kProbeUnroll; ++j) s[j] = sn[j];
+                        if (base + kRoundS < send) load_round(base + kRoundS, sn);
+                        prefetch_round(base + (1 + kPrefetchRounds) * kRoundS);
+#pragma unroll
+                        for (int j = 0; j < kProbeUnroll; ++j) {
+                            if (base + j * kJoinThreads + threadIdx.x < send) {
+                                const uint2 r = rt[(s[j].x >> hash_shift) & hmask];
+                                if (r.x == s[j].x) {
+                                    ++matches;
+                                    checksum += (unsigned long long) r.y + s[j].y;
+                                    keysum += s[j].x;
+                                }
+                            }
+                        }
+                    }
+                    continue;   // next build round
+                }
+                // collisions: the table is rebuilt with chains (the R tuples are still in registers)
+            }
             for (uint32_t i = threadIdx.x; i < N; i += kJoinThreads) bucket[i] = 0;
             __syncthreads();
 #pragma unroll
@@ -121,6 +197,7 @@ build_probe_kernel(const uint2 *__restrict__ R, const uint32_t *__restrict__ off
 #pragma unroll
                 for (int j = 0; j < kProbeUnroll; ++j) s[j] = sn[j];
                 if (base + kRound < send) load_round(base + kRound, sn);
+                prefetch_round(base + (1 + kPrefetchRounds) * kRound);
 #pragma unroll
                 for (int j = 0; j < kProbeUnroll; ++j) {
                     const bool valid = base + j * kJoinThreads + threadIdx.x < send;
