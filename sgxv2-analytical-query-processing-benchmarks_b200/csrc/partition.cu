@@ -22,6 +22,7 @@
 #include "join_internal.cuh"
 #include "block_scan.cuh"
 #include <cstdlib>
+#include <cstring>
 
 namespace aqp {
 
@@ -737,6 +738,281 @@ radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// scatter, fixed-bin variant (the default)
+//
+// Same tile pipeline as radix_scatter_kernel, but the staging buffer is 2^bits fixed bins of cap = 8192 >> bits
+// slots (64 KiB): a tuple's staging slot is (digit << log2 cap) + rank — pure arithmetic, so
+//   * no per-tile exclusive scan (a serial warp-0 section between two barriers in the staged kernel),
+//   * no lbase[] look-up per tuple and no gdst[] look-up + digit recomputation per written tuple
+//     (two random shared-memory loads out of ~24 wavefronts per 32 tuples on the pipe that bounds the kernel),
+//   * every partition's own thread reserves its run (pass 2: 2^bits global atomics in parallel instead of a
+//     warp-0 loop) and issues ONE TMA bulk store for it, in BOTH passes: an odd destination start is fixed by
+//     storing the run's LAST tuple there (order inside a partition is free), so the bulk body always starts on an
+//     even slot of an even-based bin and on a 16-byte aligned destination, however late the destination is known.
+// Pass 1 (private cursors) keeps an odd tuple per partition for the next tile (carry[]), so it issues no scalar
+// stores beyond the first run; pass 2 finishes an odd body with one scalar store.
+// One TMA input buffer instead of two (the 64 KiB of bins need the room): tile i+1 is requested right after the
+// rank phase of tile i has moved tile i into registers, and lands under its staging and write-out phases.
+// A tile in which some partition would overflow its bin (skew) takes the staged kernel's compacting path inside
+// this kernel (scan + lbase/gdst look-ups, SM-store write-out), so any distribution stays correct and fast.
+// ---------------------------------------------------------------------------------------------
+constexpr int kBinSlotsLog = 13;
+constexpr size_t kBinsSmemBytes = (size_t) (kInBufTuples + (1 << kBinSlotsLog)) * sizeof(uint2);
+static_assert(kScatterTile + kMaxFanout <= (1 << kBinSlotsLog), "the compacting path stages a whole tile plus carries");
+
+template <bool kRot, bool kPeer, bool kPriv>
+__global__ void __launch_bounds__(kScatterThreads, kScatterBlocksPerSM)
+radix_scatter_bins_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
+                          const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_tile_start,
+                          const uint32_t *__restrict__ seg_group, uint32_t nseg, DigitFn digit, uint32_t bits,
+                          uint32_t *__restrict__ cursors, const uint32_t *__restrict__ block_base,
+                          uint32_t tiles_per_block, PeerTable peers) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint2 *inbuf = reinterpret_cast<uint2 *>(smem_raw);
+    uint2 *bins = inbuf + kInBufTuples;
+    __shared__ uint32_t cnt[kMaxFanout];      // tuples of this tile per partition
+    __shared__ uint32_t scur[kMaxFanout];     // pass 1: CTA-private destination cursors
+    __shared__ uint32_t hcarry[kMaxFanout];   // pass 1: 1 if carry[d] holds the odd tuple of the previous run
+    __shared__ uint2 carry[kMaxFanout];
+    __shared__ uint32_t lbase[kMaxFanout];    // compacting path only
+    __shared__ uint32_t gdst[kMaxFanout];     // compacting path only
+    __shared__ uint2 *s_peer[8];
+    __shared__ uint32_t s_tstart[kMaxFanout + 1];
+    __shared__ uint32_t s_soff[kMaxFanout + 1];
+    __shared__ uint32_t s_ovf[2];
+    __shared__ uint32_t s_total;
+    __shared__ uint32_t s_tile[2][4];   // {begin, end, cursor group} of the tile in flight / being processed
+    __shared__ __align__(8) uint64_t mbar;
+
+    const uint32_t fan = 1u << bits;
+    const uint32_t lgcap = kBinSlotsLog - bits, cap = 1u << lgcap;
+    for (uint32_t i = threadIdx.x; i <= nseg; i += kScatterThreads) {
+        s_tstart[i] = seg_tile_start[i];
+        s_soff[i] = seg_off[i];
+    }
+    for (uint32_t i = threadIdx.x; i < fan; i += kScatterThreads) {
+        cnt[i] = 0;
+        hcarry[i] = 0;
+        scur[i] = kPriv ? block_base[(size_t) blockIdx.x * fan + i] : 0u;
+    }
+    if (kPeer && threadIdx.x < 8) s_peer[threadIdx.x] = peers.base[threadIdx.x];
+    if (threadIdx.x == 0) {
+        s_ovf[0] = s_ovf[1] = 0;
+        mbar_init(&mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t ntiles = s_tstart[nseg];
+    uint32_t first, step, n_my;
+    if (kPriv) {
+        first = blockIdx.x * tiles_per_block;
+        step = 1;
+        n_my = first < ntiles ? min(tiles_per_block, ntiles - first) : 0;
+    } else {
+        first = blockIdx.x;
+        step = gridDim.x;
+        n_my = first < ntiles ? (ntiles - first + step - 1) / step : 0;
+    }
+    auto tile_range = [&](uint32_t tile, uint32_t &seg, uint32_t &begin, uint32_t &end) {
+        uint32_t lo = 0, hi = nseg;   // last s with s_tstart[s] <= tile
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (s_tstart[mid] <= tile) lo = mid; else hi = mid;
+        }
+        seg = lo;
+        begin = s_soff[lo] + (tile - s_tstart[lo]) * kScatterTile;
+        end = min(begin + (uint32_t) kScatterTile, s_soff[lo + 1]);
+    };
+    // one thread: bulk-load tile #i of this CTA into the input buffer and publish its bounds (the other threads
+    // read them after the next barrier instead of repeating the binary search)
+    auto issue = [&](uint32_t i) {
+        uint32_t seg, begin, end;
+        tile_range(first + i * step, seg, begin, end);
+        s_tile[i & 1][0] = begin;
+        s_tile[i & 1][1] = end;
+        s_tile[i & 1][2] = seg_group ? seg_group[seg] : seg;
+        const uint2 *src = in + begin;
+        uint32_t skew = (uint32_t) ((reinterpret_cast<uintptr_t>(src) >> 3) & 1u);
+        uint32_t bytes = ((end - begin + skew + 1) & ~1u) * (uint32_t) sizeof(uint2);
+        mbar_expect_tx(&mbar, bytes);
+        tma_load_1d(inbuf, src - skew, bytes, &mbar);
+    };
+    if (threadIdx.x == 0 && n_my > 0) issue(0);
+    __syncthreads();   // s_tile[0] published
+    // The partition this thread reserves and writes out (if < fan). A bulk store takes its operands from uniform
+    // registers, so a warp issues the stores of its lanes one after another: the partitions are dealt out to ALL
+    // warps (the first fan/nwarps lanes of each) to keep that serial section short.
+    constexpr uint32_t kWarps = kScatterThreads / 32;
+    const uint32_t own_per = (fan + kWarps - 1) / kWarps;
+    const uint32_t d_own = (threadIdx.x & 31u) < own_per ? (threadIdx.x >> 5) * own_per + (threadIdx.x & 31u) : fan;
+
+    for (uint32_t i = 0; i < n_my; ++i) {
+        const uint32_t begin = s_tile[i & 1][0], end = s_tile[i & 1][1], group = s_tile[i & 1][2];
+        const uint32_t ntile = end - begin;
+        const uint32_t skew = (uint32_t) ((reinterpret_cast<uintptr_t>(in + begin) >> 3) & 1u);
+        const uint2 *buf = inbuf + skew;
+
+        mbar_wait(&mbar, i & 1);
+        uint2 v[kScatterItems];
+        uint32_t rank[kScatterItems];
+        bool tight = false;
+        if (ntile == (uint32_t) kScatterTile) {   // full tile: no per-item bounds checks
+#pragma unroll
+            for (int j = 0; j < kScatterItems; ++j) v[j] = buf[j * kScatterThreads + threadIdx.x];
+#pragma unroll
+            for (int j = 0; j < kScatterItems; ++j) {
+                rank[j] = atomicAdd(&cnt[digit.template get<kRot>(v[j].x)], 1u);
+                tight |= rank[j] + 2 > cap;   // bin full (one slot is kept for the carried tuple)
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < kScatterItems; ++j) {
+                uint32_t k = j * kScatterThreads + threadIdx.x;
+                if (k < ntile) v[j] = buf[k];
+            }
+#pragma unroll
+            for (int j = 0; j < kScatterItems; ++j) {
+                uint32_t k = j * kScatterThreads + threadIdx.x;
+                if (k < ntile) {
+                    rank[j] = atomicAdd(&cnt[digit.template get<kRot>(v[j].x)], 1u);
+                    tight |= rank[j] + 2 > cap;
+                }
+            }
+        }
+        if (tight) s_ovf[i & 1] = 1;
+        // the previous tile's bulk stores must have read the bins before anybody stages into them again
+        if (d_own < fan) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncthreads();   // (1) tile histogram complete, input buffer consumed, bins free
+
+        if (threadIdx.x == 0) {
+            if (i + 1 < n_my) issue(i + 1);
+            s_ovf[(i + 1) & 1] = 0;
+        }
+        if (!s_ovf[i & 1]) {
+            // ---------------- fixed bins: slot = (digit << lgcap) + rank ----------------
+            if (ntile == (uint32_t) kScatterTile) {
+#pragma unroll
+                for (int j = 0; j < kScatterItems; ++j) bins[(digit.template get<kRot>(v[j].x) << lgcap) + rank[j]] = v[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < kScatterItems; ++j) {
+                    uint32_t k = j * kScatterThreads + threadIdx.x;
+                    if (k < ntile) bins[(digit.template get<kRot>(v[j].x) << lgcap) + rank[j]] = v[j];
+                }
+            }
+            uint32_t n = 0, g = 0;
+            if (d_own < fan) {
+                const uint32_t c = cnt[d_own];
+                cnt[d_own] = 0;
+                n = c;
+                if (kPriv) {
+                    if (hcarry[d_own]) {
+                        bins[(d_own << lgcap) + c] = carry[d_own];
+                        ++n;
+                    }
+                    g = scur[d_own];
+                } else if (n) {
+                    g = atomicAdd(&cursors[(group << bits) + d_own], n);   // its latency hides behind the barrier
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged tuples visible to the TMA unit
+            __syncthreads();   // (2) tile staged
+            if (d_own < fan) {
+                if (n) {
+                    uint2 *dst = kPeer ? s_peer[d_own >> peers.per_shift] : out;
+                    const uint2 *src = bins + (d_own << lgcap);
+                    if (g & 1u) {   // odd destination start: the run's last tuple goes there
+                        dst[g] = src[n - 1];
+                        ++g;
+                        --n;
+                    }
+                    const uint32_t body = n & ~1u;
+                    if (body) tma_store_1d(dst + g, src, body * (uint32_t) sizeof(uint2));
+                    if (kPriv) {
+                        if (n & 1u) carry[d_own] = src[body];
+                        hcarry[d_own] = n & 1u;
+                        scur[d_own] = g + body;
+                    } else if (n & 1u) {
+                        dst[g + body] = src[body];
+                    }
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else {
+            // ---------------- a bin would overflow (skew): compact the tile like radix_scatter_kernel ----------------
+            uint32_t my_g[kMaxFanout / 32], my_b[kMaxFanout / 32];
+            if (threadIdx.x < 32) {
+                const uint32_t per = (fan + 31) / 32;
+                uint32_t c[kMaxFanout / 32], hc[kMaxFanout / 32], sum = 0;
+#pragma unroll
+                for (int k = 0; k < kMaxFanout / 32; ++k) {
+                    uint32_t d = threadIdx.x * per + k;
+                    bool ok = k < (int) per && d < fan;
+                    c[k] = ok ? cnt[d] : 0;
+                    hc[k] = (ok && kPriv) ? hcarry[d] : 0;
+                    if (ok) cnt[d] = 0;
+                    sum += c[k] + hc[k];
+                }
+                uint32_t run = warp_incl_scan(sum) - sum;
+#pragma unroll
+                for (int k = 0; k < kMaxFanout / 32; ++k) {
+                    uint32_t d = threadIdx.x * per + k;
+                    my_b[k] = run;
+                    const uint32_t n = c[k] + hc[k];
+                    if (k < (int) per && d < fan) {
+                        lbase[d] = run;
+                        if (hc[k]) {
+                            bins[run + c[k]] = carry[d];   // the carried tuple joins the run
+                            hcarry[d] = 0;
+                        }
+                        if (kPriv) {
+                            my_g[k] = scur[d];
+                            scur[d] = my_g[k] + n;
+                        } else {
+                            my_g[k] = n ? atomicAdd(&cursors[(group << bits) + d], n) : 0u;
+                        }
+                    }
+                    run += n;
+                }
+                if (threadIdx.x == 31) s_total = run;
+            }
+            __syncthreads();   // lbase ready
+#pragma unroll
+            for (int j = 0; j < kScatterItems; ++j) {
+                uint32_t k = j * kScatterThreads + threadIdx.x;
+                if (k < ntile) bins[lbase[digit.template get<kRot>(v[j].x)] + rank[j]] = v[j];
+            }
+            if (threadIdx.x < 32) {
+                const uint32_t per = (fan + 31) / 32;
+#pragma unroll
+                for (int k = 0; k < kMaxFanout / 32; ++k) {
+                    uint32_t d = threadIdx.x * per + k;
+                    if (k < (int) per && d < fan) gdst[d] = my_g[k] - my_b[k];
+                }
+            }
+            __syncthreads();   // tile compacted, destinations known
+            const uint32_t total = s_total;
+            for (uint32_t s = threadIdx.x; s < total; s += kScatterThreads) {
+                uint2 t = bins[s];
+                const uint32_t d = digit.template get<kRot>(t.x);
+                if (kPeer)
+                    s_peer[d >> peers.per_shift][gdst[d] + s] = t;
+                else
+                    out[gdst[d] + s] = t;
+            }
+            // (the next tile's barrier (1) separates these reads from its staging)
+        }
+    }
+    if (d_own < fan) {
+        if (kPriv && hcarry[d_own]) {   // flush the carried tuples
+            uint2 *dst = kPeer ? s_peer[d_own >> peers.per_shift] : out;
+            dst[scur[d_own]] = carry[d_own];
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the TMA unit is done with shared memory
+    }
+}
+
 int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_off,
                          const uint32_t *d_seg_tile_start, const uint32_t *d_seg_group, uint32_t nseg, uint64_t n_total,
                          DigitFn digit, uint32_t bits, uint32_t *d_cursors, const uint32_t *d_block_base,
@@ -776,6 +1052,44 @@ int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_
     const uint2 *in = reinterpret_cast<const uint2 *>(d_in);
     uint2 *out = reinterpret_cast<uint2 *>(d_out);
     const bool peer = peers && peers->n;
+    static const bool staged = getenv("B200_AQP_SCATTER") && !strcmp(getenv("B200_AQP_SCATTER"), "staged");
+    bool aligned16 = (reinterpret_cast<uintptr_t>(d_out) & 15u) == 0;
+    if (peer)
+        for (uint32_t i = 0; i < peers->n; ++i) aligned16 = aligned16 && (reinterpret_cast<uintptr_t>(peers->base[i]) & 15u) == 0;
+    if (!staged && aligned16 && (1u << bits) <= (uint32_t) kScatterThreads) {
+        static bool bins_attr_set = false;
+        if (!bins_attr_set) {
+#define AQP_BINS_ATTR(ROT, PEER, PRIV)                                                                                  \
+    AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_bins_kernel<ROT, PEER, PRIV>,                                        \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kBinsSmemBytes))
+            AQP_BINS_ATTR(false, false, false);
+            AQP_BINS_ATTR(false, false, true);
+            AQP_BINS_ATTR(true, false, false);
+            AQP_BINS_ATTR(true, false, true);
+            AQP_BINS_ATTR(true, true, true);
+#undef AQP_BINS_ATTR
+            bins_attr_set = true;
+        }
+#define AQP_BINS_LAUNCH(ROT, PEER, PRIV)                                                                               \
+    radix_scatter_bins_kernel<ROT, PEER, PRIV><<<grid, kScatterThreads, kBinsSmemBytes, st>>>(                          \
+        in, out, d_seg_off, d_seg_tile_start, d_seg_group, nseg, digit, bits, d_cursors, d_block_base, tiles_per_block, \
+        peer ? *peers : none)
+        if (peer) {
+            if (!d_block_base) {
+                set_error("radix_scatter: the peer variant needs CTA-private cursors");
+                return -1;
+            }
+            AQP_BINS_LAUNCH(true, true, true);
+        } else if (digit.rot) {
+            if (d_block_base) AQP_BINS_LAUNCH(true, false, true); else AQP_BINS_LAUNCH(true, false, false);
+        } else {
+            if (d_block_base) AQP_BINS_LAUNCH(false, false, true); else AQP_BINS_LAUNCH(false, false, false);
+        }
+#undef AQP_BINS_LAUNCH
+        AQP_LAUNCHED();
+        AQP_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     // bulk write-out needs CTA-private cursors (the destination parity must be known when the tile is staged) and a
     // 16-byte aligned destination buffer; B200_AQP_SCATTER_BULK=0 keeps the SM-store write-out (A/B measurements)
     static const bool bulk_off = getenv("B200_AQP_SCATTER_BULK") && atoi(getenv("B200_AQP_SCATTER_BULK")) == 0;
