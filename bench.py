@@ -12,7 +12,7 @@ larger than the 126 MB L2, so no cache flush is needed between steps). Prints ON
   e2e       same join through the drop-in C ABI call run_join(result_t*, R, S, "RHO", cfg) with
             pinned HOST relations: H2D of 8(|R|+|S|) bytes and the result read-back are inside the
             timed region
-  roofline  the dominant kernel (radix_scatter_kernel, 4 launches per join): algorithmic bytes per
+  roofline  the dominant kernel (radix_scatter_bins_kernel, 4 launches per join): algorithmic bytes per
             launch (16 B/tuple) / its mean launch time from the library's CUDA events
   join_roofline  the whole join at SURVEY.md §8d's graded 56 B/tuple
   scan      bitvector and row-id scans over 2^30 uint8 (BASELINE config 2), GB/s of input and
@@ -59,17 +59,20 @@ def measured_peaks():
 
 
 def ncu_traffic(kernel_prefix: str):
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/traffic.json, written by tools/ncu_traffic.py); None if there is no capture."""
+    """DRAM bytes per launch of the dominant kernel (mean over its captured launches and template instances) from
+    the committed `ncu --set full` capture (profiles/traffic.json, written by tools/ncu_traffic.py); None if there
+    is no capture."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f)
+        n, b = 0, 0.0
         for name, e in t.items():
             if name.startswith(kernel_prefix):
-                return e["dram_bytes_per_launch"]
+                n += e["launches"]
+                b += e["dram_bytes_per_launch"] * e["launches"]
+        return b / n if n else None
     except Exception:
-        pass
-    return None
+        return None
 
 
 class ClockSampler:
@@ -334,12 +337,12 @@ def run_b200_arm(args):
         phase[k] /= args.steps
     value = (nR + nS) / ms_step / 1e3   # Mtuples/s
 
-    # dominant kernel: radix_scatter_kernel, 4 launches per join (R and S, pass 1 and pass 2)
+    # dominant kernel: radix_scatter_bins_kernel, 4 launches per join (R and S, pass 1 and pass 2)
     scatter_ms = (phase["ms_pass1"] + phase["ms_pass2"]) / 4
     scatter_bytes = SCATTER_BYTES_PER_TUPLE * (nR_loc + nS_loc) * 2 / 4
-    roof = {"bound": "hbm", "kernel": "radix_scatter_kernel", "achieved": scatter_bytes / scatter_ms / 1e6 if scatter_ms else None,
+    roof = {"bound": "hbm", "kernel": "radix_scatter_bins_kernel", "achieved": scatter_bytes / scatter_ms / 1e6 if scatter_ms else None,
             "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-            "traffic": ncu_traffic("radix_scatter_kernel") if world == 1 else None,
+            "traffic": ncu_traffic("radix_scatter_bins_kernel") if world == 1 else None,
             "bytes_per_launch": scatter_bytes, "ms_per_launch": scatter_ms}
     roof["frac"] = roof["achieved"] / peak if roof["achieved"] else None
     join_bytes = JOIN_BYTES_PER_TUPLE * (nR + nS) / world
