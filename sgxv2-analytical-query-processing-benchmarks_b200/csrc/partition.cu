@@ -782,8 +782,7 @@ radix_scatter_bins_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
     __shared__ uint32_t s_soff[kMaxFanout + 1];
     __shared__ uint32_t s_ovf[2];
     __shared__ uint32_t s_total;
-    __shared__ uint32_t s_tile[2][4];   // {begin, end, cursor group, prefetch begin} of the tile in flight / processed
-    __shared__ uint32_t s_pfend[2];
+    __shared__ uint32_t s_tile[2][4];   // {begin, end, cursor group} of the tile in flight / being processed
     __shared__ __align__(8) uint64_t mbar;
 
     const uint32_t fan = 1u << bits;
@@ -833,13 +832,6 @@ radix_scatter_bins_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
         s_tile[i & 1][0] = begin;
         s_tile[i & 1][1] = end;
         s_tile[i & 1][2] = seg_group ? seg_group[seg] : seg;
-        // bounds of the tile two further on: all threads pull it into L2 at the top of the next iteration, long
-        // before its TMA load is issued (with one input buffer that load is only one tile ahead of its use and
-        // the CTAs spent 28 % of their time waiting for it, profiles/r01_ncu_join_kernels_final.md)
-        uint32_t pb = 0, pe = 0;
-        if (i + 2 < n_my) tile_range(first + (i + 2) * step, seg, pb, pe);
-        s_tile[i & 1][3] = pb;
-        s_pfend[i & 1] = pe;
         const uint2 *src = in + begin;
         uint32_t skew = (uint32_t) ((reinterpret_cast<uintptr_t>(src) >> 3) & 1u);
         uint32_t bytes = ((end - begin + skew + 1) & ~1u) * (uint32_t) sizeof(uint2);
@@ -858,10 +850,6 @@ radix_scatter_bins_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
     for (uint32_t i = 0; i < n_my; ++i) {
         const uint32_t begin = s_tile[i & 1][0], end = s_tile[i & 1][1], group = s_tile[i & 1][2];
         const uint32_t ntile = end - begin;
-        {
-            const uint32_t t = s_tile[i & 1][3] + threadIdx.x * 16;   // one 128-byte line per thread = one tile
-            if (t < s_pfend[i & 1]) asm volatile("prefetch.global.L2 [%0];" ::"l"(in + t));
-        }
         const uint32_t skew = (uint32_t) ((reinterpret_cast<uintptr_t>(in + begin) >> 3) & 1u);
         const uint2 *buf = inbuf + skew;
 
