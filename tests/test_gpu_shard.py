@@ -60,6 +60,15 @@ def _emulate(gpu, oracle, R, S, G, plan=None):
                            per, b1, b2, args[0][3], args[1][3], bits)
         for k in tot:
             tot[k] += st[k]
+        # the asynchronous form leaves the same three numbers on the device and reports the phase times later
+        res = torch.full((4,), -1, dtype=torch.int64, device=dev)
+        be.shard_join_async(args[0][0], args[0][1], args[0][2], args[1][0], args[1][1], args[1][2], seg_group, G * per,
+                            per, b1, b2, args[0][3], args[1][3], bits, res)
+        torch.cuda.synchronize()
+        got = [int(x) % (1 << 64) for x in res[:3].tolist()]
+        assert got == [st["matches"], st["checksum"], st["keysum"]] and int(res[3]) == -1
+        times = be.shard_join_times()
+        assert times["ms_total"] > 0 and times["ms_total"] >= times["ms_join"]
     exp = oracle.rho(R, S)
     assert (tot["matches"], tot["checksum"] % (1 << 64), tot["keysum"] % (1 << 64)) == \
         (exp["matches"], exp["checksum"], exp["keysum"])
