@@ -521,7 +521,9 @@ def run_b200_arm(args):
                            "generator": "on-device bijection, seeds 11111/22222", "radix_bits": s["radix_bits"],
                            "passes": s["num_passes"],
                            "cache": "inputs (5 GiB) exceed the 126 MB L2; no flush between steps",
-                           "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: pass-1 routes by low key bits, NCCL all-to-all"},
+                           "parallelism": "1 GPU" if world == 1 else
+                           f"{world} GPUs, one process each: pass 1 routes by the low key bits and stores every run into the owner's "
+                           f"buffer over NVLink peer memory ({s.get('exchange', 'nccl')}); NCCL carries the sizing collectives"},
                 "phases_ms": phase, "roofline": roof, "join_roofline": join_roof, "cpu_baseline": cpu, "e2e": e2e,
                 "exchange": exchange, "skew": skew, "tpch": tpch,
                 "gpu_launches": launches_timed, "gpu_launches_total": A.kernel_launch_count() - launches0,

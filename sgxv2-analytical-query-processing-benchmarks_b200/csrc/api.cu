@@ -99,10 +99,14 @@ static void log_info(const char *fmt, ...) {
 // (radix_join.cpp:295-329): partitions are sized so the build side of a co-partition fits the
 // shared-memory hash table (kBuildCap tuples) instead of a quarter of the CPU's L2.
 // ---------------------------------------------------------------------------------------------
-static void plan_bits(uint64_t nR, uint32_t *total, uint32_t *b1, uint32_t *b2) {
+// dead_bits: low key bits the caller knows to carry no information (TPC-H order keys use 8 of every 32 values, so
+// 2 of the low 5 bits are dead): the digit still is (key & MASK) >> R on raw bits, it just covers that many more
+// bits, which keeps the populated partitions at the planned size instead of 2^dead_bits times larger.
+static void plan_bits(uint64_t nR, uint32_t *total, uint32_t *b1, uint32_t *b2, uint32_t dead_bits = 0) {
     uint64_t parts = (nR + kBuildCap - 1) / kBuildCap;
     uint32_t bits = 0;
     while ((1ull << bits) < parts) ++bits;
+    if (bits) bits += dead_bits;
     if (bits > 2 * kMaxFanoutBits) bits = 2 * kMaxFanoutBits;   // larger build sides use several build rounds
     if (const char *e = getenv("B200_AQP_RADIX_BITS")) {
         int v = atoi(e);
@@ -191,7 +195,8 @@ static MetaLayout meta_layout(uint32_t bits, uint32_t b1, uint64_t nS) {
 //   pass 1/2   -> partition_copy / radix_cluster (:659-697, :715-761)
 //   join       -> bucket_chaining_join        (:359-458)
 static int join_device_locked(const row_t *dR, uint64_t nR, const row_t *dS, uint64_t nS, output_triple_t *d_out,
-                              uint64_t out_cap, b200_join_stats_t *stats, cudaStream_t st, bool keep_partitions) {
+                              uint64_t out_cap, b200_join_stats_t *stats, cudaStream_t st, bool keep_partitions,
+                              uint32_t dead_bits = 0) {
     (void) keep_partitions;
     if (ensure_init()) return -1;
     if (nR >= 0xFFFF0000ull || nS >= 0xFFFF0000ull) {
@@ -200,7 +205,7 @@ static int join_device_locked(const row_t *dR, uint64_t nR, const row_t *dS, uin
     }
     const unsigned long long launches0 = g_kernel_launches;
     uint32_t bits, b1, b2;
-    plan_bits(nR, &bits, &b1, &b2);
+    plan_bits(nR, &bits, &b1, &b2, dead_bits);
     const uint32_t P = 1u << bits, F1 = 1u << b1;
     const int passes = bits == 0 ? 0 : (b2 ? 2 : 1);
 
@@ -302,10 +307,10 @@ static int join_device_locked(const row_t *dR, uint64_t nR, const row_t *dS, uin
 
 // entry for the library's other translation units (tpch.cu): same lock, same workspace
 int join_device_internal(const row_t *dR, uint64_t nR, const row_t *dS, uint64_t nS, output_triple_t *d_out,
-                         uint64_t out_cap, b200_join_stats_t *stats, cudaStream_t st) {
+                         uint64_t out_cap, b200_join_stats_t *stats, cudaStream_t st, uint32_t dead_bits) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (ensure_init()) return -1;
-    return join_device_locked(dR, nR, dS, nS, d_out, out_cap, stats, st ? st : g.stream, false);
+    return join_device_locked(dR, nR, dS, nS, d_out, out_cap, stats, st ? st : g.stream, false, dead_bits);
 }
 cudaStream_t library_stream() {
     std::lock_guard<std::recursive_mutex> lk(g_mu);

@@ -121,7 +121,7 @@ struct JoinResult {              // device-side accumulators
 
 // api.cu
 int join_device_internal(const row_t *dR, uint64_t nR, const row_t *dS, uint64_t nS, output_triple_t *d_out,
-                         uint64_t out_cap, b200_join_stats_t *stats, cudaStream_t st);
+                         uint64_t out_cap, b200_join_stats_t *stats, cudaStream_t st, uint32_t dead_bits = 0);
 cudaStream_t library_stream();
 
 // partition.cu
