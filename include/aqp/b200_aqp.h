@@ -271,6 +271,29 @@ int b200_scan_count_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t
 int b200_index_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t num_records,
                            uint64_t id_base, uint64_t *d_out_ids, uint64_t out_capacity,
                            uint64_t *d_count, void *stream);
+/* The remaining SIMD512 variants on the 8-bit column. They share the row-id machinery
+ * (bitvector + per-tile counts -> offsets -> expansion); only what is written per match differs.
+ *   b200_scan_sum_device               SIMD512::sum  (SIMD512.cpp:34-86): sum of the values in range -> *d_sum
+ *   b200_value_scan_device             SIMD512::scan (:89-150): the matching values as uint32, in input order
+ *   b200_dict_scan_8bit_64bit_device   SIMD512::dict_scan_8bit_64bit (:289-336): dict[code] (int64) of every code whose
+ *       dictionary value lies in [predicate_low, predicate_high]. dict = 256 sorted int64 in HOST memory (it is
+ *       searched on the host exactly like the reference's two std::find_if calls, :297-305, including the uint8
+ *       wrap-around for predicates outside the dictionary's range, then copied — 2 KiB — with the call).
+ * d_count (device uint64) receives the exact match count; values beyond out_capacity are dropped. */
+int b200_scan_sum_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t num_records, uint64_t *d_sum, void *stream);
+int b200_value_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t num_records, uint32_t *d_out,
+                           uint64_t out_capacity, uint64_t *d_count, void *stream);
+int b200_dict_scan_8bit_64bit_device(int64_t predicate_low, int64_t predicate_high, const int64_t *dict,
+                                     const uint8_t *d_data, size_t num_records, int64_t *d_out, uint64_t out_capacity,
+                                     uint64_t *d_count, void *stream);
+/* Host-buffer forms in the reference functions' argument order (SIMD512.hpp:39-84) with a plain output array and its
+ * capacity instead of a CacheAlignedVector&; they return the sum resp. the exact match count and abort like the
+ * reference's allocation failures do (util.cpp:12-19) if the device is unusable. */
+uint64_t b200_sum(uint8_t predicate_low, uint8_t predicate_high, const uint8_t *data, size_t num_records);
+uint64_t b200_scan(uint8_t predicate_low, uint8_t predicate_high, const uint8_t *data, size_t num_records,
+                   uint32_t *output_buffer, size_t output_capacity);
+uint64_t b200_dict_scan_8bit_64bit(int64_t predicate_low, int64_t predicate_high, const int64_t *dict, const uint8_t *data,
+                                   size_t num_records, int64_t *output_buffer, size_t output_capacity);
 /* Allocator.hpp:95-109 tiled 0..255 column, generated in HBM; value at global position p is p mod 256 */
 int b200_fill_tiled_column_device(uint8_t *d_data, size_t n, uint64_t pos_begin, void *stream);
 /* seeded skewed column for selectivities the tiled column cannot express:

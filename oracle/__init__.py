@@ -73,6 +73,13 @@ def lib():
             f.argtypes = [C.c_uint8, C.c_uint8, C.c_void_p, C.c_size_t, C.c_void_p]
             f.restype = C.c_uint64
         L.oracle_fill_tiled_column.argtypes = [C.c_void_p, C.c_size_t]
+        L.oracle_scan_sum.argtypes = [C.c_uint8, C.c_uint8, C.c_void_p, C.c_size_t]
+        L.oracle_scan_sum.restype = C.c_uint64
+        L.oracle_value_scan.argtypes = [C.c_uint8, C.c_uint8, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.oracle_value_scan.restype = C.c_uint64
+        L.oracle_dict_code_range.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_dict_scan_8_64.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.oracle_dict_scan_8_64.restype = C.c_uint64
         _lib = L
     return _lib
 
@@ -173,6 +180,31 @@ def index_scan(lo, hi, data) -> np.ndarray:
 def scalar_index_scan(lo, hi, data) -> np.ndarray:
     out = np.zeros(data.shape[0] + 64, dtype=np.uint64)
     n = lib().oracle_scalar_index_scan(lo, hi, _ptr(data), data.shape[0], _ptr(out))
+    return out[:n]
+
+
+def scan_sum(lo, hi, data) -> int:
+    return int(lib().oracle_scan_sum(lo, hi, _ptr(data), data.shape[0]))
+
+
+def value_scan(lo, hi, data) -> np.ndarray:
+    out = np.zeros(scan_count(lo, hi, data) + 64, dtype=np.uint32)
+    n = lib().oracle_value_scan(lo, hi, _ptr(data), data.shape[0], _ptr(out))
+    return out[:n]
+
+
+def dict_code_range(lo: int, hi: int, dictionary: np.ndarray):
+    a, b = np.zeros(1, dtype=np.uint8), np.zeros(1, dtype=np.uint8)
+    d = np.ascontiguousarray(dictionary, dtype=np.int64)
+    lib().oracle_dict_code_range(lo, hi, _ptr(d), _ptr(a), _ptr(b))
+    return int(a[0]), int(b[0])
+
+
+def dict_scan_8_64(lo: int, hi: int, dictionary: np.ndarray, data) -> np.ndarray:
+    d = np.ascontiguousarray(dictionary, dtype=np.int64)
+    assert d.shape[0] == 256
+    out = np.zeros(data.shape[0] + 64, dtype=np.int64)
+    n = lib().oracle_dict_scan_8_64(lo, hi, _ptr(d), _ptr(data), data.shape[0], _ptr(out))
     return out[:n]
 
 
@@ -283,6 +315,13 @@ def ref_scan():
         L.ref_scan_mt.argtypes = [C.c_int, C.c_uint8, C.c_uint8, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int,
                                   C.c_void_p]
         L.ref_scan_mt.restype = C.c_double
+        L.ref_scan_sum.argtypes = [C.c_uint8, C.c_uint8, C.c_void_p, C.c_size_t]
+        L.ref_scan_sum.restype = C.c_uint64
+        L.ref_value_scan.argtypes = [C.c_uint8, C.c_uint8, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.ref_value_scan.restype = C.c_uint64
+        L.ref_dict_scan_8_64.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                         C.c_uint64]
+        L.ref_dict_scan_8_64.restype = C.c_uint64
         _ref_scan = L
     return _ref_scan
 
@@ -321,6 +360,35 @@ def ref_index_scan_self_alloc(lo, hi, data):
     out = np.zeros(cap, dtype=np.uint64)
     c = ref_scan().ref_index_scan_self_alloc(lo, hi, _ptr(data), data.shape[0], _ptr(out), cap)
     return out[:c]
+
+
+def ref_scan_sum(lo, hi, data):
+    assert data.ctypes.data % 64 == 0
+    return int(ref_scan().ref_scan_sum(lo, hi, _ptr(data), data.shape[0]))
+
+
+def ref_value_scan(lo, hi, data):
+    assert data.ctypes.data % 64 == 0
+    out = np.zeros(ref_scan_count(lo, hi, data) + 64, dtype=np.uint32)
+    c = ref_scan().ref_value_scan(lo, hi, _ptr(data), data.shape[0], _ptr(out))
+    return out[:c]
+
+
+def ref_dict_scan_8_64(lo, hi, dictionary, data, which: int = 0):
+    """which: 0 = dict_scan_8bit_64bit, 1 = ..._scalar_gather_scatter, 2 = ..._scalar_unroll, 3 = ..._opt_write"""
+    assert data.ctypes.data % 64 == 0
+    d = aligned_i64(256)
+    d[:] = dictionary
+    cap = data.shape[0] + 64
+    out = np.zeros(cap, dtype=np.int64)
+    c = ref_scan().ref_dict_scan_8_64(which, lo, hi, _ptr(d), _ptr(data), data.shape[0], _ptr(out), cap)
+    return out[:c]
+
+
+def aligned_i64(n: int, align: int = 64) -> np.ndarray:
+    raw = np.empty(n * 8 + align, dtype=np.uint8)
+    off = (-raw.ctypes.data) % align
+    return raw[off:off + n * 8].view(np.int64)
 
 
 # ----------------------------------------------------------------------------- TPC-H-style pipelines

@@ -67,6 +67,12 @@ void     oracle_bitvector_scan(uint8_t lo, uint8_t hi, const uint8_t *in, size_t
 uint64_t oracle_index_scan(uint8_t lo, uint8_t hi, const uint8_t *in, size_t n, uint64_t *out);     /* :225-249 */
 /* microbenchmarks/SimdScanMulti/shared/ScalarScan.hpp:8-20 (processes all n, no /64 truncation) */
 uint64_t oracle_scalar_index_scan(uint8_t lo, uint8_t hi, const uint8_t *in, size_t n, uint64_t *out);
+uint64_t oracle_scan_sum(uint8_t lo, uint8_t hi, const uint8_t *in, size_t n);                                /* :34-86   */
+uint64_t oracle_value_scan(uint8_t lo, uint8_t hi, const uint8_t *in, size_t n, uint32_t *out);               /* :89-150  */
+void     oracle_dict_code_range(int64_t predicate_low, int64_t predicate_high, const int64_t *dict, uint8_t *lo,
+                                uint8_t *hi);                                                                    /* :297-305 */
+uint64_t oracle_dict_scan_8_64(int64_t predicate_low, int64_t predicate_high, const int64_t *dict, const uint8_t *in,
+                               size_t n, int64_t *out);                                                          /* :289-336 */
 /* shared_libraries/SharedHeaders/include/Allocator.hpp:95-109: v[i] = i mod 256 */
 void     oracle_fill_tiled_column(uint8_t *data, size_t n);
 

@@ -49,3 +49,51 @@ void oracle_fill_tiled_column(uint8_t *data, size_t n) {
     for (size_t i = 0; i < copies * 256; ++i) data[i] = (uint8_t) (i & 255);
     for (size_t i = copies * 256; i < n; ++i) data[i] = 0;
 }
+
+/* ---- the remaining SIMD512 variants on the 8-bit column ------------------------------ */
+
+/* SIMD512::sum (:34-86): sum of the values in range over the n/64 whole blocks. */
+uint64_t oracle_scan_sum(uint8_t lo, uint8_t hi, const uint8_t *in, size_t n) {
+    uint64_t s = 0;
+    size_t blocks = n / 64;
+    for (size_t i = 0; i < blocks * 64; ++i)
+        if (in[i] >= lo && in[i] <= hi) s += in[i];
+    return s;
+}
+
+/* SIMD512::scan (:89-150): the matching values, widened to uint32, in input order; returns the count. */
+uint64_t oracle_value_scan(uint8_t lo, uint8_t hi, const uint8_t *in, size_t n, uint32_t *out) {
+    uint64_t w = 0;
+    size_t blocks = n / 64;
+    for (size_t i = 0; i < blocks * 64; ++i)
+        if (in[i] >= lo && in[i] <= hi) out[w++] = in[i];
+    return w;
+}
+
+/* Code range of a value predicate over a sorted 256-entry dictionary, exactly as dict_scan_8bit_64bit derives it
+ * (:297-305): low code = index of the first entry >= predicate_low (std::find_if), high code = index of the first
+ * entry > predicate_high at or after it, minus one; both are then narrowed to uint8. The narrowing is kept as is:
+ * a predicate above every entry gives low = (uint8) 256 = 0 and high = 255, one below every entry gives
+ * high = (uint8) -1 = 255 — in both cases the reference selects everything. */
+void oracle_dict_code_range(int64_t predicate_low, int64_t predicate_high, const int64_t *dict, uint8_t *lo, uint8_t *hi) {
+    long l = 0;
+    while (l < 256 && !(dict[l] >= predicate_low)) ++l;
+    long h = l;
+    while (h < 256 && !(dict[h] > predicate_high)) ++h;
+    h -= 1;
+    *lo = (uint8_t) l;
+    *hi = (uint8_t) (h & 0xff);
+}
+
+/* SIMD512::dict_scan_8bit_64bit (:289-336, cut = true): dict[code] of every code in the code range, in input
+ * order; returns the number of values written. */
+uint64_t oracle_dict_scan_8_64(int64_t predicate_low, int64_t predicate_high, const int64_t *dict, const uint8_t *in,
+                               size_t n, int64_t *out) {
+    uint8_t lo, hi;
+    oracle_dict_code_range(predicate_low, predicate_high, dict, &lo, &hi);
+    uint64_t w = 0;
+    size_t blocks = n / 64;
+    for (size_t i = 0; i < blocks * 64; ++i)
+        if (in[i] >= lo && in[i] <= hi) out[w++] = dict[in[i]];
+    return w;
+}

@@ -50,6 +50,33 @@ uint64_t ref_index_scan_self_alloc(uint8_t lo, uint8_t hi, const uint8_t *data, 
     return c;
 }
 
+uint64_t ref_scan_sum(uint8_t lo, uint8_t hi, const uint8_t *data, size_t n) {
+    return SIMD512::sum(lo, hi, reinterpret_cast<const __m512i *>(data), n);
+}
+
+/* out must hold count + 16 entries: the last compress-store of a block may be followed by nothing, but the
+ * reference gives no slack contract, so the caller is generous. Returns the count. */
+uint64_t ref_value_scan(uint8_t lo, uint8_t hi, const uint8_t *data, size_t n, uint32_t *out) {
+    return SIMD512::scan(lo, hi, reinterpret_cast<const __m512i *>(data), n, out);
+}
+
+/* which: 0 = dict_scan_8bit_64bit, 1 = ..._scalar_gather_scatter, 2 = ..._scalar_unroll, 3 = ..._opt_write
+ * (all with cut = true). Returns the count; copies min(count, cap) values to out. */
+uint64_t ref_dict_scan_8_64(int which, int64_t lo, int64_t hi, const int64_t *dict, const uint8_t *data, size_t n,
+                            int64_t *out, uint64_t cap) {
+    CacheAlignedVector<int64_t> v;
+    const __m512i *in = reinterpret_cast<const __m512i *>(data);
+    switch (which) {
+    case 0: SIMD512::dict_scan_8bit_64bit(lo, hi, dict, in, n, v, true); break;
+    case 1: SIMD512::dict_scan_8bit_64bit_scalar_gather_scatter(lo, hi, dict, in, n, v, true); break;
+    case 2: SIMD512::dict_scan_8bit_64bit_scalar_unroll(lo, hi, dict, in, n, v, true); break;
+    default: SIMD512::dict_scan_8bit_64bit_opt_write(lo, hi, dict, in, n, v, true); break;
+    }
+    uint64_t c = v.size();
+    if (out) memcpy(out, v.data(), sizeof(int64_t) * (c < cap ? c : cap));
+    return c;
+}
+
 /*
  * Multi-threaded timed runs, one row range per thread (multithreadedscan.cpp:231-235):
  * mode 0 = bitvector, 1 = row-id list (pre-allocated per thread with count()+64 as

@@ -144,6 +144,12 @@ SYMBOLS = {
     "b200_bitvector_scan_device": (_int, [_u8, _u8, _vp, _sz, _vp, _vp]),
     "b200_scan_count_device": (_int, [_u8, _u8, _vp, _sz, _vp, _vp]),
     "b200_index_scan_device": (_int, [_u8, _u8, _vp, _sz, _u64, _vp, _u64, _vp, _vp]),
+    "b200_scan_sum_device": (_int, [_u8, _u8, _vp, _sz, _vp, _vp]),
+    "b200_value_scan_device": (_int, [_u8, _u8, _vp, _sz, _vp, _u64, _vp, _vp]),
+    "b200_dict_scan_8bit_64bit_device": (_int, [C.c_int64, C.c_int64, _vp, _vp, _sz, _vp, _u64, _vp, _vp]),
+    "b200_sum": (_u64, [_u8, _u8, _vp, _sz]),
+    "b200_scan": (_u64, [_u8, _u8, _vp, _sz, _vp, _sz]),
+    "b200_dict_scan_8bit_64bit": (_u64, [C.c_int64, C.c_int64, _vp, _vp, _sz, _vp, _sz]),
     "b200_fill_tiled_column_device": (_int, [_vp, _sz, _u64, _vp]),
     "b200_fill_skewed_column_device": (_int, [_vp, _sz, _u64, _u32, _u64, _vp]),
     "b200_kernel_launch_count": (_u64, []),
@@ -391,6 +397,32 @@ def index_scan_user(lo: int, hi: int, data: np.ndarray, capacity: int | None = N
     lib().b200_index_scan_user(lo, hi, data.ctypes.data, n, out.ctypes.data, cap, C.byref(cnt), C.byref(t), num_runs,
                                warmup_runs, int(unique_data))
     return out[:min(cnt.value, cap)], int(cnt.value), int(t.value)
+
+
+def scan_sum(lo: int, hi: int, data: np.ndarray) -> int:
+    """SIMD512::sum through the host-buffer entry point"""
+    assert data.dtype == np.uint8 and data.flags["C_CONTIGUOUS"]
+    return int(lib().b200_sum(lo, hi, data.ctypes.data, data.shape[0]))
+
+
+def value_scan(lo: int, hi: int, data: np.ndarray, capacity: int | None = None):
+    """SIMD512::scan: (matching values as uint32, exact count)"""
+    assert data.dtype == np.uint8 and data.flags["C_CONTIGUOUS"]
+    cap = data.shape[0] if capacity is None else capacity
+    out = np.zeros(max(cap, 1), dtype=np.uint32)
+    cnt = int(lib().b200_scan(lo, hi, data.ctypes.data, data.shape[0], out.ctypes.data, cap))
+    return out[:min(cnt, cap)], cnt
+
+
+def dict_scan_8bit_64bit(lo: int, hi: int, dictionary: np.ndarray, data: np.ndarray, capacity: int | None = None):
+    """SIMD512::dict_scan_8bit_64bit: (dict[code] of every code whose value is in [lo, hi] as int64, exact count)"""
+    assert data.dtype == np.uint8 and data.flags["C_CONTIGUOUS"]
+    d = np.ascontiguousarray(dictionary, dtype=np.int64)
+    assert d.shape[0] == 256
+    cap = data.shape[0] if capacity is None else capacity
+    out = np.zeros(max(cap, 1), dtype=np.int64)
+    cnt = int(lib().b200_dict_scan_8bit_64bit(lo, hi, d.ctypes.data, data.ctypes.data, data.shape[0], out.ctypes.data, cap))
+    return out[:min(cnt, cap)], cnt
 
 
 def bitvector_scan_device(lo, hi, d_data, n, d_out, stream=None):

@@ -1025,6 +1025,108 @@ void b200_bitvector_scan_user(uint8_t lo, uint8_t hi, const uint8_t *data, size_
 }
 
 // Enclave.cpp:100-133 shape
+// ---- the remaining SIMD512 variants on the 8-bit column: sum, value list, dictionary scan --------------------
+int b200_scan_sum_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, uint64_t *d_sum, void *stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    return scan_sum_device(lo, hi, d_data, n, d_sum, stream ? static_cast<cudaStream_t>(stream) : g.stream);
+}
+
+int b200_value_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, uint32_t *d_out,
+                           uint64_t out_capacity, uint64_t *d_count, void *stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    if (g.scan_scratch.ensure(index_scan_scratch_bytes(n))) return -1;
+    return value_scan_device(lo, hi, d_data, n, d_out, out_capacity, d_count, g.scan_scratch.p,
+                             stream ? static_cast<cudaStream_t>(stream) : g.stream);
+}
+
+// code range of a value predicate over the sorted dictionary, derived exactly like SIMD512.cpp:297-305 (std::find_if
+// twice, then narrowed to uint8 — including the wrap-around for predicates outside the dictionary's range)
+static void dict_code_range(int64_t predicate_low, int64_t predicate_high, const int64_t *dict, uint8_t *lo, uint8_t *hi) {
+    long l = 0;
+    while (l < 256 && !(dict[l] >= predicate_low)) ++l;
+    long h = l;
+    while (h < 256 && !(dict[h] > predicate_high)) ++h;
+    *lo = (uint8_t) l;
+    *hi = (uint8_t) ((h - 1) & 0xff);
+}
+
+int b200_dict_scan_8bit_64bit_device(int64_t predicate_low, int64_t predicate_high, const int64_t *dict,
+                                     const uint8_t *d_data, size_t n, int64_t *d_out, uint64_t out_capacity,
+                                     uint64_t *d_count, void *stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : g.stream;
+    static DevBuf d_dict;
+    if (d_dict.ensure(256 * sizeof(int64_t)) || g.scan_scratch.ensure(index_scan_scratch_bytes(n))) return -1;
+    uint8_t lo, hi;
+    dict_code_range(predicate_low, predicate_high, dict, &lo, &hi);
+    // the dictionary (2 KiB, host memory) travels with the call; the copy is synchronous with respect to the
+    // host buffer, so the caller may reuse it right away
+    AQP_CUDA_OK(cudaMemcpyAsync(d_dict.p, dict, 256 * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    AQP_CUDA_OK(cudaStreamSynchronize(st));
+    return dict_scan_device(lo, hi, static_cast<const int64_t *>(d_dict.p), d_data, n, d_out, out_capacity, d_count,
+                            g.scan_scratch.p, st);
+}
+
+// host-buffer forms with the reference functions' argument order (SIMD512.hpp:39-84): H2D, kernels, D2H
+static int scan_host_common(const char *who, const uint8_t *data, size_t n, const uint8_t **d_in, uint64_t **d_count) {
+    if (ensure_init()) return -1;
+    static DevBuf cnt;
+    if (g.scan_in.ensure(n + 64) || cnt.ensure(16)) return -1;
+    AQP_CUDA_OK(cudaMemcpyAsync(g.scan_in.p, data, n / 64 * 64, cudaMemcpyHostToDevice, g.stream));
+    *d_in = static_cast<const uint8_t *>(g.scan_in.p);
+    *d_count = static_cast<uint64_t *>(cnt.p);
+    (void) who;
+    return 0;
+}
+
+uint64_t b200_sum(uint8_t lo, uint8_t hi, const uint8_t *data, size_t n) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    const uint8_t *d_in;
+    uint64_t *d_cnt, h = 0;
+    if (scan_host_common("b200_sum", data, n, &d_in, &d_cnt) || scan_sum_device(lo, hi, d_in, n, d_cnt, g.stream) ||
+        cudaMemcpyAsync(&h, d_cnt, 8, cudaMemcpyDeviceToHost, g.stream) != cudaSuccess ||
+        cudaStreamSynchronize(g.stream) != cudaSuccess)
+        die("b200_sum");
+    return h;
+}
+
+uint64_t b200_scan(uint8_t lo, uint8_t hi, const uint8_t *data, size_t n, uint32_t *output_buffer, size_t output_capacity) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    const uint8_t *d_in;
+    uint64_t *d_cnt, h = 0;
+    if (scan_host_common("b200_scan", data, n, &d_in, &d_cnt) || g.scan_out.ensure(output_capacity * 4 + 64) ||
+        g.scan_scratch.ensure(index_scan_scratch_bytes(n)) ||
+        value_scan_device(lo, hi, d_in, n, static_cast<uint32_t *>(g.scan_out.p), output_capacity, d_cnt,
+                          g.scan_scratch.p, g.stream) ||
+        cudaMemcpyAsync(&h, d_cnt, 8, cudaMemcpyDeviceToHost, g.stream) != cudaSuccess ||
+        cudaStreamSynchronize(g.stream) != cudaSuccess)
+        die("b200_scan");
+    const uint64_t c = h < output_capacity ? h : output_capacity;
+    if (c && cudaMemcpy(output_buffer, g.scan_out.p, c * 4, cudaMemcpyDeviceToHost) != cudaSuccess) die("b200_scan");
+    return h;
+}
+
+uint64_t b200_dict_scan_8bit_64bit(int64_t predicate_low, int64_t predicate_high, const int64_t *dict, const uint8_t *data,
+                                   size_t n, int64_t *output_buffer, size_t output_capacity) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    const uint8_t *d_in;
+    uint64_t *d_cnt, h = 0;
+    if (scan_host_common("b200_dict_scan_8bit_64bit", data, n, &d_in, &d_cnt) ||
+        g.scan_out.ensure(output_capacity * 8 + 64) ||
+        b200_dict_scan_8bit_64bit_device(predicate_low, predicate_high, dict, d_in, n, static_cast<int64_t *>(g.scan_out.p),
+                                         output_capacity, d_cnt, g.stream) ||
+        cudaMemcpyAsync(&h, d_cnt, 8, cudaMemcpyDeviceToHost, g.stream) != cudaSuccess ||
+        cudaStreamSynchronize(g.stream) != cudaSuccess)
+        die("b200_dict_scan_8bit_64bit");
+    const uint64_t c = h < output_capacity ? h : output_capacity;
+    if (c && cudaMemcpy(output_buffer, g.scan_out.p, c * 8, cudaMemcpyDeviceToHost) != cudaSuccess)
+        die("b200_dict_scan_8bit_64bit");
+    return h;
+}
+
 void b200_index_scan_user(uint8_t lo, uint8_t hi, const uint8_t *data, size_t n, uint64_t *output_buffer,
                           size_t output_capacity, size_t *output_count, uint64_t *time_cntr, size_t num_runs,
                           size_t warmup_runs, int unique_data) {

@@ -160,6 +160,45 @@ scan_count_kernel(const uint4 *__restrict__ in, size_t nvec, unsigned long long 
 }
 
 // ---------------------------------------------------------------------------------------------
+// sum of the values in range (SIMD512::sum, SIMD512.cpp:34-86): bytes out of range are masked to zero, the four
+// bytes of a word are added with one dp4a
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kScanThreads)
+scan_sum_kernel(const uint4 *__restrict__ in, size_t nvec, unsigned long long *__restrict__ sum, Pred p) {
+    const size_t ntiles = (nvec + kScanTileVec - 1) / kScanTileVec;
+    unsigned long long acc = 0;
+    auto word_sum = [&](uint32_t x) {
+        const uint32_t keep = (inrange_msb(x, p) >> 7) * 0xFFu;   // 0xFF in every byte that is in range
+        return __dp4a(x & keep, 0x01010101u, 0u);
+    };
+    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const size_t base = tile * kScanTileVec + threadIdx.x;
+        uint4 v[kScanUnroll];
+#pragma unroll
+        for (int j = 0; j < kScanUnroll; ++j) {
+            size_t q = base + (size_t) j * kScanThreads;
+            v[j] = q < nvec ? ld_stream_v4(in + q) : make_uint4(0, 0, 0, 0);
+        }
+        uint32_t c = 0;
+#pragma unroll
+        for (int j = 0; j < kScanUnroll; ++j) {
+            size_t q = base + (size_t) j * kScanThreads;
+            if (q < nvec) c += word_sum(v[j].x) + word_sum(v[j].y) + word_sum(v[j].z) + word_sum(v[j].w);
+        }
+        acc += c;
+    }
+    __shared__ unsigned long long wsum[kScanThreads / 32];
+    acc = warp_sum(acc);
+    if (lane_id() == 0) wsum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < kScanThreads / 32; ++w) t += wsum[w];
+        if (t) atomicAdd(sum, t);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // row-id list scan. The column is processed in chunks whose bitvector (1/8 of the chunk) fits the L2:
 //   A  bitvector_scan_kernel<true>   predicate -> bitvector scratch + matches per 16384-value tile
 //   B  tile_offsets_kernel           exclusive scan of the tile counts, carried across chunks
@@ -254,12 +293,36 @@ constexpr int kExpandWindow = 8192;   // ids per window: 32 KiB of shared memory
 __device__ __forceinline__ void st_stream_u64(uint64_t *p, uint64_t v) {
     asm volatile("st.global.cs.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void st_stream_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// What the expansion kernels write for a match at chunk-relative position pos (the remaining SIMD512 variants share
+// the row-id machinery, SIMD512.cpp:89-150,:289-336):
+//   kEmitRowId  id_base + pos as uint64      implicit_index_scan
+//   kEmitValue  the value itself as uint32   scan
+//   kEmitDict   dict[value] as int64         dict_scan_8bit_64bit
+enum { kEmitRowId = 0, kEmitValue = 1, kEmitDict = 2 };
+struct EmitArgs {
+    uint64_t id_base;          // row id of chunk position 0
+    const uint8_t *data;       // the chunk of the column (kEmitValue, kEmitDict)
+    const int64_t *dict;       // 256 entries (kEmitDict)
+};
+template <int kEmit>
+__device__ __forceinline__ void emit(void *out, uint64_t slot, uint64_t pos, const EmitArgs &e) {
+    if (kEmit == kEmitRowId)
+        st_stream_u64(static_cast<uint64_t *>(out) + slot, e.id_base + pos);
+    else if (kEmit == kEmitValue)
+        st_stream_u32(static_cast<uint32_t *>(out) + slot, __ldg(e.data + pos));
+    else
+        st_stream_u64(static_cast<uint64_t *>(out) + slot, (uint64_t) __ldg(e.dict + __ldg(e.data + pos)));
+}
 __device__ __forceinline__ uint32_t expand_phys(uint32_t slot) { return slot ^ ((slot >> 5) & 31u); }
 
-__global__ void __launch_bounds__(kScanThreads)
+template <int kEmit>
+__global__ void __launch_bounds__(kScanThreads, 6)   // 6 CTAs/SM: the 32 KiB window allows no more, so cap the registers
 expand_rowids_kernel(const uint64_t *__restrict__ bv, size_t nwords, const uint64_t *__restrict__ tile_offsets,
-                     const uint32_t *__restrict__ tile_list, const uint32_t *__restrict__ tile_list_len, uint64_t id_base,
-                     uint64_t *__restrict__ out, uint64_t out_capacity) {
+                     const uint32_t *__restrict__ tile_list, const uint32_t *__restrict__ tile_list_len, EmitArgs ea,
+                     void *__restrict__ out, uint64_t out_capacity) {
     __shared__ uint32_t stage[kExpandWindow];
     __shared__ uint32_t wtot[kScanThreads / 32];
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
@@ -315,7 +378,8 @@ expand_rowids_kernel(const uint64_t *__restrict__ bv, size_t nwords, const uint6
         }
         uint32_t slot = wbase + incl - cnt;                                  // next output slot of this thread
         const uint32_t rel0 = threadIdx.x * kExpandWordsPerThread * 64;     // tile-relative id of my first bit
-        const uint64_t idb = id_base + (uint64_t) tile * kExpandTileVals;
+        const uint64_t posb = (uint64_t) tile * kExpandTileVals;   // chunk-relative position of the tile
+        const uint64_t idb = ea.id_base + posb;
         for (uint32_t wlo = 0; wlo < total; wlo += kExpandWindow) {
             const uint32_t whi = wlo + kExpandWindow;
 #pragma unroll
@@ -333,8 +397,13 @@ expand_rowids_kernel(const uint64_t *__restrict__ bv, size_t nwords, const uint6
             const uint32_t nwin = min((uint32_t) kExpandWindow, total - wlo);
             const uint64_t g0 = gbase + wlo;
             const uint32_t nok = g0 >= out_capacity ? 0u : (uint32_t) min((uint64_t) nwin, out_capacity - g0);
-            for (uint32_t t = threadIdx.x; t < nok; t += kScanThreads)
-                st_stream_u64(out + g0 + t, idb + stage[expand_phys(t)]);
+            if (kEmit == kEmitRowId) {   // row ids: one 64-bit add per id
+                for (uint32_t t = threadIdx.x; t < nok; t += kScanThreads)
+                    st_stream_u64(static_cast<uint64_t *>(out) + g0 + t, idb + stage[expand_phys(t)]);
+            } else {
+                for (uint32_t t = threadIdx.x; t < nok; t += kScanThreads)
+                    emit<kEmit>(out, g0 + t, posb + stage[expand_phys(t)], ea);
+            }
             if (whi < total) __syncthreads();   // the window is reused
         }
     }
@@ -343,10 +412,11 @@ expand_rowids_kernel(const uint64_t *__restrict__ bv, size_t nwords, const uint6
 // Tiles that are at least 3/4 full: whole-warp expansion, one word at a time, straight from registers. Lane l
 // owns bits l and l+32 of the broadcast word; its slot is the word's offset plus the set bits below it, so each
 // store instruction writes one contiguous run (a full 256-byte line pair for a full word).
+template <int kEmit>
 __global__ void __launch_bounds__(kScanThreads)
 expand_dense_rowids_kernel(const uint64_t *__restrict__ bv, size_t nwords, const uint64_t *__restrict__ tile_offsets,
-                           const uint32_t *__restrict__ tile_list, const uint32_t *__restrict__ tile_list_len, uint64_t id_base,
-                           uint64_t *__restrict__ out, uint64_t out_capacity) {
+                           const uint32_t *__restrict__ tile_list, const uint32_t *__restrict__ tile_list_len, EmitArgs ea,
+                           void *__restrict__ out, uint64_t out_capacity) {
     __shared__ uint32_t wtot[kScanThreads / 32];
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     const unsigned lt = lanemask_lt();
@@ -405,7 +475,8 @@ expand_dense_rowids_kernel(const uint64_t *__restrict__ bv, size_t nwords, const
                 any |= nz[k];
             }
         }
-        const uint64_t idw = id_base + (uint64_t) tile * kExpandTileVals + (uint64_t) warp * 32 * kExpandWordsPerThread * 64;
+        const uint64_t idw = (kEmit == kEmitRowId ? ea.id_base : 0ull) + (uint64_t) tile * kExpandTileVals +
+                             (uint64_t) warp * 32 * kExpandWordsPerThread * 64;
         while (any) {
             const int src = __ffs(any) - 1;
             any &= any - 1;
@@ -418,11 +489,17 @@ expand_dense_rowids_kernel(const uint64_t *__restrict__ bv, size_t nwords, const
                 const uint64_t id0 = idw + (uint64_t) (src * kExpandWordsPerThread + k) * 64 + lane;
                 if ((lo >> lane) & 1u) {
                     uint64_t g = o + __popc(lo & lt);
-                    if (g < out_capacity) st_stream_u64(out + g, id0);
+                    if (g < out_capacity) {
+                        if (kEmit == kEmitRowId) st_stream_u64(static_cast<uint64_t *>(out) + g, id0);
+                        else emit<kEmit>(out, g, id0, ea);
+                    }
                 }
                 if ((hi >> lane) & 1u) {
                     uint64_t g = o + __popc(lo) + __popc(hi & lt);
-                    if (g < out_capacity) st_stream_u64(out + g, id0 + 32);
+                    if (g < out_capacity) {
+                        if (kEmit == kEmitRowId) st_stream_u64(static_cast<uint64_t *>(out) + g, id0 + 32);
+                        else emit<kEmit>(out, g, id0 + 32, ea);
+                    }
                 }
             }
         }
@@ -505,10 +582,13 @@ size_t index_scan_scratch_bytes(size_t n) {
     return align256(chunk / 8 + 64) + align256(tiles * 4) + align256(tiles * 8) + align256((2 * tiles + 2) * 4) + 256;
 }
 
-int index_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, uint64_t id_base,
-                      uint64_t *d_out, uint64_t cap, uint64_t *d_count, void *d_scratch, cudaStream_t st) {
+// emit = kEmitRowId / kEmitValue / kEmitDict (d_dict: 256 int64 on the device); d_out holds cap elements of the
+// emitted type
+static int emit_scan_device(int emit_kind, uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, uint64_t id_base,
+                            const int64_t *d_dict, void *d_out, uint64_t cap, uint64_t *d_count, void *d_scratch,
+                            cudaStream_t st) {
     if ((reinterpret_cast<uintptr_t>(d_data) & 15u) != 0) {
-        set_error("index_scan: column must be 16-byte aligned");
+        set_error("scan: column must be 16-byte aligned");
         return -1;
     }
     AQP_CUDA_OK(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
@@ -541,15 +621,55 @@ int index_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, u
         tile_offsets_kernel<<<1, kScanBlock, kPlanSmemBytes, st>>>(counts, ntiles, offsets, running, lists,
                                                                    (uint32_t) tiles_cap);
         AQP_LAUNCHED();
+        const EmitArgs ea{id_base + begin, d_data + begin, d_dict};
         size_t g = (size_t) kNumSMs * 6;   // 6 CTAs/SM resident (32 KiB window each)
-        expand_rowids_kernel<<<(unsigned) (ntiles < g ? ntiles : g), kScanThreads, 0, st>>>(
-            bv, nwords, offsets, lists + 2, lists, id_base + begin, d_out, cap);
-        AQP_LAUNCHED();
+        const unsigned g1 = (unsigned) (ntiles < g ? ntiles : g);
         g = (size_t) kNumSMs * 8;
-        expand_dense_rowids_kernel<<<(unsigned) (ntiles < g ? ntiles : g), kScanThreads, 0, st>>>(
-            bv, nwords, offsets, lists + 2 + tiles_cap, lists + 1, id_base + begin, d_out, cap);
-        AQP_LAUNCHED();
+        const unsigned g2 = (unsigned) (ntiles < g ? ntiles : g);
+#define AQP_EXPAND(KIND)                                                                                             \
+    do {                                                                                                             \
+        expand_rowids_kernel<KIND><<<g1, kScanThreads, 0, st>>>(bv, nwords, offsets, lists + 2, lists, ea, d_out, cap); \
+        AQP_LAUNCHED();                                                                                              \
+        expand_dense_rowids_kernel<KIND><<<g2, kScanThreads, 0, st>>>(bv, nwords, offsets, lists + 2 + tiles_cap,      \
+                                                                      lists + 1, ea, d_out, cap);                    \
+        AQP_LAUNCHED();                                                                                              \
+    } while (0)
+        if (emit_kind == kEmitRowId) AQP_EXPAND(kEmitRowId);
+        else if (emit_kind == kEmitValue) AQP_EXPAND(kEmitValue);
+        else AQP_EXPAND(kEmitDict);
+#undef AQP_EXPAND
     }
+    AQP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int index_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, uint64_t id_base,
+                      uint64_t *d_out, uint64_t cap, uint64_t *d_count, void *d_scratch, cudaStream_t st) {
+    return emit_scan_device(kEmitRowId, lo, hi, d_data, n, id_base, nullptr, d_out, cap, d_count, d_scratch, st);
+}
+
+int value_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, uint32_t *d_out, uint64_t cap,
+                      uint64_t *d_count, void *d_scratch, cudaStream_t st) {
+    return emit_scan_device(kEmitValue, lo, hi, d_data, n, 0, nullptr, d_out, cap, d_count, d_scratch, st);
+}
+
+int dict_scan_device(uint8_t code_lo, uint8_t code_hi, const int64_t *d_dict, const uint8_t *d_data, size_t n,
+                     int64_t *d_out, uint64_t cap, uint64_t *d_count, void *d_scratch, cudaStream_t st) {
+    return emit_scan_device(kEmitDict, code_lo, code_hi, d_data, n, 0, d_dict, d_out, cap, d_count, d_scratch, st);
+}
+
+int scan_sum_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, uint64_t *d_sum, cudaStream_t st) {
+    if ((reinterpret_cast<uintptr_t>(d_data) & 15u) != 0) {
+        set_error("scan_sum: column must be 16-byte aligned");
+        return -1;
+    }
+    AQP_CUDA_OK(cudaMemsetAsync(d_sum, 0, sizeof(uint64_t), st));
+    size_t nvec = (n / 64) * 4;
+    if (nvec == 0) return 0;
+    scan_sum_kernel<<<scan_grid(nvec, 8), kScanThreads, 0, st>>>(reinterpret_cast<const uint4 *>(d_data), nvec,
+                                                                reinterpret_cast<unsigned long long *>(d_sum),
+                                                                make_pred(lo, hi));
+    AQP_LAUNCHED();
     AQP_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -136,3 +136,39 @@ def test_full_size_properties(gpu):
     gpu.index_scan_device(0, 0, data.data_ptr(), n, ids.data_ptr(), n // 256, cnt.data_ptr(), id_base=1 << 40)
     torch.cuda.synchronize()
     assert torch.equal(ids, torch.arange(0, n, 256, device=dev) + (1 << 40))
+
+
+def test_dict_scan_reference_known_answers_on_gpu(gpu, oracle):
+    """The reference's own [main] dictionary-scan cases (testsimdscan.cpp:8-165,:217-245) through the C ABI."""
+    from test_oracle_scan import dict_kats
+    for name, col, d, lo, hi, size, spots in dict_kats(oracle):
+        r, cnt = gpu.dict_scan_8bit_64bit(lo, hi, d, col)
+        assert cnt == size == len(r), name
+        for i, v in spots.items():
+            assert r[i] == v, (name, i)
+        assert np.array_equal(r, oracle.dict_scan_8_64(lo, hi, d, col)), name
+
+
+@pytest.mark.parametrize("n", [0, 64, 64 * 3 + 17, 65536 + 64, 3_000_000])
+def test_sum_value_dict_vs_oracle(gpu, oracle, n):
+    rng = np.random.default_rng(n + 1)
+    col = rng.integers(0, 256, n, dtype=np.uint8)
+    for lo, hi in PREDS:
+        assert gpu.scan_sum(lo, hi, col) == oracle.scan_sum(lo, hi, col), (n, lo, hi)
+        vals, cnt = gpu.value_scan(lo, hi, col)
+        exp = oracle.value_scan(lo, hi, col)
+        assert cnt == len(exp) and np.array_equal(vals, exp), (n, lo, hi)
+    d = np.sort(rng.integers(-10**12, 10**12, 256))
+    for lo, hi in [(int(d[10]), int(d[90])), (int(d[0]) - 5, int(d[0]) - 1), (int(d[255]) + 1, int(d[255]) + 9),
+                   (int(d[200]), int(d[100])), (int(d[17]), int(d[17])), (int(d[0]), int(d[255]))]:
+        r, cnt = gpu.dict_scan_8bit_64bit(lo, hi, d, col)
+        exp = oracle.dict_scan_8_64(lo, hi, d, col)
+        assert cnt == len(exp) and np.array_equal(r, exp), (n, lo, hi)
+    # dense tiles (whole-warp expansion kernel) and a capacity that cuts the output
+    if n >= 65536:
+        dense = np.where(rng.random(n) < 0.9, 7, 200).astype(np.uint8)
+        vals, cnt = gpu.value_scan(0, 100, dense, capacity=1000)
+        exp = oracle.value_scan(0, 100, dense)
+        assert cnt == len(exp) and np.array_equal(vals, exp[:1000])
+        r, cnt = gpu.dict_scan_8bit_64bit(0, 100, np.arange(256), dense)
+        assert cnt == len(exp) and np.array_equal(r, exp.astype(np.int64))

@@ -49,3 +49,52 @@ def test_against_compiled_reference(oracle):
         assert np.array_equal(oracle.index_scan(lo, hi, d), oracle.ref_index_scan(lo, hi, d))
         assert np.array_equal(oracle.index_scan(lo, hi, d), oracle.ref_index_scan_self_alloc(lo, hi, d))
         assert oracle.scan_count(lo, hi, d) == oracle.ref_scan_count(lo, hi, d)
+
+
+# ---- the remaining SIMD512 variants (sum, value list, dictionary scan): the reference's OWN known-answer tests ----
+def dict_kats(O):
+    """The [main] dictionary-scan cases of Scan-Micro-Benchmarks/shared_libraries/SimdScan/tests/testsimdscan.cpp
+    (8-bit column; :8-165 and :217-245), restated: (name, column, dictionary, low, high, expected size, spot checks)."""
+    n = 1 << 20
+    tiled = O.tiled_column(n)                                       # allocate_data_array_aligned<uint8_t>, Allocator.hpp:95-109
+    mod4 = (np.arange(n) & 3).astype(np.uint8)                       # test 4: gen = in & 3
+    ident = np.arange(256, dtype=np.int64)                           # allocate_data_array_aligned<int64_t>(256): dict[i] = i
+    return [
+        ("test 1 :8-28", tiled, ident, 0, 100, n // 256 * 101, {}),
+        ("test 2 :30-54", tiled, ident, 1, 100, n // 256 * 100, {**{i: i + 1 for i in range(100)}, 100: 1}),
+        ("test 3 :56-84", tiled, ident * 2, 0, 98, n // 256 * 50, {**{i: 2 * i for i in range(50)}, 99: 98, 100: 0}),
+        ("test 4 :86-113", mod4, ident, 0, 2, n // 4 * 3, {0: 0, 1: 1, 2: 2, 3: 0}),
+        ("test 5 :115-138", tiled, ident, 100, 199, n // 256 * 100, {0: 100, 99: 199}),
+        ("test 6 :140-165", tiled, ident - 128, -10, 0, n // 256 * 11, {0: -10, 10: 0}),
+        ("scalar gather scatter :217-245", tiled, ident * 2, 0, 98, n // 256 * 50, {**{i: 2 * i for i in range(50)}, 99: 98, 100: 0}),
+    ]
+
+
+def test_dict_scan_reference_known_answers(oracle):
+    for name, col, d, lo, hi, size, spots in dict_kats(oracle):
+        r = oracle.dict_scan_8_64(lo, hi, d, col)
+        assert len(r) == size, name
+        for i, v in spots.items():
+            assert r[i] == v, (name, i)
+
+
+def test_sum_value_dict_against_compiled_reference(oracle):
+    if not (oracle.have_ref() and oracle.host_has_avx512()):
+        pytest.skip("compiled reference needs AVX-512 and oracle/_ref")
+    rng = np.random.default_rng(5)
+    n = 64 * 1000 + 37
+    col = oracle.aligned_u8(n)
+    col[:] = rng.integers(0, 256, n, dtype=np.uint8)
+    for lo, hi in [(0, 0), (0, 26), (5, 5), (17, 200), (100, 50), (0, 255), (255, 255)]:
+        assert oracle.scan_sum(lo, hi, col) == oracle.ref_scan_sum(lo, hi, col), (lo, hi)
+        assert np.array_equal(oracle.value_scan(lo, hi, col), oracle.ref_value_scan(lo, hi, col)), (lo, hi)
+    dicts = [np.arange(256, dtype=np.int64), np.arange(256, dtype=np.int64) * 3 - 300,
+             np.sort(rng.integers(-10**12, 10**12, 256))]
+    for d in dicts:
+        preds = [(int(d[10]), int(d[90])), (int(d[0]) - 5, int(d[0]) - 1), (int(d[255]) + 1, int(d[255]) + 9),
+                 (int(d[200]), int(d[100])), (int(d[17]), int(d[17])), (int(d[0]), int(d[255]))]
+        for lo, hi in preds:
+            exp = oracle.ref_dict_scan_8_64(lo, hi, d, col)
+            assert np.array_equal(oracle.dict_scan_8_64(lo, hi, d, col), exp), (lo, hi)
+            for which in (1, 2, 3):   # the reference's other 8-bit implementations agree with each other
+                assert np.array_equal(oracle.ref_dict_scan_8_64(lo, hi, d, col, which), exp), (which, lo, hi)
