@@ -1013,6 +1013,163 @@ radix_scatter_bins_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// scatter into PEER memory (the fused exchange), line-aligned variant
+//
+// Over NVLink a store — SM-issued or TMA — reaches the link rate (714 GB/s) only when it covers whole, aligned
+// 128-byte lines; 256-byte runs that start at arbitrary 16-byte offsets reach 550 GB/s (profiles/r01_bulkbench.txt),
+// because every partial line travels as its own packet and cannot be merged on the way. So here a partition's bin
+// is a RING that lives across tiles: what leaves it per tile is the part that ends on a destination line boundary,
+// the remainder (< 16 tuples) stays for the next tile. One packed shared-memory atomicAdd per tuple returns the
+// tuple's position in its partition's stream (high half; kept congruent to the destination index mod 2^16, so ring
+// slot = pos mod cap and "aligned in pos" = "aligned at the destination") and the bin's fill (low half). The owner
+// thread of a partition flushes [oldest, last line boundary) as one or two TMA bulk stores (two when the range wraps
+// around the ring) and subtracts it from the fill BEFORE the barrier that releases the next tile's rank phase, so
+// fills are always exact. A tuple that finds its bin full (skew) is stored directly behind the flushed range from
+// registers. Unaligned heads (the first run of a CTA in a partition, the run after an overflow) and the final
+// remainders are scalar stores.
+// ---------------------------------------------------------------------------------------------
+template <bool kRot>
+__global__ void __launch_bounds__(kScatterThreads, kScatterBlocksPerSM)
+radix_scatter_peer_kernel(const uint2 *__restrict__ in, uint32_t n, DigitFn digit, uint32_t bits,
+                          const uint32_t *__restrict__ block_base, uint32_t tiles_per_block, PeerTable peers) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint2 *inbuf = reinterpret_cast<uint2 *>(smem_raw);
+    uint2 *bins = inbuf + kInBufTuples;
+    __shared__ uint32_t w[kMaxFanout];      // (position of the next tuple mod 2^16) << 16 | tuples in the bin
+    __shared__ uint32_t scur[kMaxFanout];   // destination index of the bin's oldest tuple
+    __shared__ uint32_t gst[kMaxFanout];    // overflow path: destination index ...
+    __shared__ uint32_t spos[kMaxFanout];   //   ... and position of the oldest tuple when the tile was flushed
+    __shared__ uint2 *s_peer[8];
+    __shared__ uint32_t s_ovf[2];
+    __shared__ __align__(8) uint64_t mbar;
+
+    const uint32_t fan = 1u << bits;
+    const uint32_t lgcap = kBinSlotsLog - bits, cap = 1u << lgcap, cmask = cap - 1;
+    for (uint32_t i = threadIdx.x; i < fan; i += kScatterThreads) {
+        const uint32_t base = block_base[(size_t) blockIdx.x * fan + i];
+        scur[i] = base;
+        w[i] = base << 16;
+    }
+    if (threadIdx.x < 8) s_peer[threadIdx.x] = peers.base[threadIdx.x];
+    if (threadIdx.x == 0) {
+        s_ovf[0] = s_ovf[1] = 0;
+        mbar_init(&mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t ntiles = (n + kScatterTile - 1) / kScatterTile;
+    const uint32_t first = blockIdx.x * tiles_per_block;
+    const uint32_t n_my = first < ntiles ? min(tiles_per_block, ntiles - first) : 0;
+    auto issue = [&](uint32_t i) {   // one thread: bulk-load tile #i of this CTA (tiles start on even tuple indices)
+        const uint32_t begin = (first + i) * kScatterTile, end = min(begin + (uint32_t) kScatterTile, n);
+        const uint32_t bytes = ((end - begin + 1) & ~1u) * (uint32_t) sizeof(uint2);
+        mbar_expect_tx(&mbar, bytes);
+        tma_load_1d(inbuf, in + begin, bytes, &mbar);
+    };
+    if (threadIdx.x == 0 && n_my > 0) issue(0);
+    constexpr uint32_t kWarps = kScatterThreads / 32;
+    const uint32_t own_per = (fan + kWarps - 1) / kWarps;
+    const uint32_t d_own = (threadIdx.x & 31u) < own_per ? (threadIdx.x >> 5) * own_per + (threadIdx.x & 31u) : fan;
+
+    for (uint32_t i = 0; i < n_my; ++i) {
+        const uint32_t begin = (first + i) * kScatterTile, end = min(begin + (uint32_t) kScatterTile, n);
+        const uint32_t ntile = end - begin;
+        const bool last = i + 1 == n_my;
+
+        mbar_wait(&mbar, i & 1);
+        uint2 v[kScatterItems];
+        uint32_t old[kScatterItems];
+        bool full = false;
+#pragma unroll
+        for (int j = 0; j < kScatterItems; ++j) {
+            uint32_t k = j * kScatterThreads + threadIdx.x;
+            if (k < ntile) v[j] = inbuf[k];
+        }
+#pragma unroll
+        for (int j = 0; j < kScatterItems; ++j) {
+            uint32_t k = j * kScatterThreads + threadIdx.x;
+            old[j] = 0;
+            if (k < ntile) {
+                old[j] = atomicAdd(&w[digit.template get<kRot>(v[j].x)], 0x10001u);
+                full |= (old[j] & 0xFFFFu) >= cap;
+            }
+        }
+        if (full) s_ovf[i & 1] = 1;
+        if (d_own < fan) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncthreads();   // (1) positions assigned, input buffer consumed, previous flush has left the bins
+
+        if (threadIdx.x == 0) {
+            if (i + 1 < n_my) issue(i + 1);
+            s_ovf[(i + 1) & 1] = 0;
+        }
+#pragma unroll
+        for (int j = 0; j < kScatterItems; ++j) {
+            uint32_t k = j * kScatterThreads + threadIdx.x;
+            if (k < ntile && (old[j] & 0xFFFFu) < cap)
+                bins[(digit.template get<kRot>(v[j].x) << lgcap) + ((old[j] >> 16) & cmask)] = v[j];
+        }
+        uint32_t f_start = 0, f_n = 0, f_g = 0;
+        if (d_own < fan) {
+            const uint32_t wd = w[d_own];
+            const uint32_t fill = wd & 0xFFFFu, pos_end = wd >> 16;
+            const uint32_t start = (pos_end - fill) & 0xFFFFu;
+            const bool ovf = fill > cap;
+            const uint32_t inring = ovf ? cap : fill;
+            uint32_t consumed;
+            if (ovf || last) {
+                f_n = inring;
+                consumed = fill;
+            } else {
+                const uint32_t left = (start + inring) & 15u;
+                f_n = inring > left ? inring - left : 0u;
+                consumed = f_n;
+            }
+            f_start = start;
+            f_g = scur[d_own];
+            scur[d_own] = f_g + consumed;
+            w[d_own] = wd - consumed;   // the fill is exact again before the next tile's rank phase starts
+            if (ovf) {
+                gst[d_own] = f_g;
+                spos[d_own] = start;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();   // (2) tile staged, fills updated, overflow destinations published
+        if (d_own < fan) {
+            if (f_n) {
+                uint2 *dst = s_peer[d_own >> peers.per_shift] + f_g;
+                const uint2 *ring = bins + (d_own << lgcap);
+                uint32_t off = 0;
+                uint32_t head = (16u - (f_start & 15u)) & 15u;   // up to the first destination line boundary
+                head = head < f_n ? head : f_n;
+                for (; off < head; ++off) dst[off] = ring[(f_start + off) & cmask];
+                const uint32_t body = (f_n - off) & ~15u;
+                if (body) {
+                    const uint32_t r0 = (f_start + off) & cmask;
+                    const uint32_t len1 = body < cap - r0 ? body : cap - r0;
+                    tma_store_1d(dst + off, ring + r0, len1 * (uint32_t) sizeof(uint2));
+                    if (body > len1) tma_store_1d(dst + off + len1, ring, (body - len1) * (uint32_t) sizeof(uint2));
+                    off += body;
+                }
+                for (; off < f_n; ++off) dst[off] = ring[(f_start + off) & cmask];   // only after an overflow / at the end
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (s_ovf[i & 1]) {   // tuples that found their bin full: straight from registers, behind the flushed range
+#pragma unroll
+            for (int j = 0; j < kScatterItems; ++j) {
+                uint32_t k = j * kScatterThreads + threadIdx.x;
+                if (k < ntile && (old[j] & 0xFFFFu) >= cap) {
+                    const uint32_t d = digit.template get<kRot>(v[j].x);
+                    s_peer[d >> peers.per_shift][gst[d] + (((old[j] >> 16) - spos[d]) & 0xFFFFu)] = v[j];
+                }
+            }
+        }
+    }
+    if (d_own < fan) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_off,
                          const uint32_t *d_seg_tile_start, const uint32_t *d_seg_group, uint32_t nseg, uint64_t n_total,
                          DigitFn digit, uint32_t bits, uint32_t *d_cursors, const uint32_t *d_block_base,
@@ -1074,12 +1231,30 @@ int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_
     radix_scatter_bins_kernel<ROT, PEER, PRIV><<<grid, kScatterThreads, kBinsSmemBytes, st>>>(                          \
         in, out, d_seg_off, d_seg_tile_start, d_seg_group, nseg, digit, bits, d_cursors, d_block_base, tiles_per_block, \
         peer ? *peers : none)
+        static const bool peer_ring_off = getenv("B200_AQP_PEER_RING") && atoi(getenv("B200_AQP_PEER_RING")) == 0;
+        bool aligned128 = true;
+        if (peer)
+            for (uint32_t i = 0; i < peers->n; ++i) aligned128 = aligned128 && (reinterpret_cast<uintptr_t>(peers->base[i]) & 127u) == 0;
         if (peer) {
             if (!d_block_base) {
                 set_error("radix_scatter: the peer variant needs CTA-private cursors");
                 return -1;
             }
-            AQP_BINS_LAUNCH(true, true, true);
+            // line-aligned ring flush needs >= 64 slots per bin (a remainder of up to 15 tuples plus a tile's arrivals),
+            // a single input segment that starts on an even tuple and 128-byte aligned receive buffers
+            if (bits <= (uint32_t) kBinSlotsLog - 6 && nseg == 1 && aligned128 && !peer_ring_off &&
+                (reinterpret_cast<uintptr_t>(d_in) & 15u) == 0 && n_total < 0xFFFFFFFFull) {
+                static bool peer_attr_set = false;
+                if (!peer_attr_set) {
+                    AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_peer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int) kBinsSmemBytes));
+                    peer_attr_set = true;
+                }
+                radix_scatter_peer_kernel<true><<<grid, kScatterThreads, kBinsSmemBytes, st>>>(
+                    in, (uint32_t) n_total, digit, bits, d_block_base, tiles_per_block, *peers);
+            } else {
+                AQP_BINS_LAUNCH(true, true, true);
+            }
         } else if (digit.rot) {
             if (d_block_base) AQP_BINS_LAUNCH(true, false, true); else AQP_BINS_LAUNCH(true, false, false);
         } else {
