@@ -187,3 +187,19 @@ def test_exchange_plan_kernel_matches_tensor_formulation(gpu, G, b1, b2):
             assert int(hv[rel]) == int(ca.view(G, G, per).sum((0, 2)).max())
             assert int(hv[2 + rel]) == int(recv.sum())
             assert int(hv[4 + rel]) == int(ca[rank, rank * per:(rank + 1) * per].sum())
+
+
+@pytest.mark.parametrize("G", [2, 8])
+def test_fused_scatter_exchange_heavy_skew(gpu, oracle, G):
+    """128 pass-1 partitions (64-slot bins) and an S side in which one key holds half of the tuples and a second
+    one a tenth: the owning bins overflow in every tile, so the peer scatter's direct-store path, its unaligned
+    heads after an overflow and the line-aligned ring flush all run side by side."""
+    nR = 1 << 20
+    R = oracle.set_rowid_payload(oracle.gen_pk(nR, 11111))
+    rng = np.random.default_rng(99)
+    nS = (1 << 21) + 12345
+    S = oracle.gen_fk(nS, nR, 22222)[:nS].copy()
+    u = rng.random(nS)
+    S["key"] = np.where(u < 0.5, 777, np.where(u < 0.6, 4242, S["key"]))
+    S = oracle.set_rowid_payload(S)
+    _emulate_fused(gpu, oracle, R, S, G)
