@@ -10,6 +10,8 @@
 // All three are HBM-bound streaming kernels: 16-byte coalesced loads, 4 independent loads in
 // flight per thread, the byte compare done 4 values at a time with carry-free SWAR arithmetic
 // (there is no per-byte compare instruction on sm_100; __vcmpgeu4 expands to more ops).
+#include <cstring>
+
 #include "common.cuh"
 #include "block_scan.cuh"
 
@@ -27,54 +29,76 @@ constexpr int kExpandTileWords = kScanThreads * kExpandWordsPerThread;   // 1024
 constexpr int kExpandTileVals = kExpandTileWords * 64;          // 65536 values per expansion tile
 constexpr int kExpandScanTiles = kExpandTileVals / kScanTileVals;   // = 4 scan tiles per expansion tile
 
-// bit 7 of every byte of the result is set iff lo <= byte <= hi (unsigned). lo7 = lo4 & 0x7f7f7f7f,
-// hiH = hi4 | 0x80808080 are loop invariants. Per byte: (x|0x80) - lo_low never borrows across
-// bytes and its bit 7 says x_low >= lo_low; x >= lo  <=>  x7 > lo7 or (x7 == lo7 and that bit).
+// Range predicate on four packed bytes: bit 7 of every byte of the result is set iff lo <= byte <= hi (unsigned),
+// all other bits are zero. sm_100 has no per-byte compare (__vcmpgeu4 expands to more instructions), so this is
+// carry-free SWAR arithmetic on the low 7 bits of every byte plus one logic op for the top bits:
+//   b = x & 0x7f7f7f7f
+//   t = b + (0x80 - lo7)        bit 7 of each byte: low7(x) >= low7(lo)     (no carry leaves a byte: <= 0x7f + 0x80)
+//   u = (0x80 | hi7) - b        bit 7 of each byte: low7(x) <= low7(hi)     (no borrow enters a byte)
+// and, with x7 the top bit of the byte, the range test depends on the top bits of lo and hi only through WHICH
+// three-input function of (x7, t7, u7) it is - one LOP3 each:
+//   lo < 128, hi < 128  : ~x7 & t7 & u7        lo < 128 <= hi : x7 ? u7 : t7
+//   lo, hi >= 128       :  x7 & t7 & u7        lo >= 128 > hi : empty
+// The variant is a launch constant; kernels switch on it outside their inner loops.
 //
-// Pipe balance (ncu, profiles/r01_ncu_scan_kernels.md): LOP3/IADD/SHF all issue on the half-rate ALU
-// pipe and the first version of this predicate (36 ALU ops per 16 bytes) stalled on math-pipe throttle
-// at 5.1 TB/s. The two subtractions and the four combine shifts are therefore expressed as multiply-adds
-// (a - b = b * (0 - one) + a with `one` a runtime 1 the compiler cannot fold; x >> s = umulhi(x, 2^(32-s))),
-// which ptxas places on the FMA pipe: 23 LOP3 + 20 IMAD per 16 bytes.
+// Pipe balance (ncu, profiles/r01_ncu_scan_kernels.md, profiles/r02_ncu_scan_fused.md): LOP3/IADD/SHF issue on the
+// half-rate ALU pipe, which is what limits these kernels once the loads are coalesced (the round-1 predicate,
+// 6 LOP3 + 4 IMAD per word, kept the ALU pipe 62 % busy in the fused row-id kernel). The additions are therefore
+// written as multiply-adds (a + b = a * one + b with `one` a runtime 1 the compiler cannot fold) which ptxas places on
+// the FMA pipe, and the four flags of a word are gathered into a nibble by ONE dp4a (flag bytes are 0x80 or 0, the
+// weights 1,2,4,8 resp. 16,32,64,128 for the odd word: two words accumulate into one 8-bit group at bit 7).
+// Per word: 3 LOP3 + 2 IMAD + 1 IDP.4A (was 6 LOP3 + 4 IMAD).
 struct Pred {
-    uint32_t lo4, hi4, lo7, hiH, neg_one;
+    uint32_t addK, hiH, one, neg_one, variant;
 };
 static Pred make_pred(uint8_t lo, uint8_t hi) {
     Pred p;
-    p.lo4 = 0x01010101u * lo;
-    p.hi4 = 0x01010101u * hi;
-    p.lo7 = p.lo4 & 0x7f7f7f7fu;
-    p.hiH = p.hi4 | 0x80808080u;
+    p.addK = 0x01010101u * (0x80u - (lo & 0x7fu));
+    p.hiH = 0x01010101u * (0x80u | (hi & 0x7fu));
+    p.one = 1u;
     p.neg_one = 0xffffffffu;
+    p.variant = (uint32_t) (lo >> 7) | ((uint32_t) (hi >> 7) << 1);   // 0: both low, 2: lo low / hi high, 3: both high, 1: empty
     return p;
 }
 
-__device__ __forceinline__ uint32_t sub_fma(uint32_t a, uint32_t b, uint32_t neg_one) {
+__device__ __forceinline__ uint32_t mad_fma(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t r;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(neg_one), "r"(a));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
     return r;
 }
 
+template <int kVariant>
 __device__ __forceinline__ uint32_t inrange_msb(uint32_t x, const Pred &p) {
     const uint32_t H = 0x80808080u;
-    uint32_t t = sub_fma(x | H, p.lo7, p.neg_one);
-    uint32_t ge = (x & ~p.lo4) | (~(x ^ p.lo4) & t);
-    uint32_t u = sub_fma(p.hiH, x & ~H, p.neg_one);
-    uint32_t le = (p.hi4 & ~x) | (~(p.hi4 ^ x) & u);
-    return ge & le & H;
+    const uint32_t b = x & ~H;
+    const uint32_t t = mad_fma(b, p.one, p.addK);
+    const uint32_t u = mad_fma(b, p.neg_one, p.hiH);
+    uint32_t r;
+    if (kVariant == 0) r = ~x & t & u;
+    else if (kVariant == 2) r = (x & u) | (~x & t);
+    else if (kVariant == 3) r = x & t & u;
+    else r = 0;
+    return r & H;
 }
 
-// 16-bit mask of the 16 bytes of v (bit i <-> byte i in memory order). The multiply gathers the
-// four bit-7 flags of a word into its top nibble (bit 7+8k lands on 28+k, no carries collide).
+// 16-bit mask of the 16 bytes of v (bit i <-> byte i in memory order)
+template <int kVariant>
 __device__ __forceinline__ uint32_t range_mask16(uint4 v, const Pred &p) {
-    const uint32_t M = 0x00204081u;
-    uint32_t p0 = inrange_msb(v.x, p) * M;
-    uint32_t p1 = inrange_msb(v.y, p) * M;
-    uint32_t p2 = inrange_msb(v.z, p) * M;
-    uint32_t p3 = inrange_msb(v.w, p) * M;
-    return __umulhi(p0, 1u << 4) | (__umulhi(p1, 1u << 8) & 0xF0u) | (__umulhi(p2, 1u << 12) & 0xF00u) |
-           (__umulhi(p3, 1u << 16) & 0xF000u);
+    uint32_t g0 = __dp4a(inrange_msb<kVariant>(v.x, p), 0x08040201u, 0u);
+    g0 = __dp4a(inrange_msb<kVariant>(v.y, p), 0x80402010u, g0);
+    uint32_t g1 = __dp4a(inrange_msb<kVariant>(v.z, p), 0x08040201u, 0u);
+    g1 = __dp4a(inrange_msb<kVariant>(v.w, p), 0x80402010u, g1);
+    return __umulhi(g1 * 256u + g0, 1u << 25);   // both groups sit at bit 7
 }
+
+// run `body(std::integral_constant<int, variant>)` for the launch's predicate variant
+#define AQP_PRED_SWITCH(P, BODY)                                        \
+    switch ((P).variant) {                                              \
+        case 0: { constexpr int kVariant = 0; BODY } break;             \
+        case 2: { constexpr int kVariant = 2; BODY } break;             \
+        case 3: { constexpr int kVariant = 3; BODY } break;             \
+        default: { constexpr int kVariant = 1; BODY } break;            \
+    }
 
 // ---------------------------------------------------------------------------------------------
 // bitvector scan (kCount: also emit the number of matches of every 16384-value tile)
@@ -94,10 +118,9 @@ __device__ __forceinline__ uint4 ld_stream_v4_hint(const uint4 *p, uint64_t pol)
     return r;
 }
 
-template <bool kCount>
-__global__ void __launch_bounds__(kScanThreads)
-bitvector_scan_kernel(const uint4 *__restrict__ in, size_t nvec, uint64_t *__restrict__ out, Pred p,
-                      uint32_t *__restrict__ tile_counts) {
+template <bool kCount, int kVariant>
+__device__ __forceinline__ void bitvector_scan_body(const uint4 *__restrict__ in, size_t nvec, uint64_t *__restrict__ out,
+                                                    const Pred &p, uint32_t *__restrict__ tile_counts) {
     const uint64_t pol = l2_evict_first_policy();
     const size_t ntiles = (nvec + kScanTileVec - 1) / kScanTileVec;
     for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -112,7 +135,7 @@ bitvector_scan_kernel(const uint4 *__restrict__ in, size_t nvec, uint64_t *__res
 #pragma unroll
         for (int j = 0; j < kScanUnroll; ++j) {
             size_t q = base + (size_t) j * kScanThreads;
-            uint32_t m16 = range_mask16(v[j], p);
+            uint32_t m16 = range_mask16<kVariant>(v[j], p);
             if (kCount) c += q < nvec ? __popc(m16) : 0;
             // four neighbouring lanes hold the four 16-bit quarters of one output word
             uint32_t m32 = m16 | (__shfl_down_sync(0xffffffffu, m16, 1) << 16);
@@ -125,12 +148,18 @@ bitvector_scan_kernel(const uint4 *__restrict__ in, size_t nvec, uint64_t *__res
         }
     }
 }
+template <bool kCount>
+__global__ void __launch_bounds__(kScanThreads)
+bitvector_scan_kernel(const uint4 *__restrict__ in, size_t nvec, uint64_t *__restrict__ out, Pred p,
+                      uint32_t *__restrict__ tile_counts) {
+    AQP_PRED_SWITCH(p, (bitvector_scan_body<kCount, kVariant>(in, nvec, out, p, tile_counts));)
+}
 
 // ---------------------------------------------------------------------------------------------
 // count
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kScanThreads)
-scan_count_kernel(const uint4 *__restrict__ in, size_t nvec, unsigned long long *__restrict__ count, Pred p) {
+template <int kVariant>
+__device__ __forceinline__ uint32_t scan_count_body(const uint4 *__restrict__ in, size_t nvec, const Pred &p) {
     const size_t ntiles = (nvec + kScanTileVec - 1) / kScanTileVec;
     uint32_t c = 0;
     for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -144,10 +173,16 @@ scan_count_kernel(const uint4 *__restrict__ in, size_t nvec, unsigned long long 
 #pragma unroll
         for (int j = 0; j < kScanUnroll; ++j) {
             size_t q = base + (size_t) j * kScanThreads;
-            uint32_t m16 = range_mask16(v[j], p);
+            uint32_t m16 = range_mask16<kVariant>(v[j], p);
             c += q < nvec ? __popc(m16) : 0;
         }
     }
+    return c;
+}
+__global__ void __launch_bounds__(kScanThreads)
+scan_count_kernel(const uint4 *__restrict__ in, size_t nvec, unsigned long long *__restrict__ count, Pred p) {
+    uint32_t c = 0;
+    AQP_PRED_SWITCH(p, c = scan_count_body<kVariant>(in, nvec, p);)
     __shared__ uint32_t wsum[kScanThreads / 32];
     c = warp_sum(c);
     if (lane_id() == 0) wsum[threadIdx.x >> 5] = c;
@@ -163,12 +198,12 @@ scan_count_kernel(const uint4 *__restrict__ in, size_t nvec, unsigned long long 
 // sum of the values in range (SIMD512::sum, SIMD512.cpp:34-86): bytes out of range are masked to zero, the four
 // bytes of a word are added with one dp4a
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kScanThreads)
-scan_sum_kernel(const uint4 *__restrict__ in, size_t nvec, unsigned long long *__restrict__ sum, Pred p) {
+template <int kVariant>
+__device__ __forceinline__ unsigned long long scan_sum_body(const uint4 *__restrict__ in, size_t nvec, const Pred &p) {
     const size_t ntiles = (nvec + kScanTileVec - 1) / kScanTileVec;
     unsigned long long acc = 0;
     auto word_sum = [&](uint32_t x) {
-        const uint32_t keep = (inrange_msb(x, p) >> 7) * 0xFFu;   // 0xFF in every byte that is in range
+        const uint32_t keep = (inrange_msb<kVariant>(x, p) >> 7) * 0xFFu;   // 0xFF in every byte that is in range
         return __dp4a(x & keep, 0x01010101u, 0u);
     };
     for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -187,6 +222,12 @@ scan_sum_kernel(const uint4 *__restrict__ in, size_t nvec, unsigned long long *_
         }
         acc += c;
     }
+    return acc;
+}
+__global__ void __launch_bounds__(kScanThreads)
+scan_sum_kernel(const uint4 *__restrict__ in, size_t nvec, unsigned long long *__restrict__ sum, Pred p) {
+    unsigned long long acc = 0;
+    AQP_PRED_SWITCH(p, acc = scan_sum_body<kVariant>(in, nvec, p);)
     __shared__ unsigned long long wsum[kScanThreads / 32];
     acc = warp_sum(acc);
     if (lane_id() == 0) wsum[threadIdx.x >> 5] = acc;
@@ -507,6 +548,317 @@ expand_dense_rowids_kernel(const uint64_t *__restrict__ bv, size_t nwords, const
 }
 
 // ---------------------------------------------------------------------------------------------
+// single-pass row-id scan (the default): one kernel reads the column once and writes the ids, 1 + 8*sel bytes per
+// value of HBM traffic and no bitvector scratch.
+//
+// A CTA takes macro-tiles in ticket order. Per macro-tile every warp streams its own contiguous sub-range in 1 KiB
+// rounds (one 256-bit load per lane: 32 consecutive values -> one 32-bit match mask per lane, kept in shared
+// memory), the CTA publishes its match count and learns the number of matches in front of it by decoupled look-back
+// over the status words of earlier tiles, then every warp expands ITS OWN rounds on its own: a warp scan of the
+// 32 popcounts gives each lane its first slot, the lane walks its set bits into the warp's private 1024-entry
+// window (16-bit round-relative positions), and the warp copies the window out front to back, so every store
+// instruction writes 32 consecutive ids. No block barrier inside the expansion (the two-pass expand_rowids_kernel
+// spent 9 stall cycles per issue at its barriers); three block barriers per macro-tile in total.
+// Look-back: status word = flag (2 bits: 0 invalid, 1 tile aggregate, 2 inclusive prefix) | value, one 64-bit
+// relaxed store/load each, so flag and value travel together and no fence is needed. One warp reads
+// kLookWindows x 32 predecessors per round trip. Macro-tiles are large (>= 64 Ki values) so that tiles are
+// created more slowly than the prefix front can move (a first version with 16 Ki-value tiles was 3-5x slower
+// than two passes for exactly that reason).
+// ---------------------------------------------------------------------------------------------
+struct U32x8 {
+    uint32_t w[8];
+};
+__device__ __forceinline__ U32x8 ld_stream_v8_hint(const void *p, uint64_t pol) {   // SASS: LDG.E.256
+    U32x8 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]),
+                   "=r"(r.w[7])
+                 : "l"(p), "l"(pol));
+    return r;
+}
+// 32-bit mask of a lane's 32 consecutive bytes: four 8-bit dp4a groups (each at bit 7) put together on the FMA pipe
+template <int kVariant>
+__device__ __forceinline__ uint32_t range_mask32(const U32x8 &v, const Pred &p) {
+    uint32_t g[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        g[k] = __dp4a(inrange_msb<kVariant>(v.w[2 * k], p), 0x08040201u, 0u);
+        g[k] = __dp4a(inrange_msb<kVariant>(v.w[2 * k + 1], p), 0x80402010u, g[k]);
+    }
+    const uint32_t hi = g[3] * (1u << 17) + g[2] * (1u << 9);   // groups 2, 3 -> bits 16..31
+    return __umulhi(g[1] * 256u + g[0], 1u << 25) + hi;        // groups 0, 1 -> bits 0..15
+}
+
+constexpr uint64_t kStatAggregate = 1ull << 62, kStatInclusive = 2ull << 62, kStatValueMask = (1ull << 62) - 1;
+constexpr int kLookWindows = 4;   // status words per lane and round trip of the look-back
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// number of matches in tiles [0, tile): called by one whole warp, tile > 0
+__device__ __forceinline__ uint64_t lookback_exclusive(const unsigned long long *status, uint32_t tile) {
+    const unsigned lane = lane_id();
+    uint64_t sum = 0;
+    int64_t d = (int64_t) tile - 1;   // index of the nearest status word not yet accounted for
+    for (;;) {
+        unsigned long long s[kLookWindows];
+#pragma unroll
+        for (int k = 0; k < kLookWindows; ++k) {
+            const int64_t idx = d - k * 32 - (int64_t) lane;
+            s[k] = idx >= 0 ? ld_relaxed_u64(status + idx) : kStatInclusive;   // in front of tile 0: prefix 0
+        }
+        // windows nearest first; state 0 = all 32 were aggregates (go on), 1 = reached an inclusive prefix (done),
+        // 2 = met a tile that has not published yet (poll again from there)
+        int state = 0;
+        auto window = [&](const unsigned long long sk, const int k) {
+            const uint32_t flag = (uint32_t) (sk >> 62);
+            const unsigned inval = __ballot_sync(0xffffffffu, flag == 0);
+            const unsigned incl = __ballot_sync(0xffffffffu, flag == 2);
+            const unsigned first_inval = inval ? (unsigned) __ffs(inval) - 1 : 32u;
+            const unsigned first_incl = incl ? (unsigned) __ffs(incl) - 1 : 32u;
+            const unsigned upto = min(first_inval, first_incl);   // aggregates nearer than this lane count
+            const uint32_t val32 = (uint32_t) sk;                 // an aggregate is at most one tile's worth of matches
+            sum += __reduce_add_sync(0xffffffffu, lane < upto ? val32 : 0u);
+            if (first_incl < first_inval) {
+                const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t) sk, first_incl);
+                const uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t) (sk >> 32), first_incl);
+                sum += (((uint64_t) hi << 32) | lo) & kStatValueMask;
+                state = 1;
+            } else if (first_inval < 32u) {
+                d -= k * 32 + (int64_t) first_inval;
+                state = 2;
+            }
+        };
+        window(s[0], 0);
+        if (state == 0) window(s[1], 1);
+        if (state == 0) window(s[2], 2);
+        if (state == 0) window(s[3], 3);
+        static_assert(kLookWindows == 4, "unrolled by hand");
+        if (state == 1) return sum;
+        if (state == 0) d -= kLookWindows * 32;
+    }
+}
+
+constexpr size_t kFusedMinTileVals = 65536;   // smallest macro-tile any geometry uses (sizes the status array)
+constexpr int kFusedRoundVals = 1024;   // values per warp round: 32 lanes x 32 bytes
+constexpr int kFusedBatch = 4;          // 256-bit loads in flight per lane
+// mask words of one warp and tile: entry i (= round * 32 + lane) covers values [32 i, 32 i + 32) of the warp's
+// sub-range; stored at i + i / 32 so that both access patterns are conflict-free: the streaming phase writes entry
+// r * 32 + lane, the expansion reads G consecutive entries per lane (G = 1, 2, 4, 8, 16)
+__device__ __forceinline__ uint32_t mask_slot(uint32_t i) { return i + (i >> 5); }
+static size_t fused_smem_bytes(int warps, int rounds) {   // two mask buffers + one window per warp
+    return (size_t) 2 * warps * (rounds * 33) * sizeof(uint32_t) + (size_t) warps * kFusedRoundVals * sizeof(uint16_t);
+}
+
+// The CTA is software-pipelined over its macro-tiles: it streams tile k+1 (and publishes its count) BEFORE it looks
+// back for tile k, so by the time the look-back runs every earlier tile has long published its count and the
+// look-back is a few L2 round trips, never a wait (the unpipelined first version lost 6-9 us per tile waiting for
+// the slowest of its ~50 nearest predecessors). The mask buffers alternate; masks are warp-private, only the
+// per-warp counts, the prefix and the ticket cross warps (3 block barriers per tile).
+//
+// Expansion of a warp's sub-range (kRounds * 1024 values, W matches): rounds are taken in groups of G = 16, 8, 4, 2
+// or 1 - the largest group whose matches fit the warp's 1024-entry window - and lane l owns the G consecutive mask
+// words l*G .. l*G+G-1 of the group, i.e. 32*G consecutive values: one popcount sum and ONE warp scan per group give
+// every lane its first slot, the lane walks its words' set bits into the window, the warp copies the window out in
+// order. Sparse data costs ~270 instructions per 16 Ki values this way (a scan per 1 KiB round cost 1100 and made
+// the 0.1 % case instruction-bound); clustered matches (the reference's tiled column: hi+1 consecutive matches in
+// every 256 values) are balanced whenever a lane covers a multiple of 256 values. For G = 1 and very uneven lanes the
+// whole warp takes one lane's word at a time instead (lane l tests bit l).
+template <int kEmit, int kWarps, int kRounds, bool kV8>
+__global__ void __launch_bounds__(kWarps * 32, 1024 / (kWarps * 32))
+rowid_scan_fused_kernel(const uint8_t *__restrict__ in, size_t n, Pred p, EmitArgs ea, void *__restrict__ out,
+                        uint64_t out_capacity, unsigned long long *__restrict__ status, unsigned int *__restrict__ ticket,
+                        unsigned long long *__restrict__ d_count, uint32_t ntiles) {
+    constexpr int kWarpVals = kRounds * kFusedRoundVals;
+    constexpr size_t kTileVals = (size_t) kWarps * kWarpVals;
+    constexpr int kWarpWords = kRounds * 33;             // padded mask words per warp and buffer
+    constexpr int kBufWords = kWarps * kWarpWords;
+    static_assert(kRounds % kFusedBatch == 0, "whole load batches");
+    static_assert(kRounds <= 16, "a lane owns at most 16 mask words of a group");
+    extern __shared__ __align__(16) unsigned char fused_smem[];
+    uint32_t *masks = reinterpret_cast<uint32_t *>(fused_smem);   // [buffer][warp][padded entry]
+    __shared__ uint32_t wtot[2][kWarps];
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_prefix;
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    const unsigned lt = lanemask_lt();
+    uint16_t *win = reinterpret_cast<uint16_t *>(masks + 2 * kBufWords) + (size_t) warp * kFusedRoundVals;
+    const uint64_t pol = l2_evict_first_policy();
+
+    // predicate over this warp's sub-range of a tile -> one 32-bit mask per lane and round, warp count in wtot
+    auto stream = [&](const uint32_t tile, const int buf) {
+        const size_t wbase = (size_t) tile * kTileVals + (size_t) warp * kWarpVals;
+        uint32_t *my_masks = masks + buf * kBufWords + warp * kWarpWords + lane;   // entry r*32+lane -> + r*33
+        const uint8_t *src = in + wbase + lane * 32;
+        uint32_t cnt = 0;
+        auto load = [&](const uint8_t *q) {
+            if (kV8) return ld_stream_v8_hint(q, pol);
+            const uint4 a = ld_stream_v4_hint(reinterpret_cast<const uint4 *>(q), pol);
+            const uint4 c = ld_stream_v4_hint(reinterpret_cast<const uint4 *>(q) + 1, pol);
+            return U32x8{{a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w}};
+        };
+        if (wbase + kWarpVals <= n) {   // whole sub-range inside the column: no per-load bounds
+            AQP_PRED_SWITCH(p,
+                _Pragma("unroll 1")
+                for (int b = 0; b < kRounds; b += kFusedBatch) {
+                    U32x8 v[kFusedBatch];
+                    _Pragma("unroll")
+                    for (int j = 0; j < kFusedBatch; ++j) v[j] = load(src + (size_t) (b + j) * kFusedRoundVals);
+                    _Pragma("unroll")
+                    for (int j = 0; j < kFusedBatch; ++j) {
+                        const uint32_t m = range_mask32<kVariant>(v[j], p);
+                        my_masks[(b + j) * 33] = m;
+                        cnt += __popc(m);
+                    }
+                })
+        } else {   // the column's last tile: a lane's 32 bytes are inside or outside as a whole (n % 64 == 0)
+            AQP_PRED_SWITCH(p,
+                _Pragma("unroll 1")
+                for (int r = 0; r < kRounds; ++r) {
+                    const size_t pos = wbase + (size_t) r * kFusedRoundVals + lane * 32;
+                    uint32_t m = 0;
+                    if (pos < n) m = range_mask32<kVariant>(load(in + pos), p);
+                    my_masks[r * 33] = m;
+                    cnt += __popc(m);
+                })
+        }
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (lane == 0) wtot[buf][warp] = cnt;
+    };
+    // warp 0: make the tile's count visible to later tiles (tile 0 has nothing in front of it)
+    auto publish_count = [&](const uint32_t tile, const int buf) {
+        const uint32_t total = __reduce_add_sync(0xffffffffu, lane < (unsigned) kWarps ? wtot[buf][lane] : 0u);
+        if (lane == 0) st_relaxed_u64(status + tile, (tile == 0 ? kStatInclusive : kStatAggregate) | total);
+    };
+
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    uint32_t cur = s_tile;
+    if (cur >= ntiles) return;
+    int cb = 0;
+    stream(cur, cb);
+    __syncthreads();
+    if (warp == 0) publish_count(cur, cb);
+    uint32_t next_ticket = 0;
+    if (threadIdx.x == 0) next_ticket = atomicAdd(ticket, 1u);
+
+    for (;;) {
+        if (threadIdx.x == 0) s_tile = next_ticket;
+        __syncthreads();   // (A) ticket visible; every warp is done expanding the tile before `cur`
+        const uint32_t nxt = s_tile;
+        if (nxt < ntiles) stream(nxt, cb ^ 1);
+        __syncthreads();   // (B) counts of `nxt` complete
+        if (warp == 0) {
+            if (nxt < ntiles) publish_count(nxt, cb ^ 1);
+            const uint32_t total = __reduce_add_sync(0xffffffffu, lane < (unsigned) kWarps ? wtot[cb][lane] : 0u);
+            uint64_t prefix = 0;
+            if (cur > 0) {
+                prefix = lookback_exclusive(status, cur);
+                if (lane == 0) st_relaxed_u64(status + cur, kStatInclusive | (prefix + total));
+            }
+            if (lane == 0) {
+                s_prefix = prefix;
+                if (cur == ntiles - 1) *d_count = prefix + total;
+            }
+        }
+        __syncthreads();   // (C) prefix of `cur` known
+        if (threadIdx.x == 0 && nxt < ntiles) next_ticket = atomicAdd(ticket, 1u);   // consumed after the expansion
+
+        // ---- expand `cur`: every warp on its own sub-range
+        uint32_t before = 0;
+#pragma unroll
+        for (int k = 0; k < kWarps; ++k) before += (k < (int) warp) ? wtot[cb][k] : 0u;
+        const uint32_t wcount = wtot[cb][warp];
+        uint64_t g = s_prefix + before;   // output slot of this warp's next id
+        if (wcount != 0 && g < out_capacity) {
+            const size_t wbase = (size_t) cur * kTileVals + (size_t) warp * kWarpVals;
+            const uint32_t *wm = masks + cb * kBufWords + warp * kWarpWords;
+            // largest group whose expected matches fit the window with some slack
+            uint32_t G = kRounds;
+            while (G > 1 && wcount * G > 896u * kRounds) G >>= 1;
+            uint32_t r = 0;
+            while (r < (uint32_t) kRounds) {
+                const uint32_t e0 = r * 32 + G * lane;   // my first entry of this group
+                uint32_t c = 0;
+                for (uint32_t k = 0; k < G; ++k) c += __popc(wm[mask_slot(e0 + k)]);
+                const uint32_t incl = warp_incl_scan(c);
+                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                if (total > (uint32_t) kFusedRoundVals) {   // denser than the sub-range's average: smaller groups
+                    G >>= 1;
+                    continue;
+                }
+                const uint64_t pos0 = wbase + (size_t) r * kFusedRoundVals;   // chunk-relative position of the group
+                if (total == (uint32_t) kFusedRoundVals && G == 1) {   // a full round needs no window
+                    if (g + kFusedRoundVals <= out_capacity) {
+#pragma unroll 8
+                        for (uint32_t t = lane; t < (uint32_t) kFusedRoundVals; t += 32) emit<kEmit>(out, g + t, pos0 + t, ea);
+                    } else {
+                        for (uint32_t t = lane; t < (uint32_t) kFusedRoundVals; t += 32)
+                            if (g + t < out_capacity) emit<kEmit>(out, g + t, pos0 + t, ea);
+                    }
+                } else if (total) {
+                    const uint32_t excl = incl - c;
+                    bool by_word = false;
+                    if (G == 1) {
+                        const uint32_t maxc = __reduce_max_sync(0xffffffffu, c);
+                        const uint32_t nz = __popc(__ballot_sync(0xffffffffu, c != 0));
+                        by_word = 9u * maxc > 11u * nz;
+                    }
+                    if (!by_word) {   // every lane walks the set bits of its own words
+                        uint32_t slot = excl, k = 0, bits = 0, vbase = (G * lane) * 32 - 32;
+                        for (;;) {
+                            if (bits == 0) {
+                                if (k == G) break;
+                                bits = wm[mask_slot(e0 + k)];
+                                ++k;
+                                vbase += 32;
+                                continue;
+                            }
+                            win[slot++] = (uint16_t) (vbase + __ffs(bits) - 1);
+                            bits &= bits - 1;
+                        }
+                    } else {          // one lane's word at a time, lane l tests bit l
+                        const uint32_t m = wm[mask_slot(e0)];
+                        for (unsigned mm = __ballot_sync(0xffffffffu, m != 0); mm; mm &= mm - 1) {
+                            const int src = __ffs(mm) - 1;
+                            const uint32_t word = __shfl_sync(0xffffffffu, m, src);
+                            const uint32_t off = __shfl_sync(0xffffffffu, excl, src);
+                            if ((word >> lane) & 1u) win[off + __popc(word & lt)] = (uint16_t) (src * 32 + lane);
+                        }
+                    }
+                    __syncwarp();
+                    if (g + total <= out_capacity) {
+                        uint32_t t = lane;
+                        for (; t + 96 < total; t += 128) {
+                            const uint32_t w0 = win[t], w1 = win[t + 32], w2 = win[t + 64], w3 = win[t + 96];
+                            emit<kEmit>(out, g + t, pos0 + w0, ea);
+                            emit<kEmit>(out, g + t + 32, pos0 + w1, ea);
+                            emit<kEmit>(out, g + t + 64, pos0 + w2, ea);
+                            emit<kEmit>(out, g + t + 96, pos0 + w3, ea);
+                        }
+                        for (; t < total; t += 32) emit<kEmit>(out, g + t, pos0 + win[t], ea);
+                    } else {
+                        for (uint32_t t = lane; t < total; t += 32)
+                            if (g + t < out_capacity) emit<kEmit>(out, g + t, pos0 + win[t], ea);
+                    }
+                    __syncwarp();
+                }
+                g += total;
+                r += G;
+            }
+        }
+        if (nxt >= ntiles) break;
+        cur = nxt;
+        cb ^= 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // column generators (Scan-Micro-Benchmarks/shared_libraries/SharedHeaders/include/Allocator.hpp:95-109)
 // ---------------------------------------------------------------------------------------------
 __global__ void fill_tiled_kernel(uint8_t *data, size_t n, uint64_t pos_begin) {
@@ -579,7 +931,49 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t) 255; }
 size_t index_scan_scratch_bytes(size_t n) {
     size_t chunk = n < kIndexChunkVals ? n : kIndexChunkVals;
     size_t tiles = (chunk + kExpandTileVals - 1) / kExpandTileVals + 1;
-    return align256(chunk / 8 + 64) + align256(tiles * 4) + align256(tiles * 8) + align256((2 * tiles + 2) * 4) + 256;
+    const size_t two_pass = align256(chunk / 8 + 64) + align256(tiles * 4) + align256(tiles * 8) + align256((2 * tiles + 2) * 4) + 256;
+    const size_t fused = 256 + align256((n / kFusedMinTileVals + 2) * 8);   // ticket + one status word per macro-tile
+    return two_pass > fused ? two_pass : fused;
+}
+
+// ---- single-pass path: geometry (warps per CTA x rounds per warp) picked by size, B200_AQP_SCAN_GEOM=WxR overrides
+template <int kEmit, int kWarps, int kRounds>
+static int launch_fused(const uint8_t *d_data, size_t n, const Pred &p, const EmitArgs &ea, void *d_out, uint64_t cap,
+                        uint64_t *d_count, void *d_scratch, cudaStream_t st) {
+    constexpr size_t kTileVals = (size_t) kWarps * kRounds * kFusedRoundVals;
+    static_assert(kTileVals >= kFusedMinTileVals, "scratch is sized for tiles of at least kFusedMinTileVals");
+    const uint32_t ntiles = (uint32_t) ((n + kTileVals - 1) / kTileVals);
+    unsigned int *ticket = static_cast<unsigned int *>(d_scratch);
+    unsigned long long *status = reinterpret_cast<unsigned long long *>(static_cast<unsigned char *>(d_scratch) + 256);
+    AQP_CUDA_OK(cudaMemsetAsync(d_scratch, 0, 256 + (size_t) ntiles * 8, st));
+    const size_t smem = fused_smem_bytes(kWarps, kRounds);
+    const bool v8 = (reinterpret_cast<uintptr_t>(d_data) & 31u) == 0;
+    auto kern = v8 ? rowid_scan_fused_kernel<kEmit, kWarps, kRounds, true> : rowid_scan_fused_kernel<kEmit, kWarps, kRounds, false>;
+    AQP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    const uint32_t resident = (uint32_t) kNumSMs * (1024 / (kWarps * 32));
+    kern<<<ntiles < resident ? ntiles : resident, kWarps * 32, smem, st>>>(
+        d_data, n, p, ea, d_out, cap, status, ticket, reinterpret_cast<unsigned long long *>(d_count), ntiles);
+    AQP_LAUNCHED();
+    AQP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <int kEmit>
+static int fused_scan_device(const uint8_t *d_data, size_t n, const Pred &p, const EmitArgs &ea, void *d_out, uint64_t cap,
+                             uint64_t *d_count, void *d_scratch, cudaStream_t st) {
+    int w = 16, r = n >= ((size_t) 1 << 28) ? 16 : 4;
+    if (const char *e = getenv("B200_AQP_SCAN_GEOM")) sscanf(e, "%dx%d", &w, &r);
+#define AQP_GEOM(W, R) \
+    if (w == W && r == R) return launch_fused<kEmit, W, R>(d_data, n, p, ea, d_out, cap, d_count, d_scratch, st)
+    AQP_GEOM(16, 16);
+    AQP_GEOM(16, 8);
+    AQP_GEOM(16, 4);
+    AQP_GEOM(8, 8);
+    AQP_GEOM(8, 16);
+    AQP_GEOM(32, 8);
+#undef AQP_GEOM
+    set_error("B200_AQP_SCAN_GEOM: unknown geometry");
+    return -1;
 }
 
 // emit = kEmitRowId / kEmitValue / kEmitDict (d_dict: 256 int64 on the device); d_out holds cap elements of the
@@ -594,6 +988,17 @@ static int emit_scan_device(int emit_kind, uint8_t lo, uint8_t hi, const uint8_t
     AQP_CUDA_OK(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
     n = n / 64 * 64;
     if (n == 0) return 0;
+    static const bool two_pass = [] {
+        const char *e = getenv("B200_AQP_INDEX_SCAN");   // A/B switch: "twopass" = bitvector scratch + expansion kernels
+        return e && !strcmp(e, "twopass");
+    }();
+    if (!two_pass) {
+        const Pred pf = make_pred(lo, hi);
+        const EmitArgs eaf{id_base, d_data, d_dict};
+        if (emit_kind == kEmitRowId) return fused_scan_device<kEmitRowId>(d_data, n, pf, eaf, d_out, cap, d_count, d_scratch, st);
+        if (emit_kind == kEmitValue) return fused_scan_device<kEmitValue>(d_data, n, pf, eaf, d_out, cap, d_count, d_scratch, st);
+        return fused_scan_device<kEmitDict>(d_data, n, pf, eaf, d_out, cap, d_count, d_scratch, st);
+    }
     const size_t chunk_cap = n < kIndexChunkVals ? n : kIndexChunkVals;
     const size_t tiles_cap = (chunk_cap + kExpandTileVals - 1) / kExpandTileVals + 1;
     unsigned char *sb = static_cast<unsigned char *>(d_scratch);
