@@ -641,220 +641,297 @@ __device__ __forceinline__ uint64_t lookback_exclusive(const unsigned long long 
         static_assert(kLookWindows == 4, "unrolled by hand");
         if (state == 1) return sum;
         if (state == 0) d -= kLookWindows * 32;
+        else __nanosleep(100);   // a predecessor is still streaming: do not hammer the L2 while it finishes
     }
 }
 
-constexpr size_t kFusedMinTileVals = 65536;   // smallest macro-tile any geometry uses (sizes the status array)
+constexpr size_t kFusedMinTileVals = 7 * 4 * 1024;   // smallest macro-tile any geometry uses (sizes the status array)
 constexpr int kFusedRoundVals = 1024;   // values per warp round: 32 lanes x 32 bytes
 constexpr int kFusedBatch = 4;          // 256-bit loads in flight per lane
+// Where a group of matches goes: the group's first output slot and the value position its relative offsets count
+// from are folded into two 64-bit bases once per group, so that a match costs one 32-bit multiply-add for the
+// address (IMAD.WIDE) and one 64-bit add for the id.
+template <int kEmit>
+struct GroupOut {
+    unsigned char *o;        // address of output slot g
+    uint64_t idb;            // kEmitRowId: id of relative position 0
+    const uint8_t *dp;       // kEmitValue / kEmitDict: the column at relative position 0
+    const int64_t *dict;
+    __device__ __forceinline__ GroupOut(void *out, uint64_t g, uint64_t pos0, const EmitArgs &ea)
+        : o(static_cast<unsigned char *>(out) + g * (kEmit == kEmitValue ? 4 : 8)), idb(ea.id_base + pos0), dp(ea.data + pos0),
+          dict(ea.dict) {}
+    __device__ __forceinline__ void put(uint32_t t, uint32_t rel) const {   // match at relative position rel -> slot g + t
+        if (kEmit == kEmitRowId) st_stream_u64(reinterpret_cast<uint64_t *>(o) + t, idb + rel);
+        else if (kEmit == kEmitValue) st_stream_u32(reinterpret_cast<uint32_t *>(o) + t, __ldg(dp + rel));
+        else st_stream_u64(reinterpret_cast<uint64_t *>(o) + t, (uint64_t) __ldg(dict + __ldg(dp + rel)));
+    }
+};
+
 // mask words of one warp and tile: entry i (= round * 32 + lane) covers values [32 i, 32 i + 32) of the warp's
 // sub-range; stored at i + i / 32 so that both access patterns are conflict-free: the streaming phase writes entry
 // r * 32 + lane, the expansion reads G consecutive entries per lane (G = 1, 2, 4, 8, 16)
 __device__ __forceinline__ uint32_t mask_slot(uint32_t i) { return i + (i >> 5); }
-static size_t fused_smem_bytes(int warps, int rounds) {   // two mask buffers + one window per warp
-    return (size_t) 2 * warps * (rounds * 33) * sizeof(uint32_t) + (size_t) warps * kFusedRoundVals * sizeof(uint16_t);
+static size_t fused_smem_bytes(int warps, int rounds) {   // per worker warp: two mask buffers + one window
+    return (size_t) (warps - 1) * (2 * rounds * 33 * sizeof(uint32_t) + kFusedRoundVals * sizeof(uint16_t));
 }
 
-// The CTA is software-pipelined over its macro-tiles: it streams tile k+1 (and publishes its count) BEFORE it looks
-// back for tile k, so by the time the look-back runs every earlier tile has long published its count and the
-// look-back is a few L2 round trips, never a wait (the unpipelined first version lost 6-9 us per tile waiting for
-// the slowest of its ~50 nearest predecessors). The mask buffers alternate; masks are warp-private, only the
-// per-warp counts, the prefix and the ticket cross warps (3 block barriers per tile).
+// CTA = kWarps - 1 worker warps + 1 control warp, NO block barrier after start-up; the warps meet through mbarriers
+// that are normally complete long before anyone waits on them:
+//   control  iteration i: take the ticket of tile T[i+1] (-> bar_ticket), look back for T[i-1], whose count it
+//            published an iteration ago (-> s_prefix, bar_prefix), wait for the workers' counts of T[i]
+//            (bar_counts) and publish their sum to later tiles
+//   worker   iteration i: stream its sub-range of T[i] (predicate -> masks in shared memory, count -> wtot,
+//            arrive on bar_counts), THEN expand its sub-range of T[i-1] from the other mask buffer
+// so a look-back has a whole tile's streaming time to finish (the first, unpipelined version lost 6-9 us per tile
+// waiting for the slowest of its ~50 nearest predecessors; with the look-back in a worker warp between two block
+// barriers 18 % of the stall samples of the 0.1 % case were barrier waits). Workers may drift apart by one tile.
+// Slots (ticket, counts, prefix) live in a ring of kFusedStages; the control warp cannot run more than two
+// iterations ahead of the slowest worker (it waits for all counts of T[i]), so four stages never alias.
+//
+// Streaming keeps kFusedBatch 256-bit loads per lane in flight on a rolling basis (a register is reloaded for
+// round r+4 as soon as round r's mask is computed).
 //
 // Expansion of a warp's sub-range (kRounds * 1024 values, W matches): rounds are taken in groups of G = 16, 8, 4, 2
 // or 1 - the largest group whose matches fit the warp's 1024-entry window - and lane l owns the G consecutive mask
 // words l*G .. l*G+G-1 of the group, i.e. 32*G consecutive values: one popcount sum and ONE warp scan per group give
-// every lane its first slot, the lane walks its words' set bits into the window, the warp copies the window out in
-// order. Sparse data costs ~270 instructions per 16 Ki values this way (a scan per 1 KiB round cost 1100 and made
-// the 0.1 % case instruction-bound); clustered matches (the reference's tiled column: hi+1 consecutive matches in
-// every 256 values) are balanced whenever a lane covers a multiple of 256 values. For G = 1 and very uneven lanes the
-// whole warp takes one lane's word at a time instead (lane l tests bit l).
+// every lane its first slot, the lane walks the set bits of its non-empty words into the window, the warp copies
+// the window out in order. Sparse data costs ~150 instructions per 16 Ki values this way (a scan per 1 KiB round
+// cost 1100 and made the 0.1 % case instruction-bound); clustered matches (the reference's tiled column: hi+1
+// consecutive matches in every 256 values) are balanced whenever a lane covers a multiple of 256 values. For G = 1
+// and very uneven lanes the whole warp takes one lane's word at a time instead (lane l tests bit l) and stores
+// straight to global memory: a full word leaves as one 256-byte store.
+constexpr int kFusedStages = 4;
 template <int kEmit, int kWarps, int kRounds, bool kV8>
 __global__ void __launch_bounds__(kWarps * 32, 1024 / (kWarps * 32))
 rowid_scan_fused_kernel(const uint8_t *__restrict__ in, size_t n, Pred p, EmitArgs ea, void *__restrict__ out,
                         uint64_t out_capacity, unsigned long long *__restrict__ status, unsigned int *__restrict__ ticket,
                         unsigned long long *__restrict__ d_count, uint32_t ntiles) {
+    constexpr int kWorkers = kWarps - 1;
     constexpr int kWarpVals = kRounds * kFusedRoundVals;
-    constexpr size_t kTileVals = (size_t) kWarps * kWarpVals;
+    constexpr size_t kTileVals = (size_t) kWorkers * kWarpVals;
     constexpr int kWarpWords = kRounds * 33;             // padded mask words per warp and buffer
-    constexpr int kBufWords = kWarps * kWarpWords;
     static_assert(kRounds % kFusedBatch == 0, "whole load batches");
     static_assert(kRounds <= 16, "a lane owns at most 16 mask words of a group");
     extern __shared__ __align__(16) unsigned char fused_smem[];
-    uint32_t *masks = reinterpret_cast<uint32_t *>(fused_smem);   // [buffer][warp][padded entry]
-    __shared__ uint32_t wtot[2][kWarps];
-    __shared__ uint32_t s_tile;
-    __shared__ unsigned long long s_prefix;
+    __shared__ uint64_t bar_ticket[kFusedStages], bar_counts[kFusedStages], bar_prefix[kFusedStages];
+    __shared__ uint32_t s_tile[kFusedStages], want[kFusedStages];
+    __shared__ uint32_t wtot[kFusedStages][kWorkers];
+    __shared__ unsigned long long s_prefix[kFusedStages];
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kFusedStages; ++s) {
+            mbar_init(&bar_ticket[s], 1);
+            mbar_init(&bar_counts[s], kWorkers);
+            mbar_init(&bar_prefix[s], 1);
+            want[s] = 0;
+        }
+        mbar_init_fence();
+    }
+    __syncthreads();
+
+    if (warp == (unsigned) kWorkers) {
+        // ------------------------------------------------------------------ control warp
+        uint32_t t_prev = 0, total_prev = 0;
+        for (uint32_t i = 0;; ++i) {
+            const uint32_t s = i % kFusedStages, ph = (i / kFusedStages) & 1u;
+            if (i > 0) {            // matches in front of T[i-1], whose count went out at the end of the last iteration
+                uint64_t prefix = 0;
+                if (t_prev > 0) {
+                    prefix = lookback_exclusive(status, t_prev);
+                    if (lane == 0) st_relaxed_u64(status + t_prev, kStatInclusive | (prefix + total_prev));
+                }
+                if (lane == 0) {
+                    s_prefix[(i - 1) % kFusedStages] = prefix;
+                    if (t_prev == ntiles - 1) *d_count = prefix + total_prev;
+                    mbar_arrive(&bar_prefix[(i - 1) % kFusedStages]);
+                }
+            }
+            mbar_wait(&bar_ticket[s], ph);   // the first worker that got this far took the ticket of T[i]
+            const uint32_t t_cur = s_tile[s];
+            if (t_cur >= ntiles) break;
+            mbar_wait(&bar_counts[s], ph);   // every worker has streamed T[i]
+            uint32_t total = 0;
+            for (int k = lane; k < kWorkers; k += 32) total += wtot[s][k];
+            total = __reduce_add_sync(0xffffffffu, total);
+            if (lane == 0) st_relaxed_u64(status + t_cur, (t_cur == 0 ? kStatInclusive : kStatAggregate) | total);
+            t_prev = t_cur;
+            total_prev = total;
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- worker warps
     const unsigned lt = lanemask_lt();
-    uint16_t *win = reinterpret_cast<uint16_t *>(masks + 2 * kBufWords) + (size_t) warp * kFusedRoundVals;
+    uint32_t *my_masks = reinterpret_cast<uint32_t *>(fused_smem) + (size_t) warp * 2 * kWarpWords;   // [buffer][padded entry]
+    uint16_t *win = reinterpret_cast<uint16_t *>(reinterpret_cast<uint32_t *>(fused_smem) + (size_t) kWorkers * 2 * kWarpWords) +
+                    (size_t) warp * kFusedRoundVals;
     const uint64_t pol = l2_evict_first_policy();
-
-    // predicate over this warp's sub-range of a tile -> one 32-bit mask per lane and round, warp count in wtot
-    auto stream = [&](const uint32_t tile, const int buf) {
-        const size_t wbase = (size_t) tile * kTileVals + (size_t) warp * kWarpVals;
-        uint32_t *my_masks = masks + buf * kBufWords + warp * kWarpWords + lane;   // entry r*32+lane -> + r*33
-        const uint8_t *src = in + wbase + lane * 32;
-        uint32_t cnt = 0;
-        auto load = [&](const uint8_t *q) {
-            if (kV8) return ld_stream_v8_hint(q, pol);
-            const uint4 a = ld_stream_v4_hint(reinterpret_cast<const uint4 *>(q), pol);
-            const uint4 c = ld_stream_v4_hint(reinterpret_cast<const uint4 *>(q) + 1, pol);
-            return U32x8{{a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w}};
-        };
-        if (wbase + kWarpVals <= n) {   // whole sub-range inside the column: no per-load bounds
-            AQP_PRED_SWITCH(p,
-                _Pragma("unroll 1")
-                for (int b = 0; b < kRounds; b += kFusedBatch) {
-                    U32x8 v[kFusedBatch];
-                    _Pragma("unroll")
-                    for (int j = 0; j < kFusedBatch; ++j) v[j] = load(src + (size_t) (b + j) * kFusedRoundVals);
-                    _Pragma("unroll")
-                    for (int j = 0; j < kFusedBatch; ++j) {
-                        const uint32_t m = range_mask32<kVariant>(v[j], p);
-                        my_masks[(b + j) * 33] = m;
-                        cnt += __popc(m);
-                    }
-                })
-        } else {   // the column's last tile: a lane's 32 bytes are inside or outside as a whole (n % 64 == 0)
-            AQP_PRED_SWITCH(p,
-                _Pragma("unroll 1")
-                for (int r = 0; r < kRounds; ++r) {
-                    const size_t pos = wbase + (size_t) r * kFusedRoundVals + lane * 32;
-                    uint32_t m = 0;
-                    if (pos < n) m = range_mask32<kVariant>(load(in + pos), p);
-                    my_masks[r * 33] = m;
-                    cnt += __popc(m);
-                })
-        }
-        cnt = __reduce_add_sync(0xffffffffu, cnt);
-        if (lane == 0) wtot[buf][warp] = cnt;
-    };
-    // warp 0: make the tile's count visible to later tiles (tile 0 has nothing in front of it)
-    auto publish_count = [&](const uint32_t tile, const int buf) {
-        const uint32_t total = __reduce_add_sync(0xffffffffu, lane < (unsigned) kWarps ? wtot[buf][lane] : 0u);
-        if (lane == 0) st_relaxed_u64(status + tile, (tile == 0 ? kStatInclusive : kStatAggregate) | total);
+    auto load = [&](const uint8_t *q) {
+        if (kV8) return ld_stream_v8_hint(q, pol);
+        const uint4 a = ld_stream_v4_hint(reinterpret_cast<const uint4 *>(q), pol);
+        const uint4 c = ld_stream_v4_hint(reinterpret_cast<const uint4 *>(q) + 1, pol);
+        return U32x8{{a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w}};
     };
 
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    uint32_t cur = s_tile;
-    if (cur >= ntiles) return;
-    int cb = 0;
-    stream(cur, cb);
-    __syncthreads();
-    if (warp == 0) publish_count(cur, cb);
-    uint32_t next_ticket = 0;
-    if (threadIdx.x == 0) next_ticket = atomicAdd(ticket, 1u);
-
-    for (;;) {
-        if (threadIdx.x == 0) s_tile = next_ticket;
-        __syncthreads();   // (A) ticket visible; every warp is done expanding the tile before `cur`
-        const uint32_t nxt = s_tile;
-        if (nxt < ntiles) stream(nxt, cb ^ 1);
-        __syncthreads();   // (B) counts of `nxt` complete
-        if (warp == 0) {
-            if (nxt < ntiles) publish_count(nxt, cb ^ 1);
-            const uint32_t total = __reduce_add_sync(0xffffffffu, lane < (unsigned) kWarps ? wtot[cb][lane] : 0u);
-            uint64_t prefix = 0;
-            if (cur > 0) {
-                prefix = lookback_exclusive(status, cur);
-                if (lane == 0) st_relaxed_u64(status + cur, kStatInclusive | (prefix + total));
+    uint32_t prev_tile = 0;
+    for (uint32_t i = 0;; ++i) {
+        const uint32_t s = i % kFusedStages, ph = (i / kFusedStages) & 1u;
+        // the ticket of T[i] is taken by the first worker that needs it, i.e. as late as possible: tiles then start
+        // streaming in ticket order and a look-back rarely meets a tile that is still being streamed (with tickets
+        // taken an iteration ahead by the control warp, workers of the 50 % case spent 20 % of their instructions
+        // spinning on bar_prefix: a ticket was held for two expansions before its tile was read)
+        if (lane == 0) {
+            const uint32_t a = atomicAdd(&want[s], 1u);
+            if (a == 0) {
+                s_tile[s] = atomicAdd(ticket, 1u);
+                mbar_arrive(&bar_ticket[s]);
             }
-            if (lane == 0) {
-                s_prefix = prefix;
-                if (cur == ntiles - 1) *d_count = prefix + total;
-            }
+            if (a == (uint32_t) kWorkers - 1) want[s] = 0;   // free for iteration i + kFusedStages
         }
-        __syncthreads();   // (C) prefix of `cur` known
-        if (threadIdx.x == 0 && nxt < ntiles) next_ticket = atomicAdd(ticket, 1u);   // consumed after the expansion
+        mbar_wait(&bar_ticket[s], ph);
+        const uint32_t tile = s_tile[s];
 
-        // ---- expand `cur`: every warp on its own sub-range
-        uint32_t before = 0;
+        // ---- stream my sub-range of T[i]: predicate -> one 32-bit mask per lane and round
+        if (tile < ntiles) {
+            const size_t wbase = (size_t) tile * kTileVals + (size_t) warp * kWarpVals;
+            uint32_t *wm = my_masks + (i & 1u) * kWarpWords + lane;   // entry r*32+lane -> + r*33
+            const uint8_t *src = in + wbase + lane * 32;
+            uint32_t cnt = 0;
+            if (wbase + kWarpVals <= n) {   // whole sub-range inside the column: no per-load bounds
+                U32x8 v[kFusedBatch];
 #pragma unroll
-        for (int k = 0; k < kWarps; ++k) before += (k < (int) warp) ? wtot[cb][k] : 0u;
-        const uint32_t wcount = wtot[cb][warp];
-        uint64_t g = s_prefix + before;   // output slot of this warp's next id
-        if (wcount != 0 && g < out_capacity) {
-            const size_t wbase = (size_t) cur * kTileVals + (size_t) warp * kWarpVals;
-            const uint32_t *wm = masks + cb * kBufWords + warp * kWarpWords;
-            // largest group whose expected matches fit the window with some slack
-            uint32_t G = kRounds;
-            while (G > 1 && wcount * G > 896u * kRounds) G >>= 1;
-            uint32_t r = 0;
-            while (r < (uint32_t) kRounds) {
-                const uint32_t e0 = r * 32 + G * lane;   // my first entry of this group
-                uint32_t c = 0;
-                for (uint32_t k = 0; k < G; ++k) c += __popc(wm[mask_slot(e0 + k)]);
-                const uint32_t incl = warp_incl_scan(c);
-                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-                if (total > (uint32_t) kFusedRoundVals) {   // denser than the sub-range's average: smaller groups
-                    G >>= 1;
-                    continue;
-                }
-                const uint64_t pos0 = wbase + (size_t) r * kFusedRoundVals;   // chunk-relative position of the group
-                if (total == (uint32_t) kFusedRoundVals && G == 1) {   // a full round needs no window
-                    if (g + kFusedRoundVals <= out_capacity) {
-#pragma unroll 8
-                        for (uint32_t t = lane; t < (uint32_t) kFusedRoundVals; t += 32) emit<kEmit>(out, g + t, pos0 + t, ea);
-                    } else {
-                        for (uint32_t t = lane; t < (uint32_t) kFusedRoundVals; t += 32)
-                            if (g + t < out_capacity) emit<kEmit>(out, g + t, pos0 + t, ea);
-                    }
-                } else if (total) {
-                    const uint32_t excl = incl - c;
-                    bool by_word = false;
-                    if (G == 1) {
-                        const uint32_t maxc = __reduce_max_sync(0xffffffffu, c);
-                        const uint32_t nz = __popc(__ballot_sync(0xffffffffu, c != 0));
-                        by_word = 9u * maxc > 11u * nz;
-                    }
-                    if (!by_word) {   // every lane walks the set bits of its own words
-                        uint32_t slot = excl, k = 0, bits = 0, vbase = (G * lane) * 32 - 32;
-                        for (;;) {
-                            if (bits == 0) {
-                                if (k == G) break;
-                                bits = wm[mask_slot(e0 + k)];
-                                ++k;
-                                vbase += 32;
-                                continue;
-                            }
-                            win[slot++] = (uint16_t) (vbase + __ffs(bits) - 1);
-                            bits &= bits - 1;
+                for (int j = 0; j < kFusedBatch; ++j) v[j] = load(src + (size_t) j * kFusedRoundVals);
+                AQP_PRED_SWITCH(p,
+                    _Pragma("unroll 1")
+                    for (int b = 0; b < kRounds; b += kFusedBatch) {
+                        _Pragma("unroll")
+                        for (int j = 0; j < kFusedBatch; ++j) {
+                            const uint32_t m = range_mask32<kVariant>(v[j], p);
+                            if (b + kFusedBatch < kRounds) v[j] = load(src + (size_t) (b + kFusedBatch + j) * kFusedRoundVals);
+                            wm[(b + j) * 33] = m;
+                            cnt += __popc(m);
                         }
-                    } else {          // one lane's word at a time, lane l tests bit l
-                        const uint32_t m = wm[mask_slot(e0)];
-                        for (unsigned mm = __ballot_sync(0xffffffffu, m != 0); mm; mm &= mm - 1) {
-                            const int src = __ffs(mm) - 1;
-                            const uint32_t word = __shfl_sync(0xffffffffu, m, src);
-                            const uint32_t off = __shfl_sync(0xffffffffu, excl, src);
-                            if ((word >> lane) & 1u) win[off + __popc(word & lt)] = (uint16_t) (src * 32 + lane);
-                        }
-                    }
-                    __syncwarp();
-                    if (g + total <= out_capacity) {
-                        uint32_t t = lane;
-                        for (; t + 96 < total; t += 128) {
-                            const uint32_t w0 = win[t], w1 = win[t + 32], w2 = win[t + 64], w3 = win[t + 96];
-                            emit<kEmit>(out, g + t, pos0 + w0, ea);
-                            emit<kEmit>(out, g + t + 32, pos0 + w1, ea);
-                            emit<kEmit>(out, g + t + 64, pos0 + w2, ea);
-                            emit<kEmit>(out, g + t + 96, pos0 + w3, ea);
-                        }
-                        for (; t < total; t += 32) emit<kEmit>(out, g + t, pos0 + win[t], ea);
-                    } else {
-                        for (uint32_t t = lane; t < total; t += 32)
-                            if (g + t < out_capacity) emit<kEmit>(out, g + t, pos0 + win[t], ea);
-                    }
-                    __syncwarp();
-                }
-                g += total;
-                r += G;
+                    })
+            } else {   // the column's last tile: a lane's 32 bytes are inside or outside as a whole (n % 64 == 0)
+                AQP_PRED_SWITCH(p,
+                    _Pragma("unroll 1")
+                    for (int r = 0; r < kRounds; ++r) {
+                        const size_t pos = wbase + (size_t) r * kFusedRoundVals + lane * 32;
+                        uint32_t m = 0;
+                        if (pos < n) m = range_mask32<kVariant>(load(in + pos), p);
+                        wm[r * 33] = m;
+                        cnt += __popc(m);
+                    })
+            }
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if (lane == 0) {
+                wtot[s][warp] = cnt;
+                mbar_arrive(&bar_counts[s]);   // release: the control warp and the other workers see wtot after their wait
             }
         }
-        if (nxt >= ntiles) break;
-        cur = nxt;
-        cb ^= 1;
+
+        // ---- expand my sub-range of T[i-1]
+        if (i > 0) {
+            const uint32_t sp = (i - 1) % kFusedStages;
+            mbar_wait(&bar_prefix[sp], ((i - 1) / kFusedStages) & 1u);   // also: every worker's count of T[i-1] is in wtot
+            uint32_t before = 0;
+#pragma unroll
+            for (int k = 0; k < kWorkers; ++k) before += (k < (int) warp) ? wtot[sp][k] : 0u;
+            const uint32_t wcount = wtot[sp][warp];
+            uint64_t g = s_prefix[sp] + before;   // output slot of this warp's next id
+            if (wcount != 0 && g < out_capacity) {
+                const size_t wbase = (size_t) prev_tile * kTileVals + (size_t) warp * kWarpVals;
+                const uint32_t *wm = my_masks + ((i - 1) & 1u) * kWarpWords;
+                // largest group whose expected matches fit the window with some slack
+                uint32_t G = kRounds;
+                while (G > 1 && wcount * G > 896u * kRounds) G >>= 1;
+                uint32_t r = 0;
+                while (r < (uint32_t) kRounds) {
+                    const uint32_t e0 = r * 32 + G * lane;   // my first entry of this group
+                    uint32_t c = 0, nzk = 0;
+                    for (uint32_t k = 0; k < G; ++k) {
+                        const uint32_t m = wm[mask_slot(e0 + k)];
+                        c += __popc(m);
+                        nzk |= (m != 0 ? 1u : 0u) << k;
+                    }
+                    const uint32_t incl = warp_incl_scan(c);
+                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                    if (total > (uint32_t) kFusedRoundVals) {   // denser than the sub-range's average: smaller groups
+                        G >>= 1;
+                        continue;
+                    }
+                    const GroupOut<kEmit> go(out, g, wbase + (size_t) r * kFusedRoundVals, ea);   // slot and position of the group
+                    const bool fits = g + total <= out_capacity;
+                    const uint32_t room = fits ? 0xffffffffu : (uint32_t) (out_capacity - g);   // g < out_capacity here
+                    if (total == (uint32_t) kFusedRoundVals && G == 1) {   // a full round needs no window
+                        if (fits) {
+#pragma unroll 8
+                            for (uint32_t t = lane; t < (uint32_t) kFusedRoundVals; t += 32) go.put(t, t);
+                        } else {
+                            for (uint32_t t = lane; t < (uint32_t) kFusedRoundVals; t += 32)
+                                if (t < room) go.put(t, t);
+                        }
+                    } else if (total) {
+                        const uint32_t excl = incl - c;
+                        bool by_word = false;
+                        if (G == 1) {
+                            const uint32_t maxc = __reduce_max_sync(0xffffffffu, c);
+                            const uint32_t nz = __popc(__ballot_sync(0xffffffffu, c != 0));
+                            by_word = 8u * nz < 9u * maxc + 7u * ((total + 31) >> 5) + 10u;
+                        }
+                        if (by_word) {   // one lane's word at a time, lane l tests bit l, straight to global memory
+                            const uint32_t m = wm[mask_slot(e0)];
+                            for (unsigned mm = __ballot_sync(0xffffffffu, m != 0); mm; mm &= mm - 1) {
+                                const int src = __ffs(mm) - 1;
+                                const uint32_t word = __shfl_sync(0xffffffffu, m, src);
+                                const uint32_t off = __shfl_sync(0xffffffffu, excl, src);
+                                if (word == 0xffffffffu) {   // 32 consecutive ids: one 256-byte store, no popcount
+                                    if (off + lane < room) go.put(off + lane, src * 32 + lane);
+                                } else if ((word >> lane) & 1u) {
+                                    const uint32_t t = off + __popc(word & lt);
+                                    if (t < room) go.put(t, src * 32 + lane);
+                                }
+                            }
+                        } else {         // every lane walks the set bits of its own non-empty words
+                            uint32_t slot = excl, bits = 0, vbase = 0;
+                            for (;;) {
+                                if (bits == 0) {
+                                    if (nzk == 0) break;
+                                    const uint32_t k = __ffs(nzk) - 1;
+                                    nzk &= nzk - 1;
+                                    bits = wm[mask_slot(e0 + k)];
+                                    vbase = (G * lane + k) * 32;
+                                    continue;
+                                }
+                                win[slot++] = (uint16_t) (vbase + __ffs(bits) - 1);
+                                bits &= bits - 1;
+                            }
+                            __syncwarp();
+                            if (fits) {
+                                uint32_t t = lane;
+                                for (; t + 96 < total; t += 128) {
+                                    const uint32_t w0 = win[t], w1 = win[t + 32], w2 = win[t + 64], w3 = win[t + 96];
+                                    go.put(t, w0);
+                                    go.put(t + 32, w1);
+                                    go.put(t + 64, w2);
+                                    go.put(t + 96, w3);
+                                }
+                                for (; t < total; t += 32) go.put(t, win[t]);
+                            } else {
+                                for (uint32_t t = lane; t < total; t += 32)
+                                    if (t < room) go.put(t, win[t]);
+                            }
+                            __syncwarp();
+                        }
+                    }
+                    g += total;
+                    r += G;
+                }
+            }
+        }
+        if (tile >= ntiles) break;
+        prev_tile = tile;
     }
 }
 
@@ -940,7 +1017,7 @@ size_t index_scan_scratch_bytes(size_t n) {
 template <int kEmit, int kWarps, int kRounds>
 static int launch_fused(const uint8_t *d_data, size_t n, const Pred &p, const EmitArgs &ea, void *d_out, uint64_t cap,
                         uint64_t *d_count, void *d_scratch, cudaStream_t st) {
-    constexpr size_t kTileVals = (size_t) kWarps * kRounds * kFusedRoundVals;
+    constexpr size_t kTileVals = (size_t) (kWarps - 1) * kRounds * kFusedRoundVals;   // one warp of the CTA is the control warp
     static_assert(kTileVals >= kFusedMinTileVals, "scratch is sized for tiles of at least kFusedMinTileVals");
     const uint32_t ntiles = (uint32_t) ((n + kTileVals - 1) / kTileVals);
     unsigned int *ticket = static_cast<unsigned int *>(d_scratch);
