@@ -495,6 +495,7 @@ void b200_shutdown(void) {
     g.scan_in.release();
     g.scan_out.release();
     g.scan_scratch.release();
+    scan_release();
     for (auto &e : g.ev) cudaEventDestroy(e);
     cudaStreamDestroy(g.stream);
     g.stream = nullptr;

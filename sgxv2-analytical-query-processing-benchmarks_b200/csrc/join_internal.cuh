@@ -171,6 +171,7 @@ int set_rowid_payload_device(row_t *d_rel, uint64_t row_begin, uint64_t n, cudaS
 int bitvector_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, uint64_t *d_out, cudaStream_t st);
 int scan_count_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, uint64_t *d_count, cudaStream_t st);
 size_t index_scan_scratch_bytes(size_t n);
+void scan_release();
 int index_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, uint64_t id_base, uint64_t *d_out,
                       uint64_t cap, uint64_t *d_count, void *d_scratch, cudaStream_t st);
 int value_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, uint32_t *d_out, uint64_t cap,

@@ -13,6 +13,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "join_internal.cuh"
 #include "block_scan.cuh"
 
 namespace aqp {
@@ -589,7 +590,12 @@ __device__ __forceinline__ uint32_t range_mask32(const U32x8 &v, const Pred &p) 
     return __umulhi(g[1] * 256u + g[0], 1u << 25) + hi;        // groups 0, 1 -> bits 0..15
 }
 
-constexpr uint64_t kStatAggregate = 1ull << 62, kStatInclusive = 2ull << 62, kStatValueMask = (1ull << 62) - 1;
+// status word of a tile: flag (2 bits: 1 = the tile's own count, 2 = inclusive prefix) | epoch (22 bits) | value (40 bits).
+// A word counts only if its epoch is the current launch's: the status array is zeroed once when it is allocated and
+// never again (a memset node in front of every scan cost ~2 us, 10 % of a 128 MiB shard's scan).
+constexpr int kStatValueBits = 40, kStatEpochBits = 22;
+constexpr uint64_t kStatAggregate = 1ull << 62, kStatInclusive = 2ull << 62, kStatValueMask = (1ull << kStatValueBits) - 1;
+constexpr uint32_t kStatEpochMask = (1u << kStatEpochBits) - 1;
 constexpr int kLookWindows = 4;   // status words per lane and round trip of the look-back
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
     unsigned long long v;
@@ -601,7 +607,7 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned l
 }
 
 // number of matches in tiles [0, tile): called by one whole warp, tile > 0
-__device__ __forceinline__ uint64_t lookback_exclusive(const unsigned long long *status, uint32_t tile) {
+__device__ __forceinline__ uint64_t lookback_exclusive(const unsigned long long *status, uint32_t tile, uint32_t epoch) {
     const unsigned lane = lane_id();
     uint64_t sum = 0;
     int64_t d = (int64_t) tile - 1;   // index of the nearest status word not yet accounted for
@@ -610,19 +616,19 @@ __device__ __forceinline__ uint64_t lookback_exclusive(const unsigned long long 
 #pragma unroll
         for (int k = 0; k < kLookWindows; ++k) {
             const int64_t idx = d - k * 32 - (int64_t) lane;
-            s[k] = idx >= 0 ? ld_relaxed_u64(status + idx) : kStatInclusive;   // in front of tile 0: prefix 0
+            s[k] = idx >= 0 ? ld_relaxed_u64(status + idx) : (kStatInclusive | ((uint64_t) epoch << kStatValueBits));   // in front of tile 0: prefix 0
         }
         // windows nearest first; state 0 = all 32 were aggregates (go on), 1 = reached an inclusive prefix (done),
         // 2 = met a tile that has not published yet (poll again from there)
         int state = 0;
         auto window = [&](const unsigned long long sk, const int k) {
-            const uint32_t flag = (uint32_t) (sk >> 62);
+            const uint32_t flag = ((uint32_t) (sk >> kStatValueBits) & kStatEpochMask) == epoch ? (uint32_t) (sk >> 62) : 0u;   // stale epoch: not published
             const unsigned inval = __ballot_sync(0xffffffffu, flag == 0);
             const unsigned incl = __ballot_sync(0xffffffffu, flag == 2);
             const unsigned first_inval = inval ? (unsigned) __ffs(inval) - 1 : 32u;
             const unsigned first_incl = incl ? (unsigned) __ffs(incl) - 1 : 32u;
             const unsigned upto = min(first_inval, first_incl);   // aggregates nearer than this lane count
-            const uint32_t val32 = (uint32_t) sk;                 // an aggregate is at most one tile's worth of matches
+            const uint32_t val32 = (uint32_t) sk;                 // an aggregate is at most one tile's worth of matches (< 2^32)
             sum += __reduce_add_sync(0xffffffffu, lane < upto ? val32 : 0u);
             if (first_incl < first_inval) {
                 const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t) sk, first_incl);
@@ -701,11 +707,12 @@ static size_t fused_smem_bytes(int warps, int rounds) {   // per worker warp: tw
 // and very uneven lanes the whole warp takes one lane's word at a time instead (lane l tests bit l) and stores
 // straight to global memory: a full word leaves as one 256-byte store.
 constexpr int kFusedStages = 4;
+constexpr int fused_ctas_per_sm(int warps) { return 1056 / (warps * 32); }   // ~1024 threads per SM: 60+ registers each
 template <int kEmit, int kWarps, int kRounds, bool kV8>
-__global__ void __launch_bounds__(kWarps * 32, 1024 / (kWarps * 32))
+__global__ void __launch_bounds__(kWarps * 32, fused_ctas_per_sm(kWarps))
 rowid_scan_fused_kernel(const uint8_t *__restrict__ in, size_t n, Pred p, EmitArgs ea, void *__restrict__ out,
                         uint64_t out_capacity, unsigned long long *__restrict__ status, unsigned int *__restrict__ ticket,
-                        unsigned long long *__restrict__ d_count, uint32_t ntiles) {
+                        unsigned long long *__restrict__ d_count, uint32_t ntiles, uint32_t epoch) {
     constexpr int kWorkers = kWarps - 1;
     constexpr int kWarpVals = kRounds * kFusedRoundVals;
     constexpr size_t kTileVals = (size_t) kWorkers * kWarpVals;
@@ -733,13 +740,14 @@ rowid_scan_fused_kernel(const uint8_t *__restrict__ in, size_t n, Pred p, EmitAr
     if (warp == (unsigned) kWorkers) {
         // ------------------------------------------------------------------ control warp
         uint32_t t_prev = 0, total_prev = 0;
+        const uint64_t etag = (uint64_t) epoch << kStatValueBits;
         for (uint32_t i = 0;; ++i) {
             const uint32_t s = i % kFusedStages, ph = (i / kFusedStages) & 1u;
             if (i > 0) {            // matches in front of T[i-1], whose count went out at the end of the last iteration
                 uint64_t prefix = 0;
                 if (t_prev > 0) {
-                    prefix = lookback_exclusive(status, t_prev);
-                    if (lane == 0) st_relaxed_u64(status + t_prev, kStatInclusive | (prefix + total_prev));
+                    prefix = lookback_exclusive(status, t_prev, epoch);
+                    if (lane == 0) st_relaxed_u64(status + t_prev, kStatInclusive | etag | (prefix + total_prev));
                 }
                 if (lane == 0) {
                     s_prefix[(i - 1) % kFusedStages] = prefix;
@@ -754,9 +762,18 @@ rowid_scan_fused_kernel(const uint8_t *__restrict__ in, size_t n, Pred p, EmitAr
             uint32_t total = 0;
             for (int k = lane; k < kWorkers; k += 32) total += wtot[s][k];
             total = __reduce_add_sync(0xffffffffu, total);
-            if (lane == 0) st_relaxed_u64(status + t_cur, (t_cur == 0 ? kStatInclusive : kStatAggregate) | total);
+            if (lane == 0) st_relaxed_u64(status + t_cur, (t_cur == 0 ? kStatInclusive : kStatAggregate) | etag | total);
             t_prev = t_cur;
             total_prev = total;
+        }
+        // this CTA saw a ticket past the end and will not take another: the last CTA to get here re-arms the counters
+        if (lane == 0) {
+            __threadfence();
+            if (atomicAdd(ticket + 1, 1u) == gridDim.x - 1) {
+                ticket[0] = 0;
+                ticket[1] = 0;
+                __threadfence();
+            }
         }
         return;
     }
@@ -1005,31 +1022,53 @@ int scan_count_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, u
 
 // scratch layout: [bitvector of one chunk][tile counts u32][tile offsets u64][tile lists: 2 lengths + 2 lists u32]
 static size_t align256(size_t x) { return (x + 255) & ~(size_t) 255; }
+static bool index_scan_two_pass() {
+    static const bool two_pass = [] {
+        const char *e = getenv("B200_AQP_INDEX_SCAN");   // A/B switch: "twopass" = bitvector scratch + expansion kernels
+        return e && !strcmp(e, "twopass");
+    }();
+    return two_pass;
+}
 size_t index_scan_scratch_bytes(size_t n) {
+    if (!index_scan_two_pass()) return 256;   // the single-pass kernel keeps its few KiB of state in its own buffer
     size_t chunk = n < kIndexChunkVals ? n : kIndexChunkVals;
     size_t tiles = (chunk + kExpandTileVals - 1) / kExpandTileVals + 1;
-    const size_t two_pass = align256(chunk / 8 + 64) + align256(tiles * 4) + align256(tiles * 8) + align256((2 * tiles + 2) * 4) + 256;
-    const size_t fused = 256 + align256((n / kFusedMinTileVals + 2) * 8);   // ticket + one status word per macro-tile
-    return two_pass > fused ? two_pass : fused;
+    return align256(chunk / 8 + 64) + align256(tiles * 4) + align256(tiles * 8) + align256((2 * tiles + 2) * 4) + 256;   // two-pass path only
 }
 
 // ---- single-pass path: geometry (warps per CTA x rounds per warp) picked by size, B200_AQP_SCAN_GEOM=WxR overrides
+static struct {
+    DevBuf buf;
+    uint32_t epoch = 0;
+} g_fused;
+void scan_release() {   // b200_shutdown: the buffer belongs to the device that is being left
+    g_fused.buf.release();
+    g_fused.epoch = 0;
+}
 template <int kEmit, int kWarps, int kRounds>
 static int launch_fused(const uint8_t *d_data, size_t n, const Pred &p, const EmitArgs &ea, void *d_out, uint64_t cap,
                         uint64_t *d_count, void *d_scratch, cudaStream_t st) {
     constexpr size_t kTileVals = (size_t) (kWarps - 1) * kRounds * kFusedRoundVals;   // one warp of the CTA is the control warp
     static_assert(kTileVals >= kFusedMinTileVals, "scratch is sized for tiles of at least kFusedMinTileVals");
     const uint32_t ntiles = (uint32_t) ((n + kTileVals - 1) / kTileVals);
-    unsigned int *ticket = static_cast<unsigned int *>(d_scratch);
-    unsigned long long *status = reinterpret_cast<unsigned long long *>(static_cast<unsigned char *>(d_scratch) + 256);
-    AQP_CUDA_OK(cudaMemsetAsync(d_scratch, 0, 256 + (size_t) ntiles * 8, st));
+    // ticket + exit counter (256 bytes) and one status word per macro-tile live in a buffer this file owns: zeroed when
+    // it is (re)allocated, tagged with a per-launch epoch afterwards, counters re-armed by the kernel's last CTA
+    const size_t need = 256 + (size_t) ntiles * 8;
+    if (need > g_fused.buf.cap || g_fused.epoch >= kStatEpochMask) {
+        if (g_fused.buf.ensure(need)) return -1;
+        AQP_CUDA_OK(cudaMemsetAsync(g_fused.buf.p, 0, g_fused.buf.cap, st));
+        g_fused.epoch = 0;
+    }
+    const uint32_t epoch = ++g_fused.epoch;
+    unsigned int *ticket = static_cast<unsigned int *>(g_fused.buf.p);
+    unsigned long long *status = reinterpret_cast<unsigned long long *>(static_cast<unsigned char *>(g_fused.buf.p) + 256);
     const size_t smem = fused_smem_bytes(kWarps, kRounds);
     const bool v8 = (reinterpret_cast<uintptr_t>(d_data) & 31u) == 0;
     auto kern = v8 ? rowid_scan_fused_kernel<kEmit, kWarps, kRounds, true> : rowid_scan_fused_kernel<kEmit, kWarps, kRounds, false>;
-    AQP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    const uint32_t resident = (uint32_t) kNumSMs * (1024 / (kWarps * 32));
+    AQP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));   // per call: cheap, and right after a device change
+    const uint32_t resident = (uint32_t) kNumSMs * fused_ctas_per_sm(kWarps);
     kern<<<ntiles < resident ? ntiles : resident, kWarps * 32, smem, st>>>(
-        d_data, n, p, ea, d_out, cap, status, ticket, reinterpret_cast<unsigned long long *>(d_count), ntiles);
+        d_data, n, p, ea, d_out, cap, status, ticket, reinterpret_cast<unsigned long long *>(d_count), ntiles, epoch);
     AQP_LAUNCHED();
     AQP_CUDA_OK(cudaGetLastError());
     return 0;
@@ -1038,7 +1077,8 @@ static int launch_fused(const uint8_t *d_data, size_t n, const Pred &p, const Em
 template <int kEmit>
 static int fused_scan_device(const uint8_t *d_data, size_t n, const Pred &p, const EmitArgs &ea, void *d_out, uint64_t cap,
                              uint64_t *d_count, void *d_scratch, cudaStream_t st) {
-    int w = 16, r = n >= ((size_t) 1 << 28) ? 16 : 4;
+    // measured (profiles/r02_sweep_scan_v7*.txt): 15 workers x 16 KiB tiles win from 2^26 values up, half-size tiles below
+    int w = 16, r = n >= ((size_t) 1 << 26) ? 16 : 8;
     if (const char *e = getenv("B200_AQP_SCAN_GEOM")) sscanf(e, "%dx%d", &w, &r);
 #define AQP_GEOM(W, R) \
     if (w == W && r == R) return launch_fused<kEmit, W, R>(d_data, n, p, ea, d_out, cap, d_count, d_scratch, st)
@@ -1048,6 +1088,9 @@ static int fused_scan_device(const uint8_t *d_data, size_t n, const Pred &p, con
     AQP_GEOM(8, 8);
     AQP_GEOM(8, 16);
     AQP_GEOM(32, 8);
+    AQP_GEOM(11, 16);
+    AQP_GEOM(6, 16);
+    AQP_GEOM(11, 8);
 #undef AQP_GEOM
     set_error("B200_AQP_SCAN_GEOM: unknown geometry");
     return -1;
@@ -1062,20 +1105,19 @@ static int emit_scan_device(int emit_kind, uint8_t lo, uint8_t hi, const uint8_t
         set_error("scan: column must be 16-byte aligned");
         return -1;
     }
-    AQP_CUDA_OK(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
     n = n / 64 * 64;
-    if (n == 0) return 0;
-    static const bool two_pass = [] {
-        const char *e = getenv("B200_AQP_INDEX_SCAN");   // A/B switch: "twopass" = bitvector scratch + expansion kernels
-        return e && !strcmp(e, "twopass");
-    }();
-    if (!two_pass) {
+    if (n == 0) {
+        AQP_CUDA_OK(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
+        return 0;
+    }
+    if (!index_scan_two_pass()) {
         const Pred pf = make_pred(lo, hi);
         const EmitArgs eaf{id_base, d_data, d_dict};
         if (emit_kind == kEmitRowId) return fused_scan_device<kEmitRowId>(d_data, n, pf, eaf, d_out, cap, d_count, d_scratch, st);
         if (emit_kind == kEmitValue) return fused_scan_device<kEmitValue>(d_data, n, pf, eaf, d_out, cap, d_count, d_scratch, st);
-        return fused_scan_device<kEmitDict>(d_data, n, pf, eaf, d_out, cap, d_count, d_scratch, st);
+        return fused_scan_device<kEmitDict>(d_data, n, pf, eaf, d_out, cap, d_count, d_scratch, st);   // writes *d_count itself
     }
+    AQP_CUDA_OK(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
     const size_t chunk_cap = n < kIndexChunkVals ? n : kIndexChunkVals;
     const size_t tiles_cap = (chunk_cap + kExpandTileVals - 1) / kExpandTileVals + 1;
     unsigned char *sb = static_cast<unsigned char *>(d_scratch);
