@@ -50,6 +50,27 @@ METRIC = "rho_join_throughput"
 UNIT = "Mtuples/s"
 
 
+def workload_config(world: int) -> dict:
+    """`config` of the JSON line - the same dict in the B200 arm and in the reference arm (same workload, same sizes)."""
+    return {"workload": f"RHO join |R|=2^{LOG_R} |S|=2^{LOG_S} 8-byte tuples (u32 key, u32 payload), uniform FK keys, "
+                        "count+checksum (BASELINE config 3)",
+            "cache": "inputs (5 GiB) exceed every cache (126 MB L2); no flush between steps",
+            "parallelism": f"{world} GPU(s), one process per GPU"}
+
+
+def host_info() -> dict:
+    """nproc, CPU model and the measured TSC rate (SURVEY.md 8d asks for all three beside a CPU number)."""
+    info = {"nproc": os.cpu_count()}
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                info["cpu_model"] = ln.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return info
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -126,31 +147,50 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # CPU reference arm (oracle/_ref = the unmodified reference compiled from /root/reference)
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_join(steps: int, warmup: int, log_r: int = 24, log_s: int = 26):
-    """The reference's RHO on the host cores on a bounded sample (2^24 x 2^26 = BASELINE config 1, 1/8
-    of the headline workload). Throughput from the reference's own 'Total Join Time (cycles)' divided
-    by the measured TSC rate. Falls back to the oracle port if oracle/_ref cannot run."""
+def _fast_inputs(log_r: int, log_s: int):
+    """PK / FK relations with the reference generator's distribution (R = a permutation of 1..|R|, S = |S|/|R|
+    independent permutations laid end to end, payload = row id; generator.cpp:143-153,:474-512) from numpy
+    permutations: the reference's own sequential glibc shuffle needs ~1 minute at 2^29 and none of it is timed."""
+    import numpy as np
     import oracle as O
     nR, nS = 1 << log_r, 1 << log_s
+    rng = np.random.default_rng(11111)
+    R = np.empty(nR, dtype=O.ROW)
+    R["key"] = rng.permutation(nR).astype(np.uint32) + 1
+    R["payload"] = np.arange(nR, dtype=np.uint32)
+    S = np.empty(nS, dtype=O.ROW)
+    rng = np.random.default_rng(22222)
+    for c in range(nS // nR):
+        S["key"][c * nR:(c + 1) * nR] = rng.permutation(nR).astype(np.uint32) + 1
+    S["payload"] = np.arange(nS, dtype=np.uint32)
+    return R, S
+
+
+def cpu_reference_join(steps: int, warmup: int, log_r: int = LOG_R, log_s: int = LOG_S):
+    """The reference's own RHO (oracle/_ref: the unmodified sources compiled from /root/reference) on all host cores
+    at the headline size 2^27 x 2^29 (falls back to 2^24 x 2^26 only if the host cannot hold it, and says so).
+    Throughput = tuples / (the reference's own 'Total Join Time (cycles)' / measured TSC rate); the
+    wall-clock of the RHO() call (which also covers its buffer allocation) is reported beside it. Falls back to the
+    oracle port if oracle/_ref cannot run here (no AVX-512)."""
+    import oracle as O
     cores = os.cpu_count() or 1
+    note = ""
     t0 = time.time()
-    if O.have_ref():
-        R = O.ref_gen_pk(nR, 11111)
-        S = O.ref_gen_fk(nS, nR, 22222)
-        kind = "reference"
-    else:
-        R = O.gen_pk(nR, 11111)
-        S = O.gen_fk(nS, nR, 22222)
-        kind = "port"
-        cores = 1
-    O.set_rowid_payload(R)
-    O.set_rowid_payload(S)
+    try:
+        R, S = _fast_inputs(log_r, log_s)
+    except MemoryError:
+        log_r, log_s = 24, 26
+        note = " (host memory too small for 2^27 x 2^29: 1/8 sample)"
+        R, S = _fast_inputs(log_r, log_s)
+    nR, nS = 1 << log_r, 1 << log_s
     gen_s = time.time() - t0
-    times = []
+    kind = "reference" if O.have_ref() else "port"
+    times, walls = [], []
     matches = None
     best_flags = None
+    tsc = None
     if kind == "reference":
-        # paper-best flags UNROLL+FORCE_2_PHASES and the automatic pass count; keep the better (SURVEY §8d)
+        # paper-best flags UNROLL+FORCE_2_PHASES and the automatic pass count; keep the better (SURVEY 8d)
         probe = {}
         for force2 in (True, False):
             r = O.ref_rho(R, S, nthreads=cores, force_2_passes=force2)
@@ -159,20 +199,26 @@ def cpu_reference_join(steps: int, warmup: int, log_r: int = 24, log_s: int = 26
         for i in range(warmup + steps):
             r = O.ref_rho(R, S, nthreads=cores, force_2_passes=best_flags)
             matches = r["matches"]
+            tsc = r["tsc_hz"]
             if i >= warmup:
                 times.append(r["seconds"])
+                walls.append(r["wall_seconds"])
     else:
+        cores = 1
         for i in range(max(1, min(steps, 3))):
             t = time.time()
             r = O.rho(R, S, nthreads=1)
             times.append(time.time() - t)
+            walls.append(times[-1])
             matches = r["matches"]
     assert matches == nS
     mean = sum(times) / len(times)
     return {"value": (nR + nS) / mean / 1e6, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": f"|R|=2^{log_r} |S|=2^{log_s} uniform FK (1/8 of the workload), {len(times)} runs, "
-                      f"flags UNROLL{'+FORCE_2_PHASES' if best_flags else ''}, generation {gen_s:.1f}s untimed",
-            "ms_per_step": mean * 1e3}
+            "sample": f"|R|=2^{log_r} |S|=2^{log_s} uniform FK{note}, {len(times)} runs after {warmup} warm-ups, "
+                      f"flags UNROLL{'+FORCE_2_PHASES' if best_flags else ''}, numpy-permutation inputs "
+                      f"({gen_s:.1f}s, untimed)",
+            "ms_per_step": mean * 1e3, "wall_ms_per_step": sum(walls) / len(walls) * 1e3, "tsc_hz": tsc,
+            "same_size_as_headline": (log_r, log_s) == (LOG_R, LOG_S), "host": host_info()}
 
 
 def cpu_reference_scan(log_n: int = 28):
@@ -201,12 +247,12 @@ def run_reference_arm(args):
         return
     cb = cpu_reference_join(args.steps, args.warmup)
     scan = cpu_reference_scan()
+    keep = ("value", "unit", "cores", "kind", "sample", "wall_ms_per_step", "tsc_hz", "same_size_as_headline", "host")
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": f"RHO join |R|=2^{LOG_R} |S|=2^{LOG_S} 8-byte tuples uniform FK "
-                                   "(reference timed on a bounded sample, see cpu_baseline.sample)"},
-            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {k: cb[k] for k in keep},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "scan": scan}
     print(json.dumps(line))
@@ -255,8 +301,45 @@ def bench_scan(A, torch, dev, peak, steps, warmup, n_gpus=1, rank=0):
                                  "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": peak, "unit": "GB/s",
                                               "frac": alg / ms / 1e6 / peak}}
         del ids
+    # BASELINE config 2's 0.1 %: not expressible on the tiled column -> seeded skewed column, v = 0 with
+    # probability 1e-3 else uniform 1..255, predicate [0, 0]; the true selectivity is counted, not assumed
+    assert A.lib().b200_fill_skewed_column_device(data.data_ptr(), n, begin, 1000, 42, A._st(st)) == 0
+    A.scan_count_device(0, 0, data.data_ptr(), n, cnt.data_ptr(), st)
+    torch.cuda.synchronize()
+    k = int(cnt.item())
+    ids = torch.empty(max(k, 1), dtype=torch.int64, device=dev)
+    ms = timeit(lambda: A.index_scan_device(0, 0, data.data_ptr(), n, ids.data_ptr(), k, cnt.data_ptr(),
+                                            id_base=begin, stream=st))
+    assert int(cnt.item()) == k
+    alg = n + 8 * k
+    out["rowid_sel0.1"] = {"predicate": [0, 0], "column": "skewed: 0 w.p. 1e-3 else uniform 1..255, seed 42",
+                           "selectivity": k / n, "ms": ms, "input_gbs": n / ms / 1e6,
+                           "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": peak, "unit": "GB/s",
+                                        "frac": alg / ms / 1e6 / peak}}
     out["n_values_per_gpu"] = n
+    del ids, data, bv
     return out
+
+
+def bench_scan_e2e(A, np_mod, steps):
+    """Scan end to end through the ECALL-shaped host-buffer calls (b200_bitvector_scan_user / b200_index_scan_user,
+    Enclave.edl:33-41,:71-79): H2D of the column, the kernel, D2H of the bitvector / id list inside the timed region."""
+    import torch
+    n = 1 << SCAN_LOG_N
+    col = torch.empty(n, dtype=torch.uint8).pin_memory()
+    col.copy_((torch.arange(n, dtype=torch.int32) & 255).to(torch.uint8))
+    npcol = col.numpy()
+    res = {}
+    for name, fn, d2h in (("bitvector", lambda: A.bitvector_scan_user(0, 26, npcol), n // 8),
+                          ("rowid_sel10", lambda: A.index_scan_user(0, 26, npcol, capacity=n // 256 * 27 + 64), n // 256 * 27 * 8)):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        dt = (time.perf_counter() - t0) / steps
+        res[name] = {"ms": dt * 1e3, "input_gbs": n / dt / 1e9, "h2d_bytes_per_step": n, "d2h_bytes_per_step": d2h}
+    res["api"] = "b200_bitvector_scan_user / b200_index_scan_user on a pinned host column (output arrays pageable numpy)"
+    return res
 
 
 def run_b200_arm(args):
@@ -424,7 +507,59 @@ def run_b200_arm(args):
         dt = (time.perf_counter() - t0) / e2e_steps
         e2e = {"value": (nR + nS) / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": 8 * (nR + nS),
                "d2h_bytes_per_step": 32, "ms_per_step": dt * 1e3, "steps": e2e_steps,
-               "api": "run_join(result_t*, R, S, \"RHO\", joinconfig_t*) on pinned host relations"}
+               "api": "run_join(result_t*, R, S, \"RHO\", joinconfig_t*) on pinned host relations "
+                      "(what this library's create_relation_* return)"}
+        # the other corners of (pinned | pageable inputs) x (count-only | materialised output), same call
+        import numpy as np
+
+        def wall(fn, reps):
+            fn()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                g = fn()
+            return (time.perf_counter() - t0) / reps, g
+
+        variants = {}
+        pgR, pgS = np.empty(nR, dtype=A.ROW), np.empty(nS, dtype=A.ROW)   # plain malloc'd memory, as a reference caller has
+        pgR[:] = npR
+        pgS[:] = npS
+        dt2, g = wall(lambda: A.run_join(pgR, pgS), 3)
+        assert g["matches"] == nS
+        variants["pageable_count"] = {"value": (nR + nS) / dt2 / 1e6, "unit": UNIT, "ms_per_step": dt2 * 1e3,
+                                      "h2d_bytes_per_step": 8 * (nR + nS), "d2h_bytes_per_step": 32,
+                                      "note": "multi-threaded staging through pinned buffers (csrc/hostcopy.cpp)"}
+        del pgR, pgS
+        # materialised output at BASELINE config 1 (2^24 x 2^26: 67 M triples = 805 MB of 16 KiB chunks handed back in
+        # the reference's chunked_table_t layout); the reference's own numbers for this case: 740 / 929 Mtuples/s
+        n1R, n1S = 1 << 24, 1 << 26
+        d1R = torch.empty(n1R * 2, dtype=torch.int32, device=dev)
+        d1S = torch.empty(n1S * 2, dtype=torch.int32, device=dev)
+        A.gen_pk_device(d1R.data_ptr(), n1R, 11111, 0, n1R, st)
+        A.gen_fk_device(d1S.data_ptr(), n1S, n1R, 22222, 0, n1S, st)
+        torch.cuda.synchronize()
+        for name, pin in (("pinned", True), ("pageable", False)):
+            if pin:
+                tR, tS = torch.empty(n1R * 2, dtype=torch.int32).pin_memory(), torch.empty(n1S * 2, dtype=torch.int32).pin_memory()
+                tR.copy_(d1R)
+                tS.copy_(d1S)
+                aR, aS = tR.numpy().view(A.ROW).reshape(n1R), tS.numpy().view(A.ROW).reshape(n1S)
+            else:
+                aR, aS = np.empty(n1R, dtype=A.ROW), np.empty(n1S, dtype=A.ROW)
+                aR[:] = d1R.cpu().numpy().view(A.ROW).reshape(n1R)
+                aS[:] = d1S.cpu().numpy().view(A.ROW).reshape(n1S)
+            torch.cuda.synchronize()
+            for mat in (False, True):
+                dt2, g = wall(lambda: A.run_join(aR, aS, materialize=mat, keep_triples=False), 3)
+                assert g["matches"] == n1S and (not mat or g["table_num_tuples"] == n1S)
+                variants[f"c1_{name}_{'materialised' if mat else 'count'}"] = {
+                    "value": (n1R + n1S) / dt2 / 1e6, "unit": UNIT, "ms_per_step": dt2 * 1e3,
+                    "h2d_bytes_per_step": 8 * (n1R + n1S), "d2h_bytes_per_step": 12 * n1S + 8 * (n1S // 1364 + 1) if mat else 32}
+            del aR, aS
+        del d1R, d1S
+        e2e["variants"] = variants
+        e2e["variants_note"] = ("c1_* = BASELINE config 1 (2^24 x 2^26) through run_join(); materialised = MATERIALIZE=1, the "
+                                "result handed back as the reference's chunked_table_t (16 KiB chunks in one host slab) and "
+                                "released with destroy_table()")
         del hR, hS, npR, npS
     else:
         # N > 1: every rank keeps its row-range shard in pinned host memory; a step = H2D of the shard over this
@@ -460,11 +595,17 @@ def run_b200_arm(args):
     torch.cuda.empty_cache()
 
     scan = bench_scan(A, torch, dev, peak, max(args.steps, 5), args.warmup, world, rank)
+    if world == 1:
+        import numpy as np
+        scan["e2e"] = bench_scan_e2e(A, np, 3)
     if world > 1:
         for k, v in scan.items():
-            if isinstance(v, dict):
+            if isinstance(v, dict) and "ms" in v:
                 t = torch.tensor([v["ms"]], device=dev)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                r = v["roofline"]
+                r["achieved"] *= v["ms"] / float(t.item())   # per GPU, at the slowest rank's time
+                r["frac"] = r["achieved"] / r["peak"]
                 v["ms"] = float(t.item())
                 n_tot = 1 << SCAN_LOG_N
                 v["input_gbs"] = n_tot / v["ms"] / 1e6
@@ -507,7 +648,8 @@ def run_b200_arm(args):
         if world == 1 and not args.no_cpu_baseline:
             try:
                 cpu = cpu_reference_join(3, 1)
-                cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "wall_ms_per_step", "tsc_hz",
+                                           "same_size_as_headline", "host")}
                 cs = cpu_reference_scan()
                 if cs:
                     cpu["scan"] = cs
@@ -516,14 +658,12 @@ def run_b200_arm(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-                "config": {"workload": f"RHO join |R|=2^{LOG_R} |S|=2^{LOG_S} 8-byte tuples (u32 key, u32 payload), "
-                                       "uniform FK keys, count+checksum (BASELINE config 3)",
-                           "generator": "on-device bijection, seeds 11111/22222", "radix_bits": s["radix_bits"],
-                           "passes": s["num_passes"],
-                           "cache": "inputs (5 GiB) exceed the 126 MB L2; no flush between steps",
-                           "parallelism": "1 GPU" if world == 1 else
-                           f"{world} GPUs, one process each: pass 1 routes by the low key bits and stores every run into the owner's "
-                           f"buffer over NVLink peer memory ({s.get('exchange', 'nccl')}); NCCL carries the sizing collectives"},
+                "config": workload_config(world),
+                "plan": {"generator": "on-device bijection, seeds 11111/22222", "radix_bits": s["radix_bits"],
+                         "passes": s["num_passes"],
+                         "exchange": None if world == 1 else
+                         f"pass 1 routes by the low key bits and stores every run into the owner's buffer over NVLink peer "
+                         f"memory ({s.get('exchange', 'nccl')}); NCCL carries the sizing collectives"},
                 "phases_ms": phase, "roofline": roof, "join_roofline": join_roof, "cpu_baseline": cpu, "e2e": e2e,
                 "exchange": exchange, "skew": skew, "tpch": tpch,
                 "gpu_launches": launches_timed, "gpu_launches_total": A.kernel_launch_count() - launches0,

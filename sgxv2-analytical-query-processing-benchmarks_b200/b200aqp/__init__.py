@@ -225,20 +225,21 @@ def last_join_stats() -> dict:
     return s.as_dict()
 
 
-def _collect_result(res: Result, materialize: bool) -> dict:
+def _collect_result(res: Result, materialize: bool, keep_triples: bool = True) -> dict:
     out = {"matches": int(res.totalresults), "nthreads": res.nthreads, "materialized": res.materialized,
            "result_type": res.result_type, "throughput": res.throughput}
     ct = C.cast(res.result, C.POINTER(ChunkedTable))
     if materialize:
         t = ct.contents
         parts = []
-        for c in range(t.num_chunks):
+        for c in range(t.num_chunks if keep_triples else 0):
             base = t.chunks[c]
             n = C.cast(base, C.POINTER(C.c_uint64))[0]
             assert n <= TUPLES_PER_CHUNK
             buf = (C.c_uint8 * (12 * n)).from_address(base + 8)
             parts.append(np.frombuffer(buf, dtype=TRIPLE).copy())
-        out["triples"] = np.concatenate(parts) if parts else np.zeros(0, dtype=TRIPLE)
+        if keep_triples:
+            out["triples"] = np.concatenate(parts) if parts else np.zeros(0, dtype=TRIPLE)
         out["num_chunks"] = int(t.num_chunks)
         out["table_num_tuples"] = int(t.num_tuples)
     # release exactly as a reference caller does: destroy_table() + free() (tpch.cpp:82)
@@ -248,15 +249,17 @@ def _collect_result(res: Result, materialize: bool) -> dict:
     return out
 
 
-def run_join(R: np.ndarray, S: np.ndarray, materialize: bool = False, nthreads: int = 1, algorithm: bytes = b"RHO"):
-    """run_join(result_t*, R, S, "RHO", joinconfig_t*) on HOST relations (joins.hpp:4-6)."""
+def run_join(R: np.ndarray, S: np.ndarray, materialize: bool = False, nthreads: int = 1, algorithm: bytes = b"RHO",
+             keep_triples: bool = True):
+    """run_join(result_t*, R, S, "RHO", joinconfig_t*) on HOST relations (joins.hpp:4-6). keep_triples=False leaves
+    the materialised chunks uncopied (timing runs: the chunked table is produced, inspected and destroyed)."""
     cfg = JoinConfig()
     cfg.NTHREADS = nthreads
     cfg.MATERIALIZE = int(materialize)
     res = Result()
     tR, tS = _table(R), _table(S)
     lib().run_join(C.byref(res), C.byref(tR), C.byref(tS), algorithm, C.byref(cfg))
-    return _collect_result(res, materialize)
+    return _collect_result(res, materialize, keep_triples)
 
 
 def preload_relations(R: np.ndarray, S: np.ndarray):

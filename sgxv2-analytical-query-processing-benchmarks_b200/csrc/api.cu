@@ -337,8 +337,51 @@ static int rerun_probe_locked(uint64_t nS, output_triple_t *d_out, uint64_t out_
     return 0;
 }
 
-// chunk-array pointer -> slab that backs all its chunks (see destroy_table)
-static std::unordered_map<void *, void *> g_slabs;
+// chunk-array pointer -> slab that backs all its chunks (see destroy_table). Slabs are pinned host memory when a
+// device is present - the materialised result then comes back as ONE DMA at the PCIe rate - and the last slab a
+// caller destroyed is kept for the next materialising join: pinning (or first-touching) 0.8 GB costs more than the
+// join and the copy together (measured: 75 ms of an 89 ms run_join at 2^24 x 2^26 went into page faults of a fresh
+// malloc'd slab).
+struct Slab {
+    void *p = nullptr;
+    size_t bytes = 0;
+    bool pinned = false;
+};
+static std::unordered_map<void *, Slab> g_slabs;
+static Slab g_slab_cache;
+constexpr size_t kSlabCacheMax = (size_t) 16 << 30;
+static void slab_free(Slab &b) {
+    if (b.p) {
+        if (b.pinned) cudaFreeHost(b.p);
+        else free(b.p);
+    }
+    b = Slab{};
+}
+static Slab slab_alloc(size_t bytes) {
+    if (g_slab_cache.p && g_slab_cache.bytes >= bytes && g_slab_cache.bytes <= 2 * bytes + (1 << 20)) {
+        Slab b = g_slab_cache;
+        g_slab_cache = Slab{};
+        return b;
+    }
+    slab_free(g_slab_cache);
+    Slab b;
+    b.bytes = bytes;
+    if (cudaHostAlloc(&b.p, bytes, cudaHostAllocDefault) == cudaSuccess) {
+        b.pinned = true;
+    } else {
+        cudaGetLastError();
+        b.p = malloc(bytes);
+    }
+    return b;
+}
+static void slab_release(Slab b) {   // destroy_table: keep the newest slab for the next join
+    if (b.bytes > kSlabCacheMax) {
+        slab_free(b);
+        return;
+    }
+    slab_free(g_slab_cache);
+    g_slab_cache = b;
+}
 
 static void print_reference_timing_lines(uint64_t nR, uint64_t nS) {
     // radix_join.cpp:252-293 — the lines SGXv2Scripts/scripts/helpers/runner.py:19-53 scrapes. "cycles"
@@ -383,8 +426,10 @@ static int join_host_locked(const table_t *R, const table_t *S, const joinconfig
         nS = S->num_tuples;
         if (g.relR.ensure(nR * sizeof(row_t) + 16) || g.relS.ensure(nS * sizeof(row_t) + 16)) return -1;
         double t = now_s();
-        AQP_CUDA_OK(cudaMemcpyAsync(g.relR.p, R->tuples, nR * sizeof(row_t), cudaMemcpyHostToDevice, st));
-        AQP_CUDA_OK(cudaMemcpyAsync(g.relS.p, S->tuples, nS * sizeof(row_t), cudaMemcpyHostToDevice, st));
+        // pinned relations (this library's create_relation_* return pinned memory): one DMA each; pageable ones
+        // (a caller's malloc): multi-threaded staging through pinned buffers (hostcopy.cpp)
+        if (copy_h2d_any(g.relR.p, R->tuples, nR * sizeof(row_t), st) || copy_h2d_any(g.relS.p, S->tuples, nS * sizeof(row_t), st))
+            return -1;
         AQP_CUDA_OK(cudaStreamSynchronize(st));
         ms_h2d = (float) ((now_s() - t) * 1e3);
         g.preloaded = false;
@@ -430,13 +475,14 @@ static int join_host_locked(const table_t *R, const table_t *S, const joinconfig
         if (g.tmp[0].ensure(bytes)) return -1;   // partitions are dead by now; reuse their space
         chunkify_kernel<<<kNumSMs * 8, 256, 0, st>>>(d_out, static_cast<unsigned char *>(g.tmp[0].p), n);
         AQP_LAUNCHED();
-        unsigned char *slab = static_cast<unsigned char *>(malloc(bytes));
+        Slab sl = slab_alloc(bytes);
+        unsigned char *slab = static_cast<unsigned char *>(sl.p);
         table_chunk_t **arr = static_cast<table_chunk_t **>(malloc(sizeof(table_chunk_t *) * nchunks));
         if (!slab || !arr) {
             set_error("out of host memory for the materialised result");
             return -1;
         }
-        AQP_CUDA_OK(cudaMemcpyAsync(slab, g.tmp[0].p, bytes, cudaMemcpyDeviceToHost, st));
+        if (copy_d2h_any(slab, g.tmp[0].p, bytes, st)) return -1;   // one DMA when the slab is pinned, staged otherwise
         AQP_CUDA_OK(cudaStreamSynchronize(st));
         for (uint64_t c = 0; c < nchunks; ++c) arr[c] = reinterpret_cast<table_chunk_t *>(slab + c * sizeof(table_chunk_t));
         ct->chunks = arr;
@@ -444,7 +490,7 @@ static int join_host_locked(const table_t *R, const table_t *S, const joinconfig
         ct->chunk_capacity = nchunks;
         ct->current_chunk = nchunks - 1;
         ct->num_tuples = n;
-        g_slabs[arr] = slab;
+        g_slabs[arr] = sl;
         g.last.ms_materialize_host = (float) ((now_s() - t) * 1e3);
     } else {
         ct->chunks = static_cast<table_chunk_t **>(malloc(sizeof(table_chunk_t *)));
@@ -496,6 +542,8 @@ void b200_shutdown(void) {
     g.scan_out.release();
     g.scan_scratch.release();
     scan_release();
+    hostcopy_release();
+    slab_free(g_slab_cache);
     for (auto &e : g.ev) cudaEventDestroy(e);
     cudaStreamDestroy(g.stream);
     g.stream = nullptr;
@@ -573,7 +621,7 @@ void destroy_table(struct chunked_table_t *table) {
     if (!table) return;
     auto it = table->chunks ? g_slabs.find(table->chunks) : g_slabs.end();
     if (it != g_slabs.end()) {
-        free(it->second);   // all chunks live in one slab
+        slab_release(it->second);   // all chunks live in one slab
         g_slabs.erase(it);
     } else {
         for (uint64_t i = 0; i < table->num_chunks; ++i) free(table->chunks[i]);   // ChunkedTable.cpp:128-136
@@ -595,8 +643,9 @@ int b200_preload_relations(const struct table_t *relR, const struct table_t *rel
     if (ensure_init()) return -1;
     const uint64_t nR = relR->num_tuples, nS = relS->num_tuples;
     if (g.relR.ensure(nR * sizeof(row_t) + 16) || g.relS.ensure(nS * sizeof(row_t) + 16)) return -1;
-    AQP_CUDA_OK(cudaMemcpyAsync(g.relR.p, relR->tuples, nR * sizeof(row_t), cudaMemcpyHostToDevice, g.stream));
-    AQP_CUDA_OK(cudaMemcpyAsync(g.relS.p, relS->tuples, nS * sizeof(row_t), cudaMemcpyHostToDevice, g.stream));
+    if (copy_h2d_any(g.relR.p, relR->tuples, nR * sizeof(row_t), g.stream) ||
+        copy_h2d_any(g.relS.p, relS->tuples, nS * sizeof(row_t), g.stream))
+        return -1;
     AQP_CUDA_OK(cudaStreamSynchronize(g.stream));
     g.preR = nR;
     g.preS = nS;
@@ -998,7 +1047,7 @@ void b200_bitvector_scan_user(uint8_t lo, uint8_t hi, const uint8_t *data, size_
     cudaStream_t st = g.stream;
     if (g.scan_in.ensure(n + 64) || g.scan_out.ensure(nblk * 8 + 64)) die("b200_bitvector_scan_user");
     double t = now_s();
-    cudaMemcpyAsync(g.scan_in.p, data, nblk * 64, cudaMemcpyHostToDevice, st);
+    if (copy_h2d_any(g.scan_in.p, data, nblk * 64, st)) die("b200_bitvector_scan_user");
     cudaStreamSynchronize(st);
     uint64_t copy_ns = (uint64_t) ((now_s() - t) * 1e9);
     const uint8_t *d_in = static_cast<const uint8_t *>(g.scan_in.p);
@@ -1017,7 +1066,7 @@ void b200_bitvector_scan_user(uint8_t lo, uint8_t hi, const uint8_t *data, size_
     cudaEventElapsedTime(&ms, g.ev[5], g.ev[6]);
     if (time_cntr) *time_cntr += (uint64_t) ((double) ms * 1e6);
     t = now_s();
-    cudaMemcpyAsync(output_buffer, d_out, nblk * 8, cudaMemcpyDeviceToHost, st);
+    if (copy_d2h_any(output_buffer, d_out, nblk * 8, st)) die("b200_bitvector_scan_user");
     if (cudaStreamSynchronize(st) != cudaSuccess) {
         set_error("bitvector scan D2H failed");
         die("b200_bitvector_scan_user");
@@ -1076,7 +1125,7 @@ static int scan_host_common(const char *who, const uint8_t *data, size_t n, cons
     if (ensure_init()) return -1;
     static DevBuf cnt;
     if (g.scan_in.ensure(n + 64) || cnt.ensure(16)) return -1;
-    AQP_CUDA_OK(cudaMemcpyAsync(g.scan_in.p, data, n / 64 * 64, cudaMemcpyHostToDevice, g.stream));
+    if (copy_h2d_any(g.scan_in.p, data, n / 64 * 64, g.stream)) return -1;
     *d_in = static_cast<const uint8_t *>(g.scan_in.p);
     *d_count = static_cast<uint64_t *>(cnt.p);
     (void) who;
@@ -1106,7 +1155,7 @@ uint64_t b200_scan(uint8_t lo, uint8_t hi, const uint8_t *data, size_t n, uint32
         cudaStreamSynchronize(g.stream) != cudaSuccess)
         die("b200_scan");
     const uint64_t c = h < output_capacity ? h : output_capacity;
-    if (c && cudaMemcpy(output_buffer, g.scan_out.p, c * 4, cudaMemcpyDeviceToHost) != cudaSuccess) die("b200_scan");
+    if (c && (copy_d2h_any(output_buffer, g.scan_out.p, c * 4, g.stream) || cudaStreamSynchronize(g.stream) != cudaSuccess)) die("b200_scan");
     return h;
 }
 
@@ -1123,7 +1172,7 @@ uint64_t b200_dict_scan_8bit_64bit(int64_t predicate_low, int64_t predicate_high
         cudaStreamSynchronize(g.stream) != cudaSuccess)
         die("b200_dict_scan_8bit_64bit");
     const uint64_t c = h < output_capacity ? h : output_capacity;
-    if (c && cudaMemcpy(output_buffer, g.scan_out.p, c * 8, cudaMemcpyDeviceToHost) != cudaSuccess)
+    if (c && (copy_d2h_any(output_buffer, g.scan_out.p, c * 8, g.stream) || cudaStreamSynchronize(g.stream) != cudaSuccess))
         die("b200_dict_scan_8bit_64bit");
     return h;
 }
@@ -1141,7 +1190,7 @@ void b200_index_scan_user(uint8_t lo, uint8_t hi, const uint8_t *data, size_t n,
     cudaStream_t st = g.stream;
     if (g.scan_in.ensure(n + 64) || g.scan_scratch.ensure(index_scan_scratch_bytes(n))) die("b200_index_scan_user");
     double t = now_s();
-    cudaMemcpyAsync(g.scan_in.p, data, nblk * 64, cudaMemcpyHostToDevice, st);
+    if (copy_h2d_any(g.scan_in.p, data, nblk * 64, st)) die("b200_index_scan_user");
     cudaStreamSynchronize(st);
     uint64_t copy_ns = (uint64_t) ((now_s() - t) * 1e9);
     const uint8_t *d_in = static_cast<const uint8_t *>(g.scan_in.p);
@@ -1171,7 +1220,7 @@ void b200_index_scan_user(uint8_t lo, uint8_t hi, const uint8_t *data, size_t n,
     if (time_cntr) *time_cntr += (uint64_t) ((double) ms * 1e6);
     t = now_s();
     cudaMemcpyAsync(&h_count, d_count, 8, cudaMemcpyDeviceToHost, st);
-    if (cap) cudaMemcpyAsync(output_buffer, d_out, cap * 8, cudaMemcpyDeviceToHost, st);
+    if (cap && copy_d2h_any(output_buffer, d_out, cap * 8, st)) die("b200_index_scan_user");
     if (cudaStreamSynchronize(st) != cudaSuccess) {
         set_error("index scan D2H failed");
         die("b200_index_scan_user");

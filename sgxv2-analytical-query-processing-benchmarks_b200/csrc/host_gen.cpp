@@ -4,7 +4,7 @@
 // src/generator.cpp (seed_generator :75-80, create_relation_pk :352-377, create_relation_fk
 // :474-512, create_relation_fk_sel :515-553, create_relation_zipf :638-660, delete_relation
 // :663-668). The uniform generators draw from libc srand()/rand() in exactly the reference's
-// order, so for the same seed the key sequence is bit-identical (tests/test_host_gen.py checks
+// order, so for the same seed the key sequence is bit-identical (tests/test_abi.py::test_host_generators_reproduce_reference checks
 // this against the compiled reference and the committed fixtures). Differences, on purpose:
 //   * payload is zeroed (the reference leaves malloc garbage);
 //   * `sorted` != 0 is rejected (sorting helpers are out of scope of the hot path);
@@ -19,6 +19,11 @@
 #include <vector>
 
 #include "aqp/b200_aqp.h"
+
+namespace aqp {   // csrc/hostcopy.cpp
+void *host_alloc_prefer_pinned(size_t bytes);
+void host_free_any(void *p);
+}
 
 static int g_seeded = 0;
 static unsigned int g_seed_value = 0;
@@ -75,7 +80,8 @@ static int alloc_relation(table_t *rel, uint64_t n, int sorted) {
         return -1;
     }
     rel->num_tuples = n;
-    rel->tuples = (row_t *) malloc((n ? n : 1) * sizeof(row_t));
+    // pinned when a device is present: run_join() then copies the relation with one DMA at the PCIe rate
+    rel->tuples = (row_t *) aqp::host_alloc_prefer_pinned((n ? n : 1) * sizeof(row_t));
     rel->sorted = 0;
     rel->ratio_holes = 0;
     if (!rel->tuples) {
@@ -155,6 +161,6 @@ extern "C" int create_relation_zipf(table_t *rel, uint64_t n, const int64_t maxi
 }
 
 extern "C" void delete_relation(table_t *rel) {
-    free(rel->tuples);
+    aqp::host_free_any(rel->tuples);
     rel->tuples = nullptr;
 }

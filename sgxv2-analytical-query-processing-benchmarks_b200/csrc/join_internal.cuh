@@ -172,6 +172,13 @@ int bitvector_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t 
 int scan_count_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, uint64_t *d_count, cudaStream_t st);
 size_t index_scan_scratch_bytes(size_t n);
 void scan_release();
+
+// ---- host <-> device copies for the host-buffer entry points (hostcopy.cpp) ----------------------
+int copy_h2d_any(void *dev, const void *host, size_t bytes, cudaStream_t st);
+int copy_d2h_any(void *host, const void *dev, size_t bytes, cudaStream_t st);
+void hostcopy_release();
+void *host_alloc_prefer_pinned(size_t bytes);
+void host_free_any(void *p);
 int index_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, uint64_t id_base, uint64_t *d_out,
                       uint64_t cap, uint64_t *d_count, void *d_scratch, cudaStream_t st);
 int value_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, uint32_t *d_out, uint64_t cap,
