@@ -197,6 +197,32 @@ int b200_shard_join_async_device(const struct row_t *d_R, uint64_t nR, const uin
                                  uint64_t *d_result3, void *stream);
 int b200_shard_join_times(struct b200_join_stats_t *stats);
 
+/* Multi-GPU host of the sharded join (csrc/mg.cu): the C form of what join_init_run does for threads
+ * (radix_join.cpp:1369-1638), for G = 1, 2, 4 or 8 processes of one box, one per GPU. Every process calls
+ *   b200_init(local device); b200_mg_init(rank, world, id, |R| total, |S| total)     once
+ *   b200_mg_join(its row-range shard of R, of S, &result)                            per join (collective)
+ *   b200_mg_finalize()                                                              once (collective)
+ * `id` is the 128-byte NCCL unique id rank 0 obtains from b200_mg_unique_id and hands to the others by any means
+ * (the C driver host/native_mg.cpp uses shared memory between forked processes, bench.py torch.distributed).
+ * NCCL carries three small collectives per join (partition counts, histograms, the 24-byte result) and one
+ * barrier; the tuples move inside the pass-1 scatter kernel, stored straight into the owners' buffers over NVLink
+ * peer memory (CUDA IPC). A shard may hold at most ceil(total / world) tuples. result: GLOBAL matches / checksum /
+ * keysum on every rank, this rank's phase times (CUDA events). */
+struct b200_mg_result_t {
+    uint64_t matches, checksum, keysum;
+    uint64_t tuples_sent;          /* tuples this rank scattered (its shard) */
+    uint64_t tuples_kept;          /* of those, tuples whose owner is this rank (never cross NVLink) */
+    uint32_t radix_bits, bits_pass1, bits_pass2, world, kernel_launches, reserved;
+    float ms_total;                /* first histogram .. global result on the device */
+    float ms_hist, ms_scatter, ms_barrier, ms_local, ms_reduce;   /* consecutive phases of ms_total */
+    float ms_pass2, ms_join;       /* inside ms_local */
+};
+int b200_mg_unique_id(unsigned char *id_out /* 128 bytes */);
+int b200_mg_init(int rank, int world, const unsigned char *id /* 128 bytes */, uint64_t nR_total, uint64_t nS_total);
+int b200_mg_join(const struct row_t *d_R, uint64_t nR_local, const struct row_t *d_S, uint64_t nS_local,
+                 struct b200_mg_result_t *result);
+int b200_mg_finalize(void);
+
 /* ------------------------------------------------------------------------------------------------
  * 4. relation generators
  * ---------------------------------------------------------------------------------------------- */

@@ -89,6 +89,18 @@ class JoinStats(C.Structure):      # struct b200_join_stats_t
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
 
 
+class MgResult(C.Structure):       # struct b200_mg_result_t
+    _fields_ = [("matches", C.c_uint64), ("checksum", C.c_uint64), ("keysum", C.c_uint64), ("tuples_sent", C.c_uint64),
+                ("tuples_kept", C.c_uint64), ("radix_bits", C.c_uint32), ("bits_pass1", C.c_uint32),
+                ("bits_pass2", C.c_uint32), ("world", C.c_uint32), ("kernel_launches", C.c_uint32),
+                ("reserved", C.c_uint32), ("ms_total", C.c_float), ("ms_hist", C.c_float), ("ms_scatter", C.c_float),
+                ("ms_barrier", C.c_float), ("ms_local", C.c_float), ("ms_reduce", C.c_float), ("ms_pass2", C.c_float),
+                ("ms_join", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
 # every symbol include/aqp/b200_aqp.h declares: (restype, argtypes)
 _vp, _u64, _u32, _u8, _sz, _int = C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint8, C.c_size_t, C.c_int
 SYMBOLS = {
@@ -128,6 +140,10 @@ SYMBOLS = {
     "b200_ipc_export": (_int, [_vp, _vp]),
     "b200_ipc_open": (_int, [_vp, C.POINTER(_vp)]),
     "b200_ipc_close": (_int, [_vp]),
+    "b200_mg_unique_id": (_int, [_vp]),
+    "b200_mg_init": (_int, [_int, _int, _vp, _u64, _u64]),
+    "b200_mg_join": (_int, [_vp, _u64, _vp, _u64, C.POINTER(MgResult)]),
+    "b200_mg_finalize": (_int, []),
     "seed_generator": (None, [C.c_uint]),
     "create_relation_pk": (_int, [C.POINTER(Table), _u64, _int]),
     "create_relation_fk": (_int, [C.POINTER(Table), _u64, C.c_int64, _int]),
@@ -281,6 +297,29 @@ def join_device(d_R: int, nR: int, d_S: int, nS: int, d_out: int = 0, out_capaci
     _check(lib().b200_join_device(d_R, nR, d_S, nS, d_out or None, out_capacity, C.byref(s), _st(stream)),
            "b200_join_device")
     return s.as_dict()
+
+
+def mg_unique_id() -> bytes:
+    """128-byte NCCL unique id (rank 0 creates it, every rank passes it to mg_init)"""
+    buf = (C.c_ubyte * 128)()
+    _check(lib().b200_mg_unique_id(buf), "b200_mg_unique_id")
+    return bytes(buf)
+
+
+def mg_init(rank: int, world: int, unique_id: bytes, nR_total: int, nS_total: int):
+    buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+    _check(lib().b200_mg_init(rank, world, buf, nR_total, nS_total), "b200_mg_init")
+
+
+def mg_join(d_R: int, nR: int, d_S: int, nS: int) -> dict:
+    """The C multi-GPU host's sharded join on this rank's device-resident shard (collective call)."""
+    r = MgResult()
+    _check(lib().b200_mg_join(d_R, nR, d_S, nS, C.byref(r)), "b200_mg_join")
+    return r.as_dict()
+
+
+def mg_finalize():
+    _check(lib().b200_mg_finalize(), "b200_mg_finalize")
 
 
 def join_plan(nR: int):

@@ -531,3 +531,35 @@ class DmaShardedJoin(FusedShardedJoin):
         st = self.copy_streams[lane]
         st.wait_event(after)
         self.backend.copy_async(dst_ptr, src_ptr, nbytes, st.cuda_stream)
+
+
+class MgShardedJoin:
+    """The product multi-GPU path: the C host inside libb200aqp.so (csrc/mg.cu; NCCL + CUDA IPC from C++), the
+    same code host/native_mg.cpp drives. Python only hands over the NCCL unique id (torch.distributed broadcast) and
+    the device pointers. Region-layout exchange: no collective and no host read-back in front of the scatter."""
+
+    def __init__(self, nR_total: int, nS_total: int, device, backend=None, group=None):
+        import b200aqp as A
+        self.A = A
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.device = device
+        uid = torch.zeros(128, dtype=torch.uint8, device=device)
+        if self.rank == 0:
+            uid.copy_(torch.tensor(list(A.mg_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0, group=group)
+        A.mg_init(self.rank, self.world, bytes(uid.cpu().tolist()), nR_total, nS_total)
+        self.open = True
+
+    def run(self, R: torch.Tensor, S: torch.Tensor) -> dict:
+        torch.cuda.current_stream().synchronize()      # the C host runs on its own streams
+        r = self.A.mg_join(R.data_ptr(), R.numel() // 2, S.data_ptr(), S.numel() // 2)
+        r.update(num_passes=2, exchange="p2p-regions", ms_pass1=r["ms_scatter"] + r["ms_barrier"], ms_sizing=0.0,
+                 ms_scatter_kernels=r["ms_scatter"], ms_exchange=0.0)
+        return r
+
+    def close(self):
+        if self.open:
+            self.A.mg_finalize()
+            self.open = False

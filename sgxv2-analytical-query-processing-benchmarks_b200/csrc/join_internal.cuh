@@ -110,7 +110,10 @@ struct ShardRelPlan {
 struct ShardPlanArgs {
     ShardRelPlan rel[2];
     uint32_t nparts, nseg;
+    const uint32_t *seg_group;  // [nseg] or null; kGapSegment marks a hole between two sources' regions (no tiles)
 };
+constexpr uint32_t kGapSegment = 0xffffffffu;
+constexpr int kMaxSegs = kMaxFanout + 8;   // received segments: (source, local partition) + one gap per source
 
 struct JoinResult {              // device-side accumulators
     unsigned long long matches;
@@ -145,6 +148,11 @@ uint32_t pass1_blocks();
 int plan_pass1_device(const uint32_t *d_hist, uint32_t bits1, uint32_t bits2, uint32_t *d_part1_off, uint32_t *d_seg1,
                       const uint32_t *d_block_hist, uint32_t *d_block_base, uint32_t nblocks, cudaStream_t st);
 int plan_shard_device(const ShardPlanArgs &a, cudaStream_t st);
+int region_dest_device(const uint32_t *d_counts1, uint32_t world, uint32_t rank, uint32_t bits1, uint64_t cap_r, uint64_t cap_s,
+                       uint32_t *d_dest_off, unsigned long long *d_kept, cudaStream_t st);
+int region_plan_device(const uint32_t *d_counts_all, uint32_t world, uint32_t rank, uint32_t bits1, uint32_t bits2,
+                       const uint32_t *d_hist_global, uint64_t cap_r, uint64_t cap_s, uint32_t *d_seg_off,
+                       uint32_t *d_seg_group, uint32_t *d_hist_slice, cudaStream_t st);
 int exchange_plan_device(const uint32_t *d_counts_all, uint32_t world, uint32_t rank, uint32_t bits1, uint32_t bits2,
                          const uint32_t *d_hist_global, uint32_t *d_seg_off, uint32_t *d_dest_off, uint32_t *d_hist_slice,
                          unsigned long long *d_host_vals, cudaStream_t st);

@@ -409,11 +409,75 @@ __global__ void __launch_bounds__(kScanBlock) plan_shard_kernel(ShardPlanArgs a)
     uint32_t tiles = block_exclusive_scan(
         a.nseg,
         [&](uint32_t s) {
+            if (a.seg_group && a.seg_group[s] == kGapSegment) return 0u;   // unused tail of a source's region
             uint32_t len = r.seg_off[s + 1] - r.seg_off[s];
             return (len + kScatterTile - 1) / kScatterTile;
         },
         [&](uint32_t s, uint32_t v) { r.seg_tile_start[s] = v; });
     if (threadIdx.x == 0) r.seg_tile_start[a.nseg] = tiles;
+}
+
+// ---- region layout of the fused exchange (multi-GPU host, csrc/mg.cu) ------------------------------------------
+// Every owner's receive buffer is cut into one fixed region per source rank (cap tuples, sized for the worst case:
+// a source's whole shard). A source packs its partitions of that owner tightly at the start of its region, so it can
+// compute every destination from its OWN counts - no collective in front of the scatter. The receiver learns the
+// segment boundaries from the all-gathered counts, which travel while the scatter runs.
+//   dest_off[rel][p] = rank * cap_rel + (tuples of this rank in the partitions of p's owner that precede p)
+__global__ void __launch_bounds__(256)
+region_dest_kernel(const uint32_t *__restrict__ counts1, uint32_t world, uint32_t rank, uint32_t bits1, uint32_t cap_r,
+                   uint32_t cap_s, uint32_t *__restrict__ dest_off, unsigned long long *__restrict__ kept) {
+    const uint32_t F1 = 1u << bits1, per = F1 / world;
+    for (uint32_t t = threadIdx.x; t < 2 * world; t += blockDim.x) {   // one thread per (relation, owner)
+        const uint32_t rel = t / world, g = t % world;
+        uint32_t run = rank * (rel ? cap_s : cap_r);
+        for (uint32_t j = 0; j < per; ++j) {
+            dest_off[rel * F1 + g * per + j] = run;
+            run += counts1[rel * F1 + g * per + j];
+        }
+        if (g == rank && kept) kept[rel] = run - rank * (rel ? cap_s : cap_r);   // tuples that stay on this GPU
+    }
+}
+int region_dest_device(const uint32_t *d_counts1, uint32_t world, uint32_t rank, uint32_t bits1, uint64_t cap_r, uint64_t cap_s,
+                       uint32_t *d_dest_off, unsigned long long *d_kept, cudaStream_t st) {
+    region_dest_kernel<<<1, 256, 0, st>>>(d_counts1, world, rank, bits1, (uint32_t) cap_r, (uint32_t) cap_s, d_dest_off, d_kept);
+    AQP_LAUNCHED();
+    AQP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// receiver side: counts_all[s][rel][p] (all-gathered), hist_global[rel][D] (all-reduced) ->
+//   seg_off[rel][nseg + 1], nseg = world * (per + 1): for every source its per segments, then the gap up to the next
+//   region; seg_group[nseg] = local partition of a segment or kGapSegment; hist_slice[rel][per << bits2]
+__global__ void __launch_bounds__(256)
+region_plan_kernel(const uint32_t *__restrict__ counts_all, uint32_t world, uint32_t rank, uint32_t bits1, uint32_t bits2,
+                   const uint32_t *__restrict__ hist_global, uint32_t cap_r, uint32_t cap_s, uint32_t *__restrict__ seg_off,
+                   uint32_t *__restrict__ seg_group, uint32_t *__restrict__ hist_slice) {
+    const uint32_t F1 = 1u << bits1, F2 = 1u << bits2, P = F1 << bits2, per = F1 / world, nseg = world * (per + 1);
+    for (uint32_t t = threadIdx.x; t < 2 * world; t += blockDim.x) {   // one thread per (relation, source)
+        const uint32_t rel = t / world, s = t % world, cap = rel ? cap_s : cap_r;
+        uint32_t run = s * cap;
+        uint32_t *so = seg_off + rel * (nseg + 1) + s * (per + 1);
+        for (uint32_t j = 0; j < per; ++j) {
+            so[j] = run;
+            run += counts_all[((size_t) s * 2 + rel) * F1 + rank * per + j];
+        }
+        so[per] = run;                                   // the gap: [end of the source's data, next region)
+        if (s == world - 1) so[per + 1] = world * cap;   // = seg_off[rel][nseg]
+    }
+    for (uint32_t i = threadIdx.x; i < nseg; i += blockDim.x) seg_group[i] = i % (per + 1) == per ? kGapSegment : i % (per + 1);
+    for (uint32_t t = threadIdx.x; t < 2 * (per << bits2); t += blockDim.x) {
+        const uint32_t rel = t / (per << bits2), f = t % (per << bits2), j = f >> bits2, p2 = f & (F2 - 1);
+        hist_slice[t] = hist_global[(size_t) rel * P + ((size_t) p2 << bits1) + rank * per + j];
+    }
+}
+int region_plan_device(const uint32_t *d_counts_all, uint32_t world, uint32_t rank, uint32_t bits1, uint32_t bits2,
+                       const uint32_t *d_hist_global, uint64_t cap_r, uint64_t cap_s, uint32_t *d_seg_off,
+                       uint32_t *d_seg_group, uint32_t *d_hist_slice, cudaStream_t st) {
+    region_plan_kernel<<<1, 256, 0, st>>>(d_counts_all, world, rank, bits1, bits2, d_hist_global, (uint32_t) cap_r,
+                                          (uint32_t) cap_s, d_seg_off, d_seg_group, d_hist_slice);
+    AQP_LAUNCHED();
+    AQP_CUDA_OK(cudaGetLastError());
+    return 0;
 }
 
 int plan_shard_device(const ShardPlanArgs &a, cudaStream_t st) {
@@ -497,8 +561,8 @@ radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
     __shared__ uint2 *s_peer[8];             // receive buffers of the owners (fused exchange)
     __shared__ uint2 carry[kBulk ? kMaxFanout : 1];        // kBulk: the odd tuple a run left behind
     __shared__ uint32_t runlen[kBulk ? kMaxFanout : 1];    // kBulk: tuples in the run incl. the carried one | carried << 31
-    __shared__ uint32_t s_tstart[kMaxFanout + 1];
-    __shared__ uint32_t s_soff[kMaxFanout + 1];
+    __shared__ uint32_t s_tstart[kMaxSegs + 1];
+    __shared__ uint32_t s_soff[kMaxSegs + 1];
     __shared__ __align__(8) uint64_t mbar[2];
 
     const uint32_t fan = 1u << bits;
@@ -759,8 +823,8 @@ radix_scatter_bins_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
     __shared__ uint32_t lbase[kMaxFanout];    // compacting path only
     __shared__ uint32_t gdst[kMaxFanout];     // compacting path only
     __shared__ uint2 *s_peer[8];
-    __shared__ uint32_t s_tstart[kMaxFanout + 1];
-    __shared__ uint32_t s_soff[kMaxFanout + 1];
+    __shared__ uint32_t s_tstart[kMaxSegs + 1];
+    __shared__ uint32_t s_soff[kMaxSegs + 1];
     __shared__ uint32_t s_ovf[2];
     __shared__ uint32_t s_total;
     __shared__ uint32_t s_tile[2][4];   // {begin, end, cursor group} of the tile in flight / being processed

@@ -28,7 +28,7 @@ static void info(const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
-    printf("[%8.4f][ INFO] %s\n", now_s() - g_t0, buf);
+    printf("\x1b[32m[%8.4f][ INFO] %s\x1b[0m\n", now_s() - g_t0, buf);   // Logger.cpp:71-75 (green INFO, reset)
 }
 
 int main(int argc, char **argv) {

@@ -34,6 +34,22 @@ for logR, logS in ((20, 22), (24, 26)):
         assert o["checksum"] == rep * (nR * (nR - 1) // 2) + nS * (nS - 1) // 2, o
         if rank == 0: print("OK", cls.__name__, logR, logS, {k: round(v, 3) if isinstance(v, float) else v for k, v in o.items()})
         del sj
+    # the C host (csrc/mg.cu): uniform and Zipf-skewed S (the hot key's owner receives far more than the mean:
+    # worst-case regions, no overflow path), against the other variants' result on the same shards
+    mgj = D.MgShardedJoin(nR, nS, dev)
+    for _ in range(3):
+        o = mgj.run(R, S)
+    assert (o["matches"], o["keysum"]) == (nS, rep * nR * (nR + 1) // 2), o
+    assert o["checksum"] == rep * (nR * (nR - 1) // 2) + nS * (nS - 1) // 2, o
+    if rank == 0: print("OK MgShardedJoin", logR, logS, {k: round(v, 3) if isinstance(v, float) else v for k, v in o.items()})
+    for z in (0.5, 1.0):
+        A.gen_zipf_device(S.data_ptr(), nSl, nR, z, 22222, rank * nSl, st)
+        torch.cuda.synchronize()
+        ref = D.ShardedJoin(nR, nS, dev).run(R, S)
+        o = mgj.run(R, S)
+        assert o["matches"] == nS == ref["matches"] and o["checksum"] == ref["checksum"] and o["keysum"] == ref["keysum"], (z, o, ref)
+        if rank == 0: print("OK MgShardedJoin zipf", z, logR, logS, round(o["ms_total"], 3))
+    mgj.close()
 dist.destroy_process_group()
 '''
 
@@ -51,4 +67,4 @@ def test_nccl_sharded_join(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29517", str(script)], env=env,
                        capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
-    assert p.stdout.count("OK") == 6
+    assert p.stdout.count("OK") == 12
