@@ -382,8 +382,10 @@ def run_b200_arm(args):
     else:
         # headline: scatter kernel fused with the exchange over NVLink peer memory; the NCCL all-to-all
         # variant is timed beside it as the baseline (B200_AQP_EXCHANGE=nccl makes it the headline)
-        variants = {"p2p": D.FusedShardedJoin, "dma": D.DmaShardedJoin, "nccl": D.ShardedJoin}
-        default = DEFAULT_EXCHANGE.get(world, "p2p")
+        # "mg" = the C host inside the library (csrc/mg.cu, what host/native_mg.cpp drives): region-layout exchange, the
+        # sizing collectives travel beside the scatter. The round-1 Python-orchestrated variants stay for A/B.
+        variants = {"mg": D.MgShardedJoin, "p2p": D.FusedShardedJoin, "dma": D.DmaShardedJoin, "nccl": D.ShardedJoin}
+        default = DEFAULT_EXCHANGE.get(world, "mg")
         plan = variants[os.environ.get("B200_AQP_EXCHANGE", default)](nR, nS, dev)
 
         def step():
@@ -434,23 +436,29 @@ def run_b200_arm(args):
                  "actual_bytes_per_tuple": 48, "note": "the pass-2 histogram read is avoided: one full-width histogram serves both passes"}
 
     # ---- BASELINE config 4: Zipf-skewed S (z = 0.5, 1.0), same sizes, 1 GPU ----------------------------
-    skew = None
-    if world == 1:
-        skew = {}
-        for z in (0.5, 1.0):
-            A.gen_zipf_device(S.data_ptr(), nS, nR, z, 22222, 0, st)
-            torch.cuda.synchronize()
-            for _ in range(2):
-                sz = A.join_device(R.data_ptr(), nR, S.data_ptr(), nS, stream=st)
-            assert sz["matches"] == nS
-            tz = []
-            for _ in range(max(3, args.steps // 2)):
-                tz.append(A.join_device(R.data_ptr(), nR, S.data_ptr(), nS, stream=st)["ms_total"])
-            ms = sum(tz) / len(tz)
-            skew[f"z{z}"] = {"ms": ms, "value": (nR + nS) / ms / 1e3, "unit": UNIT,
-                             "join_roofline_frac": JOIN_BYTES_PER_TUPLE * (nR + nS) / ms / 1e6 / peak}
-        A.gen_fk_device(S.data_ptr(), nS, nR, 22222, 0, nS, st)   # restore the uniform S for the e2e leg
+    skew = {}
+    for z in (0.5, 1.0):
+        A.gen_zipf_device(S.data_ptr(), nS_loc, nR, z, 22222, rank * nS_loc, st)   # this rank's rows of the Zipf stream
         torch.cuda.synchronize()
+        for _ in range(2):
+            sz = step()
+        assert sz["matches"] == nS, sz          # every Zipf key is in 1..|R| and R is a primary key
+        barrier()
+        e0.record()
+        nz = max(3, args.steps // 2)
+        for _ in range(nz):
+            sz = step()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / nz
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        skew[f"z{z}"] = {"ms": ms, "value": (nR + nS) / ms / 1e3, "unit": UNIT, "checksum": sz["checksum"],
+                         "join_roofline_frac": JOIN_BYTES_PER_TUPLE * (nR + nS) / world / ms / 1e6 / peak}
+    A.gen_fk_device(S.data_ptr(), nS, nR, 22222, rank * nS_loc, nS_loc, st)   # restore the uniform S
+    torch.cuda.synchronize()
 
     # ---- multi-GPU: NVLink traffic of the shuffle, and the NCCL all-to-all variant as the baseline -------
     exchange = None
@@ -464,11 +472,14 @@ def run_b200_arm(args):
                             "all_to_all_single. Reference peaks: 770 GB/s measured peer copy, 900 GB/s nominal per direction",
                     "variants": {}}
         # the other exchange implementations timed beside the headline one (same inputs, same step count)
+        # (opt-in: B200_AQP_BENCH_VARIANTS=p2p,dma,nccl - the round-1 Python-orchestrated forms; their numbers are in
+        # profiles/r01_bench_{2,4,8}gpu_final.json and profiles/r02_bench_2gpu_a.json)
+        wanted = [v for v in os.environ.get("B200_AQP_BENCH_VARIANTS", "").split(",") if v]
         for name, cls in variants.items():
-            if cls is type(plan):
+            if cls is type(plan) or name not in wanted:
                 continue
             other = cls(nR, nS, dev)
-            for _ in range(2):
+            for _ in range(3):
                 sb = other.run(R, S)
             assert sb["matches"] == nS
             barrier()
@@ -483,6 +494,8 @@ def run_b200_arm(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             exchange["variants"][name] = {"ms_per_step": float(t.item()), "value": (nR + nS) / float(t.item()) / 1e3,
                                           "unit": UNIT, "ms_exchange": xb / args.steps}
+            if hasattr(other, "close"):
+                other.close()
             del other
 
     # ---- e2e through run_join() with pinned host relations (N=1 path of the drop-in API) ----------
@@ -670,6 +683,8 @@ def run_b200_arm(args):
                 "clocks": clocks, "scan": scan}
         print(json.dumps(line))
     if world > 1:
+        if hasattr(plan, "close"):
+            plan.close()
         dist.destroy_process_group()
 
 
