@@ -630,13 +630,34 @@ def run_b200_arm(args):
         A.tpch_generate_device(sf, 1)
         published_ms = {3: 730.0, 12: 225.0, 19: 120.0}   # reference, 16 threads, SF100, other hardware
         tpch = {"scale_factor": sf, "data": "synthetic, generated in HBM (include/aqp/b200_tpch.h)"}
+        nc, no, npart = int(150000 * sf), int(1500000 * sf), int(200000 * sf)
+        nl = 4 * no
+
+        def tpch_bytes(q, r):
+            """Algorithmic HBM bytes of a pipeline: every column a filter has to read once (key+row-id pairs 8 B, dates
+            8 B, codes 1 B, part key / size / quantity 4 B), 8 B per selected row written, the joins at the graded
+            56 B/tuple, 12 B per materialised triple written and read again by its consumer."""
+            f, j1 = r["filtered"], r["join1_rows"]
+            join = lambda a, b: JOIN_BYTES_PER_TUPLE * (a + b)
+            if q == 12:   # Q12Predicates.hpp:40-109: l_orderkey, l_shipmode, 3 dates
+                return nl * (8 + 1 + 24) + 8 * f[0] + join(no, f[0])
+            if q == 3:    # Q3Predicates.hpp:57-184
+                return (nc * (8 + 1) + 8 * f[0] + no * (8 + 8 + 4) + 8 * f[1] + join(f[0], f[1]) + 12 * j1 +
+                        (12 + 8) * j1 + nl * (8 + 8) + 8 * f[2] + join(j1, f[2]))
+            # Q19Predicates.hpp:58-78,:194-389; the post-join check gathers 10 B of columns per match by row id
+            return npart * (8 + 1 + 1 + 4) + 8 * f[0] + nl * (8 + 4 + 4 + 1 + 1) + 8 * f[1] + join(f[0], f[1]) + 12 * j1 + (12 + 10) * j1
+
         for q in (3, 12, 19):
             for _ in range(2):
                 r = A.tpch_query_device(q)
             runs = [A.tpch_query_device(q) for _ in range(3)]
             ms = sum(x["ms_total"] for x in runs) / len(runs)
+            b = tpch_bytes(q, r)
             tpch[f"q{q}"] = {"ms": ms, "mrows_per_s": r["input_rows"] / ms / 1e3, "result_rows": r["result_rows"],
                              "ms_filter": runs[-1]["ms_filter"], "ms_join": runs[-1]["ms_join"],
+                             "filtered": r["filtered"], "join1_rows": r["join1_rows"],
+                             "roofline": {"bound": "hbm", "algorithmic_bytes": b, "achieved": b / ms / 1e6, "peak": peak,
+                                          "unit": "GB/s", "frac": b / ms / 1e6 / peak},
                              "reference_published_ms_sf100": published_ms[q]}
         if not args.no_cpu_baseline:
             try:   # the reference's own pipelines on the host cores, bounded sample: the same generator at SF1

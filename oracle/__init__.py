@@ -33,6 +33,8 @@ def build(force: bool = False) -> str:
         subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
     if os.path.isdir("/root/reference/Join-Benchmarks"):
         subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+        if os.path.exists(os.path.join(os.path.dirname(HERE), "sgxv2-analytical-query-processing-benchmarks_b200", "libb200aqp.so")):
+            subprocess.check_call(["make", "-s", "-C", HERE, "dropin"])   # reference TPC-H pipelines linked against libb200aqp.so
     return so
 
 
@@ -541,6 +543,46 @@ def ref_tpch():
 def ref_tpch_query(q: int, tables: dict, nthreads: int = 4) -> dict:
     """The unmodified reference pipeline (oracle/_ref/libref_tpch.so) on the same tables."""
     L = ref_tpch()
+    st = {k: tpch_struct(k, v) for k, v in tables.items()}
+    sec = C.c_double(0)
+    out = {}
+    if q == 12:
+        r = L.ref_tpch_q12(C.byref(st["lineitem"]), C.byref(st["orders"]), nthreads, C.byref(sec))
+    elif q == 3:
+        r = L.ref_tpch_q3(C.byref(st["customer"]), C.byref(st["orders"]), C.byref(st["lineitem"]), nthreads, C.byref(sec))
+    elif q == 19:
+        j = C.c_longlong(0)
+        r = L.ref_tpch_q19(C.byref(st["lineitem"]), C.byref(st["part"]), nthreads, C.byref(j), C.byref(sec))
+        out["join1_rows"] = int(j.value)
+    else:
+        raise ValueError(q)
+    out.update(result_rows=int(r), seconds=sec.value)
+    return out
+
+
+# ---- link-level drop-in proof (tests/test_gpu_dropin.py) ----------------------------------------------------------
+_dropin_tpch = None
+
+
+def have_dropin() -> bool:
+    return host_has_avx512() and os.path.exists(os.path.join(REF_DIR, "libdropin_tpch.so"))
+
+
+def dropin_tpch_query(q: int, tables: dict, nthreads: int = 4) -> dict:
+    """The reference's UNMODIFIED tpch_q3 / q12 / q19 (compiled from /root/reference into oracle/_ref/
+    libdropin_tpch.so) running on libb200aqp.so's run_join / destroy_table instead of the reference's join library.
+    Needs a GPU: the joins inside run on the device."""
+    global _dropin_tpch
+    if _dropin_tpch is None:
+        L = C.CDLL(os.path.join(REF_DIR, "libdropin_tpch.so"))
+        L.ref_tpch_q3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, _f64p]
+        L.ref_tpch_q3.restype = C.c_longlong
+        L.ref_tpch_q12.argtypes = [C.c_void_p, C.c_void_p, C.c_int, _f64p]
+        L.ref_tpch_q12.restype = C.c_longlong
+        L.ref_tpch_q19.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_longlong), _f64p]
+        L.ref_tpch_q19.restype = C.c_longlong
+        _dropin_tpch = L
+    L = _dropin_tpch
     st = {k: tpch_struct(k, v) for k, v in tables.items()}
     sec = C.c_double(0)
     out = {}

@@ -22,10 +22,11 @@
 #include "TpcHTypes.hpp"
 #include "tpch.hpp"
 #include "joins.hpp"
-#include "radix/radix_join.h"
 #include "ChunkedTable.hpp"
 #include "Logger.hpp"
 
+#ifndef REF_TPCH_DROPIN
+#include "radix/radix_join.h"
 void run_join(result_t *res, const table_t *relR, const table_t *relS, const char *algorithm_name,
               const joinconfig_t *config) {
     if (strcmp(algorithm_name, "RHO") != 0) {
@@ -36,6 +37,20 @@ void run_join(result_t *res, const table_t *relR, const table_t *relS, const cha
     memcpy(res, tmp, sizeof(result_t));
     free(tmp);
 }
+#endif
+#if defined(REF_TPCH_DROPIN) && defined(REF_TPCH_BACKTRACE)
+#include <execinfo.h>
+#include <signal.h>
+static void segv_bt(int sig) {
+    void *frames[64];
+    int n = backtrace(frames, 64);
+    backtrace_symbols_fd(frames, n, 2);
+    _exit(128 + sig);
+}
+__attribute__((constructor)) static void install_bt() { signal(SIGSEGV, segv_bt); }
+#endif
+/* -DREF_TPCH_DROPIN (target libdropin_tpch.so): no join code of the reference is compiled in; run_join and
+ * destroy_table come from libb200aqp.so through shim/b200aqp_cxx_shim.cpp - the link-level drop-in test. */
 
 static double now_s() {
     timespec ts;

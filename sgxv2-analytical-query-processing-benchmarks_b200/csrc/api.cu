@@ -466,15 +466,17 @@ static int join_host_locked(const table_t *R, const table_t *S, const joinconfig
         set_error("out of host memory");
         return -1;
     }
-    if (mat && s.matches > 0) {
+    if (mat) {
         double t = now_s();
         const uint64_t n = (uint64_t) s.matches;
-        const uint64_t nchunks = (n + TUPLES_PER_CHUNK - 1) / TUPLES_PER_CHUNK;
-        const size_t bytes = nchunks * sizeof(table_chunk_t);
-        // lay the chunks out on the device, then one D2H into one host slab
-        if (g.tmp[0].ensure(bytes)) return -1;   // partitions are dead by now; reuse their space
-        chunkify_kernel<<<kNumSMs * 8, 256, 0, st>>>(d_out, static_cast<unsigned char *>(g.tmp[0].p), n);
-        AQP_LAUNCHED();
+        const uint64_t nreal = (n + TUPLES_PER_CHUNK - 1) / TUPLES_PER_CHUNK;
+        // The reference concatenates one chunk list per thread, each with at least one (possibly empty) chunk
+        // (radix_join.cpp:1294-1297, ChunkedTable.cpp:52-60,:147-171), and its consumers count on it: thread t of
+        // q19FilterJoinResultsChunked starts at chunks[t] unconditionally (Q19Predicates.hpp:147-151). So a materialised
+        // result always has at least NTHREADS chunks; the surplus ones are empty.
+        const uint64_t nthreads = cfg && cfg->NTHREADS > 0 ? (uint64_t) cfg->NTHREADS : 1;
+        const uint64_t nchunks = nreal > nthreads ? nreal : nthreads;
+        const size_t bytes = nchunks * sizeof(table_chunk_t), real_bytes = nreal * sizeof(table_chunk_t);
         Slab sl = slab_alloc(bytes);
         unsigned char *slab = static_cast<unsigned char *>(sl.p);
         table_chunk_t **arr = static_cast<table_chunk_t **>(malloc(sizeof(table_chunk_t *) * nchunks));
@@ -482,9 +484,18 @@ static int join_host_locked(const table_t *R, const table_t *S, const joinconfig
             set_error("out of host memory for the materialised result");
             return -1;
         }
-        if (copy_d2h_any(slab, g.tmp[0].p, bytes, st)) return -1;   // one DMA when the slab is pinned, staged otherwise
-        AQP_CUDA_OK(cudaStreamSynchronize(st));
-        for (uint64_t c = 0; c < nchunks; ++c) arr[c] = reinterpret_cast<table_chunk_t *>(slab + c * sizeof(table_chunk_t));
+        if (n) {
+            // lay the chunks out on the device, then one D2H into one host slab
+            if (g.tmp[0].ensure(real_bytes)) return -1;   // partitions are dead by now; reuse their space
+            chunkify_kernel<<<kNumSMs * 8, 256, 0, st>>>(d_out, static_cast<unsigned char *>(g.tmp[0].p), n);
+            AQP_LAUNCHED();
+            if (copy_d2h_any(slab, g.tmp[0].p, real_bytes, st)) return -1;   // one DMA when the slab is pinned, staged otherwise
+            AQP_CUDA_OK(cudaStreamSynchronize(st));
+        }
+        for (uint64_t c = 0; c < nchunks; ++c) {
+            arr[c] = reinterpret_cast<table_chunk_t *>(slab + c * sizeof(table_chunk_t));
+            if (c >= nreal) arr[c]->num_tuples = 0;
+        }
         ct->chunks = arr;
         ct->num_chunks = nchunks;
         ct->chunk_capacity = nchunks;

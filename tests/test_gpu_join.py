@@ -85,7 +85,10 @@ def test_empty_relations(gpu, oracle):
     R = oracle.set_rowid_payload(oracle.gen_pk(1000, 1))
     for a, b in ((E, R), (R, E), (E, E)):
         g = gpu.run_join(a, b, materialize=True)
-        assert g["matches"] == 0 and g["checksum"] == 0 and len(g["triples"]) == 0 and g["num_chunks"] == 0
+        # a materialised result has one (empty) chunk per thread, like the reference's concatenated per-thread lists
+        assert g["matches"] == 0 and g["checksum"] == 0 and len(g["triples"]) == 0 and g["num_chunks"] == 1
+        g = gpu.run_join(a, b, materialize=True, nthreads=6)
+        assert g["matches"] == 0 and g["num_chunks"] == 6 and g["table_num_tuples"] == 0
 
 
 def test_sparse_keys_unbalanced_partitions(gpu, oracle):
@@ -149,6 +152,10 @@ def test_chunked_table_layout(gpu, oracle):
     g = gpu.run_join(R, S, materialize=True)
     assert g["num_chunks"] == -(-20000 // gpu.TUPLES_PER_CHUNK)
     assert len(g["triples"]) == 20000
+    # never fewer chunks than threads: thread t of the reference's chunk consumers starts at chunks[t]
+    # (Q19Predicates.hpp:147-151); the surplus chunks are empty
+    g32 = gpu.run_join(R, S, materialize=True, nthreads=32)
+    assert g32["num_chunks"] == 32 and len(g32["triples"]) == 20000
     m, cs, ks = expected_pkfk(R, S)
     t = g["triples"]
     assert int(t["Rpayload"].astype(np.uint64).sum() + t["Spayload"].astype(np.uint64).sum()) == cs

@@ -46,3 +46,21 @@ def test_upload_then_device_queries(gpu, oracle):
     gpu.lib().b200_tpch_free_device()
     with pytest.raises(gpu.AqpError):
         gpu.tpch_query_device(12)
+
+
+def test_duplicate_build_keys_materialise_like_the_reference(gpu, oracle):
+    """Uploaded tables whose build side is NOT a key (every customer / part row twice): the reference materialises
+    whatever run_join produces (tpch.cpp:64-68,:281-282); the device pipeline's first buffer guess (one match per
+    probe row) is too small and the join is run again with room for all matches."""
+    t = oracle.synth_tpch(0.05, 5)
+    dup = {k: dict(v) for k, v in t.items()}
+    for name in ("customer", "part"):
+        dup[name] = {c: np.concatenate([a, a]) for c, a in t[name].items()}
+    gpu.tpch_upload(dup)
+    for q in (3, 19):
+        g = gpu.tpch_query_device(q)
+        o = oracle.tpch_query(q, dup)
+        base = oracle.tpch_query(q, t)
+        assert g["result_rows"] == o["result_rows"] == 2 * base["result_rows"], (q, g, o, base)
+        assert g["join1_rows"] == o["join1_rows"] == 2 * base["join1_rows"]
+    gpu.lib().b200_tpch_free_device()
