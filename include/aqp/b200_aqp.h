@@ -320,6 +320,29 @@ uint64_t b200_scan(uint8_t predicate_low, uint8_t predicate_high, const uint8_t 
                    uint32_t *output_buffer, size_t output_capacity);
 uint64_t b200_dict_scan_8bit_64bit(int64_t predicate_low, int64_t predicate_high, const int64_t *dict, const uint8_t *data,
                                    size_t num_records, int64_t *output_buffer, size_t output_capacity);
+/* The remaining SIMD512 scans, reference argument order, plain output array + capacity in place of the
+ * CacheAlignedVector; every call returns the exact number of matches (also when it exceeds the capacity).
+ *   explicit_index_scan  SIMD512.cpp:152-208: like the row-id scan, but a match at position p emits the caller's index entry
+ *                        index[((p / 64) + (p / 8) % 8) * 8 + p % 8] - block i's byte group j reads index register i + j,
+ *                        exactly as the reference indexes it; `index` holds (n / 64 + 7) * 8 entries.
+ *   scalar_index_scan    ScalarScan.hpp:8-20: the scalar twin of the row-id scan - ALL n values, not only n / 64 blocks.
+ *   dict_scan_16bit / 32bit_64bit  SIMD512.cpp:531-622: dict[code] of every code whose dictionary value lies in
+ *                        [predicate_low, predicate_high]; 65536-entry dictionary resp. dict_size entries; whole 512-bit
+ *                        registers only (32 resp. 16 codes); the code range goes through uint16_t as in the reference. */
+uint64_t b200_explicit_index_scan(uint8_t lo, uint8_t hi, const uint64_t *index, const uint8_t *data, size_t n,
+                                  uint64_t *output_buffer, size_t output_capacity);
+int b200_explicit_index_scan_device(uint8_t lo, uint8_t hi, const uint64_t *d_index, const uint8_t *d_data, size_t n,
+                                    uint64_t *d_out, uint64_t out_capacity, uint64_t *d_count, void *stream);
+uint64_t b200_scalar_index_scan(uint8_t lo, uint8_t hi, const uint8_t *data, size_t n, uint64_t *output_buffer,
+                                size_t output_capacity);
+uint64_t b200_dict_scan_16bit_64bit(int64_t predicate_low, int64_t predicate_high, const int64_t *dict, const uint16_t *data,
+                                    size_t n, int64_t *output_buffer, size_t output_capacity);
+uint64_t b200_dict_scan_32bit_64bit(int64_t predicate_low, int64_t predicate_high, const int64_t *dict, size_t dict_size,
+                                    const uint32_t *data, size_t n, int64_t *output_buffer, size_t output_capacity);
+/* device form of both: code_bits = 16 or 32, the code range already derived, dictionary and column in device memory */
+int b200_dict_scan_wide_device(int code_bits, uint32_t code_lo, uint32_t code_hi, const int64_t *d_dict, const void *d_data,
+                               size_t n, int64_t *d_out, uint64_t out_capacity, uint64_t *d_count, void *stream);
+
 /* Allocator.hpp:95-109 tiled 0..255 column, generated in HBM; value at global position p is p mod 256 */
 int b200_fill_tiled_column_device(uint8_t *d_data, size_t n, uint64_t pos_begin, void *stream);
 /* seeded skewed column for selectivities the tiled column cannot express:

@@ -393,6 +393,77 @@ def aligned_i64(n: int, align: int = 64) -> np.ndarray:
     return raw[off:off + n * 8].view(np.int64)
 
 
+def aligned(n: int, dtype, align: int = 64) -> np.ndarray:
+    """n elements of dtype in 64-byte aligned memory (the reference's kernels use aligned 512-bit loads)"""
+    item = np.dtype(dtype).itemsize
+    raw = np.empty(n * item + align, dtype=np.uint8)
+    off = (-raw.ctypes.data) % align
+    return raw[off:off + n * item].view(dtype)
+
+
+# ---- explicit-index scan and the 16- / 32-bit dictionary scans: restatement and compiled reference
+def explicit_index_scan(lo, hi, index, data) -> np.ndarray:
+    L = lib()
+    L.oracle_explicit_index_scan.restype = C.c_uint64
+    L.oracle_explicit_index_scan.argtypes = [C.c_uint8, C.c_uint8, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    out = np.zeros(data.shape[0] + 64, dtype=np.uint64)
+    n = L.oracle_explicit_index_scan(lo, hi, _ptr(index), _ptr(data), data.shape[0], _ptr(out))
+    return out[:n]
+
+
+def wide_code_range(lo: int, hi: int, dictionary: np.ndarray):
+    L = lib()
+    L.oracle_wide_code_range.restype = None
+    L.oracle_wide_code_range.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    a, b = np.zeros(1, dtype=np.uint32), np.zeros(1, dtype=np.uint32)
+    L.oracle_wide_code_range(lo, hi, _ptr(dictionary), dictionary.shape[0], _ptr(a), _ptr(b))
+    return int(a[0]), int(b[0])
+
+
+def dict_scan_wide(bits: int, lo: int, hi: int, dictionary: np.ndarray, data: np.ndarray) -> np.ndarray:
+    L = lib()
+    out = np.zeros(data.shape[0] + 64, dtype=np.int64)
+    d = np.ascontiguousarray(dictionary, dtype=np.int64)
+    if bits == 16:
+        assert data.dtype == np.uint16 and d.shape[0] == 1 << 16
+        L.oracle_dict_scan_16_64.restype = C.c_uint64
+        L.oracle_dict_scan_16_64.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        n = L.oracle_dict_scan_16_64(lo, hi, _ptr(d), _ptr(data), data.shape[0], _ptr(out))
+    else:
+        assert data.dtype == np.uint32
+        L.oracle_dict_scan_32_64.restype = C.c_uint64
+        L.oracle_dict_scan_32_64.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+        n = L.oracle_dict_scan_32_64(lo, hi, _ptr(d), d.shape[0], _ptr(data), data.shape[0], _ptr(out))
+    return out[:n]
+
+
+def ref_explicit_index_scan(lo, hi, index, data) -> np.ndarray:
+    L = ref_scan()
+    L.ref_explicit_index_scan.restype = C.c_uint64
+    L.ref_explicit_index_scan.argtypes = [C.c_uint8, C.c_uint8, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    out = np.zeros(data.shape[0] + 64, dtype=np.uint64)
+    n = L.ref_explicit_index_scan(lo, hi, _ptr(index), _ptr(data), data.shape[0], _ptr(out))
+    return out[:n]
+
+
+def ref_dict_scan_wide(bits: int, lo: int, hi: int, dictionary: np.ndarray, data: np.ndarray) -> np.ndarray:
+    L = ref_scan()
+    d = aligned(dictionary.shape[0], np.int64)
+    d[:] = dictionary
+    cap = data.shape[0] + 64
+    out = np.zeros(cap, dtype=np.int64)
+    if bits == 16:
+        L.ref_dict_scan_16_64.restype = C.c_uint64
+        L.ref_dict_scan_16_64.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint64]
+        c = L.ref_dict_scan_16_64(lo, hi, _ptr(d), _ptr(data), data.shape[0], _ptr(out), cap)
+    else:
+        L.ref_dict_scan_32_64.restype = C.c_uint64
+        L.ref_dict_scan_32_64.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
+                                          C.c_uint64]
+        c = L.ref_dict_scan_32_64(lo, hi, _ptr(d), d.shape[0], _ptr(data), data.shape[0], _ptr(out), cap)
+    return out[:c]
+
+
 # ----------------------------------------------------------------------------- TPC-H-style pipelines
 class _LineItem(C.Structure):
     _fields_ = [("n", C.c_uint64), ("l_orderkey", C.c_void_p), ("l_shipdate", C.c_void_p), ("l_commitdate", C.c_void_p),

@@ -72,7 +72,14 @@ uint64_t oracle_value_scan(uint8_t lo, uint8_t hi, const uint8_t *in, size_t n, 
 void     oracle_dict_code_range(int64_t predicate_low, int64_t predicate_high, const int64_t *dict, uint8_t *lo,
                                 uint8_t *hi);                                                                    /* :297-305 */
 uint64_t oracle_dict_scan_8_64(int64_t predicate_low, int64_t predicate_high, const int64_t *dict, const uint8_t *in,
-                               size_t n, int64_t *out);                                                          /* :289-336 */
+                               size_t n, int64_t *out);
+uint64_t oracle_explicit_index_scan(uint8_t lo, uint8_t hi, const uint64_t *index, const uint8_t *in, size_t n, uint64_t *out); /* :152-208 */
+void     oracle_wide_code_range(int64_t predicate_low, int64_t predicate_high, const int64_t *dict, size_t dict_size, uint32_t *lo,
+                                uint32_t *hi);                                                                   /* :539-547 */
+uint64_t oracle_dict_scan_16_64(int64_t predicate_low, int64_t predicate_high, const int64_t *dict, const uint16_t *in, size_t n,
+                                int64_t *out);                                                                   /* :531-577 */
+uint64_t oracle_dict_scan_32_64(int64_t predicate_low, int64_t predicate_high, const int64_t *dict, size_t dict_size,
+                                const uint32_t *in, size_t n, int64_t *out);                                     /* :579-622 */                                                          /* :289-336 */
 /* shared_libraries/SharedHeaders/include/Allocator.hpp:95-109: v[i] = i mod 256 */
 void     oracle_fill_tiled_column(uint8_t *data, size_t n);
 

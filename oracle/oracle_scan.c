@@ -97,3 +97,55 @@ uint64_t oracle_dict_scan_8_64(int64_t predicate_low, int64_t predicate_high, co
         if (in[i] >= lo && in[i] <= hi) out[w++] = dict[in[i]];
     return w;
 }
+
+/* SIMD512::explicit_index_scan (:152-208): for every 64-value block i and every byte group j (8 values) with a
+ * match, the matching lanes of index register i + j (8 uint64 each) are compress-stored - block i's group j reads
+ * index[(i + j) * 8 + k], NOT (8 i + j): restated as written. Returns the count. */
+uint64_t oracle_explicit_index_scan(uint8_t lo, uint8_t hi, const uint64_t *index, const uint8_t *in, size_t n, uint64_t *out) {
+    uint64_t w = 0;
+    size_t blocks = n / 64;
+    for (size_t i = 0; i < blocks; ++i)
+        for (size_t j = 0; j < 8; ++j)
+            for (size_t k = 0; k < 8; ++k) {
+                uint8_t v = in[64 * i + 8 * j + k];
+                if (v >= lo && v <= hi) out[w++] = index[(i + j) * 8 + k];
+            }
+    return w;
+}
+
+/* Code range of dict_scan_16bit_64bit / dict_scan_32bit_64bit (:539-547,:585-593): std::find_if for the first entry
+ * >= predicate_low, then for the first entry > predicate_high from there, minus one; BOTH are narrowed with
+ * static_cast<uint16_t> - in the 32-bit scan too - and then compared as unsigned codes of the column's width. */
+void oracle_wide_code_range(int64_t predicate_low, int64_t predicate_high, const int64_t *dict, size_t dict_size, uint32_t *lo,
+                            uint32_t *hi) {
+    size_t l = 0;
+    while (l < dict_size && !(dict[l] >= predicate_low)) ++l;
+    size_t h = l;
+    while (h < dict_size && !(dict[h] > predicate_high)) ++h;
+    *lo = (uint16_t) l;
+    *hi = (uint16_t) (h - 1);
+}
+
+/* SIMD512::dict_scan_16bit_64bit (:531-577): 65536-entry dictionary, whole registers of 32 codes. */
+uint64_t oracle_dict_scan_16_64(int64_t predicate_low, int64_t predicate_high, const int64_t *dict, const uint16_t *in, size_t n,
+                                int64_t *out) {
+    uint32_t lo, hi;
+    oracle_wide_code_range(predicate_low, predicate_high, dict, (size_t) 1 << 16, &lo, &hi);
+    uint64_t w = 0;
+    size_t m = n / 32 * 32;
+    for (size_t i = 0; i < m; ++i)
+        if (in[i] >= lo && in[i] <= hi) out[w++] = dict[in[i]];
+    return w;
+}
+
+/* SIMD512::dict_scan_32bit_64bit (:579-622): dict_size entries, whole registers of 16 codes. */
+uint64_t oracle_dict_scan_32_64(int64_t predicate_low, int64_t predicate_high, const int64_t *dict, size_t dict_size,
+                                const uint32_t *in, size_t n, int64_t *out) {
+    uint32_t lo, hi;
+    oracle_wide_code_range(predicate_low, predicate_high, dict, dict_size, &lo, &hi);
+    uint64_t w = 0;
+    size_t m = n / 16 * 16;
+    for (size_t i = 0; i < m; ++i)
+        if (in[i] >= lo && in[i] <= hi) out[w++] = dict[in[i]];
+    return w;
+}

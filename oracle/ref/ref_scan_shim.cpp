@@ -77,6 +77,31 @@ uint64_t ref_dict_scan_8_64(int which, int64_t lo, int64_t hi, const int64_t *di
     return c;
 }
 
+uint64_t ref_explicit_index_scan(uint8_t lo, uint8_t hi, const uint64_t *index, const uint8_t *data, size_t n, uint64_t *out) {
+    /* the function returns nothing: the count is SIMD512::count's (same predicate, same blocks) */
+    SIMD512::explicit_index_scan(lo, hi, reinterpret_cast<const __m512i *>(index), reinterpret_cast<const __m512i *>(data), n,
+                                 reinterpret_cast<size_t *>(out));
+    return SIMD512::count(lo, hi, reinterpret_cast<const __m512i *>(data), n);
+}
+
+uint64_t ref_dict_scan_16_64(int64_t lo, int64_t hi, const int64_t *dict, const uint16_t *data, size_t n, int64_t *out,
+                             uint64_t cap) {
+    CacheAlignedVector<int64_t> v;
+    SIMD512::dict_scan_16bit_64bit(lo, hi, dict, reinterpret_cast<const __m512i *>(data), n, v);
+    uint64_t c = v.size();
+    if (out) memcpy(out, v.data(), sizeof(int64_t) * (c < cap ? c : cap));
+    return c;
+}
+
+uint64_t ref_dict_scan_32_64(int64_t lo, int64_t hi, const int64_t *dict, size_t dict_size, const uint32_t *data, size_t n,
+                             int64_t *out, uint64_t cap) {
+    CacheAlignedVector<int64_t> v;
+    SIMD512::dict_scan_32bit_64bit(lo, hi, dict, dict_size, reinterpret_cast<const __m512i *>(data), n, v);
+    uint64_t c = v.size();
+    if (out) memcpy(out, v.data(), sizeof(int64_t) * (c < cap ? c : cap));
+    return c;
+}
+
 /*
  * Multi-threaded timed runs, one row range per thread (multithreadedscan.cpp:231-235):
  * mode 0 = bitvector, 1 = row-id list (pre-allocated per thread with count()+64 as

@@ -166,6 +166,12 @@ SYMBOLS = {
     "b200_sum": (_u64, [_u8, _u8, _vp, _sz]),
     "b200_scan": (_u64, [_u8, _u8, _vp, _sz, _vp, _sz]),
     "b200_dict_scan_8bit_64bit": (_u64, [C.c_int64, C.c_int64, _vp, _vp, _sz, _vp, _sz]),
+    "b200_explicit_index_scan": (_u64, [_u8, _u8, _vp, _vp, _sz, _vp, _sz]),
+    "b200_explicit_index_scan_device": (_int, [_u8, _u8, _vp, _vp, _sz, _vp, _u64, _vp, _vp]),
+    "b200_scalar_index_scan": (_u64, [_u8, _u8, _vp, _sz, _vp, _sz]),
+    "b200_dict_scan_16bit_64bit": (_u64, [C.c_int64, C.c_int64, _vp, _vp, _sz, _vp, _sz]),
+    "b200_dict_scan_32bit_64bit": (_u64, [C.c_int64, C.c_int64, _vp, _sz, _vp, _sz, _vp, _sz]),
+    "b200_dict_scan_wide_device": (_int, [_int, _u32, _u32, _vp, _vp, _sz, _vp, _u64, _vp, _vp]),
     "b200_fill_tiled_column_device": (_int, [_vp, _sz, _u64, _vp]),
     "b200_fill_skewed_column_device": (_int, [_vp, _sz, _u64, _u32, _u64, _vp]),
     "b200_kernel_launch_count": (_u64, []),
@@ -464,6 +470,39 @@ def dict_scan_8bit_64bit(lo: int, hi: int, dictionary: np.ndarray, data: np.ndar
     cap = data.shape[0] if capacity is None else capacity
     out = np.zeros(max(cap, 1), dtype=np.int64)
     cnt = int(lib().b200_dict_scan_8bit_64bit(lo, hi, d.ctypes.data, data.ctypes.data, data.shape[0], out.ctypes.data, cap))
+    return out[:min(cnt, cap)], cnt
+
+
+def explicit_index_scan(lo: int, hi: int, index: np.ndarray, data: np.ndarray, capacity: int | None = None):
+    """SIMD512::explicit_index_scan: (the index entries of the matches, exact count)"""
+    assert data.dtype == np.uint8 and index.dtype == np.uint64 and index.shape[0] >= (data.shape[0] // 64 + 7) * 8
+    cap = data.shape[0] if capacity is None else capacity
+    out = np.zeros(max(cap, 1), dtype=np.uint64)
+    cnt = int(lib().b200_explicit_index_scan(lo, hi, index.ctypes.data, data.ctypes.data, data.shape[0], out.ctypes.data, cap))
+    return out[:min(cnt, cap)], cnt
+
+
+def scalar_index_scan(lo: int, hi: int, data: np.ndarray, capacity: int | None = None):
+    """scalar_implicit_index_scan: row ids over ALL n values (not only whole 64-value blocks)"""
+    assert data.dtype == np.uint8 and data.flags["C_CONTIGUOUS"]
+    cap = data.shape[0] if capacity is None else capacity
+    out = np.zeros(max(cap, 1), dtype=np.uint64)
+    cnt = int(lib().b200_scalar_index_scan(lo, hi, data.ctypes.data, data.shape[0], out.ctypes.data, cap))
+    return out[:min(cnt, cap)], cnt
+
+
+def dict_scan_wide(bits: int, lo: int, hi: int, dictionary: np.ndarray, data: np.ndarray, capacity: int | None = None):
+    """SIMD512::dict_scan_16bit_64bit / dict_scan_32bit_64bit: (dict[code] of every selected code, exact count)"""
+    d = np.ascontiguousarray(dictionary, dtype=np.int64)
+    cap = data.shape[0] if capacity is None else capacity
+    out = np.zeros(max(cap, 1), dtype=np.int64)
+    if bits == 16:
+        assert data.dtype == np.uint16 and d.shape[0] == 1 << 16
+        cnt = int(lib().b200_dict_scan_16bit_64bit(lo, hi, d.ctypes.data, data.ctypes.data, data.shape[0], out.ctypes.data, cap))
+    else:
+        assert bits == 32 and data.dtype == np.uint32
+        cnt = int(lib().b200_dict_scan_32bit_64bit(lo, hi, d.ctypes.data, d.shape[0], data.ctypes.data, data.shape[0],
+                                                   out.ctypes.data, cap))
     return out[:min(cnt, cap)], cnt
 
 

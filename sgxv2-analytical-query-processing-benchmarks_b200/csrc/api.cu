@@ -1189,6 +1189,114 @@ uint64_t b200_dict_scan_8bit_64bit(int64_t predicate_low, int64_t predicate_high
     return h;
 }
 
+// ---- the 16- / 32-bit dictionary scans, the explicit-index scan and the scalar twin of the row-id scan -------------
+int b200_explicit_index_scan_device(uint8_t lo, uint8_t hi, const uint64_t *d_index, const uint8_t *d_data, size_t n,
+                                    uint64_t *d_out, uint64_t out_capacity, uint64_t *d_count, void *stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    return explicit_index_scan_device(lo, hi, d_index, d_data, n, d_out, out_capacity, d_count,
+                                      stream ? static_cast<cudaStream_t>(stream) : g.stream);
+}
+
+uint64_t b200_explicit_index_scan(uint8_t lo, uint8_t hi, const uint64_t *index, const uint8_t *data, size_t n,
+                                  uint64_t *output_buffer, size_t output_capacity) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    const uint8_t *d_in;
+    uint64_t *d_cnt, h = 0;
+    static DevBuf d_index;
+    const size_t index_entries = (n / 64 + 7) * 8;   // block i reads index registers i .. i+7 (SIMD512.cpp:176)
+    if (scan_host_common("b200_explicit_index_scan", data, n, &d_in, &d_cnt) || d_index.ensure(index_entries * 8 + 64) ||
+        g.scan_out.ensure(output_capacity * 8 + 64) || copy_h2d_any(d_index.p, index, index_entries * 8, g.stream) ||
+        explicit_index_scan_device(lo, hi, static_cast<const uint64_t *>(d_index.p), d_in, n,
+                                   static_cast<uint64_t *>(g.scan_out.p), output_capacity, d_cnt, g.stream) ||
+        cudaMemcpyAsync(&h, d_cnt, 8, cudaMemcpyDeviceToHost, g.stream) != cudaSuccess ||
+        cudaStreamSynchronize(g.stream) != cudaSuccess)
+        die("b200_explicit_index_scan");
+    const uint64_t c = h < output_capacity ? h : output_capacity;
+    if (c && (copy_d2h_any(output_buffer, g.scan_out.p, c * 8, g.stream) || cudaStreamSynchronize(g.stream) != cudaSuccess))
+        die("b200_explicit_index_scan");
+    return h;
+}
+
+uint64_t b200_scalar_index_scan(uint8_t lo, uint8_t hi, const uint8_t *data, size_t n, uint64_t *output_buffer,
+                                size_t output_capacity) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init()) die("b200_scalar_index_scan");
+    static DevBuf cnt;
+    uint64_t h = 0;
+    if (g.scan_in.ensure(n + 64) || cnt.ensure(16) || g.scan_out.ensure(output_capacity * 8 + 64) ||
+        g.scan_scratch.ensure(index_scan_scratch_bytes(n)) || copy_h2d_any(g.scan_in.p, data, n, g.stream) ||
+        scalar_index_scan_device(lo, hi, static_cast<const uint8_t *>(g.scan_in.p), n, 0, static_cast<uint64_t *>(g.scan_out.p),
+                                 output_capacity, static_cast<uint64_t *>(cnt.p), g.scan_scratch.p, g.stream) ||
+        cudaMemcpyAsync(&h, cnt.p, 8, cudaMemcpyDeviceToHost, g.stream) != cudaSuccess ||
+        cudaStreamSynchronize(g.stream) != cudaSuccess)
+        die("b200_scalar_index_scan");
+    const uint64_t c = h < output_capacity ? h : output_capacity;
+    if (c && (copy_d2h_any(output_buffer, g.scan_out.p, c * 8, g.stream) || cudaStreamSynchronize(g.stream) != cudaSuccess))
+        die("b200_scalar_index_scan");
+    return h;
+}
+
+// predicate on dictionary VALUES -> range of codes, exactly the reference's two std::find_if calls and its casts
+// (SIMD512.cpp:539-547,:585-593): both results go through uint16_t - also for 32-bit codes - so a predicate below the
+// first or above the last dictionary entry wraps exactly as it does there
+static void wide_code_range(int64_t lo, int64_t hi, const int64_t *dict, size_t dict_size, uint32_t *code_lo, uint32_t *code_hi) {
+    const int64_t *low = dict;
+    while (low < dict + dict_size && !(*low >= lo)) ++low;
+    const int64_t *high = low;
+    while (high < dict + dict_size && !(*high > hi)) ++high;
+    --high;
+    *code_lo = (uint16_t) (low - dict);
+    *code_hi = (uint16_t) (high - dict);
+}
+
+int b200_dict_scan_wide_device(int code_bits, uint32_t code_lo, uint32_t code_hi, const int64_t *d_dict, const void *d_data,
+                               size_t n, int64_t *d_out, uint64_t out_capacity, uint64_t *d_count, void *stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : g.stream;
+    if (code_bits == 16)
+        return dict_scan16_device(code_lo, code_hi, d_dict, static_cast<const uint16_t *>(d_data), n, d_out, out_capacity, d_count, st);
+    if (code_bits == 32)
+        return dict_scan32_device(code_lo, code_hi, d_dict, static_cast<const uint32_t *>(d_data), n, d_out, out_capacity, d_count, st);
+    set_error("b200_dict_scan_wide_device: code_bits must be 16 or 32 (8-bit codes: b200_dict_scan_8bit_64bit_device)");
+    return -1;
+}
+
+static uint64_t dict_scan_wide_host(const char *who, int code_bits, int64_t lo, int64_t hi, const int64_t *dict, size_t dict_size,
+                                    const void *data, size_t n, int64_t *output_buffer, size_t output_capacity) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init()) die(who);
+    static DevBuf d_dict, cnt;
+    uint32_t clo, chi;
+    wide_code_range(lo, hi, dict, dict_size, &clo, &chi);
+    const size_t bytes = n * (size_t) (code_bits / 8);
+    uint64_t h = 0;
+    if (g.scan_in.ensure(bytes + 64) || cnt.ensure(16) || d_dict.ensure(dict_size * 8 + 64) ||
+        g.scan_out.ensure(output_capacity * 8 + 64) || copy_h2d_any(g.scan_in.p, data, bytes, g.stream) ||
+        copy_h2d_any(d_dict.p, dict, dict_size * 8, g.stream) ||
+        b200_dict_scan_wide_device(code_bits, clo, chi, static_cast<const int64_t *>(d_dict.p), g.scan_in.p, n,
+                                   static_cast<int64_t *>(g.scan_out.p), output_capacity, static_cast<uint64_t *>(cnt.p), g.stream) ||
+        cudaMemcpyAsync(&h, cnt.p, 8, cudaMemcpyDeviceToHost, g.stream) != cudaSuccess ||
+        cudaStreamSynchronize(g.stream) != cudaSuccess)
+        die(who);
+    const uint64_t c = h < output_capacity ? h : output_capacity;
+    if (c && (copy_d2h_any(output_buffer, g.scan_out.p, c * 8, g.stream) || cudaStreamSynchronize(g.stream) != cudaSuccess)) die(who);
+    return h;
+}
+
+uint64_t b200_dict_scan_16bit_64bit(int64_t predicate_low, int64_t predicate_high, const int64_t *dict, const uint16_t *data,
+                                    size_t n, int64_t *output_buffer, size_t output_capacity) {
+    return dict_scan_wide_host("b200_dict_scan_16bit_64bit", 16, predicate_low, predicate_high, dict, (size_t) 1 << 16, data, n,
+                               output_buffer, output_capacity);
+}
+
+uint64_t b200_dict_scan_32bit_64bit(int64_t predicate_low, int64_t predicate_high, const int64_t *dict, size_t dict_size,
+                                    const uint32_t *data, size_t n, int64_t *output_buffer, size_t output_capacity) {
+    return dict_scan_wide_host("b200_dict_scan_32bit_64bit", 32, predicate_low, predicate_high, dict, dict_size, data, n,
+                               output_buffer, output_capacity);
+}
+
 void b200_index_scan_user(uint8_t lo, uint8_t hi, const uint8_t *data, size_t n, uint64_t *output_buffer,
                           size_t output_capacity, size_t *output_count, uint64_t *time_cntr, size_t num_runs,
                           size_t warmup_runs, int unique_data) {

@@ -193,6 +193,14 @@ int value_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, u
                       uint64_t *d_count, void *d_scratch, cudaStream_t st);
 int dict_scan_device(uint8_t code_lo, uint8_t code_hi, const int64_t *d_dict, const uint8_t *d_data, size_t n,
                      int64_t *d_out, uint64_t cap, uint64_t *d_count, void *d_scratch, cudaStream_t st);
+int explicit_index_scan_device(uint8_t lo, uint8_t hi, const uint64_t *d_index, const uint8_t *d_data, size_t n,
+                               uint64_t *d_out, uint64_t cap, uint64_t *d_count, cudaStream_t st);
+int scalar_index_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, uint64_t id_base, uint64_t *d_out,
+                             uint64_t cap, uint64_t *d_count, void *d_scratch, cudaStream_t st);
+int dict_scan16_device(uint32_t code_lo, uint32_t code_hi, const int64_t *d_dict, const uint16_t *d_data, size_t n,
+                       int64_t *d_out, uint64_t cap, uint64_t *d_count, cudaStream_t st);
+int dict_scan32_device(uint32_t code_lo, uint32_t code_hi, const int64_t *d_dict, const uint32_t *d_data, size_t n,
+                       int64_t *d_out, uint64_t cap, uint64_t *d_count, cudaStream_t st);
 int scan_sum_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, uint64_t *d_sum, cudaStream_t st);
 int fill_tiled_column_device(uint8_t *d, size_t n, uint64_t pos_begin, cudaStream_t st);
 int fill_skewed_column_device(uint8_t *d, size_t n, uint64_t pos_begin, uint32_t ppm, uint64_t seed, cudaStream_t st);

@@ -343,11 +343,13 @@ __device__ __forceinline__ void st_stream_u32(uint32_t *p, uint32_t v) {
 //   kEmitRowId  id_base + pos as uint64      implicit_index_scan
 //   kEmitValue  the value itself as uint32   scan
 //   kEmitDict   dict[value] as int64         dict_scan_8bit_64bit
-enum { kEmitRowId = 0, kEmitValue = 1, kEmitDict = 2 };
+//   kEmitExplicit  the caller's index entry  explicit_index_scan (SIMD512.cpp:152-208; single-pass kernel only)
+enum { kEmitRowId = 0, kEmitValue = 1, kEmitDict = 2, kEmitExplicit = 3 };
 struct EmitArgs {
     uint64_t id_base;          // row id of chunk position 0
     const uint8_t *data;       // the chunk of the column (kEmitValue, kEmitDict)
     const int64_t *dict;       // 256 entries (kEmitDict)
+    const uint64_t *index;     // kEmitExplicit: the caller's index vectors, 8 entries per 512-bit register
 };
 template <int kEmit>
 __device__ __forceinline__ void emit(void *out, uint64_t slot, uint64_t pos, const EmitArgs &e) {
@@ -663,13 +665,16 @@ struct GroupOut {
     uint64_t idb;            // kEmitRowId: id of relative position 0
     const uint8_t *dp;       // kEmitValue / kEmitDict: the column at relative position 0
     const int64_t *dict;
+    const uint64_t *ib;      // kEmitExplicit: index vector of the 64-value block at relative position 0
     __device__ __forceinline__ GroupOut(void *out, uint64_t g, uint64_t pos0, const EmitArgs &ea)
         : o(static_cast<unsigned char *>(out) + g * (kEmit == kEmitValue ? 4 : 8)), idb(ea.id_base + pos0), dp(ea.data + pos0),
-          dict(ea.dict) {}
+          dict(ea.dict), ib(kEmit == kEmitExplicit ? ea.index + (pos0 >> 6) * 8 : nullptr) {}   // pos0 is a multiple of 64
     __device__ __forceinline__ void put(uint32_t t, uint32_t rel) const {   // match at relative position rel -> slot g + t
         if (kEmit == kEmitRowId) st_stream_u64(reinterpret_cast<uint64_t *>(o) + t, idb + rel);
         else if (kEmit == kEmitValue) st_stream_u32(reinterpret_cast<uint32_t *>(o) + t, __ldg(dp + rel));
-        else st_stream_u64(reinterpret_cast<uint64_t *>(o) + t, (uint64_t) __ldg(dict + __ldg(dp + rel)));
+        else if (kEmit == kEmitDict) st_stream_u64(reinterpret_cast<uint64_t *>(o) + t, (uint64_t) __ldg(dict + __ldg(dp + rel)));
+        else   // block i = pos / 64, byte group j = (pos / 8) % 8, lane k = pos % 8 -> index_compressed[i + j] lane k (:176,:198)
+            st_stream_u64(reinterpret_cast<uint64_t *>(o) + t, __ldg(ib + ((((rel >> 6) + ((rel >> 3) & 7u)) << 3) | (rel & 7u))));
     }
 };
 
@@ -1041,9 +1046,11 @@ static struct {
     DevBuf buf;
     uint32_t epoch = 0;
 } g_fused;
-void scan_release() {   // b200_shutdown: the buffer belongs to the device that is being left
+void scan_release_codes();
+void scan_release() {   // b200_shutdown: the buffers belong to the device that is being left
     g_fused.buf.release();
     g_fused.epoch = 0;
+    scan_release_codes();
 }
 template <int kEmit, int kWarps, int kRounds>
 static int launch_fused(const uint8_t *d_data, size_t n, const Pred &p, const EmitArgs &ea, void *d_out, uint64_t cap,
@@ -1100,7 +1107,7 @@ static int fused_scan_device(const uint8_t *d_data, size_t n, const Pred &p, con
 // emitted type
 static int emit_scan_device(int emit_kind, uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, uint64_t id_base,
                             const int64_t *d_dict, void *d_out, uint64_t cap, uint64_t *d_count, void *d_scratch,
-                            cudaStream_t st) {
+                            cudaStream_t st, const uint64_t *d_index = nullptr) {
     if ((reinterpret_cast<uintptr_t>(d_data) & 15u) != 0) {
         set_error("scan: column must be 16-byte aligned");
         return -1;
@@ -1112,10 +1119,15 @@ static int emit_scan_device(int emit_kind, uint8_t lo, uint8_t hi, const uint8_t
     }
     if (!index_scan_two_pass()) {
         const Pred pf = make_pred(lo, hi);
-        const EmitArgs eaf{id_base, d_data, d_dict};
+        const EmitArgs eaf{id_base, d_data, d_dict, d_index};
         if (emit_kind == kEmitRowId) return fused_scan_device<kEmitRowId>(d_data, n, pf, eaf, d_out, cap, d_count, d_scratch, st);
         if (emit_kind == kEmitValue) return fused_scan_device<kEmitValue>(d_data, n, pf, eaf, d_out, cap, d_count, d_scratch, st);
+        if (emit_kind == kEmitExplicit) return fused_scan_device<kEmitExplicit>(d_data, n, pf, eaf, d_out, cap, d_count, d_scratch, st);
         return fused_scan_device<kEmitDict>(d_data, n, pf, eaf, d_out, cap, d_count, d_scratch, st);   // writes *d_count itself
+    }
+    if (emit_kind == kEmitExplicit) {
+        set_error("explicit_index_scan is served by the single-pass kernel only (unset B200_AQP_INDEX_SCAN=twopass)");
+        return -1;
     }
     AQP_CUDA_OK(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
     const size_t chunk_cap = n < kIndexChunkVals ? n : kIndexChunkVals;
@@ -1145,7 +1157,7 @@ static int emit_scan_device(int emit_kind, uint8_t lo, uint8_t hi, const uint8_t
         tile_offsets_kernel<<<1, kScanBlock, kPlanSmemBytes, st>>>(counts, ntiles, offsets, running, lists,
                                                                    (uint32_t) tiles_cap);
         AQP_LAUNCHED();
-        const EmitArgs ea{id_base + begin, d_data + begin, d_dict};
+        const EmitArgs ea{id_base + begin, d_data + begin, d_dict, nullptr};
         size_t g = (size_t) kNumSMs * 6;   // 6 CTAs/SM resident (32 KiB window each)
         const unsigned g1 = (unsigned) (ntiles < g ? ntiles : g);
         g = (size_t) kNumSMs * 8;
@@ -1180,6 +1192,158 @@ int value_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, u
 int dict_scan_device(uint8_t code_lo, uint8_t code_hi, const int64_t *d_dict, const uint8_t *d_data, size_t n,
                      int64_t *d_out, uint64_t cap, uint64_t *d_count, void *d_scratch, cudaStream_t st) {
     return emit_scan_device(kEmitDict, code_lo, code_hi, d_data, n, 0, d_dict, d_out, cap, d_count, d_scratch, st);
+}
+
+int explicit_index_scan_device(uint8_t lo, uint8_t hi, const uint64_t *d_index, const uint8_t *d_data, size_t n,
+                               uint64_t *d_out, uint64_t cap, uint64_t *d_count, cudaStream_t st) {
+    return emit_scan_device(kEmitExplicit, lo, hi, d_data, n, 0, nullptr, d_out, cap, d_count, nullptr, st, d_index);
+}
+
+// the < 64 values behind the last whole block, for the scalar twin of the row-id scan (ScalarScan.hpp:8-20 walks all
+// n values, the SIMD kernels only n / 64 blocks): appended behind the ids of the blocks, one thread (at most 63 values)
+__global__ void index_scan_tail_kernel(const uint8_t *data, size_t begin, size_t n, uint8_t lo, uint8_t hi, uint64_t id_base,
+                                       uint64_t *out, uint64_t cap, unsigned long long *count) {
+    unsigned long long c = *count;
+    for (size_t i = begin; i < n; ++i) {
+        const uint8_t v = data[i];
+        if (v >= lo && v <= hi) {
+            if (c < cap) out[c] = id_base + i;
+            ++c;
+        }
+    }
+    *count = c;
+}
+int scalar_index_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, uint64_t id_base, uint64_t *d_out,
+                             uint64_t cap, uint64_t *d_count, void *d_scratch, cudaStream_t st) {
+    if (index_scan_device(lo, hi, d_data, n, id_base, d_out, cap, d_count, d_scratch, st)) return -1;
+    if (n % 64) {
+        index_scan_tail_kernel<<<1, 1, 0, st>>>(d_data, n / 64 * 64, n, lo, hi, id_base, d_out, cap,
+                                                reinterpret_cast<unsigned long long *>(d_count));
+        AQP_LAUNCHED();
+        AQP_CUDA_OK(cudaGetLastError());
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dictionary scans over 16- and 32-bit codes (SIMD512::dict_scan_16bit_64bit / dict_scan_32bit_64bit,
+// SIMD512.cpp:531-622): emit dict[code] (int64) for every code with code_lo <= code <= code_hi (unsigned), in
+// column order; only whole 512-bit registers are processed (32 resp. 16 codes). Not on the headline path
+// (SURVEY 8f rank 4): a count pass, an exclusive scan of the per-tile counts and an emit pass that re-reads the
+// column - 2 reads + 8 B per match. A tile is one 128-bit load per thread (8 resp. 4 codes).
+// ---------------------------------------------------------------------------------------------
+template <typename Code>
+__device__ __forceinline__ uint32_t code_mask(uint4 v, uint32_t lo, uint32_t hi) {   // bit k <-> k-th code of the vector
+    uint32_t m = 0;
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    if (sizeof(Code) == 2) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t c = (w[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+            m |= (c >= lo && c <= hi ? 1u : 0u) << k;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) m |= (w[k] >= lo && w[k] <= hi ? 1u : 0u) << k;
+    }
+    return m;
+}
+template <typename Code>
+__global__ void __launch_bounds__(256)
+code_scan_count_kernel(const uint4 *__restrict__ in, size_t nvec, uint32_t lo, uint32_t hi, uint32_t *__restrict__ tile_counts) {
+    __shared__ uint32_t wsum[8];
+    for (size_t tile = blockIdx.x; tile * 256 < nvec; tile += gridDim.x) {
+        const size_t q = tile * 256 + threadIdx.x;
+        uint32_t c = q < nvec ? __popc(code_mask<Code>(ld_stream_v4(in + q), lo, hi)) : 0u;
+        c = warp_sum(c);
+        if (lane_id() == 0) wsum[threadIdx.x >> 5] = c;
+        __syncthreads();
+        if (threadIdx.x == 0) tile_counts[tile] = wsum[0] + wsum[1] + wsum[2] + wsum[3] + wsum[4] + wsum[5] + wsum[6] + wsum[7];
+        __syncthreads();
+    }
+}
+template <typename Code>
+__global__ void __launch_bounds__(256)
+code_scan_emit_kernel(const uint4 *__restrict__ in, size_t nvec, uint32_t lo, uint32_t hi, const uint32_t *__restrict__ tile_off,
+                      const int64_t *__restrict__ dict, int64_t *__restrict__ out, uint64_t cap,
+                      unsigned long long *__restrict__ count) {
+    __shared__ uint32_t wsum[8];
+    constexpr int kPer = 16 / sizeof(Code);
+    const size_t ntiles = (nvec + 255) / 256;
+    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const size_t q = tile * 256 + threadIdx.x;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        uint32_t m = 0;
+        if (q < nvec) {
+            v = ld_stream_v4(in + q);
+            m = code_mask<Code>(v, lo, hi);
+        }
+        const uint32_t c = __popc(m), incl = warp_incl_scan(c);
+        if (lane_id() == 31) wsum[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            before += k < (int) (threadIdx.x >> 5) ? wsum[k] : 0u;
+            total += wsum[k];
+        }
+        uint64_t slot = (uint64_t) tile_off[tile] + before + incl - c;
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            if ((m >> k) & 1u) {
+                const uint32_t code = sizeof(Code) == 2 ? (w[k >> 1] >> ((k & 1) * 16)) & 0xffffu : w[k];
+                if (slot < cap) out[slot] = __ldg(dict + code);
+                ++slot;
+            }
+        }
+        if (tile == ntiles - 1 && threadIdx.x == 0) *count = (unsigned long long) tile_off[tile] + total;
+        __syncthreads();
+    }
+}
+static struct {
+    DevBuf counts, offsets;
+} g_code;
+template <typename Code>
+static int code_dict_scan_device(uint32_t code_lo, uint32_t code_hi, const int64_t *d_dict, const Code *d_data, size_t n,
+                                 int64_t *d_out, uint64_t cap, uint64_t *d_count, cudaStream_t st) {
+    if ((reinterpret_cast<uintptr_t>(d_data) & 15u) != 0) {
+        set_error("dict scan: column must be 16-byte aligned");
+        return -1;
+    }
+    constexpr size_t kBlock = 64 / sizeof(Code);   // codes per 512-bit register
+    n = n / kBlock * kBlock;
+    AQP_CUDA_OK(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
+    if (n == 0) return 0;
+    const size_t nvec = n * sizeof(Code) / 16, ntiles = (nvec + 255) / 256;
+    if (ntiles >= 0xFFFFFFFFull) {
+        set_error("dict scan: column too large");
+        return -1;
+    }
+    if (g_code.counts.ensure(ntiles * 4 + 64) || g_code.offsets.ensure((ntiles + 1) * 4 + 64)) return -1;
+    uint32_t *counts = static_cast<uint32_t *>(g_code.counts.p), *offs = static_cast<uint32_t *>(g_code.offsets.p);
+    const unsigned grid = (unsigned) (ntiles < (size_t) kNumSMs * 8 ? ntiles : (size_t) kNumSMs * 8);
+    const uint4 *in = reinterpret_cast<const uint4 *>(d_data);
+    code_scan_count_kernel<Code><<<grid, 256, 0, st>>>(in, nvec, code_lo, code_hi, counts);
+    AQP_LAUNCHED();
+    if (exclusive_scan_u32_device(counts, (uint32_t) ntiles, offs, st)) return -1;
+    code_scan_emit_kernel<Code><<<grid, 256, 0, st>>>(in, nvec, code_lo, code_hi, offs, d_dict, d_out, cap,
+                                                      reinterpret_cast<unsigned long long *>(d_count));
+    AQP_LAUNCHED();
+    AQP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+void scan_release_codes() {
+    g_code.counts.release();
+    g_code.offsets.release();
+}
+int dict_scan16_device(uint32_t code_lo, uint32_t code_hi, const int64_t *d_dict, const uint16_t *d_data, size_t n,
+                       int64_t *d_out, uint64_t cap, uint64_t *d_count, cudaStream_t st) {
+    return code_dict_scan_device<uint16_t>(code_lo, code_hi, d_dict, d_data, n, d_out, cap, d_count, st);
+}
+int dict_scan32_device(uint32_t code_lo, uint32_t code_hi, const int64_t *d_dict, const uint32_t *d_data, size_t n,
+                       int64_t *d_out, uint64_t cap, uint64_t *d_count, cudaStream_t st) {
+    return code_dict_scan_device<uint32_t>(code_lo, code_hi, d_dict, d_data, n, d_out, cap, d_count, st);
 }
 
 int scan_sum_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, uint64_t *d_sum, cudaStream_t st) {

@@ -6,6 +6,7 @@
 //   --mode=bitvector|noIndex --num_entries=N --selectivity=PCT --num_runs=K --warmup=W --unique
 // Data = 0..255 tiled (Allocator.hpp:95-109), predicate [0, round(sel/100*255)] (types.hpp:125).
 // Prints one CSV row like PerfEventBlock does, with GB/s computed as in results/plot.py:22-23.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -49,8 +50,14 @@ int main(int argc, char **argv) {
         size_t cap = n / 256 * (hi + 1) + 64;   // pre_alloc_per_thread: count()+64 (ResultAllocators.hpp:17)
         std::vector<uint64_t> out(cap);
         b200_index_scan_user(lo, hi, data.data(), n, out.data(), cap, &count, &ns, runs, warmup, unique);
+    } else if (mode == "scalar") {   // ScalarScan.hpp:8-20: the scalar twin, all n values
+        size_t cap = n / 256 * (hi + 1) + 320;
+        std::vector<uint64_t> out(cap);
+        double t0 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+        for (size_t r = 0; r < (unique ? 1 : runs); ++r) count = b200_scalar_index_scan(lo, hi, data.data(), n, out.data(), cap);
+        ns = (uint64_t) ((std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() - t0) * 1e9);
     } else {
-        fprintf(stderr, "mode must be bitvector or noIndex\n");
+        fprintf(stderr, "mode must be bitvector, noIndex or scalar\n");
         return 2;
     }
     size_t eff_runs = unique ? 1 : runs;

@@ -174,14 +174,14 @@ def test_mg_api_world1_against_oracle(gpu, oracle):
 
 def test_simdmulti_modes(gpu):
     n = 1 << 24
-    for mode, sel in (("bitvector", 10), ("noIndex", 10), ("noIndex", 100), ("bitvector", 50)):
+    for mode, sel in (("bitvector", 10), ("noIndex", 10), ("noIndex", 100), ("bitvector", 50), ("scalar", 10)):
         out = run("simdmulti", f"--mode={mode}", f"--num_entries={n}", f"--selectivity={sel}", "--num_runs=3", "--warmup=1")
         hdr, row = out.strip().splitlines()[-2:]
         rec = dict(zip(hdr.split(","), row.split(",")))
         hi = round(sel / 100.0 * 255.0)                                     # types.hpp:125
         assert rec["mode"] == mode and int(rec["predicate_high"]) == hi
         assert int(rec["matches"]) == n // 256 * (hi + 1)
-        assert float(rec["GBs"]) > 50.0
+        assert float(rec["GBs"]) > (50.0 if mode != "scalar" else 0.05)   # scalar: timed end to end incl. copies and first-call set-up
 
 
 def test_tpch_native_stdout(gpu, golden):

@@ -172,3 +172,40 @@ def test_sum_value_dict_vs_oracle(gpu, oracle, n):
         assert cnt == len(exp) and np.array_equal(vals, exp[:1000])
         r, cnt = gpu.dict_scan_8bit_64bit(0, 100, np.arange(256), dense)
         assert cnt == len(exp) and np.array_equal(r, exp.astype(np.int64))
+
+
+def test_wide_dict_scan_reference_known_answers_on_gpu(gpu, oracle):
+    """testsimdscan.cpp:167-215,:478-528 through the C ABI"""
+    from test_oracle_scan import wide_dict_kats
+    for name, bits, col, d, lo, hi, size, check in wide_dict_kats():
+        r, cnt = gpu.dict_scan_wide(bits, lo, hi, d, col)
+        assert cnt == size == len(r), name
+        assert check is None or check(r), name
+        assert np.array_equal(r, oracle.dict_scan_wide(bits, lo, hi, d, col)), name
+
+
+@pytest.mark.parametrize("n", [0, 31, 64 * 7 + 5, 4096 + 32, 1_000_003])
+def test_wide_dict_explicit_scalar_vs_oracle(gpu, oracle, n):
+    rng = np.random.default_rng(n + 3)
+    col = rng.integers(0, 256, n, dtype=np.uint8)
+    index = rng.integers(0, 1 << 62, (n // 64 + 7) * 8, dtype=np.uint64)
+    for lo, hi in PREDS:
+        ids, cnt = gpu.explicit_index_scan(lo, hi, index, col)
+        exp = oracle.explicit_index_scan(lo, hi, index, col)
+        assert cnt == len(exp) and np.array_equal(ids, exp), (n, lo, hi)
+        ids, cnt = gpu.scalar_index_scan(lo, hi, col)            # all n values, incl. the < 64 behind the last block
+        exp = oracle.scalar_index_scan(lo, hi, col)
+        assert cnt == len(exp) and np.array_equal(ids, exp), (n, lo, hi)
+    d16 = np.sort(rng.integers(-10**9, 10**9, 1 << 16))
+    c16 = rng.integers(0, 1 << 16, n, dtype=np.uint16)
+    d32 = np.sort(rng.integers(-10**9, 10**9, 70000))
+    c32 = rng.integers(0, 70000, n, dtype=np.uint32)
+    for bits, d, c in ((16, d16, c16), (32, d32, c32)):
+        for lo, hi in [(int(d[50]), int(d[5000])), (int(d[0]) - 2, int(d[0]) - 1), (int(d[-1]) + 1, int(d[-1]) + 2),
+                       (int(d[9]), int(d[9])), (int(d[600]), int(d[500]))]:
+            r, cnt = gpu.dict_scan_wide(bits, lo, hi, d, c)
+            exp = oracle.dict_scan_wide(bits, lo, hi, d, c)
+            assert cnt == len(exp) and np.array_equal(r, exp), (bits, n, lo, hi)
+    if n > 4096:
+        r, cnt = gpu.dict_scan_wide(16, int(d16[0]), int(d16[-1]), d16, c16, capacity=100)
+        assert cnt == n // 32 * 32 and np.array_equal(r, d16[c16[:100]])

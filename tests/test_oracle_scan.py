@@ -98,3 +98,59 @@ def test_sum_value_dict_against_compiled_reference(oracle):
             assert np.array_equal(oracle.dict_scan_8_64(lo, hi, d, col), exp), (lo, hi)
             for which in (1, 2, 3):   # the reference's other 8-bit implementations agree with each other
                 assert np.array_equal(oracle.ref_dict_scan_8_64(lo, hi, d, col, which), exp), (which, lo, hi)
+
+
+# ---- 16- / 32-bit dictionary scans and the explicit-index scan ------------------------------------------------------
+def wide_dict_kats():
+    """The reference's [main] cases for the wider codes (testsimdscan.cpp:167-215 and :478-528), restated:
+    (name, code bits, column, dictionary, low, high, expected size, value check). allocate_data_array_aligned<T>(n)
+    fills element i with (T) i; the 32-bit test 1 uses gen = in & 255."""
+    n = 1 << 20
+    c16 = (np.arange(n) & 0xffff).astype(np.uint16)
+    d16 = np.arange(1 << 16, dtype=np.int64)
+    c32_mod = (np.arange(n) & 255).astype(np.uint32)
+    c32_id = np.arange(n, dtype=np.uint32)
+    d32 = np.arange(1 << 20, dtype=np.int64)
+    return [
+        ("Dict 16_64 scan test 1 :167-190", 16, c16, d16, 0, 299, n // (1 << 16) * 300, lambda r: (r == np.arange(len(r)) % 300).all()),
+        ("Dict 32_64 scan test 1 :192-215", 32, c32_mod, d32, 0, 299, n, None),
+        ("Dict 32_64 scalar gather scatter test 1 :478-502", 32, c32_mod, d32, 0, 299, n, None),
+        ("Dict 32_64 scalar gather scatter test 2 :504-528", 32, c32_id, d32, 0, 99, 100, lambda r: r[0] == 0 and r[10] == 10),
+    ]
+
+
+def test_wide_dict_scan_reference_known_answers(oracle):
+    for name, bits, col, d, lo, hi, size, check in wide_dict_kats():
+        r = oracle.dict_scan_wide(bits, lo, hi, d, col)
+        assert len(r) == size, name
+        assert check is None or check(r), name
+
+
+def test_wide_dict_and_explicit_against_compiled_reference(oracle):
+    if not (oracle.have_ref() and oracle.host_has_avx512()):
+        pytest.skip("compiled reference needs AVX-512 and oracle/_ref")
+    rng = np.random.default_rng(9)
+    n = 64 * 500 + 21
+    # explicit index scan: block i's byte group j reads index register i + j (SIMD512.cpp:176) - as written
+    col = oracle.aligned_u8(n)
+    col[:] = rng.integers(0, 256, n, dtype=np.uint8)
+    index = oracle.aligned((n // 64 + 7) * 8, np.uint64)
+    index[:] = rng.integers(0, 1 << 62, len(index), dtype=np.uint64)
+    for lo, hi in [(0, 26), (7, 7), (100, 50), (0, 255), (200, 255)]:
+        assert np.array_equal(oracle.explicit_index_scan(lo, hi, index, col), oracle.ref_explicit_index_scan(lo, hi, index, col)), (lo, hi)
+    # 16-bit codes, sorted 65536-entry dictionary; predicates inside, below, above the dictionary and inverted
+    d16 = np.sort(rng.integers(-10**12, 10**12, 1 << 16))
+    c16 = oracle.aligned(n, np.uint16)
+    c16[:] = rng.integers(0, 1 << 16, n, dtype=np.uint16)
+    for lo, hi in [(int(d16[100]), int(d16[9000])), (int(d16[0]) - 9, int(d16[0]) - 1), (int(d16[-1]) + 1, int(d16[-1]) + 5),
+                   (int(d16[500]), int(d16[400])), (int(d16[77]), int(d16[77])), (int(d16[0]), int(d16[-1]))]:
+        assert np.array_equal(oracle.dict_scan_wide(16, lo, hi, d16, c16), oracle.ref_dict_scan_wide(16, lo, hi, d16, c16)), (lo, hi)
+    # 32-bit codes: the reference narrows the code range through uint16_t (SIMD512.cpp:592-593) - dictionaries up to and
+    # beyond 65536 entries behave as written there
+    for dsize in (1000, 1 << 16, 100000):
+        d32 = np.sort(rng.integers(-10**12, 10**12, dsize))
+        c32 = oracle.aligned(n, np.uint32)
+        c32[:] = rng.integers(0, dsize, n, dtype=np.uint32)
+        for lo, hi in [(int(d32[10]), int(d32[dsize // 2])), (int(d32[0]) - 3, int(d32[0]) - 1), (int(d32[-1]) + 1, int(d32[-1]) + 2),
+                       (int(d32[dsize - 5]), int(d32[dsize - 1])), (int(d32[3]), int(d32[3]))]:
+            assert np.array_equal(oracle.dict_scan_wide(32, lo, hi, d32, c32), oracle.ref_dict_scan_wide(32, lo, hi, d32, c32)), (dsize, lo, hi)
