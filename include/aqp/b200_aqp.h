@@ -12,6 +12,13 @@
  *   3. Device-resident API, DEVICE pointers    : b200_*_device — what a multi-GPU host (one process
  *                                                 per GPU) and bench.py drive; caller owns memory.
  *
+ * Concurrency: one process drives ONE device through this library, one call at a time - like the reference's
+ * run_join, which all its callers invoke sequentially. Host-side entry is serialised by a mutex, but the
+ * device-pointer calls return with work still queued and they share ONE workspace (partition buffers, scan state,
+ * metadata, phase-timing events): issue them on one stream, or synchronise before switching streams. Per-call state a
+ * caller passes in (outputs, counters) is its own. b200_shutdown() followed by b200_init(other device) re-binds the
+ * library: every cached buffer is released and every per-device kernel attribute is set again.
+ *
  * There is no CPU fallback anywhere: if no CUDA device is usable every call fails loudly
  * (non-zero return, or for the void reference-shaped calls a message on stderr and exit(1), the
  * reference's own error convention — Joins/src/util.cpp:12-19, joins.cpp:70-73).

@@ -151,6 +151,9 @@ class CudaBackend:
         self.A._check(self.L.b200_ipc_export(buf.ptr, h), "b200_ipc_export")
         return buf, torch.tensor(list(h), dtype=torch.uint8)
 
+    def close_shared(self, ptr: int):
+        self.A._check(self.L.b200_ipc_close(ptr), "b200_ipc_close")
+
     def open_shared(self, handle: torch.Tensor) -> int:
         import ctypes as C
         h = (C.c_ubyte * 64)(*handle.tolist())
@@ -285,6 +288,22 @@ class FusedShardedJoin(ShardedJoin):
                 peers.append(buf.ptr if g == self.rank else be.open_shared(hs[g]))
         self.fallbacks = 0
         self._seg_group = None
+
+    def close(self):
+        """Collective: unmap the peers' buffers, then free this rank's own (nobody may still have it mapped)."""
+        if not self._own:
+            return
+        if self.device.type == "cuda":
+            torch.cuda.synchronize()
+        dist.barrier(group=self.group)            # every rank is done reading and writing peer memory
+        if hasattr(self.backend, "close_shared"):
+            for peers in (self.peerR, self.peerS):
+                for g, ptr in enumerate(peers):
+                    if g != self.rank:
+                        self.backend.close_shared(ptr)
+        dist.barrier(group=self.group)            # every mapping of this rank's buffers is closed
+        self._own = []
+        self.peerR, self.peerS = [], []
 
     def _sizing(self, cnt1, hist):
         """The two sizing collectives and everything derived from them. Returns (host, segR, segS, dR, dS, hR, hS,

@@ -22,10 +22,40 @@ namespace aqp {
 
 thread_local std::string g_last_error;
 unsigned long long g_kernel_launches = 0;
+unsigned g_device_epoch = 0;
 
 void set_error(const std::string &msg) {
     g_last_error = msg;
     if (getenv("B200_AQP_DEBUG")) fprintf(stderr, "b200aqp: %s\n", msg.c_str());
+}
+
+// registry of every DevBuf (see join_internal.cuh). A function-local static so that it exists before the first
+// static DevBuf of any translation unit is constructed.
+static std::vector<DevBuf *> &devbuf_list() {
+    static std::vector<DevBuf *> *v = new std::vector<DevBuf *>();
+    return *v;
+}
+static std::mutex &devbuf_mu() {
+    static std::mutex *m = new std::mutex();
+    return *m;
+}
+void devbuf_register(DevBuf *b, bool add) {
+    std::lock_guard<std::mutex> lk(devbuf_mu());
+    auto &v = devbuf_list();
+    if (add) {
+        v.push_back(b);
+    } else {
+        for (size_t i = 0; i < v.size(); ++i)
+            if (v[i] == b) {
+                v[i] = v.back();
+                v.pop_back();
+                break;
+            }
+    }
+}
+void devbuf_release_all() {
+    std::lock_guard<std::mutex> lk(devbuf_mu());
+    for (DevBuf *b : devbuf_list()) b->release();
 }
 
 static double now_s() {
@@ -555,10 +585,12 @@ void b200_shutdown(void) {
     scan_release();
     hostcopy_release();
     slab_free(g_slab_cache);
+    devbuf_release_all();   // every workspace of every translation unit, incl. function-local statics
     for (auto &e : g.ev) cudaEventDestroy(e);
     cudaStreamDestroy(g.stream);
     g.stream = nullptr;
     g.inited = false;
+    ++g_device_epoch;
     g.preloaded = false;
 }
 

@@ -285,13 +285,13 @@ int build_probe_device(const row_t *d_R, const uint32_t *d_offR, const row_t *d_
                        const uint32_t *d_item_start, const uint2 *d_items, uint32_t nparts, uint64_t max_items,
                        uint32_t hash_shift, JoinResult *d_res, output_triple_t *d_out, uint64_t out_cap,
                        cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned attr_set = ~0u;   // device epoch the opt-in was made for (b200_shutdown + b200_init(other device) re-arms it)
+    if (attr_set != g_device_epoch) {
         AQP_CUDA_OK(cudaFuncSetAttribute(build_probe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int) kJoinSmemBytes));
         AQP_CUDA_OK(cudaFuncSetAttribute(build_probe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int) kJoinSmemBytes));
-        attr_set = true;
+        attr_set = g_device_epoch;
     }
     if (max_items == 0) return 0;
     int grid = (int) (max_items < (uint64_t) kNumSMs * 2 ? max_items : (uint64_t) kNumSMs * 2);

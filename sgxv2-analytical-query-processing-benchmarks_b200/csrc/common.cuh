@@ -31,6 +31,9 @@ extern thread_local std::string g_last_error;
 
 // count every kernel this library launches (bench.py reports it as gpu_launches)
 extern unsigned long long g_kernel_launches;
+// bumped by b200_shutdown: per-function attributes (dynamic shared memory opt-ins) belong to a device context and are
+// set again when the library is re-bound to another device
+extern unsigned g_device_epoch;
 #define AQP_LAUNCHED() (++::aqp::g_kernel_launches)
 
 // ---------------------------------------------------------------------------------------------

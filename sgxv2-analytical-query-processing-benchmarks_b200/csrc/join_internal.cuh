@@ -7,9 +7,18 @@
 namespace aqp {
 
 // grow-only device buffer
+// Device buffer that grows on demand. Every instance (globals, function-local statics, members) is listed in a
+// registry so that b200_shutdown can free them all: their memory belongs to the device context that is being left.
+struct DevBuf;
+void devbuf_register(DevBuf *b, bool add);
+void devbuf_release_all();
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    DevBuf() { devbuf_register(this, true); }
+    DevBuf(const DevBuf &o) : p(o.p), cap(o.cap) { devbuf_register(this, true); }
+    DevBuf &operator=(const DevBuf &o) = default;
+    ~DevBuf() { devbuf_register(this, false); }
     int ensure(size_t bytes) {
         if (bytes <= cap) return 0;
         if (p) cudaFree(p);

@@ -102,13 +102,13 @@ int radix_hist_device(const row_t *d_in, uint64_t n, DigitFn digit, uint32_t bit
     const uint2 *in = reinterpret_cast<const uint2 *>(d_in);
     if (bits <= (uint32_t) kMaxSmemHistBits) {
         size_t smem = sizeof(uint32_t) << bits;
-        static bool attr_set = false;
-        if (!attr_set) {
+        static unsigned attr_set = ~0u;   // device epoch the opt-in was made for (b200_shutdown + b200_init(other device) re-arms it)
+        if (attr_set != g_device_epoch) {
             AQP_CUDA_OK(cudaFuncSetAttribute(radix_hist_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int) (sizeof(uint32_t) << kMaxSmemHistBits)));
             AQP_CUDA_OK(cudaFuncSetAttribute(radix_hist_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int) (sizeof(uint32_t) << kMaxSmemHistBits)));
-            attr_set = true;
+            attr_set = g_device_epoch;
         }
         uint32_t grid = nblocks;
         if (!grid) {
@@ -1228,8 +1228,8 @@ int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_
         return -1;
     }
     if (n_total == 0) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned attr_set = ~0u;   // device epoch the opt-in was made for (b200_shutdown + b200_init(other device) re-arms it)
+    if (attr_set != g_device_epoch) {
 #define AQP_SCATTER_ATTR(ROT, PEER, BULK)                                                                             \
     AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_kernel<ROT, PEER, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      (int) kScatterSmemBytes))
@@ -1240,7 +1240,7 @@ int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_
         AQP_SCATTER_ATTR(true, true, false);
         AQP_SCATTER_ATTR(true, true, true);
 #undef AQP_SCATTER_ATTR
-        attr_set = true;
+        attr_set = g_device_epoch;
     }
     uint32_t grid;
     if (d_block_base) {
@@ -1259,8 +1259,8 @@ int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_
     if (peer)
         for (uint32_t i = 0; i < peers->n; ++i) aligned16 = aligned16 && (reinterpret_cast<uintptr_t>(peers->base[i]) & 15u) == 0;
     if (!staged && aligned16 && (1u << bits) <= (uint32_t) kScatterThreads) {
-        static bool bins_attr_set = false;
-        if (!bins_attr_set) {
+        static unsigned bins_attr_set = ~0u;   // device epoch the opt-in was made for (b200_shutdown + b200_init(other device) re-arms it)
+        if (bins_attr_set != g_device_epoch) {
 #define AQP_BINS_ATTR(ROT, PEER, PRIV)                                                                                  \
     AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_bins_kernel<ROT, PEER, PRIV>,                                        \
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kBinsSmemBytes))
@@ -1270,7 +1270,7 @@ int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_
             AQP_BINS_ATTR(true, false, true);
             AQP_BINS_ATTR(true, true, true);
 #undef AQP_BINS_ATTR
-            bins_attr_set = true;
+            bins_attr_set = g_device_epoch;
         }
 #define AQP_BINS_LAUNCH(ROT, PEER, PRIV)                                                                               \
     radix_scatter_bins_kernel<ROT, PEER, PRIV><<<grid, kScatterThreads, kBinsSmemBytes, st>>>(                          \
@@ -1289,11 +1289,11 @@ int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_
             // a single input segment that starts on an even tuple and 128-byte aligned receive buffers
             if (bits <= (uint32_t) kBinSlotsLog - 6 && nseg == 1 && aligned128 && !peer_ring_off &&
                 (reinterpret_cast<uintptr_t>(d_in) & 15u) == 0 && n_total < 0xFFFFFFFFull) {
-                static bool peer_attr_set = false;
-                if (!peer_attr_set) {
+                static unsigned peer_attr_set = ~0u;   // device epoch the opt-in was made for (b200_shutdown + b200_init(other device) re-arms it)
+                if (peer_attr_set != g_device_epoch) {
                     AQP_CUDA_OK(cudaFuncSetAttribute(radix_scatter_peer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                      (int) kBinsSmemBytes));
-                    peer_attr_set = true;
+                    peer_attr_set = g_device_epoch;
                 }
                 radix_scatter_peer_kernel<true><<<grid, kScatterThreads, kBinsSmemBytes, st>>>(
                     in, (uint32_t) n_total, digit, bits, d_block_base, tiles_per_block, *peers);

@@ -1140,11 +1140,11 @@ static int emit_scan_device(int emit_kind, uint8_t lo, uint8_t hi, const uint8_t
     unsigned long long *running = reinterpret_cast<unsigned long long *>(d_count);
     const Pred p = make_pred(lo, hi);
     static_assert(kIndexChunkVals / kExpandTileVals <= kPlanMaxTiles, "one planning CTA per chunk");
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned attr_set = ~0u;   // device epoch the opt-in was made for (b200_shutdown + b200_init(other device) re-arms it)
+    if (attr_set != g_device_epoch) {
         AQP_CUDA_OK(cudaFuncSetAttribute(tile_offsets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int) kPlanSmemBytes));
-        attr_set = true;
+        attr_set = g_device_epoch;
     }
     for (size_t begin = 0; begin < n; begin += kIndexChunkVals) {
         const size_t len = n - begin < kIndexChunkVals ? n - begin : kIndexChunkVals;

@@ -33,6 +33,7 @@ for logR, logS in ((20, 22), (24, 26)):
         assert o["keysum"] == rep * nR * (nR + 1) // 2, o
         assert o["checksum"] == rep * (nR * (nR - 1) // 2) + nS * (nS - 1) // 2, o
         if rank == 0: print("OK", cls.__name__, logR, logS, {k: round(v, 3) if isinstance(v, float) else v for k, v in o.items()})
+        if hasattr(sj, "close"): sj.close()       # collective: peers unmap before anyone frees
         del sj
     # the C host (csrc/mg.cu): uniform and Zipf-skewed S (the hot key's owner receives far more than the mean:
     # worst-case regions, no overflow path), against the other variants' result on the same shards
