@@ -226,6 +226,11 @@ struct b200_mg_result_t {
 };
 int b200_mg_unique_id(unsigned char *id_out /* 128 bytes */);
 int b200_mg_init(int rank, int world, const unsigned char *id /* 128 bytes */, uint64_t nR_total, uint64_t nS_total);
+/* same with explicit limits: capR / capS = the largest shard any rank will pass to b200_mg_join (relations whose shards
+ * are uneven, e.g. the output of a row-range filter), dead_bits = low key bits known to carry no information (TPC-H
+ * order keys: 2), which the radix plan then skips as the single-GPU planner does */
+int b200_mg_init_caps(int rank, int world, const unsigned char *id /* 128 bytes */, uint64_t nR_total, uint64_t capR,
+                      uint64_t capS, uint32_t dead_bits);
 int b200_mg_join(const struct row_t *d_R, uint64_t nR_local, const struct row_t *d_S, uint64_t nS_local,
                  struct b200_mg_result_t *result);
 int b200_mg_finalize(void);

@@ -112,6 +112,25 @@ int b200_tpch_download(struct LineItemTable *l, struct OrdersTable *o, struct Cu
 void b200_tpch_free_host(struct LineItemTable *l, struct OrdersTable *o, struct CustomerTable *c, struct PartTable *p);
 void b200_tpch_free_device(void);
 
+/* The reference's binary column format (CSVConvert.cpp:16-190 writes it from dbgen's .tbl files, TpcHCommons.cpp:194-214,
+ * :235-295,:423-451,:506-537,:594-623 reads it): <root>/scaleNNN/<table>.tbl.dir/{size, <column>.bin} with <table> in
+ * lineitem / orders / customer / part. read: every column file that exists is loaded into 64-byte aligned host memory,
+ * missing ones stay NULL (release with b200_tpch_free_host; hand to b200_tpch_upload or the host drop-ins). write: the
+ * non-NULL columns of the given host tables. Host code, no GPU involved. */
+int b200_tpch_read_binary(const char *root, int scale, struct LineItemTable *l, struct OrdersTable *o, struct CustomerTable *c,
+                          struct PartTable *p);
+int b200_tpch_write_binary(const char *root, int scale, const struct LineItemTable *l, const struct OrdersTable *o,
+                           const struct CustomerTable *c, const struct PartTable *p);
+
+/* Multi-GPU, one process per GPU: every rank generates rows [total * rank / world, total * (rank+1) / world)
+ * of every table (values depend on the global row only: the shards together are the single-GPU tables), filters its own
+ * line items and joins through the sharded join of b200_mg_* (include/aqp/b200_aqp.h). b200_tpch_mg_init wraps
+ * b200_mg_init_caps with capacities derived from the shard sizes; stats->result_rows of b200_tpch_q12_mg is the GLOBAL
+ * answer, the other fields describe this rank. Finish with b200_mg_finalize(). */
+int b200_tpch_generate_shard_device(double scale_factor, uint64_t seed, uint32_t rank, uint32_t world);
+int b200_tpch_mg_init(int rank, int world, const unsigned char *nccl_unique_id /* 128 bytes */);
+int b200_tpch_q12_mg(struct b200_tpch_stats_t *stats);
+
 int b200_tpch_q3_device(struct b200_tpch_stats_t *stats);
 int b200_tpch_q12_device(struct b200_tpch_stats_t *stats);
 int b200_tpch_q19_device(struct b200_tpch_stats_t *stats);

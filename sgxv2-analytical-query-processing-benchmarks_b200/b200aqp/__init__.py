@@ -142,6 +142,7 @@ SYMBOLS = {
     "b200_ipc_close": (_int, [_vp]),
     "b200_mg_unique_id": (_int, [_vp]),
     "b200_mg_init": (_int, [_int, _int, _vp, _u64, _u64]),
+    "b200_mg_init_caps": (_int, [_int, _int, _vp, _u64, _u64, _u64, _u32]),
     "b200_mg_join": (_int, [_vp, _u64, _vp, _u64, C.POINTER(MgResult)]),
     "b200_mg_finalize": (_int, []),
     "seed_generator": (None, [C.c_uint]),
@@ -190,6 +191,13 @@ SYMBOLS = {
     "b200_tpch_free_host": (None, [C.POINTER(LineItemTable), C.POINTER(OrdersTable), C.POINTER(CustomerTable),
                                    C.POINTER(PartTable)]),
     "b200_tpch_free_device": (None, []),
+    "b200_tpch_generate_shard_device": (_int, [C.c_double, _u64, _u32, _u32]),
+    "b200_tpch_mg_init": (_int, [_int, _int, _vp]),
+    "b200_tpch_q12_mg": (_int, [C.POINTER(TpchStats)]),
+    "b200_tpch_read_binary": (_int, [C.c_char_p, _int, C.POINTER(LineItemTable), C.POINTER(OrdersTable),
+                                     C.POINTER(CustomerTable), C.POINTER(PartTable)]),
+    "b200_tpch_write_binary": (_int, [C.c_char_p, _int, C.POINTER(LineItemTable), C.POINTER(OrdersTable),
+                                      C.POINTER(CustomerTable), C.POINTER(PartTable)]),
     "b200_tpch_q3_device": (_int, [C.POINTER(TpchStats)]),
     "b200_tpch_q12_device": (_int, [C.POINTER(TpchStats)]),
     "b200_tpch_q19_device": (_int, [C.POINTER(TpchStats)]),
@@ -539,6 +547,22 @@ def tpch_generate_device(scale_factor: float, seed: int = 1):
     _check(lib().b200_tpch_generate_device(scale_factor, seed), "b200_tpch_generate_device")
 
 
+def tpch_generate_shard_device(scale_factor: float, seed: int, rank: int, world: int):
+    init()
+    _check(lib().b200_tpch_generate_shard_device(scale_factor, seed, rank, world), "b200_tpch_generate_shard_device")
+
+
+def tpch_mg_init(rank: int, world: int, unique_id: bytes):
+    buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+    _check(lib().b200_tpch_mg_init(rank, world, buf), "b200_tpch_mg_init")
+
+
+def tpch_q12_mg() -> dict:
+    s = TpchStats()
+    _check(lib().b200_tpch_q12_mg(C.byref(s)), "b200_tpch_q12_mg")
+    return s.as_dict()
+
+
 def tpch_download() -> dict:
     """Device tables -> dict of dicts of numpy columns (copies)."""
     st = {k: cls() for k, (cls, _) in _TPCH_COLS.items()}
@@ -552,6 +576,33 @@ def tpch_download() -> dict:
             dt = np.dtype(dt)
             buf = (C.c_uint8 * (n * dt.itemsize)).from_address(getattr(st[name], col)) if n else b""
             out[name][col] = np.frombuffer(buf, dtype=dt).copy()
+    lib().b200_tpch_free_host(C.byref(st["lineitem"]), C.byref(st["orders"]), C.byref(st["customer"]), C.byref(st["part"]))
+    return out
+
+
+def tpch_write_binary(root: str, scale: int, tables: dict):
+    """Host tables -> the reference's binary column files (<root>/scaleNNN/<table>.tbl.dir/...). Host code only."""
+    st = {k: tpch_host_struct(k, v) for k, v in tables.items()}
+    g = lambda k: C.byref(st[k]) if k in st else None
+    _check(lib().b200_tpch_write_binary(root.encode(), scale, g("lineitem"), g("orders"), g("customer"), g("part")),
+           "b200_tpch_write_binary")
+
+
+def tpch_read_binary(root: str, scale: int) -> dict:
+    """The reference's binary column files -> dict of dicts of numpy columns (only the columns whose files exist)."""
+    st = {k: cls() for k, (cls, _) in _TPCH_COLS.items()}
+    _check(lib().b200_tpch_read_binary(root.encode(), scale, C.byref(st["lineitem"]), C.byref(st["orders"]),
+                                       C.byref(st["customer"]), C.byref(st["part"])), "b200_tpch_read_binary")
+    out = {}
+    for name, (cls, cols) in _TPCH_COLS.items():
+        n = st[name].numTuples
+        out[name] = {}
+        for col, dt in cols:
+            dt = np.dtype(dt)
+            ptr = getattr(st[name], col)
+            if ptr:
+                buf = (C.c_uint8 * (n * dt.itemsize)).from_address(ptr) if n else b""
+                out[name][col] = np.frombuffer(buf, dtype=dt).copy()
     lib().b200_tpch_free_host(C.byref(st["lineitem"]), C.byref(st["orders"]), C.byref(st["customer"]), C.byref(st["part"]))
     return out
 

@@ -335,6 +335,10 @@ static int join_device_locked(const row_t *dR, uint64_t nR, const row_t *dS, uin
     return 0;
 }
 
+void join_plan_internal(uint64_t nR, uint32_t dead_bits, uint32_t *total, uint32_t *b1, uint32_t *b2) {
+    plan_bits(nR, total, b1, b2, dead_bits);
+}
+
 // entry for the library's other translation units (tpch.cu): same lock, same workspace
 int join_device_internal(const row_t *dR, uint64_t nR, const row_t *dS, uint64_t nS, output_triple_t *d_out,
                          uint64_t out_cap, b200_join_stats_t *stats, cudaStream_t st, uint32_t dead_bits) {

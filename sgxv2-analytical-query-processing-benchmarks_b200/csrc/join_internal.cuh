@@ -189,6 +189,8 @@ int bitvector_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t 
 int scan_count_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t n, uint64_t *d_count, cudaStream_t st);
 size_t index_scan_scratch_bytes(size_t n);
 void scan_release();
+// the planner with the caller's knowledge of dead low key bits (api.cu plan_bits)
+void join_plan_internal(uint64_t nR, uint32_t dead_bits, uint32_t *total, uint32_t *b1, uint32_t *b2);
 
 // ---- host <-> device copies for the host-buffer entry points (hostcopy.cpp) ----------------------
 int copy_h2d_any(void *dev, const void *host, size_t bytes, cudaStream_t st);

@@ -143,6 +143,13 @@ int b200_mg_finalize(void) {
 }
 
 int b200_mg_init(int rank, int world, const unsigned char *id128, uint64_t nR_total, uint64_t nS_total) {
+    if (world < 1) world = 1;
+    // worst-case regions: any source may send its whole shard to one owner (no overflow path, any skew)
+    return b200_mg_init_caps(rank, world, id128, nR_total, (nR_total + world - 1) / world, (nS_total + world - 1) / world, 0);
+}
+
+int b200_mg_init_caps(int rank, int world, const unsigned char *id128, uint64_t nR_total, uint64_t capR, uint64_t capS,
+                      uint32_t dead_bits) {
     std::lock_guard<std::mutex> lk(mg_mu);
     if (mg.on) {
         set_error("b200_mg_init: already initialised; call b200_mg_finalize first");
@@ -157,7 +164,7 @@ int b200_mg_init(int rank, int world, const unsigned char *id128, uint64_t nR_to
     mg.world = world;
     mg.lg = log2u((uint32_t) world);
     uint32_t bits, b1, b2;
-    b200_join_plan(nR_total, &bits, &b1, &b2);
+    join_plan_internal(nR_total, dead_bits, &bits, &b1, &b2);
     if (b1 < mg.lg) {   // pass 1 needs at least log2(world) bits to route on
         b1 = mg.lg;
         if (bits < b1) bits = b1;
@@ -174,10 +181,8 @@ int b200_mg_init(int rank, int world, const unsigned char *id128, uint64_t nR_to
         set_error("b200_mg_init: too many received segments for one pass-2 launch");
         return -1;
     }
-    // worst-case regions: any source may send its whole shard to one owner (no overflow path, any skew)
-    auto region = [&](uint64_t total) { return ((total + world - 1) / world + 63) & ~(uint64_t) 63; };
-    mg.capR = region(nR_total);
-    mg.capS = region(nS_total);
+    mg.capR = (capR + 63) & ~(uint64_t) 63;   // regions start on 128-byte lines
+    mg.capS = (capS + 63) & ~(uint64_t) 63;
     if (mg.capR * world >= 0xFFFF0000ull || mg.capS * world >= 0xFFFF0000ull) {
         set_error("b200_mg_init: relations of 2^32 tuples or more are not supported");
         return -1;

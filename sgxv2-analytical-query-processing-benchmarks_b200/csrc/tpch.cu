@@ -29,6 +29,8 @@ constexpr uint32_t kOrderDateDays = 2406;   // 1992-01-01 .. 1998-08-02 (TPC-H 4
 // ---------------------------------------------------------------------------------------------
 struct DeviceTables {
     uint64_t nl = 0, no = 0, nc = 0, np = 0;
+    uint64_t no_total = 0;           // orders of the whole data set (this rank holds a shard when world > 1)
+    uint32_t world = 1, rank = 0;
     DevBuf l_orderkey, l_shipdate, l_commitdate, l_receiptdate, l_shipmode, l_partkey, l_quantity, l_shipinstruct,
         l_returnflag;
     DevBuf o_orderkey, o_orderdate, o_custkey;
@@ -71,67 +73,73 @@ __device__ __forceinline__ uint64_t order_date(uint64_t seed, uint64_t order) {
     return kTs1992_01_01 + 86400ull * draw(seed, order, 1, kOrderDateDays);
 }
 
-__global__ void gen_customer_kernel(uint2 *custkey, uint8_t *mkt, uint32_t *nation, uint64_t n, uint64_t seed) {
+// Every generator kernel writes rows [r0, r0 + n) of its table to local indices 0..n-1: values depend on the GLOBAL row
+// only, so the shards of a multi-GPU run together are exactly the single-GPU tables.
+__global__ void gen_customer_kernel(uint2 *custkey, uint8_t *mkt, uint32_t *nation, uint64_t r0, uint64_t n, uint64_t seed) {
     uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        custkey[i] = make_uint2((uint32_t) i + 1, (uint32_t) i);
-        mkt[i] = draw(seed, i, 20, 5) == 0 ? B200_MKT_BUILDING : 0;   // 5 segments, only BUILDING is coded
-        nation[i] = draw(seed, i, 21, 25);
+    for (uint64_t j = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const uint64_t i = r0 + j;
+        custkey[j] = make_uint2((uint32_t) i + 1, (uint32_t) i);
+        mkt[j] = draw(seed, i, 20, 5) == 0 ? B200_MKT_BUILDING : 0;   // 5 segments, only BUILDING is coded
+        nation[j] = draw(seed, i, 21, 25);
     }
 }
 
-__global__ void gen_orders_kernel(uint2 *orderkey, uint64_t *orderdate, uint32_t *custkey, uint64_t n, uint64_t ncust,
+__global__ void gen_orders_kernel(uint2 *orderkey, uint64_t *orderdate, uint32_t *custkey, uint64_t r0, uint64_t n, uint64_t ncust,
                                   uint64_t seed) {
     uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        orderkey[i] = make_uint2(sparse_orderkey(i), (uint32_t) i);
-        orderdate[i] = order_date(seed, i);
+    for (uint64_t j = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const uint64_t i = r0 + j;
+        orderkey[j] = make_uint2(sparse_orderkey(i), (uint32_t) i);
+        orderdate[j] = order_date(seed, i);
         // dbgen: customer keys divisible by 3 place no orders
         uint32_t two_thirds = (uint32_t) (ncust - ncust / 3);
         uint32_t k = draw(seed, i, 2, two_thirds ? two_thirds : 1);
-        custkey[i] = ncust >= 3 ? k + k / 2 + 1 : 1;   // k-th key not divisible by 3: 1,2,4,5,7,8,...
+        custkey[j] = ncust >= 3 ? k + k / 2 + 1 : 1;   // k-th key not divisible by 3: 1,2,4,5,7,8,...
     }
 }
 
 __global__ void gen_lineitem_kernel(uint2 *orderkey, uint64_t *shipdate, uint64_t *commitdate, uint64_t *receiptdate,
                                     uint8_t *shipmode, uint32_t *partkey, float *quantity, uint8_t *shipinstruct,
-                                    char *returnflag, uint64_t n, uint64_t npart, uint64_t seed) {
+                                    char *returnflag, uint64_t r0, uint64_t n, uint64_t npart, uint64_t seed) {
     uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    for (uint64_t j = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const uint64_t i = r0 + j;
         const uint64_t order = i >> 2;   // 4 line items per order
         const uint64_t od = order_date(seed, order);
-        orderkey[i] = make_uint2(sparse_orderkey(order), (uint32_t) i);
+        orderkey[j] = make_uint2(sparse_orderkey(order), (uint32_t) i);
         const uint64_t sd = od + 86400ull * (1 + draw(seed, i, 3, 121));
-        shipdate[i] = sd;
-        commitdate[i] = od + 86400ull * (30 + draw(seed, i, 4, 61));
-        receiptdate[i] = sd + 86400ull * (1 + draw(seed, i, 5, 30));
+        shipdate[j] = sd;
+        commitdate[j] = od + 86400ull * (30 + draw(seed, i, 4, 61));
+        receiptdate[j] = sd + 86400ull * (1 + draw(seed, i, 5, 30));
         // 7 modes REG AIR, AIR, RAIL, SHIP, TRUCK, MAIL, FOB; the loader codes MAIL, SHIP, AIR and "AIR REG" (never)
         const uint32_t m = draw(seed, i, 6, 7);
-        shipmode[i] = m == 5 ? B200_L_SHIPMODE_MAIL : (m == 3 ? B200_L_SHIPMODE_SHIP : (m == 1 ? B200_L_SHIPMODE_AIR : 0));
-        partkey[i] = 1 + draw(seed, i, 7, (uint32_t) npart);
-        quantity[i] = (float) (1 + draw(seed, i, 8, 50));
-        shipinstruct[i] = draw(seed, i, 9, 4) == 0 ? B200_L_SHIPINSTRUCT_DELIVER_IN_PERSON : 0;
+        shipmode[j] = m == 5 ? B200_L_SHIPMODE_MAIL : (m == 3 ? B200_L_SHIPMODE_SHIP : (m == 1 ? B200_L_SHIPMODE_AIR : 0));
+        partkey[j] = 1 + draw(seed, i, 7, (uint32_t) npart);
+        quantity[j] = (float) (1 + draw(seed, i, 8, 50));
+        shipinstruct[j] = draw(seed, i, 9, 4) == 0 ? B200_L_SHIPINSTRUCT_DELIVER_IN_PERSON : 0;
         const uint32_t rf = draw(seed, i, 10, 3);
-        returnflag[i] = rf == 0 ? 'R' : (rf == 1 ? 'A' : 'N');
+        returnflag[j] = rf == 0 ? 'R' : (rf == 1 ? 'A' : 'N');
     }
 }
 
-__global__ void gen_part_kernel(uint2 *partkey, uint8_t *brand, uint32_t *size, uint8_t *container, uint64_t n,
+__global__ void gen_part_kernel(uint2 *partkey, uint8_t *brand, uint32_t *size, uint8_t *container, uint64_t r0, uint64_t n,
                                 uint64_t seed) {
     uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        partkey[i] = make_uint2((uint32_t) i + 1, (uint32_t) i);
+    for (uint64_t j = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const uint64_t i = r0 + j;
+        partkey[j] = make_uint2((uint32_t) i + 1, (uint32_t) i);
         // Brand#MN, M,N in 1..5: the loader codes 12 -> 1, 23 -> 2, 34 -> 3 (TpcHTypes.hpp:16-18)
         const uint32_t mn = (1 + draw(seed, i, 11, 5)) * 10 + 1 + draw(seed, i, 12, 5);
-        brand[i] = mn == 12 ? 1 : (mn == 23 ? 2 : (mn == 34 ? 3 : 0));
-        size[i] = 1 + draw(seed, i, 13, 50);
+        brand[j] = mn == 12 ? 1 : (mn == 23 ? 2 : (mn == 34 ? 3 : 0));
+        size[j] = 1 + draw(seed, i, 13, 50);
         // 5 x 8 containers; coded: SM {CASE,BOX,PACK,PKG} = 1..4, MED {BAG,BOX,PKG,PACK} = 5..8, LG {CASE,BOX,PACK,PKG} = 9..12
         const uint32_t s1 = draw(seed, i, 14, 5), s2 = draw(seed, i, 15, 8);   // s1: SM, LG, MED, JUMBO, WRAP; s2: CASE, BOX, BAG, JAR, PKG, PACK, CAN, DRUM
         uint8_t c = 0;
         if (s1 == 0) c = s2 == 0 ? 1 : (s2 == 1 ? 2 : (s2 == 5 ? 3 : (s2 == 4 ? 4 : 0)));
         if (s1 == 2) c = s2 == 2 ? 5 : (s2 == 1 ? 6 : (s2 == 4 ? 7 : (s2 == 5 ? 8 : 0)));
         if (s1 == 1) c = s2 == 0 ? 9 : (s2 == 1 ? 10 : (s2 == 5 ? 11 : (s2 == 4 ? 12 : 0)));
-        container[i] = c;
+        container[j] = c;
     }
 }
 
@@ -548,19 +556,23 @@ using namespace aqp;
 
 extern "C" {
 
-int b200_tpch_generate_device(double sf, uint64_t seed) {
-    std::lock_guard<std::recursive_mutex> lk(t_mu);
+// rows [total * rank / world, total * (rank + 1) / world) of every table (orders in whole orders: 4 line items each)
+static int generate_shard(double sf, uint64_t seed, uint32_t rank, uint32_t world) {
     cudaStream_t st = library_stream();
     if (!st) return -1;
-    if (!(sf > 0) || sf > 300) {
-        set_error("b200_tpch_generate_device: scale factor must be in (0, 300]");
+    if (!(sf > 0) || sf > 300 || world == 0 || rank >= world) {
+        set_error("b200_tpch_generate_device: scale factor must be in (0, 300], rank < world");
         return -1;
     }
-    const uint64_t nc = (uint64_t) (150000.0 * sf), no = (uint64_t) (1500000.0 * sf), nl = no * 4, np = (uint64_t) (200000.0 * sf);
-    if (nl >= 0xFFFF0000ull || nc < 3 || np < 1) {
+    const uint64_t nc_t = (uint64_t) (150000.0 * sf), no_t = (uint64_t) (1500000.0 * sf), np_t = (uint64_t) (200000.0 * sf);
+    if (no_t * 4 >= 0xFFFF0000ull || nc_t < 3 || np_t < 1) {
         set_error("b200_tpch_generate_device: scale factor out of range");
         return -1;
     }
+    auto lo = [&](uint64_t t) { return t * rank / world; };
+    auto hi = [&](uint64_t t) { return t * (rank + 1) / world; };
+    const uint64_t c0 = lo(nc_t), nc = hi(nc_t) - c0, o0 = lo(no_t), no = hi(no_t) - o0, l0 = o0 * 4, nl = no * 4,
+                   p0 = lo(np_t), np = hi(np_t) - p0;
     if (T.l_orderkey.ensure(nl * 8 + 64) || T.l_shipdate.ensure(nl * 8 + 64) || T.l_commitdate.ensure(nl * 8 + 64) ||
         T.l_receiptdate.ensure(nl * 8 + 64) || T.l_shipmode.ensure(nl + 64) || T.l_partkey.ensure(nl * 4 + 64) ||
         T.l_quantity.ensure(nl * 4 + 64) || T.l_shipinstruct.ensure(nl + 64) || T.l_returnflag.ensure(nl + 64) ||
@@ -570,19 +582,19 @@ int b200_tpch_generate_device(double sf, uint64_t seed) {
         T.p_container.ensure(np + 64))
         return -1;
     gen_customer_kernel<<<kNumSMs * 4, 256, 0, st>>>(ptr<uint2>(T.c_custkey), ptr<uint8_t>(T.c_mktsegment),
-                                                     ptr<uint32_t>(T.c_nationkey), nc, seed);
+                                                     ptr<uint32_t>(T.c_nationkey), c0, nc, seed);
     AQP_LAUNCHED();
     gen_orders_kernel<<<kNumSMs * 8, 256, 0, st>>>(ptr<uint2>(T.o_orderkey), ptr<uint64_t>(T.o_orderdate),
-                                                   ptr<uint32_t>(T.o_custkey), no, nc, seed);
+                                                   ptr<uint32_t>(T.o_custkey), o0, no, nc_t, seed);
     AQP_LAUNCHED();
     gen_lineitem_kernel<<<kNumSMs * 8, 256, 0, st>>>(ptr<uint2>(T.l_orderkey), ptr<uint64_t>(T.l_shipdate),
                                                      ptr<uint64_t>(T.l_commitdate), ptr<uint64_t>(T.l_receiptdate),
                                                      ptr<uint8_t>(T.l_shipmode), ptr<uint32_t>(T.l_partkey),
                                                      ptr<float>(T.l_quantity), ptr<uint8_t>(T.l_shipinstruct),
-                                                     ptr<char>(T.l_returnflag), nl, np, seed);
+                                                     ptr<char>(T.l_returnflag), l0, nl, np_t, seed);
     AQP_LAUNCHED();
     gen_part_kernel<<<kNumSMs * 4, 256, 0, st>>>(ptr<uint2>(T.p_partkey), ptr<uint8_t>(T.p_brand), ptr<uint32_t>(T.p_size),
-                                                 ptr<uint8_t>(T.p_container), np, seed);
+                                                 ptr<uint8_t>(T.p_container), p0, np, seed);
     AQP_LAUNCHED();
     AQP_CUDA_OK(cudaGetLastError());
     AQP_CUDA_OK(cudaStreamSynchronize(st));
@@ -590,6 +602,56 @@ int b200_tpch_generate_device(double sf, uint64_t seed) {
     T.no = no;
     T.nc = nc;
     T.np = np;
+    T.no_total = no_t;
+    T.world = world;
+    T.rank = rank;
+    return 0;
+}
+
+int b200_tpch_generate_device(double sf, uint64_t seed) {
+    std::lock_guard<std::recursive_mutex> lk(t_mu);
+    return generate_shard(sf, seed, 0, 1);
+}
+
+int b200_tpch_generate_shard_device(double sf, uint64_t seed, uint32_t rank, uint32_t world) {
+    std::lock_guard<std::recursive_mutex> lk(t_mu);
+    return generate_shard(sf, seed, rank, world);
+}
+
+// Q12 across `world` GPUs: every rank filters ITS line items (selection 1 is a row-range scan, no exchange) and the
+// join orders x selected line items is the sharded join of csrc/mg.cu. The caller initialises the multi-GPU host with
+// b200_tpch_mg_init (capacities follow from the shard sizes; the order keys' two dead bits go into the radix plan).
+int b200_tpch_mg_init(int rank, int world, const unsigned char *id) {
+    std::lock_guard<std::recursive_mutex> lk(t_mu);
+    if (need(T.nl && T.no && T.world == (uint32_t) world && T.rank == (uint32_t) rank, "lineitem, orders of this rank's shard")) return -1;
+    const uint64_t cap_o = (T.no_total + world - 1) / world + 1;
+    return b200_mg_init_caps(rank, world, id, T.no_total, cap_o, cap_o * 4, kOrderKeyDeadBits);
+}
+
+int b200_tpch_q12_mg(struct b200_tpch_stats_t *out) {
+    std::lock_guard<std::recursive_mutex> lk(t_mu);
+    if (need(T.nl && T.no, "lineitem, orders")) return -1;
+    cudaStream_t st = library_stream();
+    const unsigned long long l0 = g_kernel_launches;
+    Timer tm;
+    if (T.f1.ensure(T.nl * 8 + 64) || T.counters.ensure(64)) return -1;
+    unsigned long long *ctr = ptr<unsigned long long>(T.counters);
+    b200_tpch_stats_t s{};
+    cudaEventRecord(tm.e[0], st);
+    Q12Lineitem pred{ptr<uint2>(T.l_orderkey), ptr<uint8_t>(T.l_shipmode), ptr<uint64_t>(T.l_commitdate),
+                     ptr<uint64_t>(T.l_shipdate), ptr<uint64_t>(T.l_receiptdate)};
+    if (run_filter(T.nl, pred, ptr<row_t>(T.f1), ctr, st)) return -1;
+    cudaEventRecord(tm.e[1], st);
+    if (read_counter(ctr, &s.filtered[0], st)) return -1;   // this rank's selected line items
+    b200_mg_result_t r{};
+    if (b200_mg_join(ptr<row_t>(T.o_orderkey), T.no, ptr<row_t>(T.f1), s.filtered[0], &r)) return -1;
+    s.result_rows = r.matches;                              // global
+    s.input_rows = T.nl + T.no;                             // this rank's rows
+    s.ms_filter = tm.ms(0, 1);
+    s.ms_join = r.ms_total;
+    s.ms_total = s.ms_filter + s.ms_join;
+    s.kernel_launches = (uint32_t) (g_kernel_launches - l0);
+    *out = s;
     return 0;
 }
 

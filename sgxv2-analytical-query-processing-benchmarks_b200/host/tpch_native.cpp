@@ -35,11 +35,13 @@ int main(int argc, char **argv) {
     int query = 12, threads = 1, reps = 1;
     double scale = 1;
     char alg[128] = "RHO";
+    const char *binary_root = nullptr;   // -b <root>: load <root>/scaleNNN/<table>.tbl.dir/*.bin (the reference's binary tables)
     static option long_opts[] = {{"reps", required_argument, nullptr, 'R'}, {nullptr, 0, nullptr, 0}};
     int c;
     while ((c = getopt_long(argc, argv, "a:b:m:n:q:s:p", long_opts, nullptr)) != -1) {
         switch (c) {
             case 'a': strncpy(alg, optarg, sizeof alg - 1); break;
+            case 'b': binary_root = optarg; break;
             case 'n': threads = atoi(optarg); break;
             case 'q': query = atoi(optarg); break;
             case 's': scale = atof(optarg); break;
@@ -56,10 +58,25 @@ int main(int argc, char **argv) {
         fprintf(stderr, "[ERROR] %s\n", b200_last_error());
         return EXIT_FAILURE;
     }
-    info("Generating tables in device memory.");
-    if (b200_tpch_generate_device(scale, 1)) {
-        fprintf(stderr, "[ERROR] %s\n", b200_last_error());
-        return EXIT_FAILURE;
+    if (binary_root) {
+        info("Loading binary tables from %s (scale %d).", binary_root, (int) scale);
+        LineItemTable l{};
+        OrdersTable o{};
+        CustomerTable c{};
+        PartTable p{};
+        if (b200_tpch_read_binary(binary_root, (int) scale, &l, &o, &c, &p) || b200_tpch_upload(&l, &o, &c, &p)) {
+            fprintf(stderr, "[ERROR] %s\n", b200_last_error());
+            return EXIT_FAILURE;
+        }
+        info("lineitem %lu, orders %lu, customer %lu, part %lu rows", (unsigned long) l.numTuples, (unsigned long) o.numTuples,
+             (unsigned long) c.numTuples, (unsigned long) p.numTuples);
+        b200_tpch_free_host(&l, &o, &c, &p);
+    } else {
+        info("Generating tables in device memory.");
+        if (b200_tpch_generate_device(scale, 1)) {
+            fprintf(stderr, "[ERROR] %s\n", b200_last_error());
+            return EXIT_FAILURE;
+        }
     }
     info("Done.");
     for (int r = 0; r < reps; ++r) {

@@ -195,6 +195,16 @@ def test_tpch_native_stdout(gpu, golden):
         assert "Query completed" in out
 
 
+def test_tpch_native_loads_binary_tables(gpu, oracle, tmp_path):
+    """-b <root>: the reference's binary column files (CSVConvert.cpp output layout) straight into the GPU pipelines"""
+    t = oracle.synth_tpch(0.05, 4)
+    gpu.tpch_write_binary(str(tmp_path), 1, t)
+    for q in (3, 12, 19):
+        out = run("tpch_native", "-q", str(q), "-s", "1", "-b", str(tmp_path))
+        rows = int(re.search(r"result rows: (\d+)", out).group(1))
+        assert rows == oracle.tpch_query(q, t)["result_rows"], (q, out)
+
+
 def test_radixbench_runs(gpu):
     out = run("radixbench", "--data_size=4194304", "--min_radix_bits=6", "--max_radix_bits=9", "--repeat=2")
     lines = out.strip().splitlines()

@@ -64,3 +64,34 @@ def test_duplicate_build_keys_materialise_like_the_reference(gpu, oracle):
         assert g["result_rows"] == o["result_rows"] == 2 * base["result_rows"], (q, g, o, base)
         assert g["join1_rows"] == o["join1_rows"] == 2 * base["join1_rows"]
     gpu.lib().b200_tpch_free_device()
+
+
+def test_binary_column_files_round_trip_through_the_device(gpu, oracle, tmp_path):
+    """device-generated tables -> the reference's binary column files -> back onto the device: same query answers"""
+    gpu.tpch_generate_device(0.1, 5)
+    want = {q: gpu.tpch_query_device(q)["result_rows"] for q in (3, 12, 19)}
+    gpu.tpch_write_binary(str(tmp_path), 1, gpu.tpch_download())
+    gpu.lib().b200_tpch_free_device()
+    t = gpu.tpch_read_binary(str(tmp_path), 1)
+    gpu.tpch_upload(t)
+    for q in (3, 12, 19):
+        assert gpu.tpch_query_device(q)["result_rows"] == want[q] == oracle.tpch_query(q, t)["result_rows"]
+    gpu.lib().b200_tpch_free_device()
+
+
+def test_q12_through_the_multi_gpu_host_with_one_rank(gpu):
+    """b200_tpch_generate_shard_device + b200_tpch_mg_init + b200_tpch_q12_mg with world = 1 (the 2..8 GPU form runs in
+    tests/test_gpu_dist.py): the sharded path gives the single-GPU pipeline's answer"""
+    for sf, seed in ((0.05, 2), (1.0, 9)):
+        gpu.tpch_generate_device(sf, seed)
+        want = gpu.tpch_query_device(12)
+        gpu.tpch_generate_shard_device(sf, seed, 0, 1)
+        gpu.tpch_mg_init(0, 1, gpu.mg_unique_id())
+        try:
+            got = gpu.tpch_q12_mg()
+            got2 = gpu.tpch_q12_mg()
+        finally:
+            gpu.mg_finalize()
+        assert got["result_rows"] == got2["result_rows"] == want["result_rows"]
+        assert got["filtered"][0] == want["filtered"][0]
+    gpu.lib().b200_tpch_free_device()
