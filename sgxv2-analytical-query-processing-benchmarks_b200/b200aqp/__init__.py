@@ -313,14 +313,32 @@ def join_device(d_R: int, nR: int, d_S: int, nS: int, d_out: int = 0, out_capaci
     return s.as_dict()
 
 
+def _prefer_bundled_nccl():
+    """The library dlopens NCCL on first use. In a Python process torch may be imported later and needs ITS bundled
+    libnccl.so.2 (one copy per soname can be loaded): point the library at that copy unless the caller chose one."""
+    if "B200_AQP_NCCL_LIB" in os.environ:
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec and spec.submodule_search_locations:
+            cand = os.path.join(list(spec.submodule_search_locations)[0], "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["B200_AQP_NCCL_LIB"] = cand
+    except Exception:
+        pass
+
+
 def mg_unique_id() -> bytes:
     """128-byte NCCL unique id (rank 0 creates it, every rank passes it to mg_init)"""
+    _prefer_bundled_nccl()
     buf = (C.c_ubyte * 128)()
     _check(lib().b200_mg_unique_id(buf), "b200_mg_unique_id")
     return bytes(buf)
 
 
 def mg_init(rank: int, world: int, unique_id: bytes, nR_total: int, nS_total: int):
+    _prefer_bundled_nccl()
     buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
     _check(lib().b200_mg_init(rank, world, buf, nR_total, nS_total), "b200_mg_init")
 
@@ -553,6 +571,7 @@ def tpch_generate_shard_device(scale_factor: float, seed: int, rank: int, world:
 
 
 def tpch_mg_init(rank: int, world: int, unique_id: bytes):
+    _prefer_bundled_nccl()
     buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
     _check(lib().b200_tpch_mg_init(rank, world, buf), "b200_tpch_mg_init")
 

@@ -42,9 +42,16 @@ struct NcclApi {
 
 int load_nccl() {
     if (nccl.h) return 0;
+    // Order matters inside a process that also uses another NCCL client (torch bundles its own, newer libnccl.so.2):
+    // the dynamic loader keeps ONE library per soname, so whichever copy is loaded first serves everybody. (1) a copy that
+    // is already loaded, (2) the path in B200_AQP_NCCL_LIB (the Python binding points it at torch's bundled copy, so a
+    // later `import torch` finds the version it was built against), (3) the system library.
+    nccl.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!nccl.h)
+        if (const char *e = getenv("B200_AQP_NCCL_LIB")) nccl.h = dlopen(e, RTLD_NOW | RTLD_LOCAL);
     const char *names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char *n : names)
-        if ((nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+        if (!nccl.h) nccl.h = dlopen(n, RTLD_NOW | RTLD_LOCAL);
     if (!nccl.h) {
         set_error(std::string("b200_mg: cannot load NCCL: ") + dlerror());
         return -1;
