@@ -99,6 +99,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "memory");
     } while (!done);
 }
+// 1-D bulk copy global -> shared through the TMA unit; src/dst 16-byte aligned, bytes % 16 == 0
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

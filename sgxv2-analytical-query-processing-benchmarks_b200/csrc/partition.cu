@@ -504,14 +504,6 @@ int plan_shard_device(const ShardPlanArgs &a, cudaStream_t st) {
 // LDG prefetch and the staging step (no shared-memory ring) was 25 % slower: the LDG data crosses the
 // same L1 data stage the ring reads do, while TMA writes into shared memory do not.
 // ---------------------------------------------------------------------------------------------
-// 1-D bulk copy global -> shared through the TMA unit; src/dst 16-byte aligned, bytes % 16 == 0
-__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
 constexpr int kScatterThreads = AQP_SCATTER_THREADS;
 constexpr int kScatterItems = kScatterTile / kScatterThreads;
 static_assert(kScatterItems * kScatterThreads == kScatterTile, "tile shape");

@@ -156,6 +156,66 @@ bitvector_scan_kernel(const uint4 *__restrict__ in, size_t nvec, uint64_t *__res
     AQP_PRED_SWITCH(p, (bitvector_scan_body<kCount, kVariant>(in, nvec, out, p, tile_counts));)
 }
 
+// TMA-fed variant (the north star's "stream the column through TMA bulk loads"): one producer warp keeps a ring of
+// kTmaStages stages filled with cp.async.bulk (completion on an mbarrier), kTmaWarps consumer warps take 1 KiB of every
+// stage each from shared memory (two conflict-free 128-bit loads per lane), evaluate the predicate and write the words.
+// The loads cost the consumers no registers and no address arithmetic and the ring keeps ~60 KiB per CTA in flight
+// regardless of what the consumers are doing. A/B against the LDG kernel: csrc/scanbench.cu (count only: 7.08 vs
+// 6.66 TB/s) and profiles/r02_sweep_bitvector_tma.txt (this kernel).
+constexpr int kTmaWarps = 15, kTmaStages = 4;
+constexpr uint32_t kTmaStageBytes = kTmaWarps * 1024;
+template <int kVariant>
+__device__ __forceinline__ void bitvector_tma_consume(const unsigned char *ring, uint64_t *full, uint64_t *empty, size_t s_begin,
+                                                      size_t s_end, uint64_t *__restrict__ out, const Pred &p) {
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    uint32_t it = 0;
+    for (size_t q = s_begin; q < s_end; ++q, ++it) {
+        const uint32_t s = it % kTmaStages, ph = (it / kTmaStages) & 1u;
+        mbar_wait(&full[s], ph);
+        const uint4 *src = reinterpret_cast<const uint4 *>(ring + (size_t) s * kTmaStageBytes + warp * 1024);
+        const uint4 a = src[lane], b = src[lane + 32];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);   // the stage's bytes are in registers
+        uint64_t *o = out + (q * kTmaWarps + warp) * 16;   // 1 KiB of values = 16 words
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t m16 = range_mask16<kVariant>(h ? b : a, p);
+            const uint32_t m32 = m16 | (__shfl_down_sync(0xffffffffu, m16, 1) << 16);
+            const uint32_t hi = __shfl_down_sync(0xffffffffu, m32, 2);
+            if ((lane & 3) == 0) o[h * 8 + (lane >> 2)] = (uint64_t) m32 | ((uint64_t) hi << 32);
+        }
+    }
+}
+__global__ void __launch_bounds__((kTmaWarps + 1) * 32, 2)
+bitvector_scan_tma_kernel(const uint8_t *__restrict__ in, size_t nstages, uint64_t *__restrict__ out, Pred p) {
+    extern __shared__ __align__(128) unsigned char tma_ring[];
+    __shared__ uint64_t full[kTmaStages], empty[kTmaStages];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kTmaStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kTmaWarps);
+        }
+        mbar_init_fence();
+    }
+    __syncthreads();
+    // the column's stages are dealt to the CTAs in contiguous runs
+    const size_t per = (nstages + gridDim.x - 1) / gridDim.x;
+    const size_t s_begin = (size_t) blockIdx.x * per, s_end = s_begin + per < nstages ? s_begin + per : nstages;
+    if ((threadIdx.x >> 5) == kTmaWarps) {   // producer
+        if (lane_id() == 0) {
+            uint32_t it = 0;
+            for (size_t q = s_begin; q < s_end; ++q, ++it) {
+                const uint32_t s = it % kTmaStages, ph = (it / kTmaStages) & 1u;
+                if (it >= (uint32_t) kTmaStages) mbar_wait(&empty[s], ph ^ 1u);
+                mbar_expect_tx(&full[s], kTmaStageBytes);
+                tma_load_1d(tma_ring + (size_t) s * kTmaStageBytes, in + q * kTmaStageBytes, kTmaStageBytes, &full[s]);
+            }
+        }
+        return;
+    }
+    AQP_PRED_SWITCH(p, (bitvector_tma_consume<kVariant>(tma_ring, full, empty, s_begin, s_end, out, p));)
+}
+
 // ---------------------------------------------------------------------------------------------
 // count
 // ---------------------------------------------------------------------------------------------
@@ -1002,9 +1062,30 @@ int bitvector_scan_device(uint8_t lo, uint8_t hi, const uint8_t *d_data, size_t 
     }
     size_t nvec = (n / 64) * 4;
     if (nvec == 0) return 0;
-    bitvector_scan_kernel<false><<<scan_grid(nvec, 8), kScanThreads, 0, st>>>(reinterpret_cast<const uint4 *>(d_data),
-                                                                             nvec, d_out, make_pred(lo, hi), nullptr);
-    AQP_LAUNCHED();
+    // large columns: the TMA-fed kernel over whole 15 KiB stages, the LDG kernel for the rest (B200_AQP_BITVECTOR=ldg: A/B)
+    static const bool ldg_only = getenv("B200_AQP_BITVECTOR") && !strcmp(getenv("B200_AQP_BITVECTOR"), "ldg");
+    size_t done = 0;
+    const size_t nstages = (n / 64 * 64) / kTmaStageBytes;
+    // measured (profiles/r02_sweep_bitvector_tma.txt): 2^30 values 0.182 vs 0.202 ms, 2^29 0.096 vs 0.099, below that the
+    // LDG kernel wins (a column of <= 2^28 bytes is partly L2-resident between runs, and the ring's fill / drain shows)
+    if (!ldg_only && (n >> 29) != 0) {
+        static unsigned attr_set = ~0u;
+        if (attr_set != g_device_epoch) {
+            AQP_CUDA_OK(cudaFuncSetAttribute(bitvector_scan_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int) (kTmaStages * kTmaStageBytes)));
+            attr_set = g_device_epoch;
+        }
+        bitvector_scan_tma_kernel<<<2 * kNumSMs, (kTmaWarps + 1) * 32, kTmaStages * kTmaStageBytes, st>>>(d_data, nstages, d_out,
+                                                                                                        make_pred(lo, hi));
+        AQP_LAUNCHED();
+        done = nstages * kTmaStageBytes;
+    }
+    if (done < n / 64 * 64) {
+        const size_t rest = (n / 64 * 64 - done) / 16;
+        bitvector_scan_kernel<false><<<scan_grid(rest, 8), kScanThreads, 0, st>>>(reinterpret_cast<const uint4 *>(d_data + done),
+                                                                                 rest, d_out + done / 64, make_pred(lo, hi), nullptr);
+        AQP_LAUNCHED();
+    }
     AQP_CUDA_OK(cudaGetLastError());
     return 0;
 }
