@@ -317,6 +317,19 @@ def bench_scan(A, torch, dev, peak, steps, warmup, n_gpus=1, rank=0):
                            "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": peak, "unit": "GB/s",
                                         "frac": alg / ms / 1e6 / peak}}
     out["n_values_per_gpu"] = n
+    # DRAM bytes per launch from the committed `ncu --set full` capture of the same kernels at 2^30 values
+    # (profiles/r02_traffic_scan.json from tools/scan_probe.py: skewed, then the tiled column at hi = 0, 26, 128, 255)
+    if n == 1 << SCAN_LOG_N:
+        try:
+            with open(os.path.join(ROOT, "profiles", "r02_traffic_scan.json")) as f:
+                t = json.load(f)
+            fused = next(v for k, v in t.items() if k.startswith("aqp::rowid_scan_fused_kernel") or "rowid_scan_fused_kernel" in k)
+            for key, i in (("rowid_sel0.1", 0), ("rowid_sel0.4", 1), ("rowid_sel10", 2), ("rowid_sel50", 3), ("rowid_sel100", 4)):
+                out[key]["roofline"]["traffic"] = fused["per_launch"][i]
+            bvk = next(v for k, v in t.items() if "bitvector_scan_tma_kernel" in k)
+            out["bitvector"]["roofline"]["traffic"] = bvk["per_launch"][0]
+        except Exception:
+            pass
     del ids, data, bv
     return out
 
@@ -663,18 +676,21 @@ def run_b200_arm(args):
             try:   # the reference's own pipelines on the host cores, bounded sample: the same generator at SF1
                 import oracle as O
                 if O.have_ref():
-                    A.tpch_generate_device(1.0, 1)
+                    sf_cpu = float(os.environ.get("B200_AQP_TPCH_CPU_SF", "10"))
+                    A.tpch_generate_device(sf_cpu, 1)
                     t = A.tpch_download()
-                    tpch["cpu_reference_sf1"] = {"cores": os.cpu_count(), "kind": "reference"}
+                    tpch["cpu_reference"] = {"cores": os.cpu_count(), "kind": "reference", "scale_factor": sf_cpu,
+                                                 "note": "the reference's unmodified pipelines (oracle/_ref/libref_tpch.so) on the "
+                                                         "downloaded tables; result rows asserted equal to the device pipelines'"}
                     for q in (3, 12, 19):
                         g = A.tpch_query_device(q)
                         c = O.ref_tpch_query(q, t, nthreads=os.cpu_count())
                         assert c["result_rows"] == g["result_rows"], (q, c, g)
-                        tpch["cpu_reference_sf1"][f"q{q}"] = {"ms": c["seconds"] * 1e3, "gpu_ms": g["ms_total"],
+                        tpch["cpu_reference"][f"q{q}"] = {"ms": c["seconds"] * 1e3, "gpu_ms": g["ms_total"],
                                                               "result_rows": c["result_rows"]}
                     del t
             except Exception as ex:
-                tpch["cpu_reference_sf1"] = {"failed": str(ex)}
+                tpch["cpu_reference"] = {"failed": str(ex)}
         A.lib().b200_tpch_free_device()
 
     if rank == 0:
