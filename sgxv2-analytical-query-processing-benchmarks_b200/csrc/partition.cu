@@ -1211,7 +1211,7 @@ int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_
                          const uint32_t *d_seg_tile_start, const uint32_t *d_seg_group, uint32_t nseg, uint64_t n_total,
                          DigitFn digit, uint32_t bits, uint32_t *d_cursors, const uint32_t *d_block_base,
                          uint32_t nblocks, uint32_t tiles_per_block, cudaStream_t st, const PeerTable *peers) {
-    if (bits > (uint32_t) kMaxFanoutBits || nseg > (uint32_t) kMaxFanout) {
+    if (bits > (uint32_t) kMaxFanoutBits || nseg > (uint32_t) kMaxSegs) {
         set_error("radix_scatter: fan-out too large");
         return -1;
     }

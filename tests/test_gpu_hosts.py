@@ -212,3 +212,25 @@ def test_radixbench_runs(gpu):
     assert [int(l.split(",")[0]) for l in lines[1:]] == [6, 7, 8, 9]
     assert all(float(l.split(",")[3]) > 10 for l in lines[1:])
     assert lines[-1].split(",")[4] == ""          # 2^9 partitions: histogram only, one scatter pass handles up to 2^8
+
+
+def test_mg_api_world1_widest_single_pass(gpu):
+    """|R| = 2^21 plans 8 radix bits in ONE pass: 256 received segments + 1 gap segment (the pass-2 launcher once
+    capped the segment count at 256, which only showed with 2+ GPUs)"""
+    import torch
+    dev = torch.device("cuda:0")
+    nR, nS = 1 << 21, 1 << 22
+    R = torch.empty(2 * nR, dtype=torch.int32, device=dev)
+    S = torch.empty(2 * nS, dtype=torch.int32, device=dev)
+    gpu.gen_pk_device(R.data_ptr(), nR, 11111, 0, nR)
+    gpu.gen_fk_device(S.data_ptr(), nS, nR, 22222, 0, nS)
+    torch.cuda.synchronize()
+    gpu.mg_init(0, 1, gpu.mg_unique_id(), nR, nS)
+    try:
+        got = gpu.mg_join(R.data_ptr(), nR, S.data_ptr(), nS)
+    finally:
+        gpu.mg_finalize()
+    assert (got["bits_pass1"], got["bits_pass2"]) == (8, 0)
+    rep = nS // nR
+    assert got["matches"] == nS and got["keysum"] == rep * nR * (nR + 1) // 2
+    assert got["checksum"] == rep * (nR * (nR - 1) // 2) + nS * (nS - 1) // 2
