@@ -17,8 +17,9 @@ larger than the 126 MB L2, so no cache flush is needed between steps). Prints ON
   join_roofline  the whole join at SURVEY.md §8d's graded 56 B/tuple
   scan      bitvector and row-id scans over 2^30 uint8 (BASELINE config 2), GB/s of input and
             fraction of the HBM peak at 1.125 B/value resp. (1 + 8 sel) B/value
-  cpu_baseline   the reference's own RHO (oracle/_ref, compiled from /root/reference) on this box's
-            host cores on a bounded sample — a reported baseline, not the target
+  cpu_baseline   the reference's own RHO (oracle/_ref, compiled from /root/reference) on all of this box's
+            host cores at the SAME size 2^27 x 2^29 (a few runs) — a reported baseline, not the target
+  skew / tpch / exchange   BASELINE configs 4 and 5, NVLink traffic of the shuffle at N > 1
 
 --impl reference runs only that CPU reference arm and prints the same line shape.
 """
@@ -42,9 +43,10 @@ LOG_R, LOG_S = 27, 29          # BASELINE config 3
 SCAN_LOG_N = 30                # BASELINE config 2
 JOIN_BYTES_PER_TUPLE = 56      # 8 * (3 P + 1) with P = 2 passes
 SCATTER_BYTES_PER_TUPLE = 16   # read 8 + write 8
-# multi-GPU shuffle: "p2p" (scatter fused with peer stores over NVLink), "dma" (local scatter + copy engines),
-# "nccl" (all_to_all_single). Measured ms per join at 2 / 4 / 8 GPUs (profiles/r01_bench_{2,4,8}gpu_*.json):
-# p2p 6.13 / 4.25 / 2.90, dma 6.60 / 4.95 / 3.68, nccl 9.46 / 5.02 / 5.99 -> p2p everywhere
+# multi-GPU shuffle: "mg" (the C host in csrc/mg.cu: scatter fused with peer stores over NVLink, region layout),
+# "p2p" / "dma" / "nccl" (round-1 Python-orchestrated forms: fused with sizing collectives in front, copy engines,
+# all_to_all_single). Measured ms per join at 2 GPUs in one run (profiles/r02_bench_2gpu_a.json): mg 4.38, p2p 4.49,
+# dma 6.08, nccl 8.82; at 8 GPUs mg 1.86 (p2p in round 1: 2.00) -> mg everywhere
 DEFAULT_EXCHANGE = {}
 METRIC = "rho_join_throughput"
 UNIT = "Mtuples/s"

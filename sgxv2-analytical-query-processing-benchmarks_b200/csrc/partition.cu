@@ -5,19 +5,23 @@
 //                                               the histogram over ALL radix bits of both passes)
 //   prefix sums                    :886-915, -> plan_offsets_kernel (partition boundaries of both
 //                                   :739-746     passes from that one histogram)
-//   partition_copy[_unrolled]      :659-697  -> radix_scatter_kernel (pass 1: whole relation, one
+//   partition_copy[_unrolled]      :659-697  -> radix_scatter_bins_kernel (pass 1: whole relation, one
 //   radix_cluster/serial_radix_..  :715-841     segment; pass 2: every pass-1 partition is a segment)
 //
 // Digit function is the reference's: (key & MASK) >> R on raw key bits, pass 1 on bits [0,b1),
 // pass 2 on bits [b1,b1+b2) (radix_join.cpp:47,:1118-1119,:1262).
 //
-// Scatter design: a CTA takes a tile of the input, ranks every tuple inside its partition with a
-// shared-memory atomic counter, reorders the tile in shared memory so that tuples of one
-// partition are adjacent, reserves the tile's run in every partition's output range with ONE
-// global atomic per (tile, partition), and writes the runs out as contiguous coalesced stores
-// (software write-combining; the analogue of the reference's dormant SWWC path :1013-1053).
-// Order inside a partition is therefore unspecified — exactly like the reference, where it
-// depends on thread interleaving — and never affects join results.
+// Scatter design (radix_scatter_bins_kernel, the default): a CTA bulk-loads a tile of 4096 tuples with TMA, ranks every
+// tuple inside its partition with a shared-memory atomic counter, stages it in that partition's FIXED bin of the
+// staging buffer (slot = (digit << log2 cap) + rank: no per-tile scan, no offset look-ups) and drains every bin with
+// one TMA bulk store per (tile, partition); the destination comes from CTA-private cursors in pass 1 (pre-computed
+// from per-CTA histogram rows, no atomics) and from one global atomic per (tile, partition) in pass 2. This is
+// software write-combining - the analogue of the reference's dormant SWWC path (:1013-1053). A tile in which a bin
+// would overflow (skew) takes a compacting path in the same kernel. radix_scatter_kernel is the older staged kernel
+// (scan + look-ups, SM-store or bulk write-out) kept for unaligned destinations and A/B runs;
+// radix_scatter_peer_kernel is the multi-GPU variant whose bins are rings across tiles so that only whole 128-byte
+// lines cross NVLink. Order inside a partition is unspecified - exactly like the reference, where it depends on
+// thread interleaving - and never affects join results.
 #include "common.cuh"
 #include "join_internal.cuh"
 #include "block_scan.cuh"
