@@ -799,6 +799,9 @@ radix_scatter_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
 // this kernel (scan + lbase/gdst look-ups, SM-store write-out), so any distribution stays correct and fast.
 // ---------------------------------------------------------------------------------------------
 constexpr int kBinSlotsLog = 13;
+#ifndef AQP_SCATTER_EARLY_REFILL
+#define AQP_SCATTER_EARLY_REFILL 1
+#endif
 constexpr size_t kBinsSmemBytes = (size_t) (kInBufTuples + (1 << kBinSlotsLog)) * sizeof(uint2);
 static_assert(kScatterTile + kMaxFanout <= (1 << kBinSlotsLog), "the compacting path stages a whole tile plus carries");
 
@@ -825,6 +828,7 @@ radix_scatter_bins_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
     __shared__ uint32_t s_total;
     __shared__ uint32_t s_tile[2][4];   // {begin, end, cursor group} of the tile in flight / being processed
     __shared__ __align__(8) uint64_t mbar;
+    __shared__ __align__(8) uint64_t mbar_free;   // input buffer read into registers by every warp
 
     const uint32_t fan = 1u << bits;
     const uint32_t lgcap = kBinSlotsLog - bits, cap = 1u << lgcap;
@@ -841,6 +845,7 @@ radix_scatter_bins_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
     if (threadIdx.x == 0) {
         s_ovf[0] = s_ovf[1] = 0;
         mbar_init(&mbar, 1);
+        mbar_init(&mbar_free, kScatterThreads / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -881,6 +886,21 @@ radix_scatter_bins_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
     };
     if (threadIdx.x == 0 && n_my > 0) issue(0);
     __syncthreads();   // s_tile[0] published
+    // The input buffer is free again as soon as every warp holds its part of tile i in registers — before the rank
+    // phase, not after it: each warp arrives on mbar_free, thread 0 waits for all of them and requests tile i+1,
+    // which then has the rank, staging and write-out phases of tile i to land under.
+    // (Pass 2 gains 5 % from it; pass 1, whose CTAs walk private contiguous tile ranges, loses 2.5 % and keeps the
+    // request behind barrier (1): profiles/r02_sweep_join_early_refill.txt.)
+    constexpr bool kEarlyRefill = AQP_SCATTER_EARLY_REFILL && !kPriv;
+    auto refill = [&](uint32_t i) {
+        if (!kEarlyRefill) return;
+        __syncwarp();
+        if ((threadIdx.x & 31u) == 0) mbar_arrive(&mbar_free);
+        if (threadIdx.x == 0 && i + 1 < n_my) {
+            mbar_wait(&mbar_free, i & 1);
+            issue(i + 1);
+        }
+    };
     // The partition this thread reserves and writes out (if < fan). A bulk store takes its operands from uniform
     // registers, so a warp issues the stores of its lanes one after another: the partitions are dealt out to ALL
     // warps (the first fan/nwarps lanes of each) to keep that serial section short.
@@ -901,6 +921,7 @@ radix_scatter_bins_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
         if (ntile == (uint32_t) kScatterTile) {   // full tile: no per-item bounds checks
 #pragma unroll
             for (int j = 0; j < kScatterItems; ++j) v[j] = buf[j * kScatterThreads + threadIdx.x];
+            refill(i);
 #pragma unroll
             for (int j = 0; j < kScatterItems; ++j) {
                 rank[j] = atomicAdd(&cnt[digit.template get<kRot>(v[j].x)], 1u);
@@ -912,6 +933,7 @@ radix_scatter_bins_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
                 uint32_t k = j * kScatterThreads + threadIdx.x;
                 if (k < ntile) v[j] = buf[k];
             }
+            refill(i);
 #pragma unroll
             for (int j = 0; j < kScatterItems; ++j) {
                 uint32_t k = j * kScatterThreads + threadIdx.x;
@@ -927,7 +949,7 @@ radix_scatter_bins_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
         __syncthreads();   // (1) tile histogram complete, input buffer consumed, bins free
 
         if (threadIdx.x == 0) {
-            if (i + 1 < n_my) issue(i + 1);
+            if (!kEarlyRefill && i + 1 < n_my) issue(i + 1);
             s_ovf[(i + 1) & 1] = 0;
         }
         if (!s_ovf[i & 1]) {
