@@ -233,6 +233,17 @@ int b200_mg_init_caps(int rank, int world, const unsigned char *id /* 128 bytes 
                       uint64_t capS, uint32_t dead_bits);
 int b200_mg_join(const struct row_t *d_R, uint64_t nR_local, const struct row_t *d_S, uint64_t nS_local,
                  struct b200_mg_result_t *result);
+/* Materialising form (the MATERIALIZE switch of joinconfig_t, radix_join.cpp:428-447,:1556, for sharded relations): the
+ * triples {key, Rpayload, Spayload} of the co-partitions THIS rank owns are left in a library-owned device buffer
+ * (*d_triples, *local_rows of them; valid until the next b200_mg_* call) - the result stays sharded by key, ready to be
+ * the input of the next sharded join. result->matches is the global count. The buffer is sized for a unique build
+ * key and even shards; if this rank produces more, it is grown and the probe (only) runs again. */
+int b200_mg_join_materialize(const struct row_t *d_R, uint64_t nR_local, const struct row_t *d_S, uint64_t nS_local,
+                             const struct output_triple_t **d_triples, uint64_t *local_rows,
+                             struct b200_mg_result_t *result);
+/* Sum of n (1..4) host values over all ranks, in place (collective): turns per-rank counts of a sharded pipeline into
+ * its answer without a second communication layer. */
+int b200_mg_allreduce_u64(uint64_t *values, int n);
 int b200_mg_finalize(void);
 
 /* ------------------------------------------------------------------------------------------------

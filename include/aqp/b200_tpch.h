@@ -125,11 +125,16 @@ int b200_tpch_write_binary(const char *root, int scale, const struct LineItemTab
 /* Multi-GPU, one process per GPU: every rank generates rows [total * rank / world, total * (rank+1) / world)
  * of every table (values depend on the global row only: the shards together are the single-GPU tables), filters its own
  * line items and joins through the sharded join of b200_mg_* (include/aqp/b200_aqp.h). b200_tpch_mg_init wraps
- * b200_mg_init_caps with capacities derived from the shard sizes; stats->result_rows of b200_tpch_q12_mg is the GLOBAL
+ * b200_mg_init_caps with capacities derived from the shard sizes; stats->result_rows of b200_tpch_q*_mg is the GLOBAL
  * answer, the other fields describe this rank. Finish with b200_mg_finalize(). */
 int b200_tpch_generate_shard_device(double scale_factor, uint64_t seed, uint32_t rank, uint32_t world);
 int b200_tpch_mg_init(int rank, int world, const unsigned char *nccl_unique_id /* 128 bytes */);
 int b200_tpch_q12_mg(struct b200_tpch_stats_t *stats);
+/* Q3: the matches of join 1 stay sharded by customer key and feed join 2 as its build side (b200_mg_join_materialize);
+ * Q19: the attributes of the final predicate travel packed in the payloads, the per-rank counts are all-reduced.
+ * stats->join1_rows and stats->result_rows are GLOBAL. Both need b200_tpch_mg_init like Q12. */
+int b200_tpch_q3_mg(struct b200_tpch_stats_t *stats);
+int b200_tpch_q19_mg(struct b200_tpch_stats_t *stats);
 
 int b200_tpch_q3_device(struct b200_tpch_stats_t *stats);
 int b200_tpch_q12_device(struct b200_tpch_stats_t *stats);

@@ -144,6 +144,8 @@ SYMBOLS = {
     "b200_mg_init": (_int, [_int, _int, _vp, _u64, _u64]),
     "b200_mg_init_caps": (_int, [_int, _int, _vp, _u64, _u64, _u64, _u32]),
     "b200_mg_join": (_int, [_vp, _u64, _vp, _u64, C.POINTER(MgResult)]),
+    "b200_mg_join_materialize": (_int, [_vp, _u64, _vp, _u64, C.POINTER(_vp), C.POINTER(_u64), C.POINTER(MgResult)]),
+    "b200_mg_allreduce_u64": (_int, [C.POINTER(_u64), _int]),
     "b200_mg_finalize": (_int, []),
     "seed_generator": (None, [C.c_uint]),
     "create_relation_pk": (_int, [C.POINTER(Table), _u64, _int]),
@@ -194,6 +196,8 @@ SYMBOLS = {
     "b200_tpch_generate_shard_device": (_int, [C.c_double, _u64, _u32, _u32]),
     "b200_tpch_mg_init": (_int, [_int, _int, _vp]),
     "b200_tpch_q12_mg": (_int, [C.POINTER(TpchStats)]),
+    "b200_tpch_q3_mg": (_int, [C.POINTER(TpchStats)]),
+    "b200_tpch_q19_mg": (_int, [C.POINTER(TpchStats)]),
     "b200_tpch_read_binary": (_int, [C.c_char_p, _int, C.POINTER(LineItemTable), C.POINTER(OrdersTable),
                                      C.POINTER(CustomerTable), C.POINTER(PartTable)]),
     "b200_tpch_write_binary": (_int, [C.c_char_p, _int, C.POINTER(LineItemTable), C.POINTER(OrdersTable),
@@ -348,6 +352,24 @@ def mg_join(d_R: int, nR: int, d_S: int, nS: int) -> dict:
     r = MgResult()
     _check(lib().b200_mg_join(d_R, nR, d_S, nS, C.byref(r)), "b200_mg_join")
     return r.as_dict()
+
+
+def mg_join_materialize(d_R: int, nR: int, d_S: int, nS: int) -> dict:
+    """Materialising form: adds d_triples (device address of this rank's {key, Rpayload, Spayload} triples, library
+    owned, valid until the next mg_* call) and local_rows to the result dict. Collective."""
+    r = MgResult()
+    ptr, rows = _vp(), _u64()
+    _check(lib().b200_mg_join_materialize(d_R, nR, d_S, nS, C.byref(ptr), C.byref(rows), C.byref(r)), "b200_mg_join_materialize")
+    d = r.as_dict()
+    d["d_triples"] = ptr.value or 0
+    d["local_rows"] = rows.value
+    return d
+
+
+def mg_allreduce_u64(values):
+    arr = (_u64 * len(values))(*values)
+    _check(lib().b200_mg_allreduce_u64(arr, len(values)), "b200_mg_allreduce_u64")
+    return list(arr)
 
 
 def mg_finalize():
@@ -579,6 +601,18 @@ def tpch_mg_init(rank: int, world: int, unique_id: bytes):
 def tpch_q12_mg() -> dict:
     s = TpchStats()
     _check(lib().b200_tpch_q12_mg(C.byref(s)), "b200_tpch_q12_mg")
+    return s.as_dict()
+
+
+def tpch_q3_mg() -> dict:
+    s = TpchStats()
+    _check(lib().b200_tpch_q3_mg(C.byref(s)), "b200_tpch_q3_mg")
+    return s.as_dict()
+
+
+def tpch_q19_mg() -> dict:
+    s = TpchStats()
+    _check(lib().b200_tpch_q19_mg(C.byref(s)), "b200_tpch_q19_mg")
     return s.as_dict()
 
 

@@ -892,11 +892,18 @@ int b200_exchange_plan_device(const uint32_t *d_counts_all, uint32_t world, uint
                                 stream ? static_cast<cudaStream_t>(stream) : g.stream);
 }
 
+// workspace layout of the last shard join: lets the materialising form repeat the probe alone with a larger output
+struct ShardLast {
+    size_t o_res, o_offR, o_offS, o_istart, o_items;
+    uint32_t P, hash_shift;
+    uint64_t nS;
+};
+static ShardLast g_shard_last{};
 static int shard_join_locked(const struct row_t *d_R, uint64_t nR, const uint32_t *d_segoff_R, const struct row_t *d_S,
                              uint64_t nS, const uint32_t *d_segoff_S, const uint32_t *d_seg_group, uint32_t nseg,
                              uint32_t ngroups, uint32_t shift2, uint32_t bits2, const uint32_t *d_hist_R,
                              const uint32_t *d_hist_S, uint32_t hash_shift, struct b200_join_stats_t *stats,
-                             uint64_t *d_result3, void *stream);
+                             uint64_t *d_result3, void *stream, output_triple_t *d_out = nullptr, uint64_t out_cap = 0);
 
 int b200_shard_join_device(const struct row_t *d_R, uint64_t nR, const uint32_t *d_segoff_R, const struct row_t *d_S,
                            uint64_t nS, const uint32_t *d_segoff_S, const uint32_t *d_seg_group, uint32_t nseg,
@@ -937,7 +944,7 @@ static int shard_join_locked(const struct row_t *d_R, uint64_t nR, const uint32_
                              uint64_t nS, const uint32_t *d_segoff_S, const uint32_t *d_seg_group, uint32_t nseg,
                              uint32_t ngroups, uint32_t shift2, uint32_t bits2, const uint32_t *d_hist_R,
                              const uint32_t *d_hist_S, uint32_t hash_shift, struct b200_join_stats_t *stats,
-                             uint64_t *d_result3, void *stream) {
+                             uint64_t *d_result3, void *stream, output_triple_t *d_out, uint64_t out_cap) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (ensure_init()) return -1;
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : g.stream;
@@ -983,14 +990,16 @@ static int shard_join_locked(const struct row_t *d_R, uint64_t nR, const uint32_
     uint2 *d_items = reinterpret_cast<uint2 *>(mb + o_items);
     if (join_items_device(u32(o_offR), u32(o_offS), P, u32(o_istart), d_items, st)) return -1;
     if (build_probe_device(t2R, u32(o_offR), t2S, u32(o_offS), u32(o_istart), d_items, P, nS / kProbeChunk + P + 1,
-                           hash_shift, d_res, nullptr, 0, st))
+                           hash_shift, d_res, d_out, out_cap, st))
         return -1;
     AQP_CUDA_OK(cudaEventRecord(g.ev[4], st));
+    g_shard_last = ShardLast{o_res, o_offR, o_offS, o_istart, o_items, P, hash_shift, nS};
     if (d_result3) {
         // asynchronous form: {matches, checksum, keysum} stay on the device (the caller all-reduces them there);
         // nothing here waits for the GPU. Phase times: b200_shard_join_times() after the caller's own sync.
         static_assert(offsetof(JoinResult, matches) == 0 && offsetof(JoinResult, keysum) == 16, "JoinResult layout");
-        AQP_CUDA_OK(cudaMemcpyAsync(d_result3, d_res, 3 * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+        // (the materialising form also hands out word 3: the triples this GPU produced)
+        AQP_CUDA_OK(cudaMemcpyAsync(d_result3, d_res, (d_out ? 4 : 3) * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
         b200_join_stats_t s{};
         s.radix_bits = hash_shift;
         s.num_passes = 2;
@@ -1386,3 +1395,42 @@ void b200_index_scan_user(uint8_t lo, uint8_t hi, const uint8_t *data, size_t n,
 }
 
 }  // extern "C"
+
+// ---- materialising form of the shard join, for the multi-GPU host (mg.cu) ---------------------------------------
+namespace aqp {
+
+// pass 2 + build/probe over received segments like b200_shard_join_async_device, writing this GPU's matches to d_out
+// (at most out_cap triples are stored; all are counted). d_result4 = {matches, checksum, keysum, triples produced}.
+int shard_join_materialize_internal(const row_t *d_R, uint64_t nR, const uint32_t *d_segoff_R, const row_t *d_S, uint64_t nS,
+                                    const uint32_t *d_segoff_S, const uint32_t *d_seg_group, uint32_t nseg, uint32_t ngroups,
+                                    uint32_t shift2, uint32_t bits2, const uint32_t *d_hist_R, const uint32_t *d_hist_S,
+                                    uint32_t hash_shift, output_triple_t *d_out, uint64_t out_cap, uint64_t *d_result4,
+                                    cudaStream_t st) {
+    return shard_join_locked(d_R, nR, d_segoff_R, d_S, nS, d_segoff_S, d_seg_group, nseg, ngroups, shift2, bits2, d_hist_R,
+                             d_hist_S, hash_shift, nullptr, d_result4, st, d_out, out_cap);
+}
+
+// the probe of the last shard join once more, into a buffer that holds every match (the co-partitions are still in the
+// workspace) - the reference materialises whatever the probe produces, so a build side with duplicate keys must not
+// lose rows (radix_join.cpp:428-447)
+int shard_probe_again_internal(output_triple_t *d_out, uint64_t out_cap, uint64_t *d_result4, cudaStream_t st) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (ensure_init()) return -1;
+    const ShardLast &L = g_shard_last;
+    if (!L.P || !g.meta.p) {
+        set_error("shard_probe_again: no shard join to repeat");
+        return -1;
+    }
+    unsigned char *mb = static_cast<unsigned char *>(g.meta.p);
+    auto u32 = [&](size_t off) { return reinterpret_cast<uint32_t *>(mb + off); };
+    JoinResult *d_res = reinterpret_cast<JoinResult *>(mb + L.o_res);
+    AQP_CUDA_OK(cudaMemsetAsync(d_res, 0, sizeof(JoinResult), st));
+    if (build_probe_device(static_cast<row_t *>(g.tmp[2].p), u32(L.o_offR), static_cast<row_t *>(g.tmp[3].p), u32(L.o_offS),
+                           u32(L.o_istart), reinterpret_cast<uint2 *>(mb + L.o_items), L.P, L.nS / kProbeChunk + L.P + 1,
+                           L.hash_shift, d_res, d_out, out_cap, st))
+        return -1;
+    AQP_CUDA_OK(cudaMemcpyAsync(d_result4, d_res, 4 * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+}  // namespace aqp

@@ -192,6 +192,14 @@ void scan_release();
 // the planner with the caller's knowledge of dead low key bits (api.cu plan_bits)
 void join_plan_internal(uint64_t nR, uint32_t dead_bits, uint32_t *total, uint32_t *b1, uint32_t *b2);
 
+// ---- materialising shard join for the multi-GPU host (api.cu) ------------------------------------
+int shard_join_materialize_internal(const row_t *d_R, uint64_t nR, const uint32_t *d_segoff_R, const row_t *d_S, uint64_t nS,
+                                    const uint32_t *d_segoff_S, const uint32_t *d_seg_group, uint32_t nseg, uint32_t ngroups,
+                                    uint32_t shift2, uint32_t bits2, const uint32_t *d_hist_R, const uint32_t *d_hist_S,
+                                    uint32_t hash_shift, output_triple_t *d_out, uint64_t out_cap, uint64_t *d_result4,
+                                    cudaStream_t st);
+int shard_probe_again_internal(output_triple_t *d_out, uint64_t out_cap, uint64_t *d_result4, cudaStream_t st);
+
 // ---- host <-> device copies for the host-buffer entry points (hostcopy.cpp) ----------------------
 int copy_h2d_any(void *dev, const void *host, size_t bytes, cudaStream_t st);
 int copy_d2h_any(void *host, const void *dev, size_t bytes, cudaStream_t st);

@@ -91,7 +91,7 @@ struct Mg {
     cudaEvent_t ev_hist = nullptr, ev_side = nullptr;
     void *recvR = nullptr, *recvS = nullptr;   // this rank's receive buffers (device_alloc, exported)
     void *peerR[8] = {}, *peerS[8] = {};
-    DevBuf meta;
+    DevBuf meta, out;   // out: the materialised triples of this rank's co-partitions
     // carved out of meta
     uint32_t *hist = nullptr, *cnt1 = nullptr, *counts_all = nullptr, *dest = nullptr, *seg = nullptr, *seg_group = nullptr,
              *hsl = nullptr, *flag = nullptr;
@@ -145,6 +145,7 @@ int b200_mg_finalize(void) {
     cudaStreamDestroy(mg.main);
     cudaStreamDestroy(mg.side);
     mg.meta.release();
+    mg.out.release();
     mg = Mg{};
     return 0;
 }
@@ -212,7 +213,7 @@ int b200_mg_init_caps(int rank, int world, const unsigned char *id128, uint64_t 
     const size_t n2 = (size_t) mg.per << b2;
     const size_t o_hist = take(2 * mg.P * 4), o_cnt = take(2 * mg.F1 * 4), o_call = take((size_t) world * 2 * mg.F1 * 4),
                  o_dest = take(2 * mg.F1 * 4), o_seg = take(2 * (mg.nseg + 1) * 4), o_grp = take(mg.nseg * 4),
-                 o_hsl = take(2 * n2 * 4), o_flag = take(64), o_res = take(64), o_ipc = take((size_t) world * 128);
+                 o_hsl = take(2 * n2 * 4), o_flag = take(64), o_res = take(128), o_ipc = take((size_t) world * 128);
     if (mg.meta.ensure(o)) return -1;
     unsigned char *mb = static_cast<unsigned char *>(mg.meta.p);
     AQP_CUDA_OK(cudaMemset(mb, 0, o));
@@ -252,7 +253,11 @@ int b200_mg_init_caps(int rank, int world, const unsigned char *id128, uint64_t 
     return 0;
 }
 
-int b200_mg_join(const struct row_t *d_R, uint64_t nR, const struct row_t *d_S, uint64_t nS, struct b200_mg_result_t *out) {
+}  // extern "C"
+
+// mat: keep the matches of this rank's co-partitions as triples in mg.out (grown and the probe repeated if they do not fit)
+static int mg_join_impl(const struct row_t *d_R, uint64_t nR, const struct row_t *d_S, uint64_t nS, struct b200_mg_result_t *out,
+                        bool mat, uint64_t *local_rows) {
     std::lock_guard<std::mutex> lk(mg_mu);
     if (!mg.on) {
         set_error("b200_mg_join: call b200_mg_init first");
@@ -293,17 +298,40 @@ int b200_mg_join(const struct row_t *d_R, uint64_t nR, const struct row_t *d_S, 
     AQP_CUDA_OK(cudaEventRecord(mg.ev[3], st));
     // ---- 5. local pass 2 + build/probe over the received segments, global result ------------------------------
     const size_t n2 = (size_t) mg.per << mg.b2;
-    if (b200_shard_join_async_device(static_cast<const row_t *>(mg.recvR), mg.capR * G, mg.seg,
-                                     static_cast<const row_t *>(mg.recvS), mg.capS * G, mg.seg + (mg.nseg + 1), mg.seg_group,
-                                     mg.nseg, mg.per, mg.b1, mg.b2, mg.hsl, mg.hsl + n2, mg.bits,
-                                     reinterpret_cast<uint64_t *>(mg.res3), st))
+    uint64_t out_cap = 0;
+    if (mat) {
+        // a unique build key gives at most one triple per probe tuple this rank receives - about nS when the shards
+        // are even; anything larger is caught after the sync below
+        out_cap = nS + (nS >> 2) + 4096;
+        if (mg.out.ensure(out_cap * sizeof(output_triple_t))) return -1;
+        out_cap = mg.out.cap / sizeof(output_triple_t);
+        if (shard_join_materialize_internal(static_cast<const row_t *>(mg.recvR), mg.capR * G, mg.seg,
+                                            static_cast<const row_t *>(mg.recvS), mg.capS * G, mg.seg + (mg.nseg + 1),
+                                            mg.seg_group, mg.nseg, mg.per, mg.b1, mg.b2, mg.hsl, mg.hsl + n2, mg.bits,
+                                            static_cast<output_triple_t *>(mg.out.p), out_cap,
+                                            reinterpret_cast<uint64_t *>(mg.res3), st))
+            return -1;
+    } else if (b200_shard_join_async_device(static_cast<const row_t *>(mg.recvR), mg.capR * G, mg.seg,
+                                            static_cast<const row_t *>(mg.recvS), mg.capS * G, mg.seg + (mg.nseg + 1),
+                                            mg.seg_group, mg.nseg, mg.per, mg.b1, mg.b2, mg.hsl, mg.hsl + n2, mg.bits,
+                                            reinterpret_cast<uint64_t *>(mg.res3), st))
         return -1;
     AQP_CUDA_OK(cudaEventRecord(mg.ev[4], st));
     AQP_NCCL_OK(nccl.AllReduce(mg.res3, mg.res3, 3, ncclUint64, ncclSum, mg.comm, st));
     AQP_CUDA_OK(cudaEventRecord(mg.ev[5], st));
-    unsigned long long h[6];
+    unsigned long long h[6] = {};
     AQP_CUDA_OK(cudaMemcpyAsync(h, mg.res3, sizeof h, cudaMemcpyDeviceToHost, st));
     AQP_CUDA_OK(cudaStreamSynchronize(st));   // the one host sync of the join
+    if (mat) {
+        if (h[3] > out_cap) {   // duplicate build keys or a lopsided key distribution: room for all, probe again
+            if (mg.out.ensure(h[3] * sizeof(output_triple_t))) return -1;
+            if (shard_probe_again_internal(static_cast<output_triple_t *>(mg.out.p), mg.out.cap / sizeof(output_triple_t),
+                                           reinterpret_cast<uint64_t *>(mg.res3 + 8), st))
+                return -1;
+            AQP_CUDA_OK(cudaStreamSynchronize(st));
+        }
+        if (local_rows) *local_rows = h[3];
+    }
     if (out) {
         memset(out, 0, sizeof *out);
         out->matches = h[0];
@@ -328,6 +356,36 @@ int b200_mg_join(const struct row_t *d_R, uint64_t nR, const struct row_t *d_S, 
         out->tuples_sent = nR + nS;
         out->tuples_kept = h[4] + h[5];
     }
+    return 0;
+}
+
+extern "C" {
+
+// sum of n <= 4 host values over the ranks (collective): what a sharded pipeline needs to turn per-rank counts into its answer
+int b200_mg_allreduce_u64(uint64_t *values, int n) {
+    std::lock_guard<std::mutex> lk(mg_mu);
+    if (!mg.on || n < 1 || n > 4 || !values) {
+        set_error("b200_mg_allreduce_u64: needs b200_mg_init and 1 <= n <= 4");
+        return -1;
+    }
+    unsigned long long *d = mg.res3 + 12;
+    AQP_CUDA_OK(cudaMemcpyAsync(d, values, (size_t) n * 8, cudaMemcpyHostToDevice, mg.main));
+    AQP_NCCL_OK(nccl.AllReduce(d, d, (size_t) n, ncclUint64, ncclSum, mg.comm, mg.main));
+    AQP_CUDA_OK(cudaMemcpyAsync(values, d, (size_t) n * 8, cudaMemcpyDeviceToHost, mg.main));
+    AQP_CUDA_OK(cudaStreamSynchronize(mg.main));
+    return 0;
+}
+
+int b200_mg_join(const struct row_t *d_R, uint64_t nR, const struct row_t *d_S, uint64_t nS, struct b200_mg_result_t *out) {
+    return mg_join_impl(d_R, nR, d_S, nS, out, false, nullptr);
+}
+
+int b200_mg_join_materialize(const struct row_t *d_R, uint64_t nR, const struct row_t *d_S, uint64_t nS,
+                             const struct output_triple_t **d_triples, uint64_t *local_rows, struct b200_mg_result_t *out) {
+    uint64_t rows = 0;
+    if (mg_join_impl(d_R, nR, d_S, nS, out, true, &rows)) return -1;
+    if (d_triples) *d_triples = static_cast<const output_triple_t *>(mg.out.p);
+    if (local_rows) *local_rows = rows;
     return 0;
 }
 

@@ -270,7 +270,51 @@ __global__ void triples_to_sp_sp_kernel(const output_triple_t *__restrict__ t, u
     }
 }
 
-// q19FinalPredicate (Q19Predicates.hpp:58-78) over the materialised part x lineitem matches
+// q19FinalPredicate (Q19Predicates.hpp:58-78)
+__device__ __forceinline__ bool q19_final_pred(uint32_t b, uint32_t k, uint32_t s, float q) {
+    const bool p1 = b == 1 && (k >= 1 && k <= 4) && (s >= 1 && s <= 5) && (q >= 1.0f && q <= 11.0f);
+    const bool p2 = b == 2 && (k >= 5 && k <= 8) && (s >= 1 && s <= 10) && (q >= 10.0f && q <= 20.0f);
+    const bool p3 = b == 3 && (k >= 9 && k <= 12) && (s >= 1 && s <= 15) && (q >= 20.0f && q <= 30.0f);
+    return p1 || p2 || p3;
+}
+
+// Sharded Q19: after the exchange a match sits on the GPU that owns its part key, not on the ones that hold the two
+// rows, so the attributes the final predicate reads travel IN the payloads instead of being gathered by row id:
+// part -> brand | container << 8 | size << 16, lineitem -> the bits of l_quantity.
+struct Q19PartPacked {
+    const uint2 *partkey; const uint8_t *brand, *container; const uint32_t *size;
+    __device__ bool operator()(uint64_t i, uint2 &out) const {
+        const uint8_t b = brand[i], c = container[i];
+        const uint32_t s = size[i];
+        if (!((b >= 1 && b <= 3) && (c >= 1 && c <= 12) && (s >= 1 && s <= 15))) return false;
+        out = make_uint2(partkey[i].x, (uint32_t) b | ((uint32_t) c << 8) | (s << 16));
+        return true;
+    }
+};
+struct Q19LineitemPacked {
+    const uint32_t *partkey; const float *quantity; const uint8_t *shipmode, *shipinstruct;
+    __device__ bool operator()(uint64_t i, uint2 &out) const {
+        const uint8_t m = shipmode[i];
+        if (!(m == B200_L_SHIPMODE_AIR || m == B200_L_SHIPMODE_AIR_REG)) return false;
+        if (shipinstruct[i] != B200_L_SHIPINSTRUCT_DELIVER_IN_PERSON) return false;
+        const float q = quantity[i];
+        if (!(q >= 1.0f && q <= 30.0f)) return false;
+        out = make_uint2(partkey[i], __float_as_uint(q));
+        return true;
+    }
+};
+__global__ void q19_final_packed_kernel(const output_triple_t *__restrict__ t, uint64_t n, unsigned long long *__restrict__ counter) {
+    uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
+    uint32_t c = 0;
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t rp = t[i].Rpayload;
+        c += q19_final_pred(rp & 0xFFu, (rp >> 8) & 0xFFu, rp >> 16, __uint_as_float(t[i].Spayload));
+    }
+    c = warp_sum(c);
+    if (lane_id() == 0 && c) atomicAdd(counter, (unsigned long long) c);
+}
+
+// the same over the single-GPU matches, attributes gathered by row id
 __global__ void q19_final_kernel(const output_triple_t *__restrict__ t, uint64_t n, const uint8_t *__restrict__ brand,
                                  const uint8_t *__restrict__ container, const uint32_t *__restrict__ size,
                                  const float *__restrict__ quantity, unsigned long long *__restrict__ counter) {
@@ -281,10 +325,7 @@ __global__ void q19_final_kernel(const output_triple_t *__restrict__ t, uint64_t
         const uint8_t b = brand[rp], k = container[rp];
         const uint32_t s = size[rp];
         const float q = quantity[rl];
-        const bool p1 = b == 1 && (k >= 1 && k <= 4) && (s >= 1 && s <= 5) && (q >= 1.0f && q <= 11.0f);
-        const bool p2 = b == 2 && (k >= 5 && k <= 8) && (s >= 1 && s <= 10) && (q >= 10.0f && q <= 20.0f);
-        const bool p3 = b == 3 && (k >= 9 && k <= 12) && (s >= 1 && s <= 15) && (q >= 20.0f && q <= 30.0f);
-        c += p1 || p2 || p3;
+        c += q19_final_pred(b, k, s, q);
     }
     c = warp_sum(c);
     if (lane_id() == 0 && c) atomicAdd(counter, (unsigned long long) c);
@@ -650,6 +691,98 @@ int b200_tpch_q12_mg(struct b200_tpch_stats_t *out) {
     s.ms_filter = tm.ms(0, 1);
     s.ms_join = r.ms_total;
     s.ms_total = s.ms_filter + s.ms_join;
+    s.kernel_launches = (uint32_t) (g_kernel_launches - l0);
+    *out = s;
+    return 0;
+}
+
+// Q3 across `world` GPUs (tpch.cpp:40-110 on row-range shards): both selections of join 1 are local scans, the join
+// customers x orders is the materialising sharded join - its matches stay on the GPU that owns the customer key -,
+// each rank turns ITS matches into {o_orderkey, o_orderkey} and they are the (again row-sharded) build side of the
+// second sharded join with the selected line items. No table row ever moves except through the two exchanges.
+int b200_tpch_q3_mg(struct b200_tpch_stats_t *out) {
+    std::lock_guard<std::recursive_mutex> lk(t_mu);
+    if (need(T.nl && T.no && T.nc, "lineitem, orders, customer")) return -1;
+    cudaStream_t st = library_stream();
+    const unsigned long long l0 = g_kernel_launches;
+    Timer tm;
+    if (T.f1.ensure((T.nc > T.nl ? T.nc : T.nl) * 8 + 64) || T.f2.ensure(T.no * 8 + 64) || T.counters.ensure(64)) return -1;
+    unsigned long long *ctr = ptr<unsigned long long>(T.counters);
+    b200_tpch_stats_t s{};
+    cudaEventRecord(tm.e[0], st);
+    if (run_filter(T.nc, Q3Customer{ptr<uint2>(T.c_custkey), ptr<uint8_t>(T.c_mktsegment)}, ptr<row_t>(T.f1), ctr, st)) return -1;
+    if (run_filter(T.no, Q3Orders{ptr<uint2>(T.o_orderkey), ptr<uint64_t>(T.o_orderdate), ptr<uint32_t>(T.o_custkey)},
+                   ptr<row_t>(T.f2), ctr + 1, st))
+        return -1;
+    cudaEventRecord(tm.e[1], st);
+    if (read_counter(ctr, &s.filtered[0], st) || read_counter(ctr + 1, &s.filtered[1], st)) return -1;
+    b200_mg_result_t r1{}, r2{};
+    const output_triple_t *trip = nullptr;
+    uint64_t rows = 0;
+    if (b200_mg_join_materialize(ptr<row_t>(T.f1), s.filtered[0], ptr<row_t>(T.f2), s.filtered[1], &trip, &rows, &r1)) return -1;
+    s.join1_rows = r1.matches;   // global
+    cudaEventRecord(tm.e[2], st);
+    if (T.u.ensure(rows * 8 + 64)) return -1;
+    if (rows) {
+        triples_to_sp_sp_kernel<<<kNumSMs * 4, 256, 0, st>>>(trip, rows, ptr<uint2>(T.u));
+        AQP_LAUNCHED();
+    }
+    if (run_filter(T.nl, Q3Lineitem{ptr<uint2>(T.l_orderkey), ptr<uint64_t>(T.l_shipdate)}, ptr<row_t>(T.f1), ctr + 2, st)) return -1;
+    cudaEventRecord(tm.e[3], st);
+    if (read_counter(ctr + 2, &s.filtered[2], st)) return -1;
+    if (b200_mg_join(ptr<row_t>(T.u), rows, ptr<row_t>(T.f1), s.filtered[2], &r2)) return -1;
+    s.result_rows = r2.matches;   // global
+    s.input_rows = T.nl + T.no + T.nc;
+    s.ms_filter = tm.ms(0, 1) + tm.ms(2, 3);
+    s.ms_join = r1.ms_total + r2.ms_total;
+    s.ms_total = s.ms_filter + s.ms_join;
+    s.kernel_launches = (uint32_t) (g_kernel_launches - l0);
+    *out = s;
+    return 0;
+}
+
+// Q19 across `world` GPUs (tpch.cpp:256-306): local selections with the final predicate's attributes packed into the
+// payloads, materialising sharded join part x lineitem, final predicate over this rank's matches, one all-reduce.
+int b200_tpch_q19_mg(struct b200_tpch_stats_t *out) {
+    std::lock_guard<std::recursive_mutex> lk(t_mu);
+    if (need(T.nl && T.np, "lineitem, part")) return -1;
+    cudaStream_t st = library_stream();
+    const unsigned long long l0 = g_kernel_launches;
+    Timer tm;
+    if (T.f1.ensure(T.np * 8 + 64) || T.f2.ensure(T.nl * 8 + 64) || T.counters.ensure(64)) return -1;
+    unsigned long long *ctr = ptr<unsigned long long>(T.counters);
+    b200_tpch_stats_t s{};
+    cudaEventRecord(tm.e[0], st);
+    if (run_filter(T.np, Q19PartPacked{ptr<uint2>(T.p_partkey), ptr<uint8_t>(T.p_brand), ptr<uint8_t>(T.p_container), ptr<uint32_t>(T.p_size)},
+                   ptr<row_t>(T.f1), ctr, st))
+        return -1;
+    if (run_filter(T.nl, Q19LineitemPacked{ptr<uint32_t>(T.l_partkey), ptr<float>(T.l_quantity), ptr<uint8_t>(T.l_shipmode),
+                                           ptr<uint8_t>(T.l_shipinstruct)},
+                   ptr<row_t>(T.f2), ctr + 1, st))
+        return -1;
+    cudaEventRecord(tm.e[1], st);
+    if (read_counter(ctr, &s.filtered[0], st) || read_counter(ctr + 1, &s.filtered[1], st)) return -1;
+    b200_mg_result_t r{};
+    const output_triple_t *trip = nullptr;
+    uint64_t rows = 0;
+    if (b200_mg_join_materialize(ptr<row_t>(T.f1), s.filtered[0], ptr<row_t>(T.f2), s.filtered[1], &trip, &rows, &r)) return -1;
+    s.join1_rows = r.matches;   // global
+    cudaEventRecord(tm.e[2], st);
+    AQP_CUDA_OK(cudaMemsetAsync(ctr + 2, 0, sizeof(unsigned long long), st));
+    if (rows) {
+        q19_final_packed_kernel<<<kNumSMs * 4, 256, 0, st>>>(trip, rows, ctr + 2);
+        AQP_LAUNCHED();
+    }
+    cudaEventRecord(tm.e[3], st);
+    if (read_counter(ctr + 2, &s.filtered[2], st)) return -1;   // this rank's qualifying matches
+    uint64_t total = s.filtered[2];
+    if (b200_mg_allreduce_u64(&total, 1)) return -1;
+    s.result_rows = total;       // global
+    s.input_rows = T.nl + T.np;
+    s.ms_filter = tm.ms(0, 1);
+    s.ms_join = r.ms_total;
+    s.ms_other = tm.ms(2, 3);
+    s.ms_total = s.ms_filter + s.ms_join + s.ms_other;
     s.kernel_launches = (uint32_t) (g_kernel_launches - l0);
     *out = s;
     return 0;

@@ -51,19 +51,20 @@ for logR, logS in ((20, 22), (24, 26)):
         assert o["matches"] == nS == ref["matches"] and o["checksum"] == ref["checksum"] and o["keysum"] == ref["keysum"], (z, o, ref)
         if rank == 0: print("OK MgShardedJoin zipf", z, logR, logS, round(o["ms_total"], 3))
     mgj.close()
-# TPC-H Q12 sharded: every rank generates and filters its own rows, the join is the sharded join (SURVEY 8e row 3)
+# TPC-H Q12/Q3/Q19 sharded: every rank generates and filters its own rows, the joins are sharded joins (SURVEY 8e row 3)
 for sf in (0.3, 2.0):
     A.tpch_generate_shard_device(sf, 5, rank, world)
     uid = torch.zeros(128, dtype=torch.uint8, device=dev)
     if rank == 0: uid.copy_(torch.tensor(list(A.mg_unique_id()), dtype=torch.uint8))
     dist.broadcast(uid, 0)
     A.tpch_mg_init(rank, world, bytes(uid.cpu().tolist()))
-    got = A.tpch_q12_mg()
+    got = {12: A.tpch_q12_mg(), 3: A.tpch_q3_mg(), 19: A.tpch_q19_mg()}
     A.mg_finalize()
     A.tpch_generate_device(sf, 5)                       # the whole data set on every rank: single-GPU answer
-    want = A.tpch_query_device(12)
-    assert got["result_rows"] == want["result_rows"], (sf, got, want)
-    if rank == 0: print("OK tpch q12 mg", sf, got["result_rows"], round(got["ms_total"], 3))
+    for q in (12, 3, 19):
+        want = A.tpch_query_device(q)
+        assert got[q]["result_rows"] == want["result_rows"] and got[q]["join1_rows"] == want["join1_rows"], (sf, q, got[q], want)
+        if rank == 0: print("OK tpch q%d mg" % q, sf, got[q]["result_rows"], round(got[q]["ms_total"], 3))
 A.lib().b200_tpch_free_device()
 dist.destroy_process_group()
 '''
@@ -82,4 +83,4 @@ def test_nccl_sharded_join(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29517", str(script)], env=env,
                        capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
-    assert p.stdout.count("OK") == 14
+    assert p.stdout.count("OK") == 18

@@ -172,6 +172,39 @@ def test_mg_api_world1_against_oracle(gpu, oracle):
         gpu.mg_finalize()
 
 
+def test_mg_materialize_world1_against_oracle(gpu, oracle):
+    """b200_mg_join_materialize, world = 1: the triples left on the device are the oracle's, as a multiset - unique build
+    keys, misses, and a build side with 4 copies of every key (4 x |S| matches: more than the first buffer holds, so
+    the probe-again path runs)"""
+    import torch
+    from helpers import sorted_triples
+    dev = torch.device("cuda:0")
+    nR, nS = 1 << 16, 1 << 18
+    R = oracle.set_rowid_payload(oracle.gen_pk(nR, 11111))
+    S = oracle.set_rowid_payload(oracle.gen_fk(nS, nR, 22222))
+    miss = S.copy()
+    miss["key"][::3] += nR
+    dup = R.copy()
+    dup["key"] = dup["key"] // 4 + 1
+    gpu.mg_init(0, 1, gpu.mg_unique_id(), nR, nS)
+    try:
+        for name, (r, s) in {"fk": (R, S), "miss": (R, miss), "dup": (dup, S), "fk again": (R, S)}.items():
+            exp = oracle.rho(r, s, nthreads=1, materialize=True)
+            dR = torch.from_numpy(r.view(np.int32).copy()).to(dev)
+            dS = torch.from_numpy(s.view(np.int32).copy()).to(dev)
+            torch.cuda.synchronize()
+            got = gpu.mg_join_materialize(dR.data_ptr(), nR, dS.data_ptr(), nS)
+            assert (got["matches"], got["checksum"], got["keysum"]) == (exp["matches"], exp["checksum"], exp["keysum"]), name
+            assert got["local_rows"] == exp["matches"], name
+            t = np.empty(got["local_rows"], dtype=oracle.TRIPLE)
+            if got["local_rows"]:
+                assert gpu.lib().b200_memcpy_d2h(t.ctypes.data, got["d_triples"], t.nbytes) == 0
+            assert np.array_equal(sorted_triples(t), sorted_triples(exp["triples"])), name
+        assert gpu.mg_allreduce_u64([5, 7]) == [5, 7]
+    finally:
+        gpu.mg_finalize()
+
+
 def test_simdmulti_modes(gpu):
     n = 1 << 24
     for mode, sel in (("bitvector", 10), ("noIndex", 10), ("noIndex", 100), ("bitvector", 50), ("scalar", 10)):

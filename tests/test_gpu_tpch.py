@@ -79,19 +79,22 @@ def test_binary_column_files_round_trip_through_the_device(gpu, oracle, tmp_path
     gpu.lib().b200_tpch_free_device()
 
 
-def test_q12_through_the_multi_gpu_host_with_one_rank(gpu):
-    """b200_tpch_generate_shard_device + b200_tpch_mg_init + b200_tpch_q12_mg with world = 1 (the 2..8 GPU form runs in
-    tests/test_gpu_dist.py): the sharded path gives the single-GPU pipeline's answer"""
+def test_queries_through_the_multi_gpu_host_with_one_rank(gpu):
+    """b200_tpch_generate_shard_device + b200_tpch_mg_init + b200_tpch_q{12,3,19}_mg with world = 1 (the 2..8 GPU form runs in
+    tests/test_gpu_dist.py): the sharded pipelines - matches of join 1 left sharded by key (Q3), the final predicate's
+    attributes packed into the payloads (Q19) - give the single-GPU pipelines' answers"""
     for sf, seed in ((0.05, 2), (1.0, 9)):
         gpu.tpch_generate_device(sf, seed)
-        want = gpu.tpch_query_device(12)
+        want = {q: gpu.tpch_query_device(q) for q in (12, 3, 19)}
         gpu.tpch_generate_shard_device(sf, seed, 0, 1)
         gpu.tpch_mg_init(0, 1, gpu.mg_unique_id())
         try:
-            got = gpu.tpch_q12_mg()
-            got2 = gpu.tpch_q12_mg()
+            got = {12: gpu.tpch_q12_mg(), 3: gpu.tpch_q3_mg(), 19: gpu.tpch_q19_mg()}
+            again = {12: gpu.tpch_q12_mg(), 3: gpu.tpch_q3_mg(), 19: gpu.tpch_q19_mg()}
         finally:
             gpu.mg_finalize()
-        assert got["result_rows"] == got2["result_rows"] == want["result_rows"]
-        assert got["filtered"][0] == want["filtered"][0]
+        for q in (12, 3, 19):
+            assert got[q]["result_rows"] == again[q]["result_rows"] == want[q]["result_rows"], (sf, q)
+            assert got[q]["join1_rows"] == want[q]["join1_rows"], (sf, q)
+            assert got[q]["filtered"][:2] == want[q]["filtered"][:2], (sf, q)
     gpu.lib().b200_tpch_free_device()
