@@ -695,6 +695,46 @@ def run_b200_arm(args):
                 tpch["cpu_reference"] = {"failed": str(ex)}
         A.lib().b200_tpch_free_device()
 
+    # ---- the same three pipelines sharded over the N GPUs: every rank generates and filters rows
+    # [total * rank / N, total * (rank + 1) / N) of each table, the joins are the sharded join of csrc/mg.cu (Q3: the
+    # matches of join 1 stay sharded by key and build join 2; Q19: the final predicate's attributes travel in the payloads)
+    if world > 1 and not args.no_tpch:
+        if hasattr(plan, "close"):
+            plan.close()   # one multi-GPU host per process: the join's goes, TPC-H's comes
+        plan = None
+        sf = float(os.environ.get("B200_AQP_TPCH_SF", "100"))
+        A.tpch_generate_shard_device(sf, 1, rank, world)
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.tensor(list(A.mg_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        A.tpch_mg_init(rank, world, bytes(uid.cpu().tolist()))
+        fns = {3: A.tpch_q3_mg, 12: A.tpch_q12_mg, 19: A.tpch_q19_mg}
+        tpch = {"scale_factor": sf, "sharding": f"row ranges of every table over {world} GPUs, generated in HBM",
+                "data": "synthetic (include/aqp/b200_tpch.h)"}
+        for q in (3, 12, 19):
+            for _ in range(2):
+                r = fns[q]()
+            runs = [fns[q]() for _ in range(3)]
+            t = torch.tensor([sum(x["ms_total"] for x in runs) / len(runs)], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            rows_in = torch.tensor([r["input_rows"]], dtype=torch.int64, device=dev)
+            dist.all_reduce(rows_in)
+            ms = float(t.item())
+            tpch[f"q{q}"] = {"ms": ms, "mrows_per_s": int(rows_in.item()) / ms / 1e3, "result_rows": r["result_rows"],
+                             "join1_rows": r["join1_rows"], "ms_filter_rank0": runs[-1]["ms_filter"],
+                             "ms_join_rank0": runs[-1]["ms_join"]}
+        A.mg_finalize()
+        if rank == 0:   # the single-GPU pipelines on the whole data set give the answers the sharded ones must match
+            A.tpch_generate_device(sf, 1)
+            for q in (3, 12, 19):
+                g = A.tpch_query_device(q)
+                assert (g["result_rows"], g["join1_rows"]) == (tpch[f"q{q}"]["result_rows"], tpch[f"q{q}"]["join1_rows"]), (q, g, tpch)
+                tpch[f"q{q}"]["one_gpu_ms_cold"] = g["ms_total"]   # first call, no warm-up: a check, not a measurement
+            tpch["check"] = "result and join-1 rows equal to the single-GPU pipelines' on the full tables (run on rank 0)"
+        A.lib().b200_tpch_free_device()
+        dist.barrier()
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -722,7 +762,7 @@ def run_b200_arm(args):
                 "clocks": clocks, "scan": scan}
         print(json.dumps(line))
     if world > 1:
-        if hasattr(plan, "close"):
+        if plan is not None and hasattr(plan, "close"):
             plan.close()
         dist.destroy_process_group()
 

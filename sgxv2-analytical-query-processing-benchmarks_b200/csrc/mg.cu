@@ -173,6 +173,11 @@ int b200_mg_init_caps(int rank, int world, const unsigned char *id128, uint64_t 
     mg.lg = log2u((uint32_t) world);
     uint32_t bits, b1, b2;
     join_plan_internal(nR_total, dead_bits, &bits, &b1, &b2);
+    if (bits > (uint32_t) kMaxSmemHistBits) {   // the shard histogram is one shared-memory table over all 2^bits partitions;
+        bits = kMaxSmemHistBits;                // larger build sides take several build rounds per co-partition instead
+        b1 = bits / 2;
+        b2 = bits - b1;
+    }
     if (b1 < mg.lg) {   // pass 1 needs at least log2(world) bits to route on
         b1 = mg.lg;
         if (bits < b1) bits = b1;
