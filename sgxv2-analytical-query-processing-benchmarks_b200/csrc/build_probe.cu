@@ -76,6 +76,8 @@ build_probe_kernel(const uint2 *__restrict__ R, const uint32_t *__restrict__ off
     uint16_t *next = reinterpret_cast<uint16_t *>(bucket + kBuildCap);                   // chain links (1-based)
 
     __shared__ uint32_t s_collisions;
+    __shared__ uint32_t s_wsum[kJoinThreads / 32];   // materialising probe: per-warp match counts of a round
+    __shared__ unsigned long long s_obase;          // and the round's first output slot
     const uint32_t nitems = item_start[nparts];
     unsigned long long matches = 0, checksum = 0, keysum = 0;
 
@@ -190,7 +192,7 @@ build_probe_kernel(const uint2 *__restrict__ R, const uint32_t *__restrict__ off
             }
             __syncthreads();
 
-            // uniform trip count so the materialising variant can use warp-wide primitives; the next round's
+            // uniform trip count so the materialising variant can use block-wide primitives; the next round's
             // loads are issued before the current round is probed (register double buffering)
             for (uint32_t base = sbeg; base < send; base += kRound) {
                 uint2 s[kProbeUnroll];
@@ -198,12 +200,12 @@ build_probe_kernel(const uint2 *__restrict__ R, const uint32_t *__restrict__ off
                 for (int j = 0; j < kProbeUnroll; ++j) s[j] = sn[j];
                 if (base + kRound < send) load_round(base + kRound, sn);
                 prefetch_round(base + (1 + kPrefetchRounds) * kRound);
+                if (!kMaterialize) {
 #pragma unroll
-                for (int j = 0; j < kProbeUnroll; ++j) {
-                    const bool valid = base + j * kJoinThreads + threadIdx.x < send;
-                    const uint32_t head = valid ? bucket[(s[j].x >> hash_shift) & hmask] : 0u;
-                    uint32_t hit = head & 0xFFFFu;
-                    if (!kMaterialize) {
+                    for (int j = 0; j < kProbeUnroll; ++j) {
+                        const bool valid = base + j * kJoinThreads + threadIdx.x < send;
+                        const uint32_t head = valid ? bucket[(s[j].x >> hash_shift) & hmask] : 0u;
+                        uint32_t hit = head & 0xFFFFu;
                         if (!(head & kChainFlag)) {
                             // single-tuple chain (always the case for a dense primary key): no link to follow
                             if (hit) {
@@ -225,34 +227,66 @@ build_probe_kernel(const uint2 *__restrict__ R, const uint32_t *__restrict__ off
                                 hit = next[hit - 1];
                             }
                         }
-                    } else {
-                        while (__any_sync(0xffffffffu, hit != 0)) {
-                            bool m = false;
-                            uint2 r = make_uint2(0, 0);
-                            if (hit) {
-                                r = rt[hit - 1];
-                                m = r.x == s[j].x;
-                                hit = next[hit - 1];
+                    }
+                }
+                if (kMaterialize) {
+                    // ---- materialise: ONE output reservation per CTA and round. (Reserving per warp and chain step -
+                    // the first version - put 2.3 M atomics on the single out_count word for 73 M probe tuples and
+                    // made this kernel 15x slower than the counting one: profiles/r02_tpch_q3_launches.md.)
+                    // Phase 1 walks the chains, does the accounting and remembers each tuple's first match; a block-wide
+                    // exclusive scan of the per-thread match counts gives every thread a dense slot range; phase 2 writes
+                    // the single matches from registers and walks a chain again only for a duplicate build key.
+                    uint32_t cnt[kProbeUnroll], first_pay[kProbeUnroll], c = 0;
+#pragma unroll
+                    for (int j = 0; j < kProbeUnroll; ++j) {
+                        const bool valid = base + j * kJoinThreads + threadIdx.x < send;
+                        uint32_t hit = valid ? (bucket[(s[j].x >> hash_shift) & hmask] & 0xFFFFu) : 0u;
+                        cnt[j] = 0;
+                        first_pay[j] = 0;
+                        while (hit) {
+                            const uint2 r = rt[hit - 1];
+                            hit = next[hit - 1];
+                            if (r.x == s[j].x) {
+                                if (!cnt[j]) first_pay[j] = r.y;
+                                ++cnt[j];
+                                checksum += (unsigned long long) r.y + s[j].y;
+                                keysum += s[j].x;
                             }
-                            unsigned mm = __ballot_sync(0xffffffffu, m);
-                            if (mm) {
-                                unsigned long long slot = 0;
-                                int leader = __ffs(mm) - 1;
-                                if ((int) lane_id() == leader) slot = atomicAdd(&res->out_count, (unsigned long long) __popc(mm));
-                                slot = __shfl_sync(0xffffffffu, slot, leader);
-                                if (m) {
-                                    ++matches;
-                                    checksum += (unsigned long long) r.y + s[j].y;
-                                    keysum += s[j].x;
-                                    slot += __popc(mm & lanemask_lt());
-                                    if (slot < out_cap) {
-                                        output_triple_t t;
-                                        t.key = s[j].x;
-                                        t.Rpayload = r.y;
-                                        t.Spayload = s[j].y;
-                                        out[slot] = t;
-                                    }
-                                }
+                        }
+                        c += cnt[j];
+                    }
+                    matches += c;
+                    const uint32_t incl = warp_incl_scan(c);
+                    if (lane_id() == 31) s_wsum[threadIdx.x >> 5] = incl;
+                    __syncthreads();
+                    if (threadIdx.x < 32) {
+                        const uint32_t v = threadIdx.x < kJoinThreads / 32 ? s_wsum[threadIdx.x] : 0u;
+                        const uint32_t iv = warp_incl_scan(v);
+                        if (threadIdx.x < kJoinThreads / 32) s_wsum[threadIdx.x] = iv - v;
+                        if (threadIdx.x == 31) s_obase = iv ? atomicAdd(&res->out_count, (unsigned long long) iv) : 0ull;
+                    }
+                    __syncthreads();
+                    unsigned long long slot = s_obase + s_wsum[threadIdx.x >> 5] + (incl - c);
+#pragma unroll
+                    for (int j = 0; j < kProbeUnroll; ++j) {
+                        if (!cnt[j]) continue;
+                        output_triple_t t;
+                        t.key = s[j].x;
+                        t.Spayload = s[j].y;
+                        if (cnt[j] == 1) {
+                            t.Rpayload = first_pay[j];
+                            if (slot < out_cap) out[slot] = t;
+                            ++slot;
+                            continue;
+                        }
+                        uint32_t hit = bucket[(s[j].x >> hash_shift) & hmask] & 0xFFFFu;   // duplicate build keys: walk again
+                        while (hit) {
+                            const uint2 r = rt[hit - 1];
+                            hit = next[hit - 1];
+                            if (r.x == s[j].x) {
+                                t.Rpayload = r.y;
+                                if (slot < out_cap) out[slot] = t;
+                                ++slot;
                             }
                         }
                     }

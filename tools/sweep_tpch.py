@@ -1,4 +1,4 @@
-"""Tuning helper: time the device-resident TPC-H-style pipelines. usage: python tools/sweep_tpch.py [scale factor]"""
+"""Tuning helper: time the device-resident TPC-H-style pipelines. usage: python tools/sweep_tpch.py [scale factor] [query ...]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "sgxv2-analytical-query-processing-benchmarks_b200"))
@@ -7,7 +7,7 @@ import b200aqp as A
 sf = float(sys.argv[1]) if len(sys.argv) > 1 else 100.0
 A.init(0)
 A.tpch_generate_device(sf, 1)
-for q in (3, 12, 19):
+for q in ([int(a) for a in sys.argv[2:]] or (3, 12, 19)):
     for _ in range(2):
         r = A.tpch_query_device(q)
     runs = [A.tpch_query_device(q) for _ in range(3)]
