@@ -150,8 +150,31 @@ __global__ void gen_part_kernel(uint2 *partkey, uint8_t *brand, uint32_t *size, 
 // rows is unspecified (the joins that consume them do not depend on it).
 // ---------------------------------------------------------------------------------------------
 constexpr int kFilterThreads = 256, kFilterRows = 4, kFilterTile = kFilterThreads * kFilterRows;
+#ifndef AQP_Q12_BYTE_PREFILTER
+#define AQP_Q12_BYTE_PREFILTER 1
+#endif
+
+// bit k of the result = byte k of the 16-byte vector m is non-zero, for m made of 0x00 / 0xff bytes (__vcmp*4 results)
+__device__ __forceinline__ uint32_t byte_flags16(uint4 m) {
+    auto nib = [](uint32_t w) { return ((w & 0x01010101u) * 0x01020408u) >> 24; };
+    return nib(m.x) | (nib(m.y) << 4) | (nib(m.z) << 8) | (nib(m.w) << 12);
+}
+__device__ __forceinline__ uint4 eq_bytes16(uint4 v, uint8_t code) {
+    const uint32_t c = 0x01010101u * code;
+    return make_uint4(__vcmpeq4(v.x, c), __vcmpeq4(v.y, c), __vcmpeq4(v.z, c), __vcmpeq4(v.w, c));
+}
+__device__ __forceinline__ uint4 or16(uint4 a, uint4 b) { return make_uint4(a.x | b.x, a.y | b.y, a.z | b.z, a.w | b.w); }
+__device__ __forceinline__ uint4 and16(uint4 a, uint4 b) { return make_uint4(a.x & b.x, a.y & b.y, a.z & b.z, a.w & b.w); }
+__device__ __forceinline__ uint4 ld_bytes16(const uint8_t *col, uint64_t i0) {
+    return __ldcs(reinterpret_cast<const uint4 *>(col + i0));
+}
 
 struct Q12Lineitem {   // Q12Predicates.hpp:22-37
+    static constexpr bool kBytePrefilter = AQP_Q12_BYTE_PREFILTER;
+    __device__ uint32_t prefilter16(uint64_t i0) const {   // l_shipmode in (MAIL, SHIP)
+        const uint4 m = ld_bytes16(shipmode, i0);
+        return byte_flags16(or16(eq_bytes16(m, B200_L_SHIPMODE_MAIL), eq_bytes16(m, B200_L_SHIPMODE_SHIP)));
+    }
     const uint2 *orderkey; const uint8_t *shipmode; const uint64_t *commit, *ship, *receipt;
     __device__ bool operator()(uint64_t i, uint2 &out) const {
         const uint8_t m = shipmode[i];
@@ -163,6 +186,7 @@ struct Q12Lineitem {   // Q12Predicates.hpp:22-37
     }
 };
 struct Q3Customer {    // Q3Predicates.hpp:25-33
+    static constexpr bool kBytePrefilter = false;
     const uint2 *custkey; const uint8_t *mkt;
     __device__ bool operator()(uint64_t i, uint2 &out) const {
         if (mkt[i] != B200_MKT_BUILDING) return false;
@@ -171,6 +195,7 @@ struct Q3Customer {    // Q3Predicates.hpp:25-33
     }
 };
 struct Q3Orders {      // Q3Predicates.hpp:35-44: key = o_custkey, payload = o_orderkey
+    static constexpr bool kBytePrefilter = false;
     const uint2 *orderkey; const uint64_t *orderdate; const uint32_t *custkey;
     __device__ bool operator()(uint64_t i, uint2 &out) const {
         if (!(orderdate[i] < kTs1995_03_15)) return false;
@@ -179,6 +204,7 @@ struct Q3Orders {      // Q3Predicates.hpp:35-44: key = o_custkey, payload = o_o
     }
 };
 struct Q3Lineitem {    // Q3Predicates.hpp:46-54
+    static constexpr bool kBytePrefilter = false;
     const uint2 *orderkey; const uint64_t *shipdate;
     __device__ bool operator()(uint64_t i, uint2 &out) const {
         if (!(shipdate[i] >= kTs1995_03_16)) return false;
@@ -187,6 +213,7 @@ struct Q3Lineitem {    // Q3Predicates.hpp:46-54
     }
 };
 struct Q19Part {       // Q19Predicates.hpp:41-52
+    static constexpr bool kBytePrefilter = false;
     const uint2 *partkey; const uint8_t *brand, *container; const uint32_t *size;
     __device__ bool operator()(uint64_t i, uint2 &out) const {
         const uint8_t b = brand[i], c = container[i];
@@ -197,6 +224,12 @@ struct Q19Part {       // Q19Predicates.hpp:41-52
     }
 };
 struct Q19Lineitem {   // Q19Predicates.hpp:27-39: key = l_partkey, payload = lineitem row id
+    static constexpr bool kBytePrefilter = true;
+    __device__ uint32_t prefilter16(uint64_t i0) const {   // l_shipmode in (AIR, AIR REG) and l_shipinstruct = DELIVER IN PERSON
+        const uint4 m = ld_bytes16(shipmode, i0), si = ld_bytes16(shipinstruct, i0);
+        return byte_flags16(and16(or16(eq_bytes16(m, B200_L_SHIPMODE_AIR), eq_bytes16(m, B200_L_SHIPMODE_AIR_REG)),
+                                  eq_bytes16(si, B200_L_SHIPINSTRUCT_DELIVER_IN_PERSON)));
+    }
     const uint2 *orderkey; const uint32_t *partkey; const float *quantity; const uint8_t *shipmode, *shipinstruct;
     __device__ bool operator()(uint64_t i, uint2 &out) const {
         const uint8_t m = shipmode[i];
@@ -249,13 +282,70 @@ filter_compact_kernel(uint64_t n, Pred pred, uint2 *__restrict__ out, unsigned l
     }
 }
 
+// Selections whose first conjuncts test one-byte codes (Q19: l_shipmode, l_shipinstruct - 1 row in 14 survives them):
+// the row-at-a-time kernel above spends a dependent chain of 1-byte loads per row on them and runs at a quarter of the
+// bandwidth it needs. Here a thread takes 16 CONSECUTIVE rows, reads each code column with one 16-byte load, compares
+// the 16 codes with byte-SIMD instructions (Pred::prefilter16 -> candidate bit mask), and evaluates the full predicate
+// only on the candidates. The wide columns are then touched for candidate rows only, as before. Two passes over the
+// candidates (count, then - after the block-wide scan - evaluate again and store) keep the kernel free of staging
+// memory; the second evaluation hits L1/L2 and concerns few rows.
+constexpr int kByteRows = 16, kByteTile = kFilterThreads * kByteRows;
+
+template <typename Pred>
+__global__ void __launch_bounds__(kFilterThreads)
+filter_compact_bytes_kernel(uint64_t n, Pred pred, uint2 *__restrict__ out, unsigned long long *__restrict__ counter) {
+    __shared__ uint32_t wtot[kFilterThreads / 32];
+    __shared__ unsigned long long s_base;
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint64_t ntiles = (n + kByteTile - 1) / kByteTile;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t i0 = tile * kByteTile + (uint64_t) threadIdx.x * kByteRows;
+        uint32_t cand = 0;
+        if (i0 + kByteRows <= n)
+            cand = pred.prefilter16(i0);
+        else if (i0 < n)
+            cand = (1u << (uint32_t) (n - i0)) - 1;   // ragged end: every row is a candidate
+        uint32_t keep = 0;
+        uint2 v;
+        for (uint32_t m = cand; m; m &= m - 1) {
+            const uint32_t k = __ffs(m) - 1;
+            if (pred(i0 + k, v)) keep |= 1u << k;
+        }
+        const uint32_t cnt = __popc(keep);
+        const uint32_t incl = warp_incl_scan(cnt);
+        __syncthreads();   // previous tile's wtot / s_base consumed
+        if (lane == 31) wtot[warp] = incl;
+        __syncthreads();
+        uint32_t wbase = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < kFilterThreads / 32; ++k) {
+            uint32_t t = wtot[k];
+            wbase += (k < (int) warp) ? t : 0;
+            total += t;
+        }
+        if (threadIdx.x == 0 && total) s_base = atomicAdd(counter, (unsigned long long) total);
+        __syncthreads();
+        unsigned long long pos = s_base + wbase + incl - cnt;
+        for (uint32_t m = keep; m; m &= m - 1) {
+            pred(i0 + (__ffs(m) - 1), v);
+            out[pos++] = v;
+        }
+    }
+}
+
 template <typename Pred>
 static int run_filter(uint64_t n, Pred pred, row_t *d_out, unsigned long long *d_counter, cudaStream_t st) {
     AQP_CUDA_OK(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st));
     if (n == 0) return 0;
-    uint64_t tiles = (n + kFilterTile - 1) / kFilterTile;
-    unsigned grid = (unsigned) (tiles < (uint64_t) kNumSMs * 8 ? tiles : (uint64_t) kNumSMs * 8);
-    filter_compact_kernel<<<grid, kFilterThreads, 0, st>>>(n, pred, reinterpret_cast<uint2 *>(d_out), d_counter);
+    if constexpr (Pred::kBytePrefilter) {
+        uint64_t tiles = (n + kByteTile - 1) / kByteTile;
+        unsigned grid = (unsigned) (tiles < (uint64_t) kNumSMs * 8 ? tiles : (uint64_t) kNumSMs * 8);
+        filter_compact_bytes_kernel<<<grid, kFilterThreads, 0, st>>>(n, pred, reinterpret_cast<uint2 *>(d_out), d_counter);
+    } else {
+        uint64_t tiles = (n + kFilterTile - 1) / kFilterTile;
+        unsigned grid = (unsigned) (tiles < (uint64_t) kNumSMs * 8 ? tiles : (uint64_t) kNumSMs * 8);
+        filter_compact_kernel<<<grid, kFilterThreads, 0, st>>>(n, pred, reinterpret_cast<uint2 *>(d_out), d_counter);
+    }
     AQP_LAUNCHED();
     AQP_CUDA_OK(cudaGetLastError());
     return 0;
@@ -282,6 +372,7 @@ __device__ __forceinline__ bool q19_final_pred(uint32_t b, uint32_t k, uint32_t 
 // rows, so the attributes the final predicate reads travel IN the payloads instead of being gathered by row id:
 // part -> brand | container << 8 | size << 16, lineitem -> the bits of l_quantity.
 struct Q19PartPacked {
+    static constexpr bool kBytePrefilter = false;
     const uint2 *partkey; const uint8_t *brand, *container; const uint32_t *size;
     __device__ bool operator()(uint64_t i, uint2 &out) const {
         const uint8_t b = brand[i], c = container[i];
@@ -292,6 +383,12 @@ struct Q19PartPacked {
     }
 };
 struct Q19LineitemPacked {
+    static constexpr bool kBytePrefilter = true;
+    __device__ uint32_t prefilter16(uint64_t i0) const {   // l_shipmode in (AIR, AIR REG) and l_shipinstruct = DELIVER IN PERSON
+        const uint4 m = ld_bytes16(shipmode, i0), si = ld_bytes16(shipinstruct, i0);
+        return byte_flags16(and16(or16(eq_bytes16(m, B200_L_SHIPMODE_AIR), eq_bytes16(m, B200_L_SHIPMODE_AIR_REG)),
+                                  eq_bytes16(si, B200_L_SHIPINSTRUCT_DELIVER_IN_PERSON)));
+    }
     const uint32_t *partkey; const float *quantity; const uint8_t *shipmode, *shipinstruct;
     __device__ bool operator()(uint64_t i, uint2 &out) const {
         const uint8_t m = shipmode[i];
