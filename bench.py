@@ -644,7 +644,9 @@ def run_b200_arm(args):
         sf = float(os.environ.get("B200_AQP_TPCH_SF", "100"))
         A.tpch_generate_device(sf, 1)
         published_ms = {3: 730.0, 12: 225.0, 19: 120.0}   # reference, 16 threads, SF100, other hardware
-        tpch = {"scale_factor": sf, "data": "synthetic, generated in HBM (include/aqp/b200_tpch.h)"}
+        tpch = {"scale_factor": sf, "data": "synthetic, generated in HBM (include/aqp/b200_tpch.h)",
+                "roofline_note": "algorithmic_bytes counts every column a selection references once; a selection that rejects "
+                                 "on a one-byte code never touches most sectors of its wide columns, so frac can exceed 1 (Q19)"}
         nc, no, npart = int(150000 * sf), int(1500000 * sf), int(200000 * sf)
         nl = 4 * no
 
