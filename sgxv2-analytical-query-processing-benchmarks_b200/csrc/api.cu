@@ -236,6 +236,15 @@ static int join_device_locked(const row_t *dR, uint64_t nR, const row_t *dS, uin
     const unsigned long long launches0 = g_kernel_launches;
     uint32_t bits, b1, b2;
     plan_bits(nR, &bits, &b1, &b2, dead_bits);
+    if (dead_bits && bits > (uint32_t) kMaxSmemHistBits && nS <= nR && !getenv("B200_AQP_RADIX_BITS")) {
+        // The extra bits for dead key bits would push the plan past the shared-memory histogram and the CTA-private
+        // cursors of pass 1 (TPC-H Q12 at SF100: 150 M orders, 17 -> 16 bits, pass 1 on global atomic cursors at
+        // 1.8 TB/s). With a probe side no larger than the build side it is cheaper to stay at 15 bits and take a few
+        // build rounds per co-partition: the probe tuples that get re-read are few.
+        bits = kMaxSmemHistBits;
+        b1 = bits / 2;
+        b2 = bits - b1;
+    }
     const uint32_t P = 1u << bits, F1 = 1u << b1;
     const int passes = bits == 0 ? 0 : (b2 ? 2 : 1);
 
