@@ -11,7 +11,9 @@
 #include <chrono>
 #include <cstdarg>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -450,6 +452,96 @@ static void print_reference_timing_lines(uint64_t nR, uint64_t nS) {
     log_info("Checksum : %lu", (unsigned long) s.checksum);
 }
 
+// A count-only join on HOST relations is a PCIe transfer (97 ms for 5.4 GB) followed by 6 ms of kernels. The probe
+// side is therefore cut into chunks: a copier thread moves R and then S chunk by chunk on its own stream while the
+// library's stream joins R with every chunk that has arrived - the join is a sum over disjoint parts of S
+// (matches, checksum and keysum add up; radix_join.cpp:1232-1250 sums its threads' results the same way). R is
+// partitioned again for every chunk (K x 1.1 ms at 2^27), which hides under the copy; what stays exposed after the
+// last byte has landed is one join of R with the last chunk instead of the whole join. Materialising joins are not
+// chunked (their cost is the result's way back, and their output buffer may have to grow). Measured at 2^27 x 2^29,
+// pinned relations: see e2e.variants.pinned_count_overlapped in the bench line.
+static uint32_t host_join_chunks(uint64_t nS, bool materialize) {
+    if (materialize) return 1;
+    // Opt-in (B200_AQP_E2E_CHUNKS=K): the K-fold partitioning of R also shows in the device time the reference's log
+    // lines report (run_join's "Throughput" is kernel time, as in the reference), so the default stays one join.
+    uint32_t k = 1;
+    if (const char *e = getenv("B200_AQP_E2E_CHUNKS")) {
+        int v = atoi(e);
+        if (v >= 1 && v <= 64) k = (uint32_t) v;
+    }
+    while (k > 1 && nS / k < 8192) --k;
+    return k;
+}
+
+static int join_host_chunked(const table_t *R, const table_t *S, uint32_t K, b200_join_stats_t *out, float *ms_h2d, cudaStream_t st) {
+    const uint64_t nR = R->num_tuples, nS = S->num_tuples;
+    row_t *dR = static_cast<row_t *>(g.relR.p), *dS = static_cast<row_t *>(g.relS.p);
+    auto chunk_begin = [&](uint32_t k) { return k >= K ? nS : (nS / K * k) & ~(uint64_t) 4095; };   // tile-aligned cuts
+    std::mutex mu;
+    std::condition_variable cv;
+    int arrived = -1;   // -1: nothing yet, 0: R, k: R and the first k chunks of S; -2: failed
+    double t_copy = 0;
+    const int device = g.device;
+    std::thread copier([&] {
+        bool ok = cudaSetDevice(device) == cudaSuccess;
+        cudaStream_t cs = nullptr;
+        ok = ok && cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) == cudaSuccess;
+        const double t0 = now_s();
+        auto publish = [&](int v) {
+            std::lock_guard<std::mutex> lk(mu);
+            arrived = v;
+            cv.notify_all();
+        };
+        ok = ok && copy_h2d_any(dR, R->tuples, nR * sizeof(row_t), cs) == 0 && cudaStreamSynchronize(cs) == cudaSuccess;
+        if (ok) publish(0);
+        for (uint32_t k = 0; ok && k < K; ++k) {
+            const uint64_t b = chunk_begin(k), e = chunk_begin(k + 1);
+            ok = copy_h2d_any(dS + b, S->tuples + b, (e - b) * sizeof(row_t), cs) == 0 && cudaStreamSynchronize(cs) == cudaSuccess;
+            if (ok) publish((int) k + 1);
+        }
+        t_copy = now_s() - t0;
+        if (cs) cudaStreamDestroy(cs);
+        if (!ok) publish(-2);
+    });
+    b200_join_stats_t sum{};
+    int rc = 0;
+    for (uint32_t k = 0; k < K && rc == 0; ++k) {
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return arrived == -2 || arrived >= (int) k + 1; });
+            if (arrived == -2) {
+                rc = -1;
+                break;
+            }
+        }
+        const uint64_t b = chunk_begin(k), e = chunk_begin(k + 1);
+        b200_join_stats_t s{};
+        rc = join_device_locked(dR, nR, dS + b, e - b, nullptr, 0, &s, st, true);
+        sum.matches += s.matches;
+        sum.checksum += s.checksum;
+        sum.keysum += s.keysum;
+        sum.ms_hist += s.ms_hist;
+        sum.ms_pass1 += s.ms_pass1;
+        sum.ms_pass2 += s.ms_pass2;
+        sum.ms_join += s.ms_join;
+        sum.ms_total += s.ms_total;
+        sum.kernel_launches += s.kernel_launches;
+        sum.radix_bits = s.radix_bits;
+        sum.num_passes = s.num_passes;
+        sum.bits_pass1 = s.bits_pass1;
+        sum.bits_pass2 = s.bits_pass2;
+    }
+    copier.join();
+    if (rc || arrived == -2) {
+        if (arrived == -2) set_error("host join: H2D copy of a relation failed");
+        return -1;
+    }
+    *ms_h2d = (float) (t_copy * 1e3);
+    g.last = sum;
+    *out = sum;
+    return 0;
+}
+
 // host-buffer join: H2D, device join, results back in the reference's layout
 static int join_host_locked(const table_t *R, const table_t *S, const joinconfig_t *cfg, result_t *res,
                             bool use_preloaded) {
@@ -457,6 +549,7 @@ static int join_host_locked(const table_t *R, const table_t *S, const joinconfig
     cudaStream_t st = g.stream;
     uint64_t nR, nS;
     float ms_h2d = 0;
+    uint32_t chunks = 1;
     if (use_preloaded) {
         if (!g.preloaded) {
             set_error("b200_join_preload called without b200_preload_relations");
@@ -468,13 +561,16 @@ static int join_host_locked(const table_t *R, const table_t *S, const joinconfig
         nR = R->num_tuples;
         nS = S->num_tuples;
         if (g.relR.ensure(nR * sizeof(row_t) + 16) || g.relS.ensure(nS * sizeof(row_t) + 16)) return -1;
-        double t = now_s();
-        // pinned relations (this library's create_relation_* return pinned memory): one DMA each; pageable ones
-        // (a caller's malloc): multi-threaded staging through pinned buffers (hostcopy.cpp)
-        if (copy_h2d_any(g.relR.p, R->tuples, nR * sizeof(row_t), st) || copy_h2d_any(g.relS.p, S->tuples, nS * sizeof(row_t), st))
-            return -1;
-        AQP_CUDA_OK(cudaStreamSynchronize(st));
-        ms_h2d = (float) ((now_s() - t) * 1e3);
+        chunks = host_join_chunks(nS, cfg && cfg->MATERIALIZE);
+        if (chunks == 1) {
+            double t = now_s();
+            // pinned relations (this library's create_relation_* return pinned memory): one DMA each; pageable ones
+            // (a caller's malloc): multi-threaded staging through pinned buffers (hostcopy.cpp)
+            if (copy_h2d_any(g.relR.p, R->tuples, nR * sizeof(row_t), st) || copy_h2d_any(g.relS.p, S->tuples, nS * sizeof(row_t), st))
+                return -1;
+            AQP_CUDA_OK(cudaStreamSynchronize(st));
+            ms_h2d = (float) ((now_s() - t) * 1e3);
+        }
         g.preloaded = false;
     }
     const row_t *dR = static_cast<row_t *>(g.relR.p), *dS = static_cast<row_t *>(g.relS.p);
@@ -488,7 +584,11 @@ static int join_host_locked(const table_t *R, const table_t *S, const joinconfig
         d_out = static_cast<output_triple_t *>(g.out.p);
     }
     b200_join_stats_t s{};
-    if (join_device_locked(dR, nR, dS, nS, d_out, cap, &s, st, true)) return -1;
+    if (chunks > 1) {
+        if (join_host_chunked(R, S, chunks, &s, &ms_h2d, st)) return -1;
+    } else if (join_device_locked(dR, nR, dS, nS, d_out, cap, &s, st, true)) {
+        return -1;
+    }
     if (mat && (uint64_t) s.matches > cap) {
         cap = (uint64_t) s.matches;
         if (g.out.ensure(cap * sizeof(output_triple_t))) return -1;

@@ -146,6 +146,24 @@ def test_preload_split(gpu, oracle):
         gpu.join_preload()
 
 
+def test_host_join_overlapped_with_its_copy(gpu, oracle, monkeypatch):
+    """B200_AQP_E2E_CHUNKS: the probe side travels in chunks and R is joined with each as it lands - same result as one join,
+    for pageable and pinned relations, duplicates and misses included; materialising joins ignore the switch"""
+    nR, nS = 1 << 16, (1 << 18) + 12345
+    R = oracle.set_rowid_payload(oracle.gen_pk(nR, 11111))
+    S = oracle.set_rowid_payload(oracle.gen_fk(nS, nR, 22222))
+    S["key"][::5] += nR            # misses
+    R["key"][1::7] = R["key"][::7][:len(R["key"][1::7])]   # duplicate build keys
+    o = oracle.rho(R, S, nthreads=2, materialize=True)
+    for k in ("1", "4", "7"):
+        monkeypatch.setenv("B200_AQP_E2E_CHUNKS", k)
+        g = gpu.run_join(R, S, materialize=False)
+        assert (g["matches"], g["checksum"], g["keysum"]) == (o["matches"], o["checksum"], o["keysum"]), k
+        g = gpu.run_join(R, S, materialize=True)
+        assert np.array_equal(sorted_triples(g["triples"]), sorted_triples(o["triples"])), k
+    monkeypatch.delenv("B200_AQP_E2E_CHUNKS")
+
+
 def test_chunked_table_layout(gpu, oracle):
     R = oracle.set_rowid_payload(oracle.gen_pk(5000, 1))
     S = oracle.set_rowid_payload(oracle.gen_fk(20000, 5000, 2))
