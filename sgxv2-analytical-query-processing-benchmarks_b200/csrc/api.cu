@@ -126,6 +126,8 @@ static void log_info(const char *fmt, ...) {
     exit(EXIT_FAILURE);
 }
 
+constexpr uint32_t kSharedCursorMinBits = 7;   // pass-1 fan-out from which shared (atomic) cursors beat CTA-private ones
+
 // ---------------------------------------------------------------------------------------------
 // join planning — the GPU analogue of calc_num_radix_bits / calc_num_passes
 // (radix_join.cpp:295-329): partitions are sized so the build side of a co-partition fits the
@@ -272,7 +274,16 @@ static int join_device_locked(const row_t *dR, uint64_t nR, const row_t *dS, uin
         // pass-1 scatter geometry: NB CTAs, CTA b owns tiles [b*tpb, (b+1)*tpb) of its relation; the
         // histogram kernel runs with the same geometry so it can emit per-CTA pass-1 histogram rows
         const uint32_t NB = pass1_blocks();
-        const bool priv = bits <= (uint32_t) kMaxSmemHistBits && !getenv("B200_AQP_ATOMIC_PASS1");
+        // Pass-1 cursors. CTA-private (every CTA owns a tile range and, from the per-CTA histogram rows, a private slice of
+        // every partition: no atomics) or shared (one global atomicAdd per partition and tile, tiles interleaved over the
+        // CTAs like pass 2, the next input tile requested early). Shared wins when the fan-out spreads the atomics over
+        // enough addresses - 2^27 x 2^29, 128 partitions: pass 1 1.98 -> 1.86 ms, also under Zipf 0.5 / 1.0 - and loses
+        // when it does not - 2^24 x 2^26, 32 partitions: 0.23 -> 0.35 ms (profiles/r02_sweep_join_pass1_cursors.txt).
+        bool priv = bits <= (uint32_t) kMaxSmemHistBits && (b1 < kSharedCursorMinBits || dead_bits);   // dead bits: few, overfull bins
+        if (const char *e = getenv("B200_AQP_PASS1")) {
+            if (!strcmp(e, "shared")) priv = false;
+            if (!strcmp(e, "private")) priv = bits <= (uint32_t) kMaxSmemHistBits;
+        }
         const uint32_t tpbR = (uint32_t) (((nR + kScatterTile - 1) / kScatterTile + NB - 1) / NB);
         const uint32_t tpbS = (uint32_t) (((nS + kScatterTile - 1) / kScatterTile + NB - 1) / NB);
         if (radix_hist_device(dR, nR, make_digit(0, bits), bits, u32(m.histR), priv ? NB : 0,
