@@ -82,6 +82,7 @@ build_probe_kernel(const uint2 *__restrict__ R, const uint32_t *__restrict__ off
     unsigned long long matches = 0, checksum = 0, keysum = 0;
 
     for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x) {
+        uint32_t m32 = 0;   // matches of this thread in this item (<= 64 probe tuples x 8192 build tuples): one register
         const uint2 item = items[it];
         const uint32_t p = item.x;
         const uint32_t rbeg = offR[p], rend = offR[p + 1];
@@ -115,7 +116,7 @@ build_probe_kernel(const uint2 *__restrict__ R, const uint32_t *__restrict__ off
             while (N < nr) N <<= 1;
             const uint32_t hmask = N - 1;
             // the first round of S tuples is put in flight BEFORE the build so its latency hides behind it
-            uint2 sn[kProbeUnroll];
+            uint2 sn[kProbeUnroll] = {};
             load_round(sbeg, sn);
 #pragma unroll
             for (uint32_t r = 1; r <= kPrefetchRounds; ++r) prefetch_round(sbeg + r * kRound);
@@ -161,12 +162,15 @@ build_probe_kernel(const uint2 *__restrict__ R, const uint32_t *__restrict__ off
                         for (int j = 0; j < kProbeUnroll; ++j) s[j] = sn[j];
                         if (base + kRoundS < send) load_round(base + kRoundS, sn);
                         prefetch_round(base + (1 + kPrefetchRounds) * kRoundS);
+                        // (one table load next to its compare per tuple: issuing the four loads of a round together
+                        // costs registers this kernel does not have - 40 bytes of spills, 1.086 -> 1.132 ms - and buys
+                        // nothing here, the shared-memory pipe is already the limit)
 #pragma unroll
                         for (int j = 0; j < kProbeUnroll; ++j) {
                             if (base + j * kJoinThreads + threadIdx.x < send) {
                                 const uint2 r = rt[(s[j].x >> hash_shift) & hmask];
                                 if (r.x == s[j].x) {
-                                    ++matches;
+                                    ++m32;
                                     checksum += (unsigned long long) r.y + s[j].y;
                                     keysum += s[j].x;
                                 }
@@ -201,26 +205,30 @@ build_probe_kernel(const uint2 *__restrict__ R, const uint32_t *__restrict__ off
                 if (base + kRound < send) load_round(base + kRound, sn);
                 prefetch_round(base + (1 + kPrefetchRounds) * kRound);
                 if (!kMaterialize) {
+                    // the four chain heads first, then the chains: behind a per-tuple bounds branch the compiler kept each
+                    // head load next to its use and every probe paid two dependent shared-memory round trips in a row.
+                    // (Also issuing the four first chain elements together spills: the direct-mapped path above shares
+                    // this kernel's 64 registers and loses 6 %.) Only a flagged chain (more than one tuple) is walked.
+                    uint32_t heads[kProbeUnroll];
+#pragma unroll
+                    for (int j = 0; j < kProbeUnroll; ++j) heads[j] = bucket[(s[j].x >> hash_shift) & hmask];
 #pragma unroll
                     for (int j = 0; j < kProbeUnroll; ++j) {
                         const bool valid = base + j * kJoinThreads + threadIdx.x < send;
-                        const uint32_t head = valid ? bucket[(s[j].x >> hash_shift) & hmask] : 0u;
-                        uint32_t hit = head & 0xFFFFu;
-                        if (!(head & kChainFlag)) {
-                            // single-tuple chain (always the case for a dense primary key): no link to follow
-                            if (hit) {
-                                uint2 r = rt[hit - 1];
-                                if (r.x == s[j].x) {
-                                    ++matches;
-                                    checksum += (unsigned long long) r.y + s[j].y;
-                                    keysum += s[j].x;
-                                }
-                            }
-                        } else {
+                        uint32_t hit = valid ? heads[j] & 0xFFFFu : 0u;
+                        if (!hit) continue;
+                        uint2 r = rt[hit - 1];
+                        if (r.x == s[j].x) {
+                            ++m32;
+                            checksum += (unsigned long long) r.y + s[j].y;
+                            keysum += s[j].x;
+                        }
+                        if (heads[j] & kChainFlag) {
+                            hit = next[hit - 1];
                             while (hit) {
-                                uint2 r = rt[hit - 1];
+                                r = rt[hit - 1];
                                 if (r.x == s[j].x) {
-                                    ++matches;
+                                    ++m32;
                                     checksum += (unsigned long long) r.y + s[j].y;
                                     keysum += s[j].x;
                                 }
@@ -255,7 +263,7 @@ build_probe_kernel(const uint2 *__restrict__ R, const uint32_t *__restrict__ off
                         }
                         c += cnt[j];
                     }
-                    matches += c;
+                    m32 += c;
                     const uint32_t incl = warp_incl_scan(c);
                     if (lane_id() == 31) s_wsum[threadIdx.x >> 5] = incl;
                     __syncthreads();
@@ -293,6 +301,7 @@ build_probe_kernel(const uint2 *__restrict__ R, const uint32_t *__restrict__ off
                 }
             }
         }
+        matches += m32;
     }
 
     // block reduction of the three accumulators -> 3 global atomics per CTA
