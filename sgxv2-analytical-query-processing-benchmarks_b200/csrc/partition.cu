@@ -802,6 +802,9 @@ constexpr int kBinSlotsLog = 13;
 #ifndef AQP_SCATTER_EARLY_REFILL
 #define AQP_SCATTER_EARLY_REFILL 1
 #endif
+#ifndef AQP_SCATTER_LATE_WRITEOUT
+#define AQP_SCATTER_LATE_WRITEOUT 0
+#endif
 constexpr size_t kBinsSmemBytes = (size_t) (kInBufTuples + (1 << kBinSlotsLog)) * sizeof(uint2);
 static_assert(kScatterTile + kMaxFanout <= (1 << kBinSlotsLog), "the compacting path stages a whole tile plus carries");
 
@@ -908,32 +911,47 @@ radix_scatter_bins_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
     const uint32_t own_per = (fan + kWarps - 1) / kWarps;
     const uint32_t d_own = (threadIdx.x & 31u) < own_per ? (threadIdx.x >> 5) * own_per + (threadIdx.x & 31u) : fan;
 
-    for (uint32_t i = 0; i < n_my; ++i) {
-        const uint32_t begin = s_tile[i & 1][0], end = s_tile[i & 1][1], group = s_tile[i & 1][2];
-        const uint32_t ntile = end - begin;
-        const uint32_t skew = (uint32_t) ((reinterpret_cast<uintptr_t>(in + begin) >> 3) & 1u);
-        const uint2 *buf = inbuf + skew;
-
+    // tile #i of this CTA: wait for it, move it into registers, let the input buffer be refilled
+    uint2 v[kScatterItems];
+    auto load_tile = [&](uint32_t i) {
+        const uint32_t begin = s_tile[i & 1][0], ntile = s_tile[i & 1][1] - begin;
+        const uint2 *buf = inbuf + (uint32_t) ((reinterpret_cast<uintptr_t>(in + begin) >> 3) & 1u);
         mbar_wait(&mbar, i & 1);
-        uint2 v[kScatterItems];
-        uint32_t rank[kScatterItems];
-        bool tight = false;
         if (ntile == (uint32_t) kScatterTile) {   // full tile: no per-item bounds checks
 #pragma unroll
             for (int j = 0; j < kScatterItems; ++j) v[j] = buf[j * kScatterThreads + threadIdx.x];
-            refill(i);
-#pragma unroll
-            for (int j = 0; j < kScatterItems; ++j) {
-                rank[j] = atomicAdd(&cnt[digit.template get<kRot>(v[j].x)], 1u);
-                tight |= rank[j] + 2 > cap;   // bin full (one slot is kept for the carried tuple)
-            }
         } else {
 #pragma unroll
             for (int j = 0; j < kScatterItems; ++j) {
                 uint32_t k = j * kScatterThreads + threadIdx.x;
                 if (k < ntile) v[j] = buf[k];
             }
-            refill(i);
+        }
+        refill(i);
+    };
+    // Experiment kept behind AQP_SCATTER_LATE_WRITEOUT (off): with shared cursors a run's destination comes back from a
+    // global atomicAdd issued after barrier (1), and the owner threads wait for it in front of their bulk stores (ncu
+    // source view: 24 % of the kernel's stall samples, long scoreboard, in the store issue). Moving the write-out of
+    // tile i behind the next tile's input wait and register loads gives the atomic one more phase to come home - but
+    // takes the same time away from the bulk stores, which must have read the bins before the next staging phase:
+    // pass 2 1.85 -> 1.96 ms, pass 1 1.86 -> 1.91 ms (profiles/r02_sweep_join_late_writeout.txt). Not used.
+    constexpr bool kLateWriteOut = AQP_SCATTER_LATE_WRITEOUT && !kPriv;
+    if (kLateWriteOut && n_my > 0) load_tile(0);
+
+    for (uint32_t i = 0; i < n_my; ++i) {
+        const uint32_t begin = s_tile[i & 1][0], end = s_tile[i & 1][1], group = s_tile[i & 1][2];
+        const uint32_t ntile = end - begin;
+
+        if (!kLateWriteOut) load_tile(i);
+        uint32_t rank[kScatterItems];
+        bool tight = false;
+        if (ntile == (uint32_t) kScatterTile) {
+#pragma unroll
+            for (int j = 0; j < kScatterItems; ++j) {
+                rank[j] = atomicAdd(&cnt[digit.template get<kRot>(v[j].x)], 1u);
+                tight |= rank[j] + 2 > cap;   // bin full (one slot is kept for the carried tuple)
+            }
+        } else {
 #pragma unroll
             for (int j = 0; j < kScatterItems; ++j) {
                 uint32_t k = j * kScatterThreads + threadIdx.x;
@@ -981,6 +999,7 @@ radix_scatter_bins_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged tuples visible to the TMA unit
             __syncthreads();   // (2) tile staged
+            if (kLateWriteOut && i + 1 < n_my) load_tile(i + 1);
             if (d_own < fan) {
                 if (n) {
                     uint2 *dst = kPeer ? s_peer[d_own >> peers.per_shift] : out;
@@ -1061,6 +1080,7 @@ radix_scatter_bins_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
                 }
             }
             __syncthreads();   // tile compacted, destinations known
+            if (kLateWriteOut && i + 1 < n_my) load_tile(i + 1);
             const uint32_t total = s_total;
             for (uint32_t s = threadIdx.x; s < total; s += kScatterThreads) {
                 uint2 t = bins[s];
