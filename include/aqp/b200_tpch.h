@@ -132,7 +132,9 @@ int b200_tpch_mg_init(int rank, int world, const unsigned char *nccl_unique_id /
 int b200_tpch_q12_mg(struct b200_tpch_stats_t *stats);
 /* Q3: the matches of join 1 stay sharded by customer key and feed join 2 as its build side (b200_mg_join_materialize);
  * Q19: the attributes of the final predicate travel packed in the payloads, the per-rank counts are all-reduced.
- * stats->join1_rows and stats->result_rows are GLOBAL. Both need b200_tpch_mg_init like Q12. */
+ * stats->join1_rows and stats->result_rows are GLOBAL. Both need b200_tpch_mg_init like Q12. (Q3: the matches of join 1
+ * a rank ends up owning are its build-side shard of join 2 and must fit the capacity b200_tpch_mg_init derived from the
+ * orders shard - they do unless almost all qualifying orders hash to one rank; the call fails with an error otherwise.) */
 int b200_tpch_q3_mg(struct b200_tpch_stats_t *stats);
 int b200_tpch_q19_mg(struct b200_tpch_stats_t *stats);
 
