@@ -449,6 +449,10 @@ def run_b200_arm(args):
     join_roof = {"bound": "hbm", "bytes_per_tuple": JOIN_BYTES_PER_TUPLE, "achieved": join_bytes / ms_step / 1e6,
                  "peak": peak, "unit": "GB/s", "frac": join_bytes / ms_step / 1e6 / peak,
                  "actual_bytes_per_tuple": 48, "note": "the pass-2 histogram read is avoided: one full-width histogram serves both passes"}
+    if s.get("plan_flags", 0) & 1:   # B200_PLAN_HISTOGRAM_FREE: partitions live in fixed-capacity regions, no histogram pass at all
+        join_roof["actual_bytes_per_tuple"] = 40
+        join_roof["note"] = ("histogram-free plan (fixed-capacity partition regions, exact-offset repeat on overflow): no histogram "
+                             "read at all, 2 x 16 B/tuple scatter + 8 B/tuple build/probe; frac is still quoted at the graded 56 B/tuple")
 
     # ---- BASELINE config 4: Zipf-skewed S (z = 0.5, 1.0), same sizes, 1 GPU ----------------------------
     skew = {}
@@ -768,7 +772,7 @@ def run_b200_arm(args):
                 "vs_baseline": None, "dtype": "u32", "data": "synthetic",
                 "config": workload_config(world),
                 "plan": {"generator": "on-device bijection, seeds 11111/22222", "radix_bits": s["radix_bits"],
-                         "passes": s["num_passes"],
+                         "passes": s["num_passes"], "histogram_free": bool(s.get("plan_flags", 0) & 1),
                          "exchange": None if world == 1 else
                          f"pass 1 routes by the low key bits and stores every run into the owner's buffer over NVLink peer "
                          f"memory ({s.get('exchange', 'nccl')}); NCCL carries the sizing collectives"},

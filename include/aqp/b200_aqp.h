@@ -75,6 +75,10 @@ void destroy_table(struct chunked_table_t *table);
 /* Extra facts about the most recent join on this thread's context. The reference's result_t has
  * no checksum; checksum = sum over matches of (uint64)Rpayload + (uint64)Spayload
  * (CHT's convention, Joins/include/cht/CHTJoin.hpp:174), keysum = sum over matches of key. */
+/* plan_flags: the join ran without a histogram pass (fixed-capacity partition regions) / it tried to,
+ * a region overflowed (skew), and it was repeated with exact offsets - ms_* then describe the repeat only */
+#define B200_PLAN_HISTOGRAM_FREE 1u
+#define B200_PLAN_HISTOGRAM_FREE_OVERFLOWED 2u
 struct b200_join_stats_t {
     int64_t matches;
     uint64_t checksum;
@@ -84,7 +88,7 @@ struct b200_join_stats_t {
     uint32_t bits_pass1;
     uint32_t bits_pass2;
     uint32_t kernel_launches; /* kernels launched for this join */
-    uint32_t reserved;
+    uint32_t plan_flags;      /* B200_PLAN_* */
     float ms_total;           /* device time, CUDA events: histogram .. build/probe */
     float ms_hist;
     float ms_pass1;

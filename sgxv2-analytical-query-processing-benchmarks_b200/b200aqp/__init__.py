@@ -81,7 +81,7 @@ class PartTable(C.Structure):      # TpcHTypes.hpp:77-83
 class JoinStats(C.Structure):      # struct b200_join_stats_t
     _fields_ = [("matches", C.c_int64), ("checksum", C.c_uint64), ("keysum", C.c_uint64), ("radix_bits", C.c_uint32),
                 ("num_passes", C.c_uint32), ("bits_pass1", C.c_uint32), ("bits_pass2", C.c_uint32),
-                ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32), ("ms_total", C.c_float),
+                ("kernel_launches", C.c_uint32), ("plan_flags", C.c_uint32), ("ms_total", C.c_float),
                 ("ms_hist", C.c_float), ("ms_pass1", C.c_float), ("ms_pass2", C.c_float), ("ms_join", C.c_float),
                 ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("ms_materialize_host", C.c_float)]
 

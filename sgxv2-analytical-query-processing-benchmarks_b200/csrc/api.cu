@@ -228,6 +228,155 @@ static MetaLayout meta_layout(uint32_t bits, uint32_t b1, uint64_t nS) {
 //   plan       -> prefix sums                 (:886-915)
 //   pass 1/2   -> partition_copy / radix_cluster (:659-697, :715-761)
 //   join       -> bucket_chaining_join        (:359-458)
+// ---------------------------------------------------------------------------------------------
+// The histogram-free plan. The reference sizes every partition exactly from a histogram pass (partition_hist,
+// radix_join.cpp:617-654) because its partitions are packed back to back; here that pass is 0.8 of the join's 5.6 ms
+// (8 of 48 B/tuple). With shared cursors (api.cu: kSharedCursorMinBits) the scatter needs only a START per partition,
+// so every partition of both passes gets a REGION of fixed capacity - the mean size plus slack - and the cursors
+// run inside the regions: no histogram, no prefix sums. Pass 2 reads the regions of pass 1 as segments with gaps (the
+// multi-GPU receive layout, kGapSegment), build/probe takes [begin, end) per partition. A run that does not fit its
+// region is dropped and raises a flag; the join is then repeated with exact offsets (join_device_locked below), so any
+// input stays correct. Skew cannot be told from uniform without reading the data, so pass 1 itself is the test: its
+// flag is read before pass 2 is launched, and a skewed probe side costs one wasted pass, not a join.
+// Count/checksum joins with two passes and >= 128 pass-1 partitions only; opt-in: B200_AQP_HISTFREE=1.
+// ---------------------------------------------------------------------------------------------
+struct HistFreeLayout {
+    size_t result, flag, zero_bytes, cur1[2], lim1[2], seg1[2], seg_off[2], seg_tile[2], cur2[2], lim2[2], beg[2], end[2],
+        seg_group, item_start, items, total;
+};
+static HistFreeLayout histfree_layout(uint32_t bits, uint32_t b1, uint64_t nS) {
+    const size_t P = (size_t) 1 << bits, F1 = (size_t) 1 << b1;
+    HistFreeLayout m{};
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        size_t r = o;
+        o += (bytes + 255) & ~(size_t) 255;
+        return r;
+    };
+    m.result = take(sizeof(JoinResult));
+    m.flag = take(16);
+    m.zero_bytes = o;
+    for (int r = 0; r < 2; ++r) {
+        m.cur1[r] = take(F1 * 4);
+        m.lim1[r] = take(F1 * 4);
+        m.seg1[r] = take(16);
+        m.seg_off[r] = take((2 * F1 + 1) * 4);
+        m.seg_tile[r] = take((2 * F1 + 1) * 4);
+        m.cur2[r] = take(P * 4);
+        m.lim2[r] = take(P * 4);
+        m.beg[r] = take(P * 4);
+        m.end[r] = take(P * 4);
+    }
+    m.seg_group = take(2 * F1 * 4);
+    m.item_start = take((P + 1) * 4);
+    m.items = take((nS / kProbeChunk + P + 1) * sizeof(uint2));
+    m.total = o;
+    return m;
+}
+// region capacity for `parts` partitions of n tuples: the mean plus 1/16 and a constant (even: bulk stores start on
+// 16-byte boundaries). A dense key or a uniform foreign key deviates by well under 1 % at these sizes.
+static uint64_t region_cap(uint64_t n, uint64_t parts) {
+    const uint64_t mean = (n + parts - 1) / parts;
+    return (mean + (mean >> 4) + 256 + 1) & ~(uint64_t) 1;
+}
+
+// returns 0 and *overflowed = false when the join is done; *overflowed = true when a region was too small (nothing valid
+// in stats then); -1 on errors
+static int join_device_histfree(const row_t *dR, uint64_t nR, const row_t *dS, uint64_t nS, b200_join_stats_t *stats,
+                                cudaStream_t st, uint32_t bits, uint32_t b1, uint32_t b2, bool *overflowed) {
+    const uint32_t P = 1u << bits, F1 = 1u << b1;
+    const uint64_t n[2] = {nR, nS};
+    uint64_t cap1[2], cap2[2];
+    for (int r = 0; r < 2; ++r) {
+        cap1[r] = region_cap(n[r], F1);
+        cap2[r] = region_cap(n[r], P);
+        if (cap1[r] * F1 >= 0xFFFF0000ull || cap2[r] * P >= 0xFFFF0000ull) {   // 32-bit offsets
+            *overflowed = true;
+            return 0;
+        }
+    }
+    const unsigned long long launches0 = g_kernel_launches;
+    HistFreeLayout m = histfree_layout(bits, b1, nS);
+    if (g.meta.ensure(m.total)) return -1;
+    for (int r = 0; r < 2; ++r)
+        if (g.tmp[r].ensure(cap1[r] * F1 * sizeof(row_t) + 16) || g.tmp[2 + r].ensure(cap2[r] * P * sizeof(row_t) + 16)) return -1;
+    unsigned char *mb = static_cast<unsigned char *>(g.meta.p);
+    auto u32 = [&](size_t off) { return reinterpret_cast<uint32_t *>(mb + off); };
+    JoinResult *d_res = reinterpret_cast<JoinResult *>(mb + m.result);
+    uint32_t *d_flag = u32(m.flag);
+    RegionArgs ra{};
+    ra.bits1 = b1;
+    ra.bits2 = b2;
+    ra.seg_group = u32(m.seg_group);
+    for (int r = 0; r < 2; ++r)
+        ra.rel[r] = RegionRel{(uint32_t) n[r], (uint32_t) cap1[r], (uint32_t) cap2[r], u32(m.cur1[r]), u32(m.lim1[r]),
+                              u32(m.seg1[r]), u32(m.seg_off[r]), u32(m.seg_tile[r]), u32(m.cur2[r]), u32(m.lim2[r]),
+                              u32(m.beg[r]), u32(m.end[r])};
+    const row_t *in[2] = {dR, dS};
+    row_t *t1[2] = {static_cast<row_t *>(g.tmp[0].p), static_cast<row_t *>(g.tmp[1].p)};
+    row_t *t2[2] = {static_cast<row_t *>(g.tmp[2].p), static_cast<row_t *>(g.tmp[3].p)};
+
+    AQP_CUDA_OK(cudaEventRecord(g.ev[0], st));
+    AQP_CUDA_OK(cudaMemsetAsync(mb, 0, m.zero_bytes, st));
+    if (region_init_device(ra, st)) return -1;
+    AQP_CUDA_OK(cudaEventRecord(g.ev[1], st));
+    for (int r = 0; r < 2; ++r)
+        if (radix_scatter_launch(in[r], t1[r], u32(m.seg1[r]), u32(m.seg1[r]) + 2, nullptr, 1, n[r], make_digit(0, b1), b1,
+                                 u32(m.cur1[r]), nullptr, 0, 0, st, nullptr, u32(m.lim1[r]), d_flag))
+            return -1;
+    AQP_CUDA_OK(cudaEventRecord(g.ev[2], st));
+    // pass 1 is the test of the input: a region that overflowed here (a skewed probe side) ends the attempt before
+    // pass 2 and build/probe are spent on it. One small read-back; the next kernels are queued behind it at once.
+    uint32_t h_flag = 0;
+    AQP_CUDA_OK(cudaMemcpyAsync(&h_flag, d_flag, sizeof h_flag, cudaMemcpyDeviceToHost, st));
+    if (region_plan2_device(ra, st)) return -1;
+    AQP_CUDA_OK(cudaStreamSynchronize(st));
+    if (h_flag) {
+        *overflowed = true;
+        return 0;
+    }
+    for (int r = 0; r < 2; ++r)
+        if (radix_scatter_launch(t1[r], t2[r], u32(m.seg_off[r]), u32(m.seg_tile[r]), u32(m.seg_group), 2 * F1, n[r],
+                                 make_digit(b1, b2), b2, u32(m.cur2[r]), nullptr, 0, 0, st, nullptr, u32(m.lim2[r]), d_flag))
+            return -1;
+    AQP_CUDA_OK(cudaEventRecord(g.ev[3], st));
+    if (region_plan3_device(ra, st)) return -1;
+    uint2 *d_items = reinterpret_cast<uint2 *>(mb + m.items);
+    if (join_items_device(u32(m.beg[0]), u32(m.beg[1]), P, u32(m.item_start), d_items, st, u32(m.end[0]), u32(m.end[1])))
+        return -1;
+    if (build_probe_device(t2[0], u32(m.beg[0]), t2[1], u32(m.beg[1]), u32(m.item_start), d_items, P,
+                           nS / kProbeChunk + P + 1, bits, d_res, nullptr, 0, st, u32(m.end[0]), u32(m.end[1])))
+        return -1;
+    AQP_CUDA_OK(cudaEventRecord(g.ev[4], st));
+    JoinResult h{};
+    AQP_CUDA_OK(cudaMemcpyAsync(&h, d_res, sizeof h, cudaMemcpyDeviceToHost, st));
+    AQP_CUDA_OK(cudaMemcpyAsync(&h_flag, d_flag, sizeof h_flag, cudaMemcpyDeviceToHost, st));
+    AQP_CUDA_OK(cudaStreamSynchronize(st));
+    if (h_flag) {
+        *overflowed = true;
+        return 0;
+    }
+    *overflowed = false;
+    b200_join_stats_t s{};
+    s.matches = (int64_t) h.matches;
+    s.checksum = h.checksum;
+    s.keysum = h.keysum;
+    s.radix_bits = bits;
+    s.num_passes = 2;
+    s.bits_pass1 = b1;
+    s.bits_pass2 = b2;
+    s.plan_flags = B200_PLAN_HISTOGRAM_FREE;
+    cudaEventElapsedTime(&s.ms_hist, g.ev[0], g.ev[1]);
+    cudaEventElapsedTime(&s.ms_pass1, g.ev[1], g.ev[2]);
+    cudaEventElapsedTime(&s.ms_pass2, g.ev[2], g.ev[3]);
+    cudaEventElapsedTime(&s.ms_join, g.ev[3], g.ev[4]);
+    cudaEventElapsedTime(&s.ms_total, g.ev[0], g.ev[4]);
+    s.kernel_launches = (uint32_t) (g_kernel_launches - launches0);
+    g.last = s;
+    if (stats) *stats = s;
+    return 0;
+}
+
 static int join_device_locked(const row_t *dR, uint64_t nR, const row_t *dS, uint64_t nS, output_triple_t *d_out,
                               uint64_t out_cap, b200_join_stats_t *stats, cudaStream_t st, bool keep_partitions,
                               uint32_t dead_bits = 0) {
@@ -251,6 +400,16 @@ static int join_device_locked(const row_t *dR, uint64_t nR, const row_t *dS, uin
     }
     const uint32_t P = 1u << bits, F1 = 1u << b1;
     const int passes = bits == 0 ? 0 : (b2 ? 2 : 1);
+
+    uint32_t plan_flags = 0;
+    const bool histfree_on = getenv("B200_AQP_HISTFREE") && atoi(getenv("B200_AQP_HISTFREE")) == 1;   // opt-in while it is being measured
+    if (histfree_on && passes == 2 && !d_out && !dead_bits && b1 >= kSharedCursorMinBits && 2 * F1 <= (uint32_t) kMaxSegs &&
+        bits <= (uint32_t) kMaxSmemHistBits && !getenv("B200_AQP_PASS1")) {
+        bool overflowed = false;
+        if (join_device_histfree(dR, nR, dS, nS, stats, st, bits, b1, b2, &overflowed)) return -1;
+        if (!overflowed) return 0;
+        plan_flags = B200_PLAN_HISTOGRAM_FREE_OVERFLOWED;   // a region was too small: exact offsets from here on
+    }
 
     MetaLayout m = meta_layout(bits, b1, nS);
     if (g.meta.ensure(m.total)) return -1;
@@ -346,6 +505,7 @@ static int join_device_locked(const row_t *dR, uint64_t nR, const row_t *dS, uin
     s.num_passes = (uint32_t) passes;
     s.bits_pass1 = b1;
     s.bits_pass2 = b2;
+    s.plan_flags = plan_flags;
     cudaEventElapsedTime(&s.ms_hist, g.ev[0], g.ev[1]);
     cudaEventElapsedTime(&s.ms_pass1, g.ev[1], g.ev[2]);
     cudaEventElapsedTime(&s.ms_pass2, g.ev[2], g.ev[3]);

@@ -22,10 +22,11 @@ namespace aqp {
 // work list: items[i] = {partition, S-chunk}
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kScanBlock)
-join_items_kernel(const uint32_t *__restrict__ offR, const uint32_t *__restrict__ offS, uint32_t nparts,
-                  uint32_t *__restrict__ item_start, uint2 *__restrict__ items) {
+join_items_kernel(const uint32_t *__restrict__ offR, const uint32_t *__restrict__ endR, const uint32_t *__restrict__ offS,
+                  const uint32_t *__restrict__ endS, uint32_t nparts, uint32_t *__restrict__ item_start,
+                  uint2 *__restrict__ items) {
     auto chunks_of = [&](uint32_t p) {
-        uint32_t nr = offR[p + 1] - offR[p], ns = offS[p + 1] - offS[p];
+        uint32_t nr = endR[p] - offR[p], ns = endS[p] - offS[p];
         return (nr > 0 && ns > 0) ? (ns + kProbeChunk - 1) / kProbeChunk : 0u;
     };
     uint32_t total = block_exclusive_scan(nparts, chunks_of, [&](uint32_t p, uint32_t v) { item_start[p] = v; });
@@ -37,9 +38,11 @@ join_items_kernel(const uint32_t *__restrict__ offR, const uint32_t *__restrict_
     }
 }
 
+// partition p of a relation is [off[p], end[p]); end = nullptr means the partitions are dense: end[p] = off[p + 1]
 int join_items_device(const uint32_t *d_offR, const uint32_t *d_offS, uint32_t nparts, uint32_t *d_item_start,
-                      uint2 *d_items, cudaStream_t st) {
-    join_items_kernel<<<1, kScanBlock, 0, st>>>(d_offR, d_offS, nparts, d_item_start, d_items);
+                      uint2 *d_items, cudaStream_t st, const uint32_t *d_endR, const uint32_t *d_endS) {
+    join_items_kernel<<<1, kScanBlock, 0, st>>>(d_offR, d_endR ? d_endR : d_offR + 1, d_offS, d_endS ? d_endS : d_offS + 1,
+                                                nparts, d_item_start, d_items);
     AQP_LAUNCHED();
     AQP_CUDA_OK(cudaGetLastError());
     return 0;
@@ -66,8 +69,9 @@ constexpr uint32_t kPrefetchRounds = AQP_PROBE_PREFETCH_ROUNDS;   // S rounds (1
 
 template <bool kMaterialize>
 __global__ void __launch_bounds__(kJoinThreads, 2)
-build_probe_kernel(const uint2 *__restrict__ R, const uint32_t *__restrict__ offR, const uint2 *__restrict__ S,
-                   const uint32_t *__restrict__ offS, const uint32_t *__restrict__ item_start,
+build_probe_kernel(const uint2 *__restrict__ R, const uint32_t *__restrict__ offR, const uint32_t *__restrict__ endR,
+                   const uint2 *__restrict__ S, const uint32_t *__restrict__ offS, const uint32_t *__restrict__ endS,
+                   const uint32_t *__restrict__ item_start,
                    const uint2 *__restrict__ items, uint32_t nparts, uint32_t hash_shift,
                    JoinResult *__restrict__ res, output_triple_t *__restrict__ out, unsigned long long out_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -85,9 +89,9 @@ build_probe_kernel(const uint2 *__restrict__ R, const uint32_t *__restrict__ off
         uint32_t m32 = 0;   // matches of this thread in this item (<= 64 probe tuples x 8192 build tuples): one register
         const uint2 item = items[it];
         const uint32_t p = item.x;
-        const uint32_t rbeg = offR[p], rend = offR[p + 1];
+        const uint32_t rbeg = offR[p], rend = endR[p];
         const uint32_t sbeg = offS[p] + item.y * kProbeChunk;
-        const uint32_t send = min(sbeg + (uint32_t) kProbeChunk, offS[p + 1]);
+        const uint32_t send = min(sbeg + (uint32_t) kProbeChunk, endS[p]);
 
         constexpr uint32_t kRound = kJoinThreads * kProbeUnroll;
         // lines of S round `base` .. : 16 tuples per line, kRound / 16 lines per round
@@ -99,7 +103,7 @@ build_probe_kernel(const uint2 *__restrict__ R, const uint32_t *__restrict__ off
         };
         if (it + gridDim.x < nitems) {   // the next item's R side (one line per thread covers 8192 tuples)
             const uint2 nx = items[it + gridDim.x];
-            const uint32_t nrb = offR[nx.x], nre = offR[nx.x + 1];
+            const uint32_t nrb = offR[nx.x], nre = endR[nx.x];
             for (uint32_t i = nrb + threadIdx.x * 16; i < nre && i < nrb + kBuildCap; i += kJoinThreads * 16) prefetch_l2(R + i);
         }
         auto load_round = [&](uint32_t base, uint2 (&dst)[kProbeUnroll]) {
@@ -327,7 +331,9 @@ build_probe_kernel(const uint2 *__restrict__ R, const uint32_t *__restrict__ off
 int build_probe_device(const row_t *d_R, const uint32_t *d_offR, const row_t *d_S, const uint32_t *d_offS,
                        const uint32_t *d_item_start, const uint2 *d_items, uint32_t nparts, uint64_t max_items,
                        uint32_t hash_shift, JoinResult *d_res, output_triple_t *d_out, uint64_t out_cap,
-                       cudaStream_t st) {
+                       cudaStream_t st, const uint32_t *d_endR, const uint32_t *d_endS) {
+    if (!d_endR) d_endR = d_offR + 1;   // dense partitions
+    if (!d_endS) d_endS = d_offS + 1;
     static unsigned attr_set = ~0u;   // device epoch the opt-in was made for (b200_shutdown + b200_init(other device) re-arms it)
     if (attr_set != g_device_epoch) {
         AQP_CUDA_OK(cudaFuncSetAttribute(build_probe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -340,11 +346,11 @@ int build_probe_device(const row_t *d_R, const uint32_t *d_offR, const row_t *d_
     int grid = (int) (max_items < (uint64_t) kNumSMs * 2 ? max_items : (uint64_t) kNumSMs * 2);
     const uint2 *R = reinterpret_cast<const uint2 *>(d_R), *S = reinterpret_cast<const uint2 *>(d_S);
     if (d_out)
-        build_probe_kernel<true><<<grid, kJoinThreads, kJoinSmemBytes, st>>>(R, d_offR, S, d_offS, d_item_start, d_items,
-                                                                             nparts, hash_shift, d_res, d_out, out_cap);
+        build_probe_kernel<true><<<grid, kJoinThreads, kJoinSmemBytes, st>>>(R, d_offR, d_endR, S, d_offS, d_endS, d_item_start,
+                                                                             d_items, nparts, hash_shift, d_res, d_out, out_cap);
     else
-        build_probe_kernel<false><<<grid, kJoinThreads, kJoinSmemBytes, st>>>(R, d_offR, S, d_offS, d_item_start, d_items,
-                                                                              nparts, hash_shift, d_res, nullptr, 0);
+        build_probe_kernel<false><<<grid, kJoinThreads, kJoinSmemBytes, st>>>(R, d_offR, d_endR, S, d_offS, d_endS, d_item_start,
+                                                                              d_items, nparts, hash_shift, d_res, nullptr, 0);
     AQP_LAUNCHED();
     AQP_CUDA_OK(cudaGetLastError());
     return 0;

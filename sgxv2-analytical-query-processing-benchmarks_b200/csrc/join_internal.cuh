@@ -150,7 +150,28 @@ int plan_offsets_device(const PlanArgs &a, cudaStream_t st);
 int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_off, const uint32_t *d_seg_tile_start,
                          const uint32_t *d_seg_group, uint32_t nseg, uint64_t n_total, DigitFn digit, uint32_t bits,
                          uint32_t *d_cursors, const uint32_t *d_block_base, uint32_t nblocks, uint32_t tiles_per_block,
-                         cudaStream_t st, const PeerTable *peers = nullptr);
+                         cudaStream_t st, const PeerTable *peers = nullptr, const uint32_t *d_limits = nullptr,
+                         uint32_t *d_overflow = nullptr);
+
+// ---- histogram-free plan (api.cu: join_device_optimistic): every partition of both passes gets a region of fixed
+// capacity instead of an exact offset, so no histogram pass is needed; cursors run inside the regions, a run that does
+// not fit raises a flag and the join is repeated with exact offsets.
+struct RegionRel {
+    uint32_t n, cap1, cap2;             // tuples; region capacity (tuples) of a pass-1 / a final partition
+    uint32_t *cur1, *lim1;              // [F1]   pass-1 cursors and region ends
+    uint32_t *seg1;                     // [4]    pass-1 input: {0, n} and its tile table {0, tiles}
+    uint32_t *seg_off, *seg_tile;       // [2 F1 + 1] pass-2 input segments (data, gap, data, gap, ...) and tile table
+    uint32_t *cur2, *lim2;              // [P]    pass-2 cursors and region ends
+    uint32_t *beg, *end;                // [P]    final partitions for build/probe
+};
+struct RegionArgs {
+    uint32_t bits1, bits2;
+    uint32_t *seg_group;                // [2 F1] pass-1 partition of a pass-2 segment, kGapSegment for the gaps
+    RegionRel rel[2];
+};
+int region_init_device(const RegionArgs &a, cudaStream_t st);    // before pass 1
+int region_plan2_device(const RegionArgs &a, cudaStream_t st);   // between the passes
+int region_plan3_device(const RegionArgs &a, cudaStream_t st);   // before build/probe
 int block_base_device(const uint32_t *d_block_hist, const uint32_t *d_part_start, uint32_t fan, uint32_t nblocks,
                       uint32_t *d_block_base, uint32_t *d_counts, uint32_t *d_seg1, uint32_t n, cudaStream_t st);
 uint32_t pass1_blocks();
@@ -170,11 +191,11 @@ int single_segment_setup(uint32_t n, const uint32_t *d_offsets, uint32_t fan, ui
 
 // build_probe.cu
 int join_items_device(const uint32_t *d_offR, const uint32_t *d_offS, uint32_t nparts, uint32_t *d_item_start,
-                      uint2 *d_items, cudaStream_t st);
+                      uint2 *d_items, cudaStream_t st, const uint32_t *d_endR = nullptr, const uint32_t *d_endS = nullptr);
 int build_probe_device(const row_t *d_R, const uint32_t *d_offR, const row_t *d_S, const uint32_t *d_offS,
                        const uint32_t *d_item_start, const uint2 *d_items, uint32_t nparts, uint64_t max_items,
                        uint32_t hash_shift, JoinResult *d_res, output_triple_t *d_out, uint64_t out_cap,
-                       cudaStream_t st);
+                       cudaStream_t st, const uint32_t *d_endR = nullptr, const uint32_t *d_endS = nullptr);
 
 // gen.cu
 int gen_pk_device(row_t *d_rel, uint64_t n_total, uint64_t row_begin, uint64_t n, uint64_t seed, cudaStream_t st);

@@ -484,6 +484,71 @@ int region_plan_device(const uint32_t *d_counts_all, uint32_t world, uint32_t ra
     return 0;
 }
 
+// ---- histogram-free plan: regions of fixed capacity (RegionArgs, join_internal.cuh). blockIdx.x = relation. ----
+__global__ void __launch_bounds__(kScanBlock) region_init_kernel(RegionArgs a) {
+    const RegionRel &r = a.rel[blockIdx.x];
+    const uint32_t F1 = 1u << a.bits1, P = F1 << a.bits2;
+    for (uint32_t p = threadIdx.x; p < F1; p += kScanBlock) {
+        r.cur1[p] = p * r.cap1;
+        r.lim1[p] = (p + 1) * r.cap1;
+        if (blockIdx.x == 0) {
+            a.seg_group[2 * p] = p;
+            a.seg_group[2 * p + 1] = kGapSegment;
+        }
+    }
+    for (uint32_t f = threadIdx.x; f < P; f += kScanBlock) {
+        r.cur2[f] = f * r.cap2;
+        r.lim2[f] = (f + 1) * r.cap2;
+    }
+    if (threadIdx.x == 0) {
+        r.seg1[0] = 0;
+        r.seg1[1] = r.n;
+        r.seg1[2] = 0;
+        r.seg1[3] = (r.n + kScatterTile - 1) / kScatterTile;
+    }
+}
+// pass-2 input: partition p of pass 1 is the segment [p cap1, p cap1 + what pass 1 put there), followed by a gap
+__global__ void __launch_bounds__(kScanBlock) region_plan2_kernel(RegionArgs a) {
+    const RegionRel &r = a.rel[blockIdx.x];
+    const uint32_t F1 = 1u << a.bits1;
+    auto filled = [&](uint32_t p) { return min(r.cur1[p], r.lim1[p]) - p * r.cap1; };
+    for (uint32_t p = threadIdx.x; p < F1; p += kScanBlock) {
+        r.seg_off[2 * p] = p * r.cap1;
+        r.seg_off[2 * p + 1] = p * r.cap1 + filled(p);
+    }
+    if (threadIdx.x == 0) r.seg_off[2 * F1] = F1 * r.cap1;
+    uint32_t tiles = block_exclusive_scan(
+        2 * F1, [&](uint32_t s) { return (s & 1u) ? 0u : (filled(s >> 1) + kScatterTile - 1) / kScatterTile; },
+        [&](uint32_t s, uint32_t v) { r.seg_tile[s] = v; });
+    if (threadIdx.x == 0) r.seg_tile[2 * F1] = tiles;
+}
+__global__ void __launch_bounds__(kScanBlock) region_plan3_kernel(RegionArgs a) {
+    const RegionRel &r = a.rel[blockIdx.x];
+    const uint32_t P = 1u << (a.bits1 + a.bits2);
+    for (uint32_t f = threadIdx.x; f < P; f += kScanBlock) {
+        r.beg[f] = f * r.cap2;
+        r.end[f] = min(r.cur2[f], r.lim2[f]);
+    }
+}
+int region_init_device(const RegionArgs &a, cudaStream_t st) {
+    region_init_kernel<<<2, kScanBlock, 0, st>>>(a);
+    AQP_LAUNCHED();
+    AQP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int region_plan2_device(const RegionArgs &a, cudaStream_t st) {
+    region_plan2_kernel<<<2, kScanBlock, 0, st>>>(a);
+    AQP_LAUNCHED();
+    AQP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int region_plan3_device(const RegionArgs &a, cudaStream_t st) {
+    region_plan3_kernel<<<2, kScanBlock, 0, st>>>(a);
+    AQP_LAUNCHED();
+    AQP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int plan_shard_device(const ShardPlanArgs &a, cudaStream_t st) {
     plan_shard_kernel<<<2, kScanBlock, 0, st>>>(a);
     AQP_LAUNCHED();
@@ -814,7 +879,8 @@ radix_scatter_bins_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
                           const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_tile_start,
                           const uint32_t *__restrict__ seg_group, uint32_t nseg, DigitFn digit, uint32_t bits,
                           uint32_t *__restrict__ cursors, const uint32_t *__restrict__ block_base,
-                          uint32_t tiles_per_block, PeerTable peers) {
+                          uint32_t tiles_per_block, PeerTable peers, const uint32_t *__restrict__ limits,
+                          uint32_t *__restrict__ overflow) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint2 *inbuf = reinterpret_cast<uint2 *>(smem_raw);
     uint2 *bins = inbuf + kInBufTuples;
@@ -829,6 +895,7 @@ radix_scatter_bins_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
     __shared__ uint32_t s_soff[kMaxSegs + 1];
     __shared__ uint32_t s_ovf[2];
     __shared__ uint32_t s_total;
+    __shared__ uint32_t s_skip;         // histogram-free plan: a run of this tile found its region full (see `limits`)
     __shared__ uint32_t s_tile[2][4];   // {begin, end, cursor group} of the tile in flight / being processed
     __shared__ __align__(8) uint64_t mbar;
     __shared__ __align__(8) uint64_t mbar_free;   // input buffer read into registers by every warp
@@ -969,6 +1036,7 @@ radix_scatter_bins_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
         if (threadIdx.x == 0) {
             if (!kEarlyRefill && i + 1 < n_my) issue(i + 1);
             s_ovf[(i + 1) & 1] = 0;
+            s_skip = 0;
         }
         if (!s_ovf[i & 1]) {
             // ---------------- fixed bins: slot = (digit << lgcap) + rank ----------------
@@ -995,6 +1063,12 @@ radix_scatter_bins_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
                     g = scur[d_own];
                 } else if (n) {
                     g = atomicAdd(&cursors[(group << bits) + d_own], n);   // its latency hides behind the barrier
+                    // histogram-free plan (api.cu): the cursor runs inside a region of fixed capacity; a run that does
+                    // not fit is dropped and reported - the caller then repeats the join with exact offsets
+                    if (limits && g + n > limits[(group << bits) + d_own]) {
+                        *overflow = 1;
+                        n = 0;
+                    }
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged tuples visible to the TMA unit
@@ -1064,7 +1138,12 @@ radix_scatter_bins_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
                 // at 2^8 partitions, cost 8 round trips per tile: TPC-H Q12's pass 1 ran at 1.8 TB/s that way)
                 const uint32_t n = cnt[d_own];
                 cnt[d_own] = 0;
-                gdst[d_own] = (n ? atomicAdd(&cursors[(group << bits) + d_own], n) : 0u) - lbase[d_own];
+                const uint32_t g = n ? atomicAdd(&cursors[(group << bits) + d_own], n) : 0u;
+                if (limits && n && g + n > limits[(group << bits) + d_own]) {   // region full: drop the tile, report
+                    *overflow = 1;
+                    s_skip = 1;
+                }
+                gdst[d_own] = g - lbase[d_own];
             }
 #pragma unroll
             for (int j = 0; j < kScatterItems; ++j) {
@@ -1081,7 +1160,7 @@ radix_scatter_bins_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
             }
             __syncthreads();   // tile compacted, destinations known
             if (kLateWriteOut && i + 1 < n_my) load_tile(i + 1);
-            const uint32_t total = s_total;
+            const uint32_t total = s_skip ? 0u : s_total;
             for (uint32_t s = threadIdx.x; s < total; s += kScatterThreads) {
                 uint2 t = bins[s];
                 const uint32_t d = digit.template get<kRot>(t.x);
@@ -1262,7 +1341,8 @@ radix_scatter_peer_kernel(const uint2 *__restrict__ in, uint32_t n, DigitFn digi
 int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_off,
                          const uint32_t *d_seg_tile_start, const uint32_t *d_seg_group, uint32_t nseg, uint64_t n_total,
                          DigitFn digit, uint32_t bits, uint32_t *d_cursors, const uint32_t *d_block_base,
-                         uint32_t nblocks, uint32_t tiles_per_block, cudaStream_t st, const PeerTable *peers) {
+                         uint32_t nblocks, uint32_t tiles_per_block, cudaStream_t st, const PeerTable *peers,
+                         const uint32_t *d_limits, uint32_t *d_overflow) {
     if (bits > (uint32_t) kMaxFanoutBits || nseg > (uint32_t) kMaxSegs) {
         set_error("radix_scatter: fan-out too large");
         return -1;
@@ -1319,7 +1399,7 @@ int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_
 #define AQP_BINS_LAUNCH(ROT, PEER, PRIV)                                                                               \
     radix_scatter_bins_kernel<ROT, PEER, PRIV><<<grid, kScatterThreads, kBinsSmemBytes, st>>>(                          \
         in, out, d_seg_off, d_seg_tile_start, d_seg_group, nseg, digit, bits, d_cursors, d_block_base, tiles_per_block, \
-        peer ? *peers : none)
+        peer ? *peers : none, d_limits, d_overflow)
         static const bool peer_ring_off = getenv("B200_AQP_PEER_RING") && atoi(getenv("B200_AQP_PEER_RING")) == 0;
         bool aligned128 = true;
         if (peer)
@@ -1353,6 +1433,10 @@ int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_
         AQP_LAUNCHED();
         AQP_CUDA_OK(cudaGetLastError());
         return 0;
+    }
+    if (d_limits) {
+        set_error("radix_scatter: region limits need the fixed-bin kernel (16-byte aligned output, fan-out <= 256)");
+        return -1;
     }
     // bulk write-out needs CTA-private cursors (the destination parity must be known when the tile is staged) and a
     // 16-byte aligned destination buffer; B200_AQP_SCATTER_BULK=0 keeps the SM-store write-out (A/B measurements)

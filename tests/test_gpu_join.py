@@ -132,6 +132,32 @@ def test_forced_radix_bits(gpu, oracle, bits):
         del os.environ["B200_AQP_RADIX_BITS"]
 
 
+@pytest.mark.parametrize("bits", [14, 15])
+def test_histogram_free_plan(gpu, oracle, bits, monkeypatch):
+    """Count joins with two passes and >= 128 pass-1 partitions run without a histogram pass: every partition gets a region
+    of fixed capacity (plan_flags 1). A region that overflows - Zipf - sends the join back to exact offsets (plan_flags 2).
+    Same results either way and with the plan switched off. Forced at a small size through the radix-bit override."""
+    nR, nS = 300007, 1000003
+    R = oracle.set_rowid_payload(oracle.gen_pk(nR, 11111))
+    fk = oracle.set_rowid_payload(oracle.gen_fk(nS, nR, 22222))
+    miss = fk.copy()
+    miss["key"][::3] += nR
+    dup = R.copy()
+    dup["key"] = dup["key"] // 4 + 1
+    zipf = oracle.set_rowid_payload(oracle.gen_zipf(nS, nR, 1.0, seed=9))
+    monkeypatch.setenv("B200_AQP_RADIX_BITS", str(bits))
+    monkeypatch.setenv("B200_AQP_HISTFREE", "1")
+    for name, r, s, flags in (("fk", R, fk, 1), ("miss", R, miss, 1), ("dup", dup, fk, None), ("zipf", R, zipf, 2)):
+        g = _check(gpu, oracle, r, s, materialize=False)
+        assert g["radix_bits"] == bits and g["num_passes"] == 2, name
+        assert flags is None or g["plan_flags"] == flags, (name, g["plan_flags"])
+    monkeypatch.setenv("B200_AQP_HISTFREE", "0")
+    g = _check(gpu, oracle, R, fk, materialize=False)
+    assert g["plan_flags"] == 0
+    g = _check(gpu, oracle, R, fk, materialize=True)     # materialising joins keep exact offsets
+    assert g["plan_flags"] == 0
+
+
 def test_preload_split(gpu, oracle):
     R = oracle.set_rowid_payload(oracle.gen_pk(1 << 16, 11111))
     S = oracle.set_rowid_payload(oracle.gen_fk(1 << 18, 1 << 16, 22222))
