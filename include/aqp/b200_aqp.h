@@ -79,6 +79,7 @@ void destroy_table(struct chunked_table_t *table);
  * a region overflowed (skew), and it was repeated with exact offsets - ms_* then describe the repeat only */
 #define B200_PLAN_HISTOGRAM_FREE 1u
 #define B200_PLAN_HISTOGRAM_FREE_OVERFLOWED 2u
+#define B200_PLAN_HISTOGRAM_FREE_DECLINED 4u   /* a sample of the inputs showed skew: exact offsets from the start */
 struct b200_join_stats_t {
     int64_t matches;
     uint64_t checksum;

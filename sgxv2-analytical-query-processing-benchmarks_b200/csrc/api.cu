@@ -236,12 +236,12 @@ static MetaLayout meta_layout(uint32_t bits, uint32_t b1, uint64_t nS) {
 // run inside the regions: no histogram, no prefix sums. Pass 2 reads the regions of pass 1 as segments with gaps (the
 // multi-GPU receive layout, kGapSegment), build/probe takes [begin, end) per partition. A run that does not fit its
 // region is dropped and raises a flag; the join is then repeated with exact offsets (join_device_locked below), so any
-// input stays correct. Skew cannot be told from uniform without reading the data, so pass 1 itself is the test: its
-// flag is read before pass 2 is launched, and a skewed probe side costs one wasted pass, not a join.
-// Count/checksum joins with two passes and >= 128 pass-1 partitions only; opt-in: B200_AQP_HISTFREE=1.
+// input stays correct. To keep skewed inputs from paying for a failed attempt, 1/256 of the lines of both relations is
+// histogrammed first (~0.05 ms) and the plan is declined when the sample shows partitions beyond what the regions hold.
+// Count/checksum joins with two passes and >= 128 pass-1 partitions only; B200_AQP_HISTFREE=0 turns it off.
 // ---------------------------------------------------------------------------------------------
 struct HistFreeLayout {
-    size_t result, flag, zero_bytes, cur1[2], lim1[2], seg1[2], seg_off[2], seg_tile[2], cur2[2], lim2[2], beg[2], end[2],
+    size_t result, flag, verdict, sample[2], zero_bytes, cur1[2], seg1[2], seg_off[2], seg_tile[2], cur2[2], beg[2], end[2],
         seg_group, item_start, items, total;
 };
 static HistFreeLayout histfree_layout(uint32_t bits, uint32_t b1, uint64_t nS) {
@@ -255,15 +255,16 @@ static HistFreeLayout histfree_layout(uint32_t bits, uint32_t b1, uint64_t nS) {
     };
     m.result = take(sizeof(JoinResult));
     m.flag = take(16);
+    m.verdict = take(32);
+    m.sample[0] = take(P * 4);
+    m.sample[1] = take(P * 4);
     m.zero_bytes = o;
     for (int r = 0; r < 2; ++r) {
         m.cur1[r] = take(F1 * 4);
-        m.lim1[r] = take(F1 * 4);
         m.seg1[r] = take(16);
         m.seg_off[r] = take((2 * F1 + 1) * 4);
         m.seg_tile[r] = take((2 * F1 + 1) * 4);
         m.cur2[r] = take(P * 4);
-        m.lim2[r] = take(P * 4);
         m.beg[r] = take(P * 4);
         m.end[r] = take(P * 4);
     }
@@ -273,25 +274,37 @@ static HistFreeLayout histfree_layout(uint32_t bits, uint32_t b1, uint64_t nS) {
     m.total = o;
     return m;
 }
-// region capacity for `parts` partitions of n tuples: the mean plus 1/16 and a constant (even: bulk stores start on
-// 16-byte boundaries). A dense key or a uniform foreign key deviates by well under 1 % at these sizes.
-static uint64_t region_cap(uint64_t n, uint64_t parts) {
+// Region capacities and the sampled test that goes with them (every kSampleStride-th 128-byte line, fewer lines apart for
+// small inputs so that a final partition still sees ~64 samples):
+//   pass 1 (128+ partitions, thousands of samples each, sigma ~1 %): accepted up to 1.07 x the mean, capacity 1.125 x
+//   final partitions (~64-128 samples each, sigma ~10 %): the test only looks for heavy hitters - accepted up to 2 x the
+//   mean in the sample, capacity 2.5 x. A uniform or dense key stays near 1.0; Zipf 0.5 over 2^27 keys puts +70 % on
+//   its hottest partition and still fits; Zipf 1.0 is turned away by the pass-1 test.
+// What the sample misses the region limits in the scatter kernel catch (flag -> repeat with exact offsets).
+// Pass-1 regions start on 32 KiB boundaries (measured: 1.91 -> 1.87 ms), final ones on 128-byte lines.
+static uint64_t region_cap1(uint64_t n, uint64_t parts) {
     const uint64_t mean = (n + parts - 1) / parts;
-    return (mean + (mean >> 4) + 256 + 1) & ~(uint64_t) 1;
+    return (mean + (mean >> 3) + 256 + 4095) / 4096 * 4096;
+}
+static uint64_t region_cap2(uint64_t n, uint64_t parts) {
+    const uint64_t mean = (n + parts - 1) / parts;
+    return (2 * mean + (mean >> 1) + 256 + 15) / 16 * 16;
 }
 
 // returns 0 and *overflowed = false when the join is done; *overflowed = true when a region was too small (nothing valid
 // in stats then); -1 on errors
 static int join_device_histfree(const row_t *dR, uint64_t nR, const row_t *dS, uint64_t nS, b200_join_stats_t *stats,
-                                cudaStream_t st, uint32_t bits, uint32_t b1, uint32_t b2, bool *overflowed) {
+                                cudaStream_t st, uint32_t bits, uint32_t b1, uint32_t b2, bool *overflowed, bool *declined) {
+    *declined = false;
     const uint32_t P = 1u << bits, F1 = 1u << b1;
     const uint64_t n[2] = {nR, nS};
     uint64_t cap1[2], cap2[2];
     for (int r = 0; r < 2; ++r) {
-        cap1[r] = region_cap(n[r], F1);
-        cap2[r] = region_cap(n[r], P);
-        if (cap1[r] * F1 >= 0xFFFF0000ull || cap2[r] * P >= 0xFFFF0000ull) {   // 32-bit offsets
+        cap1[r] = region_cap1(n[r], F1);
+        cap2[r] = region_cap2(n[r], P);
+        if (cap1[r] * F1 >= 0xFFFF0000ull || cap2[r] * P >= 0xFFFF0000ull) {   // 32-bit offsets: exact plan
             *overflowed = true;
+            *declined = true;
             return 0;
         }
     }
@@ -309,35 +322,45 @@ static int join_device_histfree(const row_t *dR, uint64_t nR, const row_t *dS, u
     ra.bits2 = b2;
     ra.seg_group = u32(m.seg_group);
     for (int r = 0; r < 2; ++r)
-        ra.rel[r] = RegionRel{(uint32_t) n[r], (uint32_t) cap1[r], (uint32_t) cap2[r], u32(m.cur1[r]), u32(m.lim1[r]),
-                              u32(m.seg1[r]), u32(m.seg_off[r]), u32(m.seg_tile[r]), u32(m.cur2[r]), u32(m.lim2[r]),
-                              u32(m.beg[r]), u32(m.end[r])};
+        ra.rel[r] = RegionRel{(uint32_t) n[r], (uint32_t) cap1[r], (uint32_t) cap2[r], u32(m.cur1[r]), u32(m.seg1[r]),
+                              u32(m.seg_off[r]), u32(m.seg_tile[r]), u32(m.cur2[r]), u32(m.beg[r]), u32(m.end[r])};
     const row_t *in[2] = {dR, dS};
     row_t *t1[2] = {static_cast<row_t *>(g.tmp[0].p), static_cast<row_t *>(g.tmp[1].p)};
     row_t *t2[2] = {static_cast<row_t *>(g.tmp[2].p), static_cast<row_t *>(g.tmp[3].p)};
 
     AQP_CUDA_OK(cudaEventRecord(g.ev[0], st));
     AQP_CUDA_OK(cudaMemsetAsync(mb, 0, m.zero_bytes, st));
+    // the sampled test (one small read-back; the plan kernel of the regions is queued behind it meanwhile)
+    uint32_t verdict[6] = {};
+    for (int r = 0; r < 2; ++r) {
+        uint64_t stride = n[r] / ((uint64_t) P * 64);
+        stride = stride < 1 ? 1 : (stride > 256 ? 256 : stride);
+        if (region_sample_device(in[r], n[r], bits, (uint32_t) stride, u32(m.sample[r]), st)) return -1;
+    }
+    if (region_verdict_device(u32(m.sample[0]), u32(m.sample[1]), b1, b2, u32(m.verdict), st)) return -1;
+    AQP_CUDA_OK(cudaMemcpyAsync(verdict, u32(m.verdict), sizeof verdict, cudaMemcpyDeviceToHost, st));
     if (region_init_device(ra, st)) return -1;
+    AQP_CUDA_OK(cudaStreamSynchronize(st));
+    const bool ignore_sample = getenv("B200_AQP_HISTFREE_NOSAMPLE") != nullptr;   // test hook: reach the overflow path
+    for (int r = 0; r < 2 && !ignore_sample; ++r) {
+        const uint64_t total = verdict[r * 3], max1 = verdict[r * 3 + 1], max2 = verdict[r * 3 + 2];
+        if (max1 * F1 * 100 > total * 107 || max2 * P > 2 * total + (uint64_t) P * 8) {   // (+8 samples: tiny inputs)
+            *overflowed = true;
+            *declined = true;
+            return 0;
+        }
+    }
     AQP_CUDA_OK(cudaEventRecord(g.ev[1], st));
     for (int r = 0; r < 2; ++r)
         if (radix_scatter_launch(in[r], t1[r], u32(m.seg1[r]), u32(m.seg1[r]) + 2, nullptr, 1, n[r], make_digit(0, b1), b1,
-                                 u32(m.cur1[r]), nullptr, 0, 0, st, nullptr, u32(m.lim1[r]), d_flag))
+                                 u32(m.cur1[r]), nullptr, 0, 0, st, nullptr, (uint32_t) cap1[r], d_flag))
             return -1;
     AQP_CUDA_OK(cudaEventRecord(g.ev[2], st));
-    // pass 1 is the test of the input: a region that overflowed here (a skewed probe side) ends the attempt before
-    // pass 2 and build/probe are spent on it. One small read-back; the next kernels are queued behind it at once.
     uint32_t h_flag = 0;
-    AQP_CUDA_OK(cudaMemcpyAsync(&h_flag, d_flag, sizeof h_flag, cudaMemcpyDeviceToHost, st));
     if (region_plan2_device(ra, st)) return -1;
-    AQP_CUDA_OK(cudaStreamSynchronize(st));
-    if (h_flag) {
-        *overflowed = true;
-        return 0;
-    }
     for (int r = 0; r < 2; ++r)
         if (radix_scatter_launch(t1[r], t2[r], u32(m.seg_off[r]), u32(m.seg_tile[r]), u32(m.seg_group), 2 * F1, n[r],
-                                 make_digit(b1, b2), b2, u32(m.cur2[r]), nullptr, 0, 0, st, nullptr, u32(m.lim2[r]), d_flag))
+                                 make_digit(b1, b2), b2, u32(m.cur2[r]), nullptr, 0, 0, st, nullptr, (uint32_t) cap2[r], d_flag))
             return -1;
     AQP_CUDA_OK(cudaEventRecord(g.ev[3], st));
     if (region_plan3_device(ra, st)) return -1;
@@ -402,13 +425,14 @@ static int join_device_locked(const row_t *dR, uint64_t nR, const row_t *dS, uin
     const int passes = bits == 0 ? 0 : (b2 ? 2 : 1);
 
     uint32_t plan_flags = 0;
-    const bool histfree_on = getenv("B200_AQP_HISTFREE") && atoi(getenv("B200_AQP_HISTFREE")) == 1;   // opt-in while it is being measured
+    const bool histfree_on = !(getenv("B200_AQP_HISTFREE") && atoi(getenv("B200_AQP_HISTFREE")) == 0);
     if (histfree_on && passes == 2 && !d_out && !dead_bits && b1 >= kSharedCursorMinBits && 2 * F1 <= (uint32_t) kMaxSegs &&
         bits <= (uint32_t) kMaxSmemHistBits && !getenv("B200_AQP_PASS1")) {
-        bool overflowed = false;
-        if (join_device_histfree(dR, nR, dS, nS, stats, st, bits, b1, b2, &overflowed)) return -1;
+        bool overflowed = false, declined = false;
+        if (join_device_histfree(dR, nR, dS, nS, stats, st, bits, b1, b2, &overflowed, &declined)) return -1;
         if (!overflowed) return 0;
-        plan_flags = B200_PLAN_HISTOGRAM_FREE_OVERFLOWED;   // a region was too small: exact offsets from here on
+        // the sample showed skew, or (rarely) a region was too small after all: exact offsets from here on
+        plan_flags = declined ? B200_PLAN_HISTOGRAM_FREE_DECLINED : B200_PLAN_HISTOGRAM_FREE_OVERFLOWED;
     }
 
     MetaLayout m = meta_layout(bits, b1, nS);

@@ -150,7 +150,7 @@ int plan_offsets_device(const PlanArgs &a, cudaStream_t st);
 int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_off, const uint32_t *d_seg_tile_start,
                          const uint32_t *d_seg_group, uint32_t nseg, uint64_t n_total, DigitFn digit, uint32_t bits,
                          uint32_t *d_cursors, const uint32_t *d_block_base, uint32_t nblocks, uint32_t tiles_per_block,
-                         cudaStream_t st, const PeerTable *peers = nullptr, const uint32_t *d_limits = nullptr,
+                         cudaStream_t st, const PeerTable *peers = nullptr, uint32_t region_cap = 0,
                          uint32_t *d_overflow = nullptr);
 
 // ---- histogram-free plan (api.cu: join_device_optimistic): every partition of both passes gets a region of fixed
@@ -158,10 +158,10 @@ int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_
 // not fit raises a flag and the join is repeated with exact offsets.
 struct RegionRel {
     uint32_t n, cap1, cap2;             // tuples; region capacity (tuples) of a pass-1 / a final partition
-    uint32_t *cur1, *lim1;              // [F1]   pass-1 cursors and region ends
+    uint32_t *cur1;                     // [F1]   pass-1 cursors: cursor p runs inside [p cap1, (p + 1) cap1)
     uint32_t *seg1;                     // [4]    pass-1 input: {0, n} and its tile table {0, tiles}
     uint32_t *seg_off, *seg_tile;       // [2 F1 + 1] pass-2 input segments (data, gap, data, gap, ...) and tile table
-    uint32_t *cur2, *lim2;              // [P]    pass-2 cursors and region ends
+    uint32_t *cur2;                     // [P]    pass-2 cursors, likewise with cap2
     uint32_t *beg, *end;                // [P]    final partitions for build/probe
 };
 struct RegionArgs {
@@ -169,6 +169,12 @@ struct RegionArgs {
     uint32_t *seg_group;                // [2 F1] pass-1 partition of a pass-2 segment, kGapSegment for the gaps
     RegionRel rel[2];
 };
+// the test that comes before it: every `line_stride`-th 128-byte line of a relation is counted into a full-width
+// histogram (d_hist[2^bits], zeroed by the caller); region_verdict_device reduces the two sampled histograms to
+// d_out[rel * 3 + {0, 1, 2}] = {samples, largest pass-1 partition, largest final partition} (in samples)
+int region_sample_device(const row_t *d_in, uint64_t n, uint32_t bits, uint32_t line_stride, uint32_t *d_hist, cudaStream_t st);
+int region_verdict_device(const uint32_t *d_hist_R, const uint32_t *d_hist_S, uint32_t bits1, uint32_t bits2, uint32_t *d_out,
+                          cudaStream_t st);
 int region_init_device(const RegionArgs &a, cudaStream_t st);    // before pass 1
 int region_plan2_device(const RegionArgs &a, cudaStream_t st);   // between the passes
 int region_plan3_device(const RegionArgs &a, cudaStream_t st);   // before build/probe

@@ -490,7 +490,6 @@ __global__ void __launch_bounds__(kScanBlock) region_init_kernel(RegionArgs a) {
     const uint32_t F1 = 1u << a.bits1, P = F1 << a.bits2;
     for (uint32_t p = threadIdx.x; p < F1; p += kScanBlock) {
         r.cur1[p] = p * r.cap1;
-        r.lim1[p] = (p + 1) * r.cap1;
         if (blockIdx.x == 0) {
             a.seg_group[2 * p] = p;
             a.seg_group[2 * p + 1] = kGapSegment;
@@ -498,7 +497,6 @@ __global__ void __launch_bounds__(kScanBlock) region_init_kernel(RegionArgs a) {
     }
     for (uint32_t f = threadIdx.x; f < P; f += kScanBlock) {
         r.cur2[f] = f * r.cap2;
-        r.lim2[f] = (f + 1) * r.cap2;
     }
     if (threadIdx.x == 0) {
         r.seg1[0] = 0;
@@ -511,7 +509,7 @@ __global__ void __launch_bounds__(kScanBlock) region_init_kernel(RegionArgs a) {
 __global__ void __launch_bounds__(kScanBlock) region_plan2_kernel(RegionArgs a) {
     const RegionRel &r = a.rel[blockIdx.x];
     const uint32_t F1 = 1u << a.bits1;
-    auto filled = [&](uint32_t p) { return min(r.cur1[p], r.lim1[p]) - p * r.cap1; };
+    auto filled = [&](uint32_t p) { return min(r.cur1[p], (p + 1) * r.cap1) - p * r.cap1; };
     for (uint32_t p = threadIdx.x; p < F1; p += kScanBlock) {
         r.seg_off[2 * p] = p * r.cap1;
         r.seg_off[2 * p + 1] = p * r.cap1 + filled(p);
@@ -527,8 +525,63 @@ __global__ void __launch_bounds__(kScanBlock) region_plan3_kernel(RegionArgs a) 
     const uint32_t P = 1u << (a.bits1 + a.bits2);
     for (uint32_t f = threadIdx.x; f < P; f += kScanBlock) {
         r.beg[f] = f * r.cap2;
-        r.end[f] = min(r.cur2[f], r.lim2[f]);
+        r.end[f] = min(r.cur2[f], (f + 1) * r.cap2);
     }
+}
+// one thread per tuple of the sampled lines (16 tuples per line); fire-and-forget global atomics - a few million per join
+__global__ void __launch_bounds__(256)
+region_sample_kernel(const uint2 *__restrict__ in, uint32_t n, uint32_t mask, uint32_t line_stride, uint32_t *__restrict__ hist) {
+    const uint32_t nlines = (n + 15) / 16, nsampled = (nlines + line_stride - 1) / line_stride;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nsampled * 16; t += gridDim.x * blockDim.x) {
+        const uint32_t i = (t >> 4) * line_stride * 16 + (t & 15u);
+        if (i < n) atomicAdd(&hist[in[i].x & mask], 1u);
+    }
+}
+// blockIdx.x = relation. Full digit d = key & (P - 1): pass-1 partition d & (F1 - 1), final partition = the digit itself.
+__global__ void __launch_bounds__(kScanBlock)
+region_verdict_kernel(const uint32_t *__restrict__ hist_R, const uint32_t *__restrict__ hist_S, uint32_t bits1, uint32_t bits2,
+                      uint32_t *__restrict__ out) {
+    __shared__ uint32_t part1[kMaxFanout];
+    __shared__ uint32_t s_total, s_max1, s_max2;
+    const uint32_t *hist = blockIdx.x ? hist_S : hist_R;
+    const uint32_t F1 = 1u << bits1, P = F1 << bits2;
+    for (uint32_t p = threadIdx.x; p < F1; p += kScanBlock) part1[p] = 0;
+    if (threadIdx.x == 0) s_total = s_max1 = s_max2 = 0;
+    __syncthreads();
+    uint32_t total = 0, mx = 0;
+    for (uint32_t d = threadIdx.x; d < P; d += kScanBlock) {
+        const uint32_t c = hist[d];
+        total += c;
+        mx = max(mx, c);
+        if (c) atomicAdd(&part1[d & (F1 - 1)], c);
+    }
+    atomicAdd(&s_total, total);
+    atomicMax(&s_max2, mx);
+    __syncthreads();
+    for (uint32_t p = threadIdx.x; p < F1; p += kScanBlock) atomicMax(&s_max1, part1[p]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        out[blockIdx.x * 3 + 0] = s_total;
+        out[blockIdx.x * 3 + 1] = s_max1;
+        out[blockIdx.x * 3 + 2] = s_max2;
+    }
+}
+int region_sample_device(const row_t *d_in, uint64_t n, uint32_t bits, uint32_t line_stride, uint32_t *d_hist, cudaStream_t st) {
+    if (n == 0) return 0;
+    const uint64_t threads = ((n + 15) / 16 + line_stride - 1) / line_stride * 16;
+    const uint64_t want = (threads + 255) / 256, cap = (uint64_t) kNumSMs * 8;
+    region_sample_kernel<<<(unsigned) (want < cap ? want : cap), 256, 0, st>>>(reinterpret_cast<const uint2 *>(d_in), (uint32_t) n,
+                                                                             (1u << bits) - 1, line_stride, d_hist);
+    AQP_LAUNCHED();
+    AQP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int region_verdict_device(const uint32_t *d_hist_R, const uint32_t *d_hist_S, uint32_t bits1, uint32_t bits2, uint32_t *d_out,
+                          cudaStream_t st) {
+    region_verdict_kernel<<<2, kScanBlock, 0, st>>>(d_hist_R, d_hist_S, bits1, bits2, d_out);
+    AQP_LAUNCHED();
+    AQP_CUDA_OK(cudaGetLastError());
+    return 0;
 }
 int region_init_device(const RegionArgs &a, cudaStream_t st) {
     region_init_kernel<<<2, kScanBlock, 0, st>>>(a);
@@ -879,7 +932,7 @@ radix_scatter_bins_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
                           const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_tile_start,
                           const uint32_t *__restrict__ seg_group, uint32_t nseg, DigitFn digit, uint32_t bits,
                           uint32_t *__restrict__ cursors, const uint32_t *__restrict__ block_base,
-                          uint32_t tiles_per_block, PeerTable peers, const uint32_t *__restrict__ limits,
+                          uint32_t tiles_per_block, PeerTable peers, uint32_t region_cap,
                           uint32_t *__restrict__ overflow) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint2 *inbuf = reinterpret_cast<uint2 *>(smem_raw);
@@ -893,9 +946,10 @@ radix_scatter_bins_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
     __shared__ uint2 *s_peer[8];
     __shared__ uint32_t s_tstart[kMaxSegs + 1];
     __shared__ uint32_t s_soff[kMaxSegs + 1];
+    __shared__ uint32_t s_group[kMaxSegs + 1];   // cursor group of a segment: read per tile by the thread that requests the input
     __shared__ uint32_t s_ovf[2];
     __shared__ uint32_t s_total;
-    __shared__ uint32_t s_skip;         // histogram-free plan: a run of this tile found its region full (see `limits`)
+    __shared__ uint32_t s_skip;         // histogram-free plan: a run of this tile found its region full (see region_cap)
     __shared__ uint32_t s_tile[2][4];   // {begin, end, cursor group} of the tile in flight / being processed
     __shared__ __align__(8) uint64_t mbar;
     __shared__ __align__(8) uint64_t mbar_free;   // input buffer read into registers by every warp
@@ -905,6 +959,7 @@ radix_scatter_bins_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
     for (uint32_t i = threadIdx.x; i <= nseg; i += kScatterThreads) {
         s_tstart[i] = seg_tile_start[i];
         s_soff[i] = seg_off[i];
+        s_group[i] = (seg_group && i < nseg) ? seg_group[i] : i;
     }
     for (uint32_t i = threadIdx.x; i < fan; i += kScatterThreads) {
         cnt[i] = 0;
@@ -947,7 +1002,7 @@ radix_scatter_bins_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
         tile_range(first + i * step, seg, begin, end);
         s_tile[i & 1][0] = begin;
         s_tile[i & 1][1] = end;
-        s_tile[i & 1][2] = seg_group ? seg_group[seg] : seg;
+        s_tile[i & 1][2] = s_group[seg];   // (from shared memory: a global load here sat in front of every input request)
         const uint2 *src = in + begin;
         uint32_t skew = (uint32_t) ((reinterpret_cast<uintptr_t>(src) >> 3) & 1u);
         uint32_t bytes = ((end - begin + skew + 1) & ~1u) * (uint32_t) sizeof(uint2);
@@ -1063,18 +1118,20 @@ radix_scatter_bins_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
                     g = scur[d_own];
                 } else if (n) {
                     g = atomicAdd(&cursors[(group << bits) + d_own], n);   // its latency hides behind the barrier
-                    // histogram-free plan (api.cu): the cursor runs inside a region of fixed capacity; a run that does
-                    // not fit is dropped and reported - the caller then repeats the join with exact offsets
-                    if (limits && g + n > limits[(group << bits) + d_own]) {
-                        *overflow = 1;
-                        n = 0;
-                    }
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged tuples visible to the TMA unit
             __syncthreads();   // (2) tile staged
             if (kLateWriteOut && i + 1 < n_my) load_tile(i + 1);
             if (d_own < fan) {
+                // histogram-free plan (api.cu): cursor c runs inside the region [c cap, (c + 1) cap); a run that does
+                // not fit is dropped and reported - the caller then repeats the join with exact offsets. (Checked here,
+                // where g is needed anyway: next to the atomicAdd the check waited for it in front of the barrier and
+                // cost both passes 4-6 %.)
+                if (!kPriv && region_cap && n && g + n > ((group << bits) + d_own + 1) * region_cap) {
+                    *overflow = 1;
+                    n = 0;
+                }
                 if (n) {
                     uint2 *dst = kPeer ? s_peer[d_own >> peers.per_shift] : out;
                     const uint2 *src = bins + (d_own << lgcap);
@@ -1132,23 +1189,26 @@ radix_scatter_bins_kernel(const uint2 *__restrict__ in, uint2 *__restrict__ out,
                 if (threadIdx.x == 31) s_total = run;
             }
             __syncthreads();   // lbase ready
+            uint32_t own_n = 0, own_g = 0;
             if (!kPriv && d_own < fan) {
                 // shared cursors: every partition's owner thread reserves its run - 2^bits global atomics in flight at
                 // once, their latency under the staging stores below (warp 0 doing them one after another, 8 per lane
                 // at 2^8 partitions, cost 8 round trips per tile: TPC-H Q12's pass 1 ran at 1.8 TB/s that way)
-                const uint32_t n = cnt[d_own];
+                own_n = cnt[d_own];
                 cnt[d_own] = 0;
-                const uint32_t g = n ? atomicAdd(&cursors[(group << bits) + d_own], n) : 0u;
-                if (limits && n && g + n > limits[(group << bits) + d_own]) {   // region full: drop the tile, report
-                    *overflow = 1;
-                    s_skip = 1;
-                }
-                gdst[d_own] = g - lbase[d_own];
+                own_g = own_n ? atomicAdd(&cursors[(group << bits) + d_own], own_n) : 0u;
             }
 #pragma unroll
             for (int j = 0; j < kScatterItems; ++j) {
                 uint32_t k = j * kScatterThreads + threadIdx.x;
                 if (k < ntile) bins[lbase[digit.template get<kRot>(v[j].x)] + rank[j]] = v[j];
+            }
+            if (!kPriv && d_own < fan) {   // the atomics have had the staging stores to come back
+                if (region_cap && own_n && own_g + own_n > ((group << bits) + d_own + 1) * region_cap) {
+                    *overflow = 1;   // region full (histogram-free plan): drop the tile, report
+                    s_skip = 1;
+                }
+                gdst[d_own] = own_g - lbase[d_own];
             }
             if (kPriv && threadIdx.x < 32) {
                 const uint32_t per = (fan + 31) / 32;
@@ -1342,7 +1402,7 @@ int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_
                          const uint32_t *d_seg_tile_start, const uint32_t *d_seg_group, uint32_t nseg, uint64_t n_total,
                          DigitFn digit, uint32_t bits, uint32_t *d_cursors, const uint32_t *d_block_base,
                          uint32_t nblocks, uint32_t tiles_per_block, cudaStream_t st, const PeerTable *peers,
-                         const uint32_t *d_limits, uint32_t *d_overflow) {
+                         uint32_t region_cap, uint32_t *d_overflow) {
     if (bits > (uint32_t) kMaxFanoutBits || nseg > (uint32_t) kMaxSegs) {
         set_error("radix_scatter: fan-out too large");
         return -1;
@@ -1399,7 +1459,7 @@ int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_
 #define AQP_BINS_LAUNCH(ROT, PEER, PRIV)                                                                               \
     radix_scatter_bins_kernel<ROT, PEER, PRIV><<<grid, kScatterThreads, kBinsSmemBytes, st>>>(                          \
         in, out, d_seg_off, d_seg_tile_start, d_seg_group, nseg, digit, bits, d_cursors, d_block_base, tiles_per_block, \
-        peer ? *peers : none, d_limits, d_overflow)
+        peer ? *peers : none, region_cap, d_overflow)
         static const bool peer_ring_off = getenv("B200_AQP_PEER_RING") && atoi(getenv("B200_AQP_PEER_RING")) == 0;
         bool aligned128 = true;
         if (peer)
@@ -1434,7 +1494,7 @@ int radix_scatter_launch(const row_t *d_in, row_t *d_out, const uint32_t *d_seg_
         AQP_CUDA_OK(cudaGetLastError());
         return 0;
     }
-    if (d_limits) {
+    if (region_cap) {
         set_error("radix_scatter: region limits need the fixed-bin kernel (16-byte aligned output, fan-out <= 256)");
         return -1;
     }

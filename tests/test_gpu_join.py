@@ -135,7 +135,8 @@ def test_forced_radix_bits(gpu, oracle, bits):
 @pytest.mark.parametrize("bits", [14, 15])
 def test_histogram_free_plan(gpu, oracle, bits, monkeypatch):
     """Count joins with two passes and >= 128 pass-1 partitions run without a histogram pass: every partition gets a region
-    of fixed capacity (plan_flags 1). A region that overflows - Zipf - sends the join back to exact offsets (plan_flags 2).
+    of fixed capacity (plan_flags 1). A sample of the inputs that shows skew - Zipf - declines the plan (4); a region that
+    overflows anyway sends the join back to exact offsets (2).
     Same results either way and with the plan switched off. Forced at a small size through the radix-bit override."""
     nR, nS = 300007, 1000003
     R = oracle.set_rowid_payload(oracle.gen_pk(nR, 11111))
@@ -147,10 +148,14 @@ def test_histogram_free_plan(gpu, oracle, bits, monkeypatch):
     zipf = oracle.set_rowid_payload(oracle.gen_zipf(nS, nR, 1.0, seed=9))
     monkeypatch.setenv("B200_AQP_RADIX_BITS", str(bits))
     monkeypatch.setenv("B200_AQP_HISTFREE", "1")
-    for name, r, s, flags in (("fk", R, fk, 1), ("miss", R, miss, 1), ("dup", dup, fk, None), ("zipf", R, zipf, 2)):
+    for name, r, s, flags in (("fk", R, fk, 1), ("miss", R, miss, 1), ("dup", dup, fk, None), ("zipf", R, zipf, 4)):
         g = _check(gpu, oracle, r, s, materialize=False)
         assert g["radix_bits"] == bits and g["num_passes"] == 2, name
         assert flags is None or g["plan_flags"] == flags, (name, g["plan_flags"])
+    monkeypatch.setenv("B200_AQP_HISTFREE_NOSAMPLE", "1")    # without the sampled test the regions themselves catch it
+    g = _check(gpu, oracle, R, zipf, materialize=False)
+    assert g["plan_flags"] == 2
+    monkeypatch.delenv("B200_AQP_HISTFREE_NOSAMPLE")
     monkeypatch.setenv("B200_AQP_HISTFREE", "0")
     g = _check(gpu, oracle, R, fk, materialize=False)
     assert g["plan_flags"] == 0
