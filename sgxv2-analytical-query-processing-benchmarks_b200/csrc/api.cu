@@ -356,7 +356,6 @@ static int join_device_histfree(const row_t *dR, uint64_t nR, const row_t *dS, u
                                  u32(m.cur1[r]), nullptr, 0, 0, st, nullptr, (uint32_t) cap1[r], d_flag))
             return -1;
     AQP_CUDA_OK(cudaEventRecord(g.ev[2], st));
-    uint32_t h_flag = 0;
     if (region_plan2_device(ra, st)) return -1;
     for (int r = 0; r < 2; ++r)
         if (radix_scatter_launch(t1[r], t2[r], u32(m.seg_off[r]), u32(m.seg_tile[r]), u32(m.seg_group), 2 * F1, n[r],
@@ -372,6 +371,7 @@ static int join_device_histfree(const row_t *dR, uint64_t nR, const row_t *dS, u
         return -1;
     AQP_CUDA_OK(cudaEventRecord(g.ev[4], st));
     JoinResult h{};
+    uint32_t h_flag = 0;   // a region overflowed in one of the four scatter launches: nothing below is valid
     AQP_CUDA_OK(cudaMemcpyAsync(&h, d_res, sizeof h, cudaMemcpyDeviceToHost, st));
     AQP_CUDA_OK(cudaMemcpyAsync(&h_flag, d_flag, sizeof h_flag, cudaMemcpyDeviceToHost, st));
     AQP_CUDA_OK(cudaStreamSynchronize(st));
