@@ -332,11 +332,12 @@ static int join_device_histfree(const row_t *dR, uint64_t nR, const row_t *dS, u
     AQP_CUDA_OK(cudaMemsetAsync(mb, 0, m.zero_bytes, st));
     // the sampled test (one small read-back; the plan kernel of the regions is queued behind it meanwhile)
     uint32_t verdict[6] = {};
+    uint32_t stride[2];
     for (int r = 0; r < 2; ++r) {
-        uint64_t stride = n[r] / ((uint64_t) P * 64);
-        stride = stride < 1 ? 1 : (stride > 256 ? 256 : stride);
-        if (region_sample_device(in[r], n[r], bits, (uint32_t) stride, u32(m.sample[r]), st)) return -1;
+        const uint64_t v = n[r] / ((uint64_t) P * 64);   // ~64 samples per final partition, at most every line
+        stride[r] = (uint32_t) (v < 1 ? 1 : (v > 256 ? 256 : v));
     }
+    if (region_sample_device(dR, nR, stride[0], u32(m.sample[0]), dS, nS, stride[1], u32(m.sample[1]), bits, st)) return -1;
     if (region_verdict_device(u32(m.sample[0]), u32(m.sample[1]), b1, b2, u32(m.verdict), st)) return -1;
     AQP_CUDA_OK(cudaMemcpyAsync(verdict, u32(m.verdict), sizeof verdict, cudaMemcpyDeviceToHost, st));
     if (region_init_device(ra, st)) return -1;

@@ -169,10 +169,11 @@ struct RegionArgs {
     uint32_t *seg_group;                // [2 F1] pass-1 partition of a pass-2 segment, kGapSegment for the gaps
     RegionRel rel[2];
 };
-// the test that comes before it: every `line_stride`-th 128-byte line of a relation is counted into a full-width
-// histogram (d_hist[2^bits], zeroed by the caller); region_verdict_device reduces the two sampled histograms to
+// the test that comes before it: every `stride`-th 128-byte line of each relation is counted into a full-width
+// histogram (d_hist_*[2^bits], zeroed by the caller), both relations in one launch; region_verdict_device reduces the two sampled histograms to
 // d_out[rel * 3 + {0, 1, 2}] = {samples, largest pass-1 partition, largest final partition} (in samples)
-int region_sample_device(const row_t *d_in, uint64_t n, uint32_t bits, uint32_t line_stride, uint32_t *d_hist, cudaStream_t st);
+int region_sample_device(const row_t *d_R, uint64_t nR, uint32_t stride_R, uint32_t *d_hist_R, const row_t *d_S, uint64_t nS,
+                         uint32_t stride_S, uint32_t *d_hist_S, uint32_t bits, cudaStream_t st);
 int region_verdict_device(const uint32_t *d_hist_R, const uint32_t *d_hist_S, uint32_t bits1, uint32_t bits2, uint32_t *d_out,
                           cudaStream_t st);
 int region_init_device(const RegionArgs &a, cudaStream_t st);    // before pass 1

@@ -528,13 +528,35 @@ __global__ void __launch_bounds__(kScanBlock) region_plan3_kernel(RegionArgs a) 
         r.end[f] = min(r.cur2[f], (f + 1) * r.cap2);
     }
 }
-// one thread per tuple of the sampled lines (16 tuples per line); fire-and-forget global atomics - a few million per join
-__global__ void __launch_bounds__(256)
-region_sample_kernel(const uint2 *__restrict__ in, uint32_t n, uint32_t mask, uint32_t line_stride, uint32_t *__restrict__ hist) {
-    const uint32_t nlines = (n + 15) / 16, nsampled = (nlines + line_stride - 1) / line_stride;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nsampled * 16; t += gridDim.x * blockDim.x) {
-        const uint32_t i = (t >> 4) * line_stride * 16 + (t & 15u);
-        if (i < n) atomicAdd(&hist[in[i].x & mask], 1u);
+// one thread per tuple of the sampled lines (16 tuples per line) of BOTH relations in one launch, four independent
+// loads in flight per thread; fire-and-forget global atomics - a few million per join
+struct SampleRel {
+    const uint2 *in;
+    uint32_t n, line_stride, nthreads;   // nthreads = sampled lines * 16
+    uint32_t *hist;
+};
+__global__ void __launch_bounds__(256) region_sample_kernel(SampleRel a, SampleRel b, uint32_t mask) {
+    const uint32_t total = a.nthreads + b.nthreads, step = gridDim.x * blockDim.x;
+    for (uint32_t t0 = blockIdx.x * blockDim.x + threadIdx.x; t0 < total; t0 += 4 * step) {
+        uint32_t key[4];
+        uint32_t *dst[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t t = t0 + k * step;
+            dst[k] = nullptr;
+            if (t < total) {
+                const SampleRel &r = t < a.nthreads ? a : b;
+                const uint32_t u = t < a.nthreads ? t : t - a.nthreads;
+                const uint32_t i = (u >> 4) * r.line_stride * 16 + (u & 15u);
+                if (i < r.n) {
+                    key[k] = r.in[i].x;
+                    dst[k] = r.hist;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (dst[k]) atomicAdd(&dst[k][key[k] & mask], 1u);
     }
 }
 // blockIdx.x = relation. Full digit d = key & (P - 1): pass-1 partition d & (F1 - 1), final partition = the digit itself.
@@ -566,12 +588,17 @@ region_verdict_kernel(const uint32_t *__restrict__ hist_R, const uint32_t *__res
         out[blockIdx.x * 3 + 2] = s_max2;
     }
 }
-int region_sample_device(const row_t *d_in, uint64_t n, uint32_t bits, uint32_t line_stride, uint32_t *d_hist, cudaStream_t st) {
-    if (n == 0) return 0;
-    const uint64_t threads = ((n + 15) / 16 + line_stride - 1) / line_stride * 16;
-    const uint64_t want = (threads + 255) / 256, cap = (uint64_t) kNumSMs * 8;
-    region_sample_kernel<<<(unsigned) (want < cap ? want : cap), 256, 0, st>>>(reinterpret_cast<const uint2 *>(d_in), (uint32_t) n,
-                                                                             (1u << bits) - 1, line_stride, d_hist);
+int region_sample_device(const row_t *d_R, uint64_t nR, uint32_t stride_R, uint32_t *d_hist_R, const row_t *d_S, uint64_t nS,
+                         uint32_t stride_S, uint32_t *d_hist_S, uint32_t bits, cudaStream_t st) {
+    auto rel = [](const row_t *d, uint64_t n, uint32_t stride, uint32_t *hist) {
+        const uint64_t lines = (n + 15) / 16;
+        return SampleRel{reinterpret_cast<const uint2 *>(d), (uint32_t) n, stride, (uint32_t) ((lines + stride - 1) / stride * 16), hist};
+    };
+    const SampleRel a = rel(d_R, nR, stride_R, d_hist_R), b = rel(d_S, nS, stride_S, d_hist_S);
+    const uint64_t threads = (uint64_t) a.nthreads + b.nthreads;
+    if (threads == 0) return 0;
+    const uint64_t want = (threads + 4 * 256 - 1) / (4 * 256), cap = (uint64_t) kNumSMs * 8;
+    region_sample_kernel<<<(unsigned) (want < cap ? want : cap), 256, 0, st>>>(a, b, (1u << bits) - 1);
     AQP_LAUNCHED();
     AQP_CUDA_OK(cudaGetLastError());
     return 0;
