@@ -276,7 +276,7 @@ static HistFreeLayout histfree_layout(uint32_t bits, uint32_t b1, uint64_t nS) {
 }
 // Region capacities and the sampled test that goes with them (every kSampleStride-th 128-byte line, fewer lines apart for
 // small inputs so that a final partition still sees ~64 samples):
-//   pass 1 (128+ partitions, thousands of samples each, sigma ~1 %): accepted up to 1.07 x the mean, capacity 1.125 x
+//   pass 1 (128+ partitions, thousands of samples each, sigma <= 2 %): accepted up to 1.12 x the mean, capacity 1.25 x
 //   final partitions (~64-128 samples each, sigma ~10 %): the test only looks for heavy hitters - accepted up to 2 x the
 //   mean in the sample, capacity 2.5 x. A uniform or dense key stays near 1.0; Zipf 0.5 over 2^27 keys puts +70 % on
 //   its hottest partition and still fits; Zipf 1.0 is turned away by the pass-1 test.
@@ -284,7 +284,7 @@ static HistFreeLayout histfree_layout(uint32_t bits, uint32_t b1, uint64_t nS) {
 // Pass-1 regions start on 32 KiB boundaries (measured: 1.91 -> 1.87 ms), final ones on 128-byte lines.
 static uint64_t region_cap1(uint64_t n, uint64_t parts) {
     const uint64_t mean = (n + parts - 1) / parts;
-    return (mean + (mean >> 3) + 256 + 4095) / 4096 * 4096;
+    return (mean + (mean >> 2) + 256 + 4095) / 4096 * 4096;
 }
 static uint64_t region_cap2(uint64_t n, uint64_t parts) {
     const uint64_t mean = (n + parts - 1) / parts;
@@ -334,7 +334,9 @@ static int join_device_histfree(const row_t *dR, uint64_t nR, const row_t *dS, u
     uint32_t verdict[6] = {};
     uint32_t stride[2];
     for (int r = 0; r < 2; ++r) {
-        const uint64_t v = n[r] / ((uint64_t) P * 64);   // ~64 samples per final partition, at most every line
+        // >= 64 samples per final partition and >= 2560 per pass-1 partition (sigma 2 % against a 12 % margin), every
+        // line at most, every 256th at least
+        const uint64_t v2 = n[r] / ((uint64_t) P * 64), v1 = n[r] / ((uint64_t) F1 * 2560), v = v1 < v2 ? v1 : v2;
         stride[r] = (uint32_t) (v < 1 ? 1 : (v > 256 ? 256 : v));
     }
     if (region_sample_device(dR, nR, stride[0], u32(m.sample[0]), dS, nS, stride[1], u32(m.sample[1]), bits, st)) return -1;
@@ -345,7 +347,7 @@ static int join_device_histfree(const row_t *dR, uint64_t nR, const row_t *dS, u
     const bool ignore_sample = getenv("B200_AQP_HISTFREE_NOSAMPLE") != nullptr;   // test hook: reach the overflow path
     for (int r = 0; r < 2 && !ignore_sample; ++r) {
         const uint64_t total = verdict[r * 3], max1 = verdict[r * 3 + 1], max2 = verdict[r * 3 + 2];
-        if (max1 * F1 * 100 > total * 107 || max2 * P > 2 * total + (uint64_t) P * 8) {   // (+8 samples: tiny inputs)
+        if (max1 * F1 * 100 > total * 112 || max2 * P > 2 * total + (uint64_t) P * 8) {   // (+8 samples: tiny inputs)
             *overflowed = true;
             *declined = true;
             return 0;
@@ -422,13 +424,20 @@ static int join_device_locked(const row_t *dR, uint64_t nR, const row_t *dS, uin
         b1 = bits / 2;
         b2 = bits - b1;
     }
+    // Count joins from 11 radix bits on are candidates for the histogram-free plan (below), which needs the shared pass-1
+    // cursors and therefore 128 pass-1 partitions: the split becomes 7 + (bits - 7) instead of the reference's
+    // floor(bits / 2) + rest (2^26 x 2^28: 2.84 -> 2.48 ms, 2^25 x 2^27: 1.44 -> 1.30 ms).
+    const bool histfree_candidate = !(getenv("B200_AQP_HISTFREE") && atoi(getenv("B200_AQP_HISTFREE")) == 0) && !d_out &&
+                                    !dead_bits && !getenv("B200_AQP_PASS1") && bits >= 11 && bits <= (uint32_t) kMaxSmemHistBits;
+    if (histfree_candidate && b1 < kSharedCursorMinBits) {
+        b1 = kSharedCursorMinBits;
+        b2 = bits - b1;
+    }
     const uint32_t P = 1u << bits, F1 = 1u << b1;
     const int passes = bits == 0 ? 0 : (b2 ? 2 : 1);
 
     uint32_t plan_flags = 0;
-    const bool histfree_on = !(getenv("B200_AQP_HISTFREE") && atoi(getenv("B200_AQP_HISTFREE")) == 0);
-    if (histfree_on && passes == 2 && !d_out && !dead_bits && b1 >= kSharedCursorMinBits && 2 * F1 <= (uint32_t) kMaxSegs &&
-        bits <= (uint32_t) kMaxSmemHistBits && !getenv("B200_AQP_PASS1")) {
+    if (histfree_candidate && passes == 2 && b1 >= kSharedCursorMinBits && 2 * F1 <= (uint32_t) kMaxSegs) {
         bool overflowed = false, declined = false;
         if (join_device_histfree(dR, nR, dS, nS, stats, st, bits, b1, b2, &overflowed, &declined)) return -1;
         if (!overflowed) return 0;
