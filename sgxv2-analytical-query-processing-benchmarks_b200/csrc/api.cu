@@ -238,7 +238,7 @@ static MetaLayout meta_layout(uint32_t bits, uint32_t b1, uint64_t nS) {
 // region is dropped and raises a flag; the join is then repeated with exact offsets (join_device_locked below), so any
 // input stays correct. To keep skewed inputs from paying for a failed attempt, 1/256 of the lines of both relations is
 // histogrammed first (~0.05 ms) and the plan is declined when the sample shows partitions beyond what the regions hold.
-// Count/checksum joins with two passes and >= 128 pass-1 partitions only; B200_AQP_HISTFREE=0 turns it off.
+// Count/checksum joins from 11 radix bits on (their bits are split 7 + rest for it); B200_AQP_HISTFREE=0 turns it off.
 // ---------------------------------------------------------------------------------------------
 struct HistFreeLayout {
     size_t result, flag, verdict, sample[2], zero_bytes, cur1[2], seg1[2], seg_off[2], seg_tile[2], cur2[2], beg[2], end[2],
