@@ -10,7 +10,8 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "sgxv2-analytical-query-processing-benchmarks_b200", "libb200aqp.so")
 HOT = ["radix_hist_smem_kernel", "radix_scatter_bins_kernel", "radix_scatter_peer_kernel", "build_probe_kernel",
-       "bitvector_scan_kernel", "rowid_scan_fused_kernel<0, 16, 16, true>", "scan_count_kernel", "filter_compact_kernel"]
+       "bitvector_scan_kernel", "rowid_scan_fused_kernel<0, 16, 16, true>", "scan_count_kernel", "filter_compact_kernel",
+       "filter_compact_bytes_kernel", "region_sample_kernel"]
 COLS = ["total", "UBLKCP", "SYNCS", "LDG.256", "LDG", "STG", "LDS", "STS", "ATOMS", "ATOMG/RED", "REDUX", "IDP", "LOP3", "IMAD", "SHFL",
         "BAR"]
 
